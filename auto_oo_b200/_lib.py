@@ -1,0 +1,89 @@
+"""ctypes binding of ``liboo_b200.so`` (C ABI in ``include/oo_b200.h``).
+
+There is deliberately no fallback: if the library is missing it is built with
+nvcc, and if that is impossible importing a compute entry point raises.  Nothing
+here routes to a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_c_double_p = C.c_void_p      # device pointers are passed as integers
+_i32 = C.c_int
+_i64 = C.c_int64
+_f64 = C.c_double
+_ptr = C.c_void_p
+_size = C.c_size_t
+
+OO_WS_ROTATION, OO_WS_INT2E, OO_WS_HESSIAN, OO_WS_INT1E = 1, 2, 3, 4
+
+# name -> (restype, argtypes); mirrors include/oo_b200.h one to one
+_SIGNATURES = {
+    "oo_abi_version": (_i32, []),
+    "oo_error_string": (C.c_char_p, [_i32]),
+    "oo_last_cuda_error": (_i32, []),
+    "oo_device_info": (_i32, [C.POINTER(_i32)] * 3),
+    "oo_workspace_bytes": (_size, [_i32, _i32, _i32, _i32, _i32]),
+    "oo_dgemm_tn_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
+                               _i64, _i64, _i64, _ptr]),
+    "oo_dgemm_small_f64": (_i32, [_i32, _i32, _i32, _i32, _i32, _f64, _ptr, _i32, _i64, _ptr, _i32,
+                                  _i64, _f64, _ptr, _i32, _i64, _f64, _ptr, _i32, _i64, _i32, _ptr]),
+    "oo_kappa_rotation_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
+                                     _size, _ptr]),
+    "oo_expm_f64": (_i32, [_ptr, _f64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_mo_coeff_f64": (_i32, [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_int1e_transform_f64": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_int2e_transform_f64": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32,
+                                      _ptr, _ptr, _size, _ptr]),
+    "oo_active_hamiltonian_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr,
+                                         _ptr, _ptr]),
+    "oo_energy_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _ptr, _ptr]),
+    "oo_fock_gradient_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32,
+                                    _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "oo_fock_gradient_vjp_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
+    "oo_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32,
+                              _ptr, _ptr, _size, _ptr]),
+    "oo_pad_copy_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class OOError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if necessary) and return the ctypes library handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build_library()          # raises if nvcc is unavailable
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)                # AttributeError = symbol missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.oo_abi_version() != 1:
+        raise OOError(f"ABI mismatch: library {lib.oo_abi_version()} != binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        lib = load()
+        msg = lib.oo_error_string(rc).decode()
+        extra = f" (cudaError {lib.oo_last_cuda_error()})" if rc == -4 else ""
+        raise OOError(f"{what or 'liboo_b200'} failed: {msg}{extra}")

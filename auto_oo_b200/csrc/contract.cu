@@ -1,0 +1,380 @@
+// K3 / K4-gradient: the RDM contractions of the hot path.  All are HBM/L2-bound
+// gather-reduce kernels over slices of the transformed integrals g' (ld^4):
+//   active_hamiltonian : c0, c1, c2      (reference utils/active_space.py:111-212)
+//   energy             : E = c0 + <c1,gamma> + <c2,Gamma>      (oo_energy.py:194-197)
+//   fock_core_active   : F^I, F^A                              (oo_energy.py:272-298)
+//   fock_general       : generalized Fock                      (oo_energy.py:238-270)
+//   gradient           : G = 2 (F - F^T) and its packed vector (oo_energy.py:300-309, :221-224)
+//   fock_gradient_vjp  : adjoint w.r.t. the RDMs (what autograd provides in oo_pqc.py:113-123)
+// Index patterns follow the reference exactly (no use of the 8-fold symmetry of g),
+// so results agree for arbitrary input tensors.  Reductions are warp-shuffle trees
+// in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace oo {
+namespace {
+
+__device__ __forceinline__ int64_t idx4(int p, int q, int r, int s, int ld) {
+    return (((int64_t)p * ld + q) * ld + r) * ld + s;
+}
+
+// ---------------------------------------------------------------- active Hamiltonian
+// grid (1 + na*na + ceil(na^4/256), batch).  block 0: c0; blocks 1..na^2: c1[t,u]; rest: c2.
+__global__ void __launch_bounds__(256)
+active_hamiltonian_kernel(const double *__restrict__ h, const double *__restrict__ g, int no, int na,
+                          int ld, double e_nuc, double *__restrict__ c0, double *__restrict__ c1,
+                          double *__restrict__ c2) {
+    __shared__ double scratch[32];
+    const int b = blockIdx.y;
+    const double *hb = h + (int64_t)b * ld * ld;
+    const double *gb = g + (int64_t)b * ld * ld * ld * ld;
+    const int na2 = na * na;
+    const int64_t na4 = (int64_t)na2 * na2;
+    const int blk = blockIdx.x;
+    if (blk == 0) {
+        // c0 = e_nuc + 2 sum_i h_ii + sum_ij (2 g_iijj - g_ijji)
+        double s = 0.0;
+        for (int e = threadIdx.x; e < no * no; e += blockDim.x) {
+            const int i = e / no, j = e % no;
+            s += 2.0 * gb[idx4(i, i, j, j, ld)] - gb[idx4(i, j, j, i, ld)];
+            if (j == 0) s += 2.0 * hb[(int64_t)i * ld + i];
+        }
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) c0[b] = s + e_nuc;
+    } else if (blk <= na2) {
+        const int t = (blk - 1) / na, u = (blk - 1) % na;
+        const int T = no + t, U = no + u;
+        double s = 0.0;
+        for (int i = threadIdx.x; i < no; i += blockDim.x)
+            s += 2.0 * gb[idx4(T, U, i, i, ld)] - gb[idx4(T, i, i, U, ld)];
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) c1[(int64_t)b * na2 + t * na + u] = s + hb[(int64_t)T * ld + U];
+    } else {
+        const int64_t e = (int64_t)(blk - 1 - na2) * blockDim.x + threadIdx.x;
+        if (e < na4) {
+            const int w = (int)(e % na), v = (int)((e / na) % na), u = (int)((e / na2) % na),
+                      t = (int)(e / ((int64_t)na2 * na));
+            c2[(int64_t)b * na4 + e] = 0.5 * gb[idx4(no + t, no + u, no + v, no + w, ld)];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- energy
+__global__ void __launch_bounds__(1024)
+energy_kernel(const double *__restrict__ c0, const double *__restrict__ c1, const double *__restrict__ c2,
+              const double *__restrict__ d1, int64_t sd1, const double *__restrict__ d2, int64_t sd2,
+              int na, double *__restrict__ E) {
+    __shared__ double scratch[32];
+    const int b = blockIdx.x;
+    const int na2 = na * na;
+    const int64_t na4 = (int64_t)na2 * na2;
+    const double *c1b = c1 + (int64_t)b * na2, *c2b = c2 + (int64_t)b * na4;
+    const double *d1b = d1 + (int64_t)b * sd1, *d2b = d2 + (int64_t)b * sd2;
+    double s1 = 0.0, s2 = 0.0;
+    for (int e = threadIdx.x; e < na2; e += blockDim.x) s1 += c1b[e] * d1b[e];
+    for (int64_t e = threadIdx.x; e < na4; e += blockDim.x) s2 += c2b[e] * d2b[e];
+    s1 = block_sum(s1, scratch);
+    s2 = block_sum(s2, scratch);
+    if (threadIdx.x == 0) E[b] = (c0[b] + s1) + s2;   // same association as sum((c0, e1, e2))
+}
+
+// ---------------------------------------------------------------- F^I and F^A
+// one warp per (m, n); lanes split the i / (v,w) sums.  grid (ceil(ld*ld/8), batch), 256 threads.
+__global__ void __launch_bounds__(256)
+fock_core_active_kernel(const double *__restrict__ h, const double *__restrict__ g,
+                        const double *__restrict__ d1, int64_t sd1, int no, int na, int N, int ld,
+                        double *__restrict__ FI, double *__restrict__ FA) {
+    extern __shared__ double s_d1[];   // gamma (na*na)
+    const int b = blockIdx.y;
+    const double *d1b = d1 + (int64_t)b * sd1;
+    for (int e = threadIdx.x; e < na * na; e += blockDim.x) s_d1[e] = d1b[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= ld * ld) return;
+    const int m = pair / ld, n = pair % ld;
+    const int64_t mat = (int64_t)ld * ld;
+    double fi = 0.0, fa = 0.0;
+    if (m < N && n < N) {
+        const double *gb = g + (int64_t)b * mat * mat;
+        const double *g_mn = gb + ((int64_t)m * ld + n) * mat;   // g[m,n,:,:]
+        const double *g_m = gb + (int64_t)m * ld * mat;          // g[m,:,:,:]
+        for (int i = lane; i < no; i += 32)
+            fi += 2.0 * g_mn[(int64_t)i * ld + i] - g_m[((int64_t)i * ld + i) * ld + n];
+        for (int e = lane; e < na * na; e += 32) {
+            const int v = e / na, w = e % na;
+            fa += s_d1[e] * (g_mn[(int64_t)(no + v) * ld + (no + w)]
+                             - 0.5 * g_m[((int64_t)(no + w) * ld + (no + v)) * ld + n]);
+        }
+        fi = warp_sum(fi);
+        fa = warp_sum(fa);
+        fi += h[(int64_t)b * mat + (int64_t)m * ld + n];
+    }
+    if (lane == 0) {
+        FI[(int64_t)b * mat + pair] = fi;
+        if (FA) FA[(int64_t)b * mat + pair] = fa;
+    }
+}
+
+// ---------------------------------------------------------------- generalized Fock
+// grid (ld, batch): block n computes column n of F (rows = first index).
+//   F[i,n] = 2 (FI[n,i] + FA[n,i])                       i in occ
+//   F[v,n] = sum_w FI[n,w] d1[v,w] + sum_wxy d2[v,w,x,y] g[n,w,x,y]    v in act
+//   F[a,n] = 0                                           a in virt / padding
+__global__ void __launch_bounds__(256)
+fock_general_kernel(const double *__restrict__ g, const double *__restrict__ FI,
+                    const double *__restrict__ FA, const double *__restrict__ d1, int64_t sd1,
+                    const double *__restrict__ d2, int64_t sd2, int no, int na, int N, int ld,
+                    double *__restrict__ F) {
+    extern __shared__ double s_g[];   // g[n, act, act, act]  (na^3)
+    const int b = blockIdx.y, n = blockIdx.x;
+    const int64_t mat = (int64_t)ld * ld;
+    const double *FIb = FI + (int64_t)b * mat, *FAb = FA + (int64_t)b * mat;
+    double *Fb = F + (int64_t)b * mat;
+    const int na2 = na * na, na3 = na2 * na;
+    if (n >= N) {
+        for (int r = threadIdx.x; r < ld; r += blockDim.x) Fb[(int64_t)r * ld + n] = 0.0;
+        return;
+    }
+    const double *gn = g + (int64_t)b * mat * mat + (int64_t)n * ld * mat;   // g[n,:,:,:]
+    for (int e = threadIdx.x; e < na3; e += blockDim.x) {
+        const int w = e / na2, x = (e / na) % na, y = e % na;
+        s_g[e] = gn[((int64_t)(no + w) * ld + (no + x)) * ld + (no + y)];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < ld; r += blockDim.x) {
+        if (r < no) Fb[(int64_t)r * ld + n] = 2.0 * (FIb[(int64_t)n * ld + r] + FAb[(int64_t)n * ld + r]);
+        else if (r >= no + na) Fb[(int64_t)r * ld + n] = 0.0;
+    }
+    const double *d1b = d1 + (int64_t)b * sd1;
+    const double *d2b = d2 + (int64_t)b * sd2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int v = warp; v < na; v += nwarp) {
+        double s = 0.0;
+        for (int w = lane; w < na; w += 32) s += FIb[(int64_t)n * ld + no + w] * d1b[v * na + w];
+        const double *d2v = d2b + (int64_t)v * na3;
+        double s2 = 0.0;
+        for (int e = lane; e < na3; e += 32) s2 += d2v[e] * s_g[e];
+        s = warp_sum(s);
+        s2 = warp_sum(s2);
+        if (lane == 0) Fb[(int64_t)(no + v) * ld + n] = s + s2;
+    }
+}
+
+// ---------------------------------------------------------------- gradient
+__global__ void gradient_matrix_kernel(const double *__restrict__ F, int ld, double *__restrict__ G) {
+    const int b = blockIdx.z;
+    const int p = blockIdx.y * blockDim.y + threadIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ld || q >= ld) return;
+    const int64_t mat = (int64_t)ld * ld;
+    const double *Fb = F + (int64_t)b * mat;
+    G[(int64_t)b * mat + (int64_t)p * ld + q] = 2.0 * (Fb[(int64_t)p * ld + q] - Fb[(int64_t)q * ld + p]);
+}
+
+__global__ void gradient_pack_kernel(const double *__restrict__ F, const int32_t *__restrict__ pl,
+                                     const int32_t *__restrict__ pr, int nk, int ld,
+                                     double *__restrict__ gvec) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nk) return;
+    const double *Fb = F + (int64_t)b * ld * ld;
+    const int l = pl[j], r = pr[j];
+    gvec[(int64_t)b * nk + j] = 2.0 * (Fb[(int64_t)l * ld + r] - Fb[(int64_t)r * ld + l]);
+}
+
+// ---------------------------------------------------------------- VJP w.r.t. the RDMs
+// Fbar = 2 (Gbar - Gbar^T).
+//  blocks [0, na^2):  gbar1[v,w] = sum_{i,n} Fbar[i,n] 2 (g[n,i,v,w] - g[n,w,v,i]/2) + sum_n Fbar[v,n] FI[n,w]
+//  blocks [na^2, na^2 + na^4): gbar2[v,w,x,y] = sum_n Fbar[v,n] g[n,w,x,y]
+__global__ void __launch_bounds__(128)
+fock_gradient_vjp_kernel(const double *__restrict__ g, const double *__restrict__ FI,
+                         const double *__restrict__ Gbar, int no, int na, int N, int ld,
+                         double *__restrict__ gbar1, double *__restrict__ gbar2) {
+    __shared__ double scratch[32];
+    const int na2 = na * na;
+    const int64_t mat = (int64_t)ld * ld;
+    auto fbar = [&](int p, int q) {
+        return 2.0 * (Gbar[(int64_t)p * ld + q] - Gbar[(int64_t)q * ld + p]);
+    };
+    const int64_t blk = blockIdx.x;
+    if (blk < na2) {
+        const int v = (int)(blk / na), w = (int)(blk % na);
+        const int V = no + v, W = no + w;
+        double s = 0.0;
+        for (int e = threadIdx.x; e < no * N; e += blockDim.x) {
+            const int i = e / N, n = e % N;
+            const double *gn = g + (int64_t)n * ld * mat;
+            s += fbar(i, n) * 2.0 * (gn[((int64_t)i * ld + V) * ld + W] - 0.5 * gn[((int64_t)W * ld + V) * ld + i]);
+        }
+        for (int n = threadIdx.x; n < N; n += blockDim.x) s += fbar(V, n) * FI[(int64_t)n * ld + W];
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) gbar1[v * na + w] = s;
+    } else {
+        const int64_t e = blk - na2;
+        const int y = (int)(e % na), x = (int)((e / na) % na), w = (int)((e / na2) % na),
+                  v = (int)(e / ((int64_t)na2 * na));
+        double s = 0.0;
+        for (int n = threadIdx.x; n < N; n += blockDim.x)
+            s += fbar(no + v, n) * g[(int64_t)n * ld * mat + ((int64_t)(no + w) * ld + (no + x)) * ld + (no + y)];
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) gbar2[e] = s;
+    }
+}
+
+// ---------------------------------------------------------------- padded <-> dense copies
+__global__ void pad_copy_kernel(const double *__restrict__ src, double *__restrict__ dst, int N, int ld,
+                                int rank, int to_padded, int64_t total) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t per_pad = rank == 2 ? (int64_t)ld * ld : (int64_t)ld * ld * ld * ld;
+    const int64_t per_dense = rank == 2 ? (int64_t)N * N : (int64_t)N * N * N * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        if (to_padded) {
+            const int64_t b = i / per_pad;
+            int64_t e = i % per_pad;
+            int idx[4] = {0, 0, 0, 0};
+            bool inside = true;
+            for (int d = rank - 1; d >= 0; --d) {
+                idx[d] = (int)(e % ld);
+                e /= ld;
+                inside = inside && idx[d] < N;
+            }
+            double v = 0.0;
+            if (inside) {
+                int64_t s = 0;
+                for (int d = 0; d < rank; ++d) s = s * N + idx[d];
+                v = src[b * per_dense + s];
+            }
+            dst[i] = v;
+        } else {
+            const int64_t b = i / per_dense;
+            int64_t e = i % per_dense;
+            int idx[4] = {0, 0, 0, 0};
+            for (int d = rank - 1; d >= 0; --d) {
+                idx[d] = (int)(e % N);
+                e /= N;
+            }
+            int64_t s = 0;
+            for (int d = 0; d < rank; ++d) s = s * ld + idx[d];
+            dst[i] = src[b * per_pad + s];
+        }
+    }
+}
+
+}  // namespace
+
+int active_hamiltonian(const double *h, const double *g, int no, int na, int N, int ld, int batch,
+                       double e_nuc, double *c0, double *c1, double *c2, cudaStream_t stream) {
+    OO_REQUIRE(h && g && c0 && c1 && c2);
+    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && batch > 0);
+    if (batch > 65535) return OO_ERR_UNSUPPORTED;
+    const int64_t na4 = (int64_t)na * na * na * na;
+    dim3 grid((unsigned)(1 + na * na + ceil_div(na4, 256)), (unsigned)batch);
+    active_hamiltonian_kernel<<<grid, 256, 0, stream>>>(h, g, no, na, ld, e_nuc, c0, c1, c2);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+int energy(const double *c0, const double *c1, const double *c2, const double *d1, int64_t sd1,
+           const double *d2, int64_t sd2, int na, int batch, double *E, cudaStream_t stream) {
+    OO_REQUIRE(c0 && c1 && c2 && d1 && d2 && E && na > 0 && batch > 0);
+    energy_kernel<<<batch, 1024, 0, stream>>>(c0, c1, c2, d1, sd1, d2, sd2, na, E);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+int fock_gradient(const double *h, const double *g, const double *d1, int64_t sd1, const double *d2,
+                  int64_t sd2, int no, int na, int N, int ld, int batch, const int32_t *pl,
+                  const int32_t *pr, int nk, double *FI, double *FA, double *F, double *Gmat,
+                  double *gvec, cudaStream_t stream) {
+    OO_REQUIRE(h && g && d1 && d2 && FI && FA && F);
+    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && batch > 0);
+    OO_REQUIRE(!gvec || nk == 0 || (pl && pr));
+    if (batch > 65535) return OO_ERR_UNSUPPORTED;
+    const size_t sm1 = (size_t)na * na * sizeof(double);
+    const size_t sm3 = (size_t)na * na * na * sizeof(double);
+    if (sm1 > 48 * 1024 || sm3 > 48 * 1024) return OO_ERR_UNSUPPORTED;   // na <= 18
+    {
+        dim3 grid((unsigned)ceil_div((int64_t)ld * ld, 8), (unsigned)batch);
+        fock_core_active_kernel<<<grid, 256, sm1, stream>>>(h, g, d1, sd1, no, na, N, ld, FI, FA);
+        OO_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid((unsigned)ld, (unsigned)batch);
+        fock_general_kernel<<<grid, 256, sm3, stream>>>(g, FI, FA, d1, sd1, d2, sd2, no, na, N, ld, F);
+        OO_LAUNCH_CHECK();
+    }
+    if (Gmat) {
+        dim3 block(32, 8);
+        dim3 grid((unsigned)ceil_div(ld, 32), (unsigned)ceil_div(ld, 8), (unsigned)batch);
+        gradient_matrix_kernel<<<grid, block, 0, stream>>>(F, ld, Gmat);
+        OO_LAUNCH_CHECK();
+    }
+    if (gvec && nk > 0) {
+        dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)batch);
+        gradient_pack_kernel<<<grid, 256, 0, stream>>>(F, pl, pr, nk, ld, gvec);
+        OO_LAUNCH_CHECK();
+    }
+    return OO_OK;
+}
+
+int fock_gradient_vjp(const double *g, const double *FI, const double *Gbar, int no, int na, int N,
+                      int ld, double *gbar1, double *gbar2, cudaStream_t stream) {
+    OO_REQUIRE(g && FI && Gbar && gbar1 && gbar2);
+    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N);
+    const int64_t blocks = (int64_t)na * na + (int64_t)na * na * na * na;
+    if (blocks > 0x7fffffffll) return OO_ERR_UNSUPPORTED;
+    fock_gradient_vjp_kernel<<<(unsigned)blocks, 128, 0, stream>>>(g, FI, Gbar, no, na, N, ld, gbar1, gbar2);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+int pad_copy(const double *src, double *dst, int N, int ld, int rank, int batch, int to_padded,
+             cudaStream_t stream) {
+    OO_REQUIRE(src && dst && N > 0 && ld >= N && batch > 0 && (rank == 2 || rank == 4));
+    const int64_t per = to_padded ? (rank == 2 ? (int64_t)ld * ld : (int64_t)ld * ld * ld * ld)
+                                  : (rank == 2 ? (int64_t)N * N : (int64_t)N * N * N * N);
+    const int64_t total = per * batch;
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    pad_copy_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, N, ld, rank, to_padded, total);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+}  // namespace oo
+
+extern "C" {
+
+int oo_active_hamiltonian_f64(const double *h_mo, const double *g_mo, int no, int na, int N, int ld,
+                              int batch, double e_nuc, double *c0, double *c1, double *c2,
+                              void *stream) {
+    return oo::active_hamiltonian(h_mo, g_mo, no, na, N, ld, batch, e_nuc, c0, c1, c2,
+                                  (cudaStream_t)stream);
+}
+
+int oo_energy_f64(const double *c0, const double *c1, const double *c2, const double *gamma,
+                  int64_t stride_rdm1, const double *Gamma, int64_t stride_rdm2, int na, int batch,
+                  double *E, void *stream) {
+    return oo::energy(c0, c1, c2, gamma, stride_rdm1, Gamma, stride_rdm2, na, batch, E,
+                      (cudaStream_t)stream);
+}
+
+int oo_fock_gradient_f64(const double *h_mo, const double *g_mo, const double *gamma,
+                         int64_t stride_rdm1, const double *Gamma, int64_t stride_rdm2, int no, int na,
+                         int N, int ld, int batch, const int32_t *pair_l, const int32_t *pair_r, int nk,
+                         double *FI, double *FA, double *F, double *Gmat, double *gvec, void *stream) {
+    return oo::fock_gradient(h_mo, g_mo, gamma, stride_rdm1, Gamma, stride_rdm2, no, na, N, ld, batch,
+                             pair_l, pair_r, nk, FI, FA, F, Gmat, gvec, (cudaStream_t)stream);
+}
+
+int oo_fock_gradient_vjp_f64(const double *g_mo, const double *FI, const double *Gbar, int no, int na,
+                             int N, int ld, double *gbar1, double *gbar2, void *stream) {
+    return oo::fock_gradient_vjp(g_mo, FI, Gbar, no, na, N, ld, gbar1, gbar2, (cudaStream_t)stream);
+}
+
+int oo_pad_copy_f64(const double *src, double *dst, int N, int ld, int rank, int batch, int to_padded,
+                    void *stream) {
+    return oo::pad_copy(src, dst, N, ld, rank, batch, to_padded, (cudaStream_t)stream);
+}
+}

@@ -1,0 +1,129 @@
+// General small batched DGEMM with fused epilogue on FP64 tensor cores (DMMA.8x8x4):
+//   D[b] = alpha * op(A[b]) op(B[b]) + beta * E[b] + gamma * I
+// Used for the N x N products of the hot path: Pade/Newton-Schulz/squaring steps
+// of expm(-kappa) (reference oo_energy.py:226-230), C' = X C_oao U (:173-176, :201)
+// and C^T h C (:44-46).  Operands may be transposed and arbitrarily strided, so
+// tiles are staged through padded shared memory with plain loads (these products
+// are latency-bound: 2 N^3 flop on <= 256^2 outputs); the large contractions use
+// the TMA kernel in dgemm_tn.cu instead.
+#include "common.cuh"
+
+namespace oo {
+
+namespace {
+constexpr int TS = 32;        // CTA tile (TS x TS), 4 warps of 16 x 16
+constexpr int TK = 16;        // k-block
+constexpr int SPAD = TS + 4;  // smem row stride (doubles): (t*36 + g) mod 16 distinct per half-warp
+
+struct SmallArgs {
+    const double *A, *B, *E;
+    double *D;
+    int M, N, K;
+    int lda, ldb, lde, ldd;
+    int64_t sA, sB, sE, sD;
+    double alpha, beta, gamma;
+    int transA, transB;
+    int eye_n;   // gamma * I is added on rows < eye_n only (keeps zero padding zero)
+};
+
+__global__ void __launch_bounds__(128) dgemm_small_kernel(const SmallArgs p) {
+    __shared__ double sA[TK][SPAD];   // sA[k][m]
+    __shared__ double sB[TK][SPAD];   // sB[k][n]
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+    const double *A = p.A + (int64_t)b * p.sA;
+    const double *B = p.B + (int64_t)b * p.sB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
+
+    double acc[2][2][2] = {};
+    for (int k0 = 0; k0 < p.K; k0 += TK) {
+        // stage op(A)[m0.., k0..] as sA[k][m]
+        for (int idx = threadIdx.x; idx < TS * TK; idx += blockDim.x) {
+            int k, f;
+            if (p.transA) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
+            const int gm = m0 + f, gk = k0 + k;
+            double v = 0.0;
+            if (gm < p.M && gk < p.K)
+                v = p.transA ? A[(int64_t)gk * p.lda + gm] : A[(int64_t)gm * p.lda + gk];
+            sA[k][f] = v;
+        }
+        for (int idx = threadIdx.x; idx < TS * TK; idx += blockDim.x) {
+            int k, f;
+            if (!p.transB) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
+            const int gn = n0 + f, gk = k0 + k;
+            double v = 0.0;
+            if (gn < p.N && gk < p.K)
+                v = p.transB ? B[(int64_t)gn * p.ldb + gk] : B[(int64_t)gk * p.ldb + gn];
+            sB[k][f] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+            double a[2], bf[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                a[i] = sA[kk + t][wm + i * 8 + g];
+                bf[i] = sB[kk + t][wn + i * 8 + g];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+        }
+        __syncthreads();
+    }
+
+    double *D = p.D + (int64_t)b * p.sD;
+    const double *E = p.E ? p.E + (int64_t)b * p.sE : nullptr;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int row = m0 + wm + i * 8 + g;
+        if (row >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col = n0 + wn + j * 8 + 2 * t + c;
+                if (col >= p.N) continue;
+                double v = p.alpha * acc[i][j][c];
+                if (E) v += p.beta * E[(int64_t)row * p.lde + col];
+                if (row == col && row < p.eye_n) v += p.gamma;
+                D[(int64_t)row * p.ldd + col] = v;
+            }
+    }
+}
+}  // namespace
+
+int dgemm_small(int transA, int transB, int M, int N, int K, double alpha, const double *A, int lda,
+                int64_t strideA, const double *B, int ldb, int64_t strideB, double beta,
+                const double *E, int lde, int64_t strideE, double gamma, double *D, int ldd,
+                int64_t strideD, int batch, cudaStream_t stream, int eye_n) {
+    OO_REQUIRE(A && B && D);
+    OO_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0);
+    if (batch > 65535) return OO_ERR_UNSUPPORTED;
+    SmallArgs p;
+    p.A = A; p.B = B; p.E = E; p.D = D;
+    p.M = M; p.N = N; p.K = K;
+    p.lda = lda; p.ldb = ldb; p.lde = lde; p.ldd = ldd;
+    p.sA = strideA; p.sB = strideB; p.sE = strideE; p.sD = strideD;
+    p.alpha = alpha; p.beta = beta; p.gamma = gamma;
+    p.transA = transA; p.transB = transB;
+    p.eye_n = eye_n < 0 ? (M < N ? M : N) : eye_n;
+    dim3 grid((unsigned)ceil_div(N, TS), (unsigned)ceil_div(M, TS), (unsigned)batch);
+    dgemm_small_kernel<<<grid, 128, 0, stream>>>(p);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+}  // namespace oo
+
+extern "C" int oo_dgemm_small_f64(int transA, int transB, int M, int N, int K, double alpha,
+                                  const double *A, int lda, int64_t strideA, const double *B, int ldb,
+                                  int64_t strideB, double beta, const double *E, int lde,
+                                  int64_t strideE, double gamma, double *D, int ldd, int64_t strideD,
+                                  int batch, void *stream) {
+    return oo::dgemm_small(transA, transB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, E,
+                           lde, strideE, gamma, D, ldd, strideD, batch, (cudaStream_t)stream, -1);
+}

@@ -1,0 +1,267 @@
+// TN DGEMM for sm_100a:  C[b][m][n] = sum_k At[b][k][m] * B[b][k][n]
+//
+// This is the dense contraction behind the four-index transform
+// (reference oo_energy.py:26-29, one launch per quarter) and the Hessian
+// Y-matrix (oo_energy.py:390-392).  Both operands are K-major with the free
+// index contiguous, so both are fetched by the same TMA path:
+//   * cp.async.bulk.tensor 3-D boxes of [BK k-rows][16 doubles] with 128-byte
+//     swizzle, landing in a STAGES-deep shared-memory ring guarded by
+//     full/empty mbarriers (one producer warp, NCW consumer warps);
+//   * consumers issue FP64 tensor-core MMAs (mma.sync m8n8k4 -> DMMA.8x8x4;
+//     tcgen05 has no f64 kind).  Within a k8 step lane (g,t) takes k = 2t and
+//     k = 2t+1 for its two MMAs; with the 128B swizzle that makes every
+//     fragment load (LDS.64) bank-conflict free;
+//   * persistent CTAs (one per SM) walk the tile list with n-tiles adjacent so
+//     the A tile shared by neighbouring n-tiles is served from L2; the producer
+//     runs ahead into the next tile while consumers store the finished one.
+// OOB rows/cols/k are zero-filled by TMA, so M, N, K need no alignment; only the
+// leading dimensions must be even (16-byte global strides).
+#include "common.cuh"
+
+namespace oo {
+
+template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_>
+struct TnCfg {
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_;
+    static constexpr int NCW = WGM * WGN;            // consumer warps
+    static constexpr int THREADS = (NCW + 1) * 32;   // + 1 producer warp
+    static constexpr int WTM = BM / WGM, WTN = BN / WGN;
+    static constexpr int MT = WTM / 8, NT = WTN / 8;
+    static constexpr int CHUNK_BYTES = BK * 128;     // one TMA box: [BK][16 doubles]
+    static constexpr int A_BYTES = (BM / 16) * CHUNK_BYTES;
+    static constexpr int B_BYTES = (BN / 16) * CHUNK_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
+    static_assert(WTM % 16 == 0 && WTN % 16 == 0, "warp tile must cover whole 16-wide chunks");
+    static_assert(BK % 8 == 0, "BK must be a multiple of 8");
+    static_assert(CHUNK_BYTES % 1024 == 0, "chunks must keep the 1024B swizzle alignment");
+};
+
+struct TnArgs {
+    double *C;
+    int64_t M, N;
+    int64_t ldc, strideC;
+    int kblocks;
+    int tiles_m, tiles_n, batch;
+    int a_batched, b_batched;
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const TnArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + Cfg::STAGES;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], Cfg::NCW);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    __syncthreads();
+
+    const int tiles_per_batch = args.tiles_m * args.tiles_n;
+    const int64_t total_tiles = (int64_t)tiles_per_batch * args.batch;
+
+    if (warp == Cfg::NCW) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = (int)(tile / tiles_per_batch);
+                const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
+                const int m0 = (rem / args.tiles_n) * Cfg::BM;
+                const int n0 = (rem % args.tiles_n) * Cfg::BN;
+                const int ba = args.a_batched ? b : 0;
+                const int bb = args.b_batched ? b : 0;
+                for (int kb = 0; kb < args.kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t *sA = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t *sB = sA + Cfg::A_BYTES;
+                    const int k0 = kb * Cfg::BK;
+#pragma unroll
+                    for (int c = 0; c < Cfg::BM / 16; ++c)
+                        tma_load_3d(sA + c * Cfg::CHUNK_BYTES, &mapA, &full_bar[stage], m0 + 16 * c, k0, ba);
+#pragma unroll
+                    for (int c = 0; c < Cfg::BN / 16; ++c)
+                        tma_load_3d(sB + c * Cfg::CHUNK_BYTES, &mapB, &full_bar[stage], n0 + 16 * c, k0, bb);
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== DMMA consumers =====================
+        const int g = lane >> 2, t = lane & 3;
+        const int wm = warp / Cfg::WGN, wn = warp % Cfg::WGN;
+        // swizzled in-chunk byte offsets: x[h][j], h = which 8-column half of the
+        // 16-wide chunk, j = which of the lane's two k rows (k = 2t + j)
+        uint32_t x[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t krow = 2 * t + j;
+                x[h][j] = krow * 128u + ((((uint32_t)(h * 8 + g)) * 8u) ^ (krow << 4));
+            }
+        const uint32_t a_warp_off = (uint32_t)(wm * Cfg::WTM / 16) * Cfg::CHUNK_BYTES;
+        const uint32_t b_warp_off = Cfg::A_BYTES + (uint32_t)(wn * Cfg::WTN / 16) * Cfg::CHUNK_BYTES;
+
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int b = (int)(tile / tiles_per_batch);
+            const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
+            const int m0 = (rem / args.tiles_n) * Cfg::BM;
+            const int n0 = (rem % args.tiles_n) * Cfg::BN;
+
+            double acc[Cfg::MT][Cfg::NT][2];
+#pragma unroll
+            for (int mi = 0; mi < Cfg::MT; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < Cfg::NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+            for (int kb = 0; kb < args.kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                const uint32_t sbase = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint32_t abase = sbase + a_warp_off;
+                const uint32_t bbase = sbase + b_warp_off;
+#pragma unroll
+                for (int kk = 0; kk < Cfg::BK / 8; ++kk) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        double a[Cfg::MT], bf[Cfg::NT];
+#pragma unroll
+                        for (int mi = 0; mi < Cfg::MT; ++mi)
+                            a[mi] = lds_f64(abase + (mi >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[mi & 1][j]);
+#pragma unroll
+                        for (int ni = 0; ni < Cfg::NT; ++ni)
+                            bf[ni] = lds_f64(bbase + (ni >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[ni & 1][j]);
+#pragma unroll
+                        for (int mi = 0; mi < Cfg::MT; ++mi)
+#pragma unroll
+                            for (int ni = 0; ni < Cfg::NT; ++ni)
+                                dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                if (++stage == Cfg::STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+
+            // epilogue: registers -> global (16-byte stores, rows of 64 B per MMA tile)
+            double *Cb = args.C + (int64_t)b * args.strideC;
+#pragma unroll
+            for (int mi = 0; mi < Cfg::MT; ++mi) {
+                const int64_t row = (int64_t)m0 + wm * Cfg::WTM + mi * 8 + g;
+                if (row < args.M) {
+                    double *crow = Cb + row * args.ldc;
+#pragma unroll
+                    for (int ni = 0; ni < Cfg::NT; ++ni) {
+                        const int64_t col = (int64_t)n0 + wn * Cfg::WTN + ni * 8 + 2 * t;
+                        if (col + 1 < args.N) {
+                            *reinterpret_cast<double2 *>(crow + col) =
+                                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                        } else if (col < args.N) {
+                            crow[col] = acc[mi][ni][0];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <class Cfg>
+static int launch_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
+                     int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA,
+                     int64_t strideB, int64_t strideC, cudaStream_t stream) {
+    CUtensorMap mapA, mapB;
+    const int a_batched = (batch > 1 && strideA != 0);
+    const int b_batched = (batch > 1 && strideB != 0);
+    int rc = encode_tmap_3d_f64(&mapA, At, (uint64_t)M, (uint64_t)K, a_batched ? batch : 1,
+                                (uint64_t)lda, a_batched ? (uint64_t)strideA : (uint64_t)lda * K, 16,
+                                Cfg::BK);
+    if (rc) return rc;
+    rc = encode_tmap_3d_f64(&mapB, B, (uint64_t)N, (uint64_t)K, b_batched ? batch : 1, (uint64_t)ldb,
+                            b_batched ? (uint64_t)strideB : (uint64_t)ldb * K, 16, Cfg::BK);
+    if (rc) return rc;
+
+    TnArgs args;
+    args.C = C;
+    args.M = M;
+    args.N = N;
+    args.ldc = ldc;
+    args.strideC = strideC;
+    args.kblocks = (int)ceil_div(K, Cfg::BK);
+    args.tiles_m = (int)ceil_div(M, Cfg::BM);
+    args.tiles_n = (int)ceil_div(N, Cfg::BN);
+    args.batch = batch;
+    args.a_batched = a_batched;
+    args.b_batched = b_batched;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    dgemm_tn_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+//                     BM   BN  BK WGM WGN STAGES
+using TnWide = TnCfg<128, 128, 16, 2, 4, 4>;   // N > 64 : warp tile 64x32
+using TnMid = TnCfg<256, 64, 16, 4, 2, 4>;     // N in (32, 64]
+using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (16, 32] : warp tile 32x32
+using TnSlim = TnCfg<256, 16, 16, 8, 1, 4>;    // N <= 16 : warp tile 32x16
+
+int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
+             int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
+             int64_t strideC, cudaStream_t stream) {
+    OO_REQUIRE(At && B && C);
+    OO_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0);
+    OO_REQUIRE(lda >= M && ldb >= N && ldc >= N);
+    OO_REQUIRE((lda % 2) == 0 && (ldb % 2) == 0 && (ldc % 2) == 0);
+    OO_REQUIRE((strideA % 2) == 0 && (strideB % 2) == 0 && (strideC % 2) == 0);
+    OO_REQUIRE(((uintptr_t)At % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0);
+    if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
+    if (N > 64)
+        return launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+    if (N > 32)
+        return launch_tn<TnMid>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+    if (N > 16)
+        return launch_tn<TnNarrow>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+    return launch_tn<TnSlim>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+}
+
+}  // namespace oo
+
+extern "C" int oo_dgemm_tn_f64(const double *At, const double *B, double *C, int64_t M, int64_t N,
+                               int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int batch,
+                               int64_t strideA, int64_t strideB, int64_t strideC, void *stream) {
+    return oo::dgemm_tn(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC,
+                        (cudaStream_t)stream);
+}

@@ -1,0 +1,212 @@
+// K4-Hessian: analytic orbital Hessian reduced to the non-redundant kappa block.
+//
+// Reference: analytic_hessian_from_integrals (oo_energy.py:311-340) builds
+//   X_pqrs = 2 gf_pr h_qs - (F_pr + F_rp) d_qs + 2 Y_pqrs,
+//   Y_pqrs = sum_mn [(Gf_pmrn + Gf_pmnr) g_qmns + Gf_prmn g_qsmn]   (y_matrix, :381-393)
+//   H_pqrs = X_pqrs - X_pqsr - X_qprs + X_qpsr,
+// from full-space RDMs gf, Gf (full_rdms, :342-379) as dense N^4 tensors and three
+// N^6 einsums, then gathers H[l_j, r_j, l_k, r_k] (full_hessian_to_matrix, :395-402).
+//
+// Here: Gf and gf vanish unless all their indices are in I = occ+act (nI = no+na),
+// so Y and the gf (x) h term only exist for p, r in I.  With k = (m,n) in I x I:
+//   T[(p r),(q s)] = sum_k At[k,(p r)] B[k,(q s)]
+//     At[(m n),      (p r)] = 2 (Gf_pmrn + Gf_pmnr)     B[(m n),      (q s)] = g_qmns
+//     At[nI^2+(m n), (p r)] = 2  Gf_prmn                B[nI^2+(m n), (q s)] = g_qsmn
+//     At[2 nI^2,     (p r)] = 2  gf_pr                  B[2 nI^2,     (q s)] = h_qs
+// is ONE TN-DGEMM (dgemm_tn.cu: TMA + DMMA) of size nI^2 x ld^2 x (2 nI^2 + 1), and
+//   X(p,q,r,s) = -(F_pr + F_rp) d_qs + [p,r in I] T[(p r),(q s)]
+// is combined four ways directly into the (nk x nk) output.
+#include "common.cuh"
+
+namespace oo {
+
+int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
+             int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
+             int64_t strideC, cudaStream_t stream);
+
+namespace {
+
+struct RdmView {
+    const double *d1, *d2;
+    int no, na;
+};
+
+// full-space 1-RDM on I x I  (oo_energy.py:359-361)
+__device__ __forceinline__ double gf1(const RdmView &r, int p, int q) {
+    if (p < r.no || q < r.no) return (p == q) ? 2.0 : 0.0;
+    return r.d1[(p - r.no) * r.na + (q - r.no)];
+}
+
+// full-space 2-RDM on I^4  (oo_energy.py:363-378)
+__device__ __forceinline__ double gf2(const RdmView &r, int p, int q, int s, int t) {
+    const int no = r.no, na = r.na;
+    const bool op = p < no, oq = q < no, os = s < no, ot = t < no;
+    const int code = (op ? 8 : 0) | (oq ? 4 : 0) | (os ? 2 : 0) | (ot ? 1 : 0);
+    switch (code) {
+        case 15:  // occ occ occ occ : 4 d_pq d_st - 2 d_pt d_qs
+            return (p == q && s == t ? 4.0 : 0.0) - (p == t && q == s ? 2.0 : 0.0);
+        case 12:  // occ occ act act : 2 gamma_st d_pq
+            return p == q ? 2.0 * r.d1[(s - no) * na + (t - no)] : 0.0;
+        case 3:   // act act occ occ : 2 gamma_pq d_st
+            return s == t ? 2.0 * r.d1[(p - no) * na + (q - no)] : 0.0;
+        case 9:   // occ act act occ : -gamma_qs d_pt
+            return p == t ? -r.d1[(q - no) * na + (s - no)] : 0.0;
+        case 6:   // act occ occ act : -gamma_tp d_qs
+            return q == s ? -r.d1[(t - no) * na + (p - no)] : 0.0;
+        case 0:   // act act act act
+            return r.d2[(((int64_t)(p - no) * na + (q - no)) * na + (s - no)) * na + (t - no)];
+        default:
+            return 0.0;
+    }
+}
+
+// At rows: [0,nI^2) exchange-type, [nI^2, 2nI^2) Coulomb-type, 2nI^2: one-body.  lda >= nI^2 (even).
+__global__ void hess_build_at_kernel(RdmView rdm, int nI, int64_t lda, double *__restrict__ At) {
+    const int nI2 = nI * nI;
+    const int64_t total = (int64_t)(2 * nI2 + 1) * lda;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t k = i / lda;
+        const int col = (int)(i % lda);
+        double v = 0.0;
+        if (col < nI2) {
+            const int p = col / nI, r = col % nI;
+            if (k < nI2) {
+                const int m = (int)(k / nI), n = (int)(k % nI);
+                v = 2.0 * (gf2(rdm, p, m, r, n) + gf2(rdm, p, m, n, r));
+            } else if (k < 2 * nI2) {
+                const int kk = (int)(k - nI2);
+                const int m = kk / nI, n = kk % nI;
+                v = 2.0 * gf2(rdm, p, r, m, n);
+            } else {
+                v = 2.0 * gf1(rdm, p, r);
+            }
+        }
+        At[i] = v;
+    }
+}
+
+// B rows as above; columns (q s) over ld x ld (padding columns come out as the zero padding of g, h).
+__global__ void hess_gather_b_kernel(const double *__restrict__ h, const double *__restrict__ g, int nI,
+                                     int ld, double *__restrict__ B) {
+    const int nI2 = nI * nI;
+    const int64_t mat = (int64_t)ld * ld;
+    const int64_t total = (int64_t)(2 * nI2 + 1) * mat;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t k = i / mat;
+        const int64_t c = i % mat;
+        const int q = (int)(c / ld), s = (int)(c % ld);
+        double v;
+        if (k < nI2) {
+            const int m = (int)(k / nI), n = (int)(k % nI);
+            v = g[(((int64_t)q * ld + m) * ld + n) * ld + s];
+        } else if (k < 2 * nI2) {
+            const int kk = (int)(k - nI2);
+            const int m = kk / nI, n = kk % nI;
+            v = g[(((int64_t)q * ld + s) * ld + m) * ld + n];
+        } else {
+            v = h[c];
+        }
+        B[i] = v;
+    }
+}
+
+__device__ __forceinline__ double hess_x(const double *__restrict__ T, const double *__restrict__ F,
+                                         int nI, int ld, int a, int b, int c, int d) {
+    // X(a,b,c,d) = -(F_ac + F_ca) delta_bd + [a,c in I] T[(a c),(b d)]
+    double v = 0.0;
+    if (b == d) v = -(F[(int64_t)a * ld + c] + F[(int64_t)c * ld + a]);
+    if (a < nI && c < nI) v += T[((int64_t)a * nI + c) * ld * ld + (int64_t)b * ld + d];
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+hess_assemble_kernel(const double *__restrict__ T, const double *__restrict__ F,
+                     const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int nI,
+                     int ld, double *__restrict__ H) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (k >= nk) return;
+    const int p = pl[j], q = pr[j];
+    const int r = pl[k], s = pr[k];
+    const double v = hess_x(T, F, nI, ld, p, q, r, s) - hess_x(T, F, nI, ld, p, q, s, r)
+                   - hess_x(T, F, nI, ld, q, p, r, s) + hess_x(T, F, nI, ld, q, p, s, r);
+    H[(int64_t)j * nk + k] = v;
+}
+
+struct HessLayout {
+    int64_t lda, krows;
+    size_t off_b, off_t, total;
+};
+
+HessLayout hess_layout(int ld, int nI) {
+    HessLayout L;
+    const int64_t nI2 = (int64_t)nI * nI;
+    L.lda = (nI2 + 1) & ~1ll;
+    L.krows = 2 * nI2 + 1;
+    const size_t at_bytes = align_up((size_t)L.krows * L.lda * sizeof(double), 1024);
+    const size_t b_bytes = align_up((size_t)L.krows * ld * ld * sizeof(double), 1024);
+    const size_t t_bytes = align_up((size_t)nI2 * ld * ld * sizeof(double), 1024);
+    L.off_b = at_bytes;
+    L.off_t = at_bytes + b_bytes;
+    L.total = at_bytes + b_bytes + t_bytes;
+    return L;
+}
+
+}  // namespace
+
+size_t hessian_ws_bytes(int ld, int nI) { return hess_layout(ld, nI).total; }
+
+int hessian(const double *h, const double *g, const double *F, const double *d1, const double *d2,
+            int no, int na, int N, int ld, const int32_t *pl, const int32_t *pr, int nk, double *H,
+            void *ws, size_t ws_bytes, cudaStream_t stream) {
+    OO_REQUIRE(h && g && F && d1 && d2 && H && ws && pl && pr);
+    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0);
+    const int nI = no + na;
+    const HessLayout L = hess_layout(ld, nI);
+    if (ws_bytes < L.total) return OO_ERR_WORKSPACE;
+    if (nk > 65535 * 1) {
+        // grid.y carries j
+        if (nk > 2147483647 / 1) return OO_ERR_UNSUPPORTED;
+    }
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    double *At = reinterpret_cast<double *>(w);
+    double *B = reinterpret_cast<double *>(w + L.off_b);
+    double *T = reinterpret_cast<double *>(w + L.off_t);
+    const int64_t nI2 = (int64_t)nI * nI;
+    const int64_t mat = (int64_t)ld * ld;
+
+    RdmView rdm{d1, d2, no, na};
+    {
+        int64_t blocks = ceil_div(L.krows * L.lda, 256);
+        if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+        hess_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nI, L.lda, At);
+        OO_LAUNCH_CHECK();
+    }
+    {
+        int64_t blocks = ceil_div(L.krows * mat, 256);
+        if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+        hess_gather_b_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h, g, nI, ld, B);
+        OO_LAUNCH_CHECK();
+    }
+    int rc = dgemm_tn(At, B, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
+    if (rc) return rc;
+    {
+        if (nk > 65535) return OO_ERR_UNSUPPORTED;
+        dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
+        hess_assemble_kernel<<<grid, 256, 0, stream>>>(T, F, pl, pr, nk, nI, ld, H);
+        OO_LAUNCH_CHECK();
+    }
+    return OO_OK;
+}
+
+}  // namespace oo
+
+extern "C" int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
+                              const double *gamma, const double *Gamma, int no, int na, int N, int ld,
+                              const int32_t *pair_l, const int32_t *pair_r, int nk, double *H, void *ws,
+                              size_t ws_bytes, void *stream) {
+    return oo::hessian(h_mo, g_mo, F, gamma, Gamma, no, na, N, ld, pair_l, pair_r, nk, H, ws, ws_bytes,
+                       (cudaStream_t)stream);
+}

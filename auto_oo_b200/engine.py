@@ -1,0 +1,307 @@
+"""Device-resident orchestration of the hot path on one B200.
+
+``HotPathEngine`` owns the padded AO integrals in HBM and drives the C-ABI library
+(``include/oo_b200.h``) on torch's current CUDA stream.  torch is used only for
+device memory, streams and index tables; every arithmetic step is a kernel of
+``liboo_b200.so``.  All N-sized tensors live in the padded layout (leading dimension
+``ld`` = N rounded up to even, zero padding) that the TMA descriptors require.
+"""
+from __future__ import annotations
+
+import math as _math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def pad_even(n):
+    return n + (n & 1)
+
+
+def tril_pair_table(nao, params_idx):
+    """(row, col) of every non-redundant rotation, in kappa order (oo_energy.py:63-94)."""
+    rows, cols = np.tril_indices(nao, k=-1)
+    pidx = np.asarray(params_idx, dtype=np.int64)
+    return rows[pidx].astype(np.int32), cols[pidx].astype(np.int32)
+
+
+class HotPathEngine:
+    def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.OOError("auto_oo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.N = int(nao)
+        self.ld = pad_even(self.N)
+        self.no, self.na = int(no), int(na)
+        self.nI = self.no + self.na
+        self.nuc = float(nuc)
+        pl, pr = tril_pair_table(self.N, params_idx)
+        self.nk = len(pl)
+        self.pair_l = torch.as_tensor(pl, device=self.device)
+        self.pair_r = torch.as_tensor(pr, device=self.device)
+        with torch.cuda.device(self.device):
+            self.h_ao = self.to_padded(int1e_ao, 2)
+            self.X = self.to_padded(oao_coeff, 2)
+            self.g_ao = self.to_padded(int2e_ao, 4)
+        self._ws = {}
+        self._cache_key = None
+        self._cache_val = None
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check(self, rc, what):
+        _lib.check(rc, what)
+
+    def dev(self, x):
+        """float64 contiguous tensor on the engine's device (no copy if already there)."""
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.ascontiguousarray(x))
+        return x.detach().to(device=self.device, dtype=F64).contiguous()
+
+    def to_padded(self, x, rank, batch=None):
+        """dense (.., N^rank) -> zero padded (.., ld^rank) on device."""
+        x = self.dev(x)
+        N, ld = self.N, self.ld
+        b = 1 if batch is None else batch
+        if N == ld:
+            out = x.reshape((b,) + (ld,) * rank)        # already in the padded layout: no copy
+            return out if batch is not None else out[0]
+        out = torch.empty((b,) + (ld,) * rank, dtype=F64, device=self.device)
+        self._check(self.lib.oo_pad_copy_f64(_p(x), _p(out), N, ld, rank, b, 1, self.stream), "pad_copy")
+        return out if batch is not None else out[0]
+
+    def from_padded(self, x, rank):
+        """padded (ld^rank) or (B, ld^rank) -> dense, on device."""
+        N, ld = self.N, self.ld
+        batched = x.dim() == rank + 1
+        b = x.shape[0] if batched else 1
+        if N == ld:
+            return x
+        out = torch.empty((b,) + (N,) * rank, dtype=F64, device=self.device)
+        self._check(self.lib.oo_pad_copy_f64(_p(x.contiguous()), _p(out), N, ld, rank, b, 0, self.stream),
+                    "pad_copy")
+        return out if batched else out[0]
+
+    def workspace(self, key, nbytes):
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self._ws[key] = None
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    def release_workspaces(self):
+        self._ws.clear()
+        self._cache_key = self._cache_val = None
+
+    # ------------------------------------------------------------------ K1
+    def squarings_for(self, kappa):
+        """s = max(0, ceil(log2(||K||_1 / 0.95))) from the packed parameters (max over a batch)."""
+        k = kappa.detach().abs().reshape(-1, self.nk).to(F64)
+        if self.nk == 0:
+            return 0
+        if k.device.type == "cpu":
+            colsum = torch.zeros(k.shape[0], self.N, dtype=F64)
+            pl, pr = self.pair_l.cpu().long(), self.pair_r.cpu().long()
+        else:
+            colsum = torch.zeros(k.shape[0], self.N, dtype=F64, device=k.device)
+            pl, pr = self.pair_l.long(), self.pair_r.long()
+        colsum.index_add_(1, pl, k)
+        colsum.index_add_(1, pr, k)
+        norm1 = float(colsum.max())
+        if not _math.isfinite(norm1):
+            raise ValueError("kappa contains non-finite values")
+        if norm1 <= 0.95:
+            return 0
+        return int(_math.ceil(_math.log2(norm1 / 0.95)))
+
+    def rotation(self, kappa, squarings=None):
+        """kappa (B, nk) on device -> U (B, ld, ld) = expm(-K(kappa))."""
+        kappa = self.dev(kappa).reshape(-1, self.nk)
+        B = kappa.shape[0]
+        if squarings is None:
+            squarings = self.squarings_for(kappa)
+        U = torch.empty(B, self.ld, self.ld, dtype=F64, device=self.device)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_ROTATION, self.N, self.ld, 0, B)
+        ws = self.workspace("rot", nbytes)
+        self._check(self.lib.oo_kappa_rotation_f64(_p(kappa), _p(self.pair_l), _p(self.pair_r), self.nk,
+                                                   self.N, self.ld, B, int(squarings), _p(U), _p(ws),
+                                                   nbytes, self.stream), "kappa_rotation")
+        return U
+
+    def mo_coeff(self, oao_mo_coeff, U=None):
+        """C' = X C_oao U  (padded, batched over U)."""
+        Coao = oao_mo_coeff if oao_mo_coeff.dim() == 3 else oao_mo_coeff[None]
+        B = max(Coao.shape[0], 1 if U is None else U.shape[0])
+        out = torch.empty(B, self.ld, self.ld, dtype=F64, device=self.device)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, self.ld, 0, B)
+        ws = self.workspace("i1e", nbytes)
+        mat = self.ld * self.ld
+        sC = mat if Coao.shape[0] > 1 else 0
+        sU = 0 if U is None or U.shape[0] == 1 else mat
+        self._check(self.lib.oo_mo_coeff_f64(_p(self.X), _p(Coao), sC, _p(U), sU, self.N, self.ld, B,
+                                             _p(out), _p(ws), nbytes, self.stream), "mo_coeff")
+        return out
+
+    # ------------------------------------------------------------------ K2
+    def int1e_transform(self, C, h_ao=None):
+        C = C if C.dim() == 3 else C[None]
+        B = C.shape[0]
+        out = torch.empty(B, self.ld, self.ld, dtype=F64, device=self.device)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, self.ld, 0, B)
+        ws = self.workspace("i1e", nbytes)
+        mat = self.ld * self.ld
+        h = self.h_ao if h_ao is None else h_ao
+        self._check(self.lib.oo_int1e_transform_f64(_p(h), _p(C), mat if B > 1 else 0, self.N, self.ld, B,
+                                                    _p(out), _p(ws), nbytes, self.stream), "int1e_transform")
+        return out
+
+    def int2e_transform(self, C0, C1=None, C2=None, C3=None, g_ao=None, out=None):
+        """g'[b] from padded coefficient matrices (B, ld, ld); g_ao shared unless (B, ld^4) given."""
+        C0 = C0 if C0.dim() == 3 else C0[None]
+        Cs = [C0] + [C0 if c is None else (c if c.dim() == 3 else c[None]) for c in (C1, C2, C3)]
+        B = C0.shape[0]
+        ld = self.ld
+        g = self.g_ao if g_ao is None else g_ao
+        strideG = ld ** 4 if (g.dim() == 5 and g.shape[0] > 1) else 0
+        if out is None:
+            out = torch.empty((B, ld, ld, ld, ld), dtype=F64, device=self.device)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_INT2E, self.N, ld, 0, B)
+        ws = self.workspace("i2e", nbytes)
+        self._check(self.lib.oo_int2e_transform_f64(_p(g), strideG, _p(Cs[0]), _p(Cs[1]), _p(Cs[2]),
+                                                    _p(Cs[3]), ld * ld if B > 1 else 0, self.N, ld, B,
+                                                    _p(out), _p(ws), nbytes, self.stream), "int2e_transform")
+        return out
+
+    def mo_integrals(self, C):
+        """(h', g') for padded C (B, ld, ld); the last single-matrix result is cached by value."""
+        C = C if C.dim() == 3 else C[None]
+        if C.shape[0] == 1 and self._cache_key is not None and torch.equal(self._cache_key, C):
+            return self._cache_val
+        if C.shape[0] == 1 and self._cache_val is not None:
+            out = self._cache_val[1]                      # reuse the N^4 buffer
+            self._cache_key = self._cache_val = None
+        else:
+            out = None
+        h = self.int1e_transform(C)
+        g = self.int2e_transform(C, out=out)
+        if C.shape[0] == 1:
+            self._cache_key, self._cache_val = C.clone(), (h, g)
+        return h, g
+
+    # ------------------------------------------------------------------ K3
+    def active_hamiltonian(self, h, g):
+        B, na = h.shape[0], self.na
+        c0 = torch.empty(B, dtype=F64, device=self.device)
+        c1 = torch.empty(B, na, na, dtype=F64, device=self.device)
+        c2 = torch.empty(B, na, na, na, na, dtype=F64, device=self.device)
+        self._check(self.lib.oo_active_hamiltonian_f64(_p(h), _p(g), self.no, na, self.N, self.ld, B,
+                                                       self.nuc, _p(c0), _p(c1), _p(c2), self.stream),
+                    "active_hamiltonian")
+        return c0, c1, c2
+
+    def _rdm_strides(self, d1, d2, B):
+        na = self.na
+        s1 = na * na if (d1.dim() == 3 and d1.shape[0] > 1) else 0
+        s2 = na ** 4 if (d2.dim() == 5 and d2.shape[0] > 1) else 0
+        assert s1 == 0 or d1.shape[0] == B
+        assert s2 == 0 or d2.shape[0] == B
+        return s1, s2
+
+    def energy(self, c0, c1, c2, d1, d2):
+        B = c0.shape[0]
+        s1, s2 = self._rdm_strides(d1, d2, B)
+        E = torch.empty(B, dtype=F64, device=self.device)
+        self._check(self.lib.oo_energy_f64(_p(c0), _p(c1), _p(c2), _p(d1), s1, _p(d2), s2, self.na, B,
+                                           _p(E), self.stream), "energy")
+        return E
+
+    # ------------------------------------------------------------------ K4
+    def fock_gradient(self, h, g, d1, d2, want_matrix=True, want_vector=True):
+        B, ld = h.shape[0], self.ld
+        s1, s2 = self._rdm_strides(d1, d2, B)
+        FI = torch.empty(B, ld, ld, dtype=F64, device=self.device)
+        FA = torch.empty_like(FI)
+        F = torch.empty_like(FI)
+        G = torch.empty_like(FI) if want_matrix else None
+        gv = torch.empty(B, self.nk, dtype=F64, device=self.device) if want_vector else None
+        self._check(self.lib.oo_fock_gradient_f64(_p(h), _p(g), _p(d1), s1, _p(d2), s2, self.no, self.na,
+                                                  self.N, ld, B, _p(self.pair_l), _p(self.pair_r), self.nk,
+                                                  _p(FI), _p(FA), _p(F), _p(G), _p(gv), self.stream),
+                    "fock_gradient")
+        return FI, FA, F, G, gv
+
+    def fock_gradient_vjp(self, g, FI, Gbar):
+        na = self.na
+        g1 = torch.empty(na, na, dtype=F64, device=self.device)
+        g2 = torch.empty(na, na, na, na, dtype=F64, device=self.device)
+        self._check(self.lib.oo_fock_gradient_vjp_f64(_p(g), _p(FI), _p(Gbar), self.no, na, self.N, self.ld,
+                                                      _p(g1), _p(g2), self.stream), "fock_gradient_vjp")
+        return g1, g2
+
+    def hessian(self, h, g, F, d1, d2, out=None):
+        """(nk, nk) Hessian for ONE evaluation (h, g, F are single padded tensors)."""
+        nk = self.nk
+        H = out if out is not None else torch.empty(nk, nk, dtype=F64, device=self.device)
+        if nk == 0:
+            return H
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_HESSIAN, self.N, self.ld, self.nI, 1)
+        ws = self.workspace("hess", nbytes)
+        self._check(self.lib.oo_hessian_f64(_p(h), _p(g), _p(F), _p(d1), _p(d2), self.no, self.na, self.N,
+                                            self.ld, _p(self.pair_l), _p(self.pair_r), nk, _p(H), _p(ws),
+                                            nbytes, self.stream), "hessian")
+        return H
+
+    # ------------------------------------------------------------------ whole evaluations
+    def evaluate(self, oao_mo_coeff, d1, d2, kappa=None, want_hessian=True, squarings=None,
+                 H_out=None):
+        """E (B,), packed gradient (B, nk) and Hessian (B, nk, nk) at C' = X C_oao expm(-K(kappa_b)).
+
+        ``oao_mo_coeff``: padded (ld, ld) or (B, ld, ld) device tensor; ``kappa``: (B, nk) or None.
+        One 4-index transform per evaluation serves E, G and H (the reference repeats it
+        three times: oo_energy.py:207-208, :410-411, :421-422).  Evaluations are processed
+        one at a time through the N^4 stages (one g' buffer + one workspace in HBM)."""
+        Coao = oao_mo_coeff if oao_mo_coeff.dim() == 3 else oao_mo_coeff[None]
+        if kappa is not None:
+            kappa = self.dev(kappa).reshape(-1, self.nk)
+            U = self.rotation(kappa, squarings)
+            C = self.mo_coeff(Coao, U)
+        else:
+            C = self.mo_coeff(Coao)
+        B = C.shape[0]
+        d1 = self.dev(d1)
+        d2 = self.dev(d2)
+        E = torch.empty(B, dtype=F64, device=self.device)
+        G = torch.empty(B, self.nk, dtype=F64, device=self.device)
+        H = None
+        if want_hessian:
+            H = H_out if H_out is not None else torch.empty(B, self.nk, self.nk, dtype=F64, device=self.device)
+        hs = self.int1e_transform(C)
+        gbuf = None
+        if self._cache_val is not None:
+            gbuf = self._cache_val[1]
+            self._cache_key = self._cache_val = None
+        for b in range(B):
+            gbuf = self.int2e_transform(C[b:b + 1], out=gbuf)
+            h1 = hs[b:b + 1]
+            d1b = d1[b] if d1.dim() == 3 else d1
+            d2b = d2[b] if d2.dim() == 5 else d2
+            c0, c1, c2 = self.active_hamiltonian(h1, gbuf)
+            E[b:b + 1] = self.energy(c0, c1, c2, d1b, d2b)
+            FI, FA, F, _, gv = self.fock_gradient(h1, gbuf, d1b, d2b, want_matrix=False)
+            G[b] = gv[0]
+            if want_hessian:
+                self.hessian(h1[0], gbuf[0], F[0], d1b, d2b, out=H[b])
+        return E, G, H

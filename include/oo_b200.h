@@ -1,0 +1,183 @@
+/*
+ * oo_b200.h -- C ABI of the B200-native orbital-optimization hot path.
+ *
+ * The reference (Emieeel/auto_oo) has no FFI boundary: the path lives behind
+ * Python methods of `OO_energy` (src/auto_oo/oo_energy.py:121-474) and the free
+ * functions in oo_energy.py:21-118 / utils/active_space.py:111-212, whose
+ * arithmetic is dispatched to torch CPU ops.  Each entry point below replaces
+ * one group of those call sites; the citation says which.  INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions (all entry points)
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *    the name ends in `_host`; all data are float64, row-major.
+ *  - N  = number of orbitals (logical), ld = padded leading dimension used for
+ *    EVERY axis of every N-sized tensor (ld even, ld >= N; rows/cols N..ld-1
+ *    must be zero on input and are zero on output).  A 4-index tensor is
+ *    ld*ld*ld*ld doubles.
+ *  - orbital classes are the contiguous ranges occ [0,no), act [no,no+na),
+ *    virt [no+na,N)  (reference moldata_pyscf.py:42-56).
+ *  - the caller owns every buffer, including workspaces (size from
+ *    oo_workspace_bytes); the library never allocates, frees or retains them.
+ *  - all work is enqueued on `stream` (a cudaStream_t); no host sync, so calls
+ *    may be captured into a CUDA graph.
+ *  - return 0 on success, a negative OO_ERR_* code otherwise (oo_error_string).
+ */
+#ifndef OO_B200_H
+#define OO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OO_ABI_VERSION 1
+
+enum {
+    OO_OK = 0,
+    OO_ERR_INVALID_ARG = -1,   /* null pointer, negative size, odd ld, ...        */
+    OO_ERR_UNSUPPORTED = -2,   /* size outside what the kernels were built for     */
+    OO_ERR_WORKSPACE   = -3,   /* workspace too small                              */
+    OO_ERR_CUDA        = -4,   /* a CUDA runtime/driver call failed (see oo_last_cuda_error) */
+    OO_ERR_NO_DEVICE   = -5    /* no sm_100 device / driver entry point missing    */
+};
+
+/* workspace selectors for oo_workspace_bytes */
+enum {
+    OO_WS_ROTATION   = 1,      /* oo_kappa_rotation_f64                            */
+    OO_WS_INT2E      = 2,      /* oo_int2e_transform_f64                           */
+    OO_WS_HESSIAN    = 3,      /* oo_hessian_f64                                   */
+    OO_WS_INT1E      = 4       /* oo_int1e_transform_f64 / oo_mo_coeff_f64         */
+};
+
+int         oo_abi_version(void);
+const char *oo_error_string(int code);
+int         oo_last_cuda_error(void);                 /* cudaError_t of the last OO_ERR_CUDA */
+int         oo_device_info(int *sm_count, int *cc_major, int *cc_minor);
+size_t      oo_workspace_bytes(int which, int N, int ld, int nI, int batch);
+
+/* ---- dense building block -------------------------------------------------
+ * C[b][m][n] = sum_k At[b][k][m] * B[b][k][n]     (both operands K-major)
+ * TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring -> FP64 DMMA.
+ * lda/ldb/ldc in elements (even); stride* = per-batch element strides, 0 = shared.
+ * Exposed because the 4-index transform and the Hessian Y-matrix are this GEMM. */
+int oo_dgemm_tn_f64(const double *At, const double *B, double *C,
+                    int64_t M, int64_t N, int64_t K,
+                    int64_t lda, int64_t ldb, int64_t ldc,
+                    int batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                    void *stream);
+
+/* general small batched product with fused epilogue (expm, C^T h C, X C U):
+ * D[b] = alpha * op(A[b]) op(B[b]) + beta * E[b] + gamma * I ; op = transpose if trans* != 0;
+ * E may be NULL (beta ignored) and may alias D.                                 */
+int oo_dgemm_small_f64(int transA, int transB, int M, int N, int K,
+                       double alpha, const double *A, int lda, int64_t strideA,
+                       const double *B, int ldb, int64_t strideB,
+                       double beta, const double *E, int lde, int64_t strideE,
+                       double gamma, double *D, int ldd, int64_t strideD,
+                       int batch, void *stream);
+
+/* ---- K1: kappa -> U = expm(-K(kappa)) --------------------------------------
+ * replaces oo_energy.py:213-219 (kappa_vector_to_matrix), :63-87
+ * (vector_to_skew_symmetric) and :226-230 (math.expm(-kappa_matrix)).
+ * kappa[b][nk]; pair_l/pair_r[nk] = (row, col) of each non-redundant parameter
+ * (row > col): K[l,r] = +kappa, K[r,l] = -kappa.  `squarings` >= ceil(log2(||K||_1/0.95))
+ * (host-chosen; Pade-[7/7] of K/2^s, Newton-Schulz solve, s squarings).
+ * U[b] is ld x ld.  ws: oo_workspace_bytes(OO_WS_ROTATION, N, ld, 0, batch).      */
+int oo_kappa_rotation_f64(const double *kappa, const int32_t *pair_l, const int32_t *pair_r,
+                          int nk, int N, int ld, int batch, int squarings,
+                          double *U, void *ws, size_t ws_bytes, void *stream);
+
+/* expm(sign * A) of arbitrary (not nec. skew) ld x ld matrices with ||A||_1 <= 0.95 * 2^squarings */
+int oo_expm_f64(const double *A, double sign, int N, int ld, int batch, int squarings,
+                double *U, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- K1 epilogue / K2a ------------------------------------------------------
+ * C'[b] = X * Coao[b] * U[b]          (oo_energy.py:173-176 mo_coeff, :201/:235)
+ * strideCoao / strideU = 0 shares the matrix across the batch; U may be NULL.   */
+int oo_mo_coeff_f64(const double *X, const double *Coao, int64_t strideCoao,
+                    const double *U, int64_t strideU, int N, int ld, int batch,
+                    double *Cout, void *ws, size_t ws_bytes, void *stream);
+
+/* h'[b] = C[b]^T h C[b]               (oo_energy.py:44-46 int1e_transform)      */
+int oo_int1e_transform_f64(const double *h_ao, const double *C, int64_t strideC,
+                           int N, int ld, int batch, double *h_mo,
+                           void *ws, size_t ws_bytes, void *stream);
+
+/* ---- K2b: four-index transform ---------------------------------------------
+ * g'[i,j,k,l] = sum_pqrs C0[p,i] C1[q,j] C2[r,k] C3[s,l] g[p,q,r,s]
+ * replaces oo_energy.py:21-30 (general_4index_transform), :33-41, :49-51.
+ * Four quarter transforms, each one TN-DGEMM [ld^3 x ld] = [ld x ld^3]^T [ld x ld]
+ * that rotates the transformed index to the back, so after four quarters the
+ * layout is [i,j,k,l] again.  strideG = 0 shares g_ao over the batch
+ * (kappa sweep); strideC = per-batch stride of each C matrix.
+ * ws: oo_workspace_bytes(OO_WS_INT2E, N, ld, 0, batch) = batch * ld^4 doubles.  */
+int oo_int2e_transform_f64(const double *g_ao, int64_t strideG,
+                           const double *C0, const double *C1, const double *C2,
+                           const double *C3, int64_t strideC,
+                           int N, int ld, int batch, double *g_mo,
+                           void *ws, size_t ws_bytes, void *stream);
+
+/* ---- K3: active-space Hamiltonian and energy -------------------------------
+ * c0 = e_nuc + 2 sum_i h_ii + 2 sum_ij g_iijj - sum_ij g_ijji
+ * c1_tu = h_tu + sum_i (2 g_tuii - g_tiiu) ; c2_tuvw = g_tuvw / 2
+ * replaces utils/active_space.py:111-174 and :177-212.
+ * c0[b], c1[b][na*na], c2[b][na^4] (dense, no padding).                          */
+int oo_active_hamiltonian_f64(const double *h_mo, const double *g_mo, int no, int na,
+                              int N, int ld, int batch, double e_nuc,
+                              double *c0, double *c1, double *c2, void *stream);
+
+/* E[b] = c0[b] + <c1[b],gamma[b]> + <c2[b],Gamma[b]>   (oo_energy.py:194-197)
+ * stride_rdm1/2 = 0 shares the RDMs across the batch.                            */
+int oo_energy_f64(const double *c0, const double *c1, const double *c2,
+                  const double *gamma, int64_t stride_rdm1,
+                  const double *Gamma, int64_t stride_rdm2,
+                  int na, int batch, double *E, void *stream);
+
+/* ---- K3/K4: Fock matrices and orbital gradient ------------------------------
+ * FI (oo_energy.py:272-284), FA (:286-298), generalized F (:238-270),
+ * Gmat = 2 (F - F^T) (:300-309), gvec[j] = Gmat[pair_l[j], pair_r[j]] (:221-224, :90-94).
+ * FI, FA, F, Gmat are ld x ld per batch; any of FA, Gmat, gvec may be NULL.      */
+int oo_fock_gradient_f64(const double *h_mo, const double *g_mo,
+                         const double *gamma, int64_t stride_rdm1,
+                         const double *Gamma, int64_t stride_rdm2,
+                         int no, int na, int N, int ld, int batch,
+                         const int32_t *pair_l, const int32_t *pair_r, int nk,
+                         double *FI, double *FA, double *F, double *Gmat, double *gvec,
+                         void *stream);
+
+/* adjoint of (gamma, Gamma) -> Gmat, needed by jacobian(orbital_gradient, theta)
+ * (oo_pqc.py:113-123): given Gbar (ld x ld), with Fbar = 2 (Gbar - Gbar^T):
+ * gbar1_vw = sum_{i,n} Fbar_in 2 (g_nivw - g_nwvi / 2) + sum_n Fbar_vn FI_nw
+ * gbar2_vwxy = sum_n Fbar_vn g_nwxy                                             */
+int oo_fock_gradient_vjp_f64(const double *g_mo, const double *FI, const double *Gbar,
+                             int no, int na, int N, int ld,
+                             double *gbar1, double *gbar2, void *stream);
+
+/* ---- K4: orbital Hessian -----------------------------------------------------
+ * H[j][k] = Hfull[l_j, r_j, l_k, r_k], Hfull = (1-P_pq)(1-P_rs)(2 gf_pr h_qs
+ * - (F_pr + F_rp) d_qs + 2 Y_pqrs)  -- oo_energy.py:311-340 (analytic_hessian_from_integrals),
+ * :342-379 (full_rdms), :381-393 (y_matrix), :395-402 (full_hessian_to_matrix).
+ * Evaluated in the I = occ+act index space (the full-space RDMs vanish outside
+ * it): T[(p r),(q s)] = sum_(m n) A[(m n),(p r)] B[(m n),(q s)] is one TN-DGEMM of
+ * size nI^2 x ld^2 x (2 nI^2 + 1), followed by a fused 4-term assembly.
+ * F is the generalized Fock matrix from oo_fock_gradient_f64.  H is nk x nk.
+ * ws: oo_workspace_bytes(OO_WS_HESSIAN, N, ld, no+na, 1).                         */
+int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
+                   const double *gamma, const double *Gamma,
+                   int no, int na, int N, int ld,
+                   const int32_t *pair_l, const int32_t *pair_r, int nk,
+                   double *H, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- layout helpers ----------------------------------------------------------
+ * zero-padded copy between a dense N^rank tensor and its ld^rank padded image
+ * (rank 2 or 4).  to_padded != 0: src dense -> dst padded (padding zeroed).     */
+int oo_pad_copy_f64(const double *src, double *dst, int N, int ld, int rank,
+                    int batch, int to_padded, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OO_B200_H */
