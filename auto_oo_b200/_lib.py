@@ -18,13 +18,14 @@ _f64 = C.c_double
 _ptr = C.c_void_p
 _size = C.c_size_t
 
-OO_WS_ROTATION, OO_WS_INT2E, OO_WS_HESSIAN, OO_WS_INT1E = 1, 2, 3, 4
+OO_WS_ROTATION, OO_WS_INT2E, OO_WS_HESSIAN, OO_WS_INT1E, OO_WS_YMATRIX = 1, 2, 3, 4, 5
 
 # name -> (restype, argtypes); mirrors include/oo_b200.h one to one
 _SIGNATURES = {
     "oo_abi_version": (_i32, []),
     "oo_error_string": (C.c_char_p, [_i32]),
     "oo_last_cuda_error": (_i32, []),
+    "oo_launch_count": (C.c_ulonglong, []),
     "oo_device_info": (_i32, [C.POINTER(_i32)] * 3),
     "oo_workspace_bytes": (_size, [_i32, _i32, _i32, _i32, _i32]),
     "oo_dgemm_tn_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
@@ -46,6 +47,8 @@ _SIGNATURES = {
     "oo_fock_gradient_vjp_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "oo_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32,
                               _ptr, _ptr, _size, _ptr]),
+    "oo_full_rdms_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
+    "oo_y_matrix_f64": (_i32, [_ptr, _ptr, _i32, _i32, _ptr, _ptr, _size, _ptr]),
     "oo_pad_copy_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }
 

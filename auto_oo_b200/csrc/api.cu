@@ -7,6 +7,7 @@
 namespace oo {
 
 int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
 
 int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
              int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
@@ -14,6 +15,7 @@ int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N,
 size_t rotation_ws_bytes(int ld, int batch);
 size_t int1e_ws_bytes(int ld, int batch);
 size_t hessian_ws_bytes(int ld, int nI);
+size_t y_matrix_ws_bytes(int ld, int N);
 
 int sm_count() {
     static int cached = 0;
@@ -109,6 +111,8 @@ const char *oo_error_string(int code) {
 
 int oo_last_cuda_error(void) { return oo::g_last_cuda_error; }
 
+unsigned long long oo_launch_count(void) { return oo::g_launch_count; }
+
 int oo_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     int dev = 0;
     cudaDeviceProp prop;
@@ -128,6 +132,7 @@ size_t oo_workspace_bytes(int which, int N, int ld, int nI, int batch) {
         case OO_WS_INT2E: return (size_t)batch * ld * ld * ld * ld * sizeof(double);
         case OO_WS_HESSIAN: return oo::hessian_ws_bytes(ld, nI);
         case OO_WS_INT1E: return oo::int1e_ws_bytes(ld, batch);
+        case OO_WS_YMATRIX: return oo::y_matrix_ws_bytes(ld, N);
         default: return 0;
     }
 }

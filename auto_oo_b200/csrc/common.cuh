@@ -12,6 +12,7 @@ namespace oo {
 
 // ---- error plumbing ---------------------------------------------------------
 extern int g_last_cuda_error;
+extern unsigned long long g_launch_count;   // kernels launched by this library (oo_launch_count)
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -24,7 +25,11 @@ inline int cuda_fail(cudaError_t e) {
         if (_e != cudaSuccess) return ::oo::cuda_fail(_e);    \
     } while (0)
 
-#define OO_LAUNCH_CHECK() OO_CUDA_CHECK(cudaGetLastError())
+#define OO_LAUNCH_CHECK()                      \
+    do {                                       \
+        ++::oo::g_launch_count;                \
+        OO_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
 
 #define OO_REQUIRE(cond)                          \
     do {                                          \

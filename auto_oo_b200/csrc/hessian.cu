@@ -33,6 +33,7 @@ struct RdmView {
 
 // full-space 1-RDM on I x I  (oo_energy.py:359-361)
 __device__ __forceinline__ double gf1(const RdmView &r, int p, int q) {
+    if (p >= r.no + r.na || q >= r.no + r.na) return 0.0;
     if (p < r.no || q < r.no) return (p == q) ? 2.0 : 0.0;
     return r.d1[(p - r.no) * r.na + (q - r.no)];
 }
@@ -40,6 +41,8 @@ __device__ __forceinline__ double gf1(const RdmView &r, int p, int q) {
 // full-space 2-RDM on I^4  (oo_energy.py:363-378)
 __device__ __forceinline__ double gf2(const RdmView &r, int p, int q, int s, int t) {
     const int no = r.no, na = r.na;
+    const int nI = no + na;
+    if (p >= nI || q >= nI || s >= nI || t >= nI) return 0.0;
     const bool op = p < no, oq = q < no, os = s < no, ot = t < no;
     const int code = (op ? 8 : 0) | (oq ? 4 : 0) | (os ? 2 : 0) | (ot ? 1 : 0);
     switch (code) {
@@ -91,7 +94,7 @@ __global__ void hess_gather_b_kernel(const double *__restrict__ h, const double 
                                      int ld, double *__restrict__ B) {
     const int nI2 = nI * nI;
     const int64_t mat = (int64_t)ld * ld;
-    const int64_t total = (int64_t)(2 * nI2 + 1) * mat;
+    const int64_t total = (int64_t)(2 * nI2 + (h ? 1 : 0)) * mat;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int64_t k = i / mat;
@@ -133,6 +136,50 @@ hess_assemble_kernel(const double *__restrict__ T, const double *__restrict__ F,
     const double v = hess_x(T, F, nI, ld, p, q, r, s) - hess_x(T, F, nI, ld, p, q, s, r)
                    - hess_x(T, F, nI, ld, q, p, r, s) + hess_x(T, F, nI, ld, q, p, s, r);
     H[(int64_t)j * nk + k] = v;
+}
+
+
+// ---- API-parity helpers: dense full-space RDMs and the dense Y-matrix -----------------
+// (reference full_rdms oo_energy.py:342-379 and y_matrix :381-393 for an arbitrary dense
+// two_full; the Hessian path above never materialises either)
+__global__ void full_rdms_kernel(RdmView rdm, int N, double *__restrict__ d1, double *__restrict__ d2) {
+    const int64_t n2 = (int64_t)N * N, n4 = n2 * n2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int t = (int)(i % N), s = (int)((i / N) % N), q = (int)((i / n2) % N), p = (int)(i / (n2 * N));
+        d2[i] = gf2(rdm, p, q, s, t);
+        if (i < n2) d1[i] = gf1(rdm, (int)(i / N), (int)(i % N));
+    }
+}
+
+// At rows [0,N^2): G[p,m,r,n] + G[p,m,n,r]; rows [N^2, 2N^2): G[p,r,m,n]; column (p r); dense G (N^4)
+__global__ void y_build_at_kernel(const double *__restrict__ G, int N, int64_t lda, double *__restrict__ At) {
+    const int N2 = N * N;
+    const int64_t total = (int64_t)2 * N2 * lda;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto at = [&](int a, int b, int c, int d) { return G[(((int64_t)a * N + b) * N + c) * N + d]; };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t k = i / lda;
+        const int col = (int)(i % lda);
+        double v = 0.0;
+        if (col < N2) {
+            const int p = col / N, r = col % N;
+            const int kk = (int)(k % N2);
+            const int m = kk / N, n = kk % N;
+            v = (k < N2) ? at(p, m, r, n) + at(p, m, n, r) : at(p, r, m, n);
+        }
+        At[i] = v;
+    }
+}
+
+// Y[p,q,r,s] (dense N^4) = T[(p r),(q s)] (row pitch ld*ld)
+__global__ void y_permute_kernel(const double *__restrict__ T, int N, int ld, double *__restrict__ Y) {
+    const int64_t n2 = (int64_t)N * N, n4 = n2 * n2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int s = (int)(i % N), r = (int)((i / N) % N), q = (int)((i / n2) % N), p = (int)(i / (n2 * N));
+        Y[i] = T[((int64_t)p * N + r) * ld * ld + (int64_t)q * ld + s];
+    }
 }
 
 struct HessLayout {
@@ -201,7 +248,50 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     return OO_OK;
 }
 
+int full_rdms(const double *d1, const double *d2, int no, int na, int N, double *one_full,
+              double *two_full, cudaStream_t stream) {
+    OO_REQUIRE(d1 && d2 && one_full && two_full);
+    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N);
+    RdmView rdm{d1, d2, no, na};
+    int64_t blocks = ceil_div((int64_t)N * N * N * N, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    full_rdms_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, N, one_full, two_full);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+size_t y_matrix_ws_bytes(int ld, int N) { return hess_layout(ld, N).total; }
+
+int y_matrix(const double *g, const double *two_full, int N, int ld, double *Y, void *ws,
+             size_t ws_bytes, cudaStream_t stream) {
+    OO_REQUIRE(g && two_full && Y && ws);
+    OO_REQUIRE(N > 0 && ld >= N && (ld % 2) == 0);
+    const HessLayout L = hess_layout(ld, N);
+    if (ws_bytes < L.total) return OO_ERR_WORKSPACE;
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    double *At = reinterpret_cast<double *>(w);
+    double *B = reinterpret_cast<double *>(w + L.off_b);
+    double *T = reinterpret_cast<double *>(w + L.off_t);
+    const int64_t N2 = (int64_t)N * N, mat = (int64_t)ld * ld;
+    int64_t blocks = ceil_div(2 * N2 * L.lda, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    y_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(two_full, N, L.lda, At);
+    OO_LAUNCH_CHECK();
+    blocks = ceil_div(2 * N2 * mat, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    hess_gather_b_kernel<<<(unsigned)blocks, 256, 0, stream>>>(nullptr, g, N, ld, B);
+    OO_LAUNCH_CHECK();
+    int rc = dgemm_tn(At, B, T, N2, mat, 2 * N2, L.lda, mat, mat, 1, 0, 0, 0, stream);
+    if (rc) return rc;
+    blocks = ceil_div(N2 * N2, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    y_permute_kernel<<<(unsigned)blocks, 256, 0, stream>>>(T, N, ld, Y);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
 }  // namespace oo
+
 
 extern "C" int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
                               const double *gamma, const double *Gamma, int no, int na, int N, int ld,
@@ -209,4 +299,14 @@ extern "C" int oo_hessian_f64(const double *h_mo, const double *g_mo, const doub
                               size_t ws_bytes, void *stream) {
     return oo::hessian(h_mo, g_mo, F, gamma, Gamma, no, na, N, ld, pair_l, pair_r, nk, H, ws, ws_bytes,
                        (cudaStream_t)stream);
+}
+
+extern "C" int oo_full_rdms_f64(const double *gamma, const double *Gamma, int no, int na, int N,
+                                double *one_full, double *two_full, void *stream) {
+    return oo::full_rdms(gamma, Gamma, no, na, N, one_full, two_full, (cudaStream_t)stream);
+}
+
+extern "C" int oo_y_matrix_f64(const double *g_mo, const double *two_full, int N, int ld, double *Y,
+                               void *ws, size_t ws_bytes, void *stream) {
+    return oo::y_matrix(g_mo, two_full, N, ld, Y, ws, ws_bytes, (cudaStream_t)stream);
 }

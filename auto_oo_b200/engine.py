@@ -34,6 +34,20 @@ def tril_pair_table(nao, params_idx):
 
 
 class HotPathEngine:
+    _tensor_engines = {}
+
+    @classmethod
+    def for_tensors(cls, nao, device=None):
+        """An engine without resident integrals, for the module-level transform functions
+        (``int1e_transform``, ``general_4index_transform``); cached per (size, device)."""
+        if not torch.cuda.is_available():
+            raise _lib.OOError("auto_oo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        key = (int(nao), str(dev))
+        if key not in cls._tensor_engines:
+            cls._tensor_engines[key] = cls(None, None, None, 0.0, nao, 0, max(1, min(2, int(nao))), [], device=dev)
+        return cls._tensor_engines[key]
+
     def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None):
         if not torch.cuda.is_available():
             raise _lib.OOError("auto_oo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -49,9 +63,9 @@ class HotPathEngine:
         self.pair_l = torch.as_tensor(pl, device=self.device)
         self.pair_r = torch.as_tensor(pr, device=self.device)
         with torch.cuda.device(self.device):
-            self.h_ao = self.to_padded(int1e_ao, 2)
-            self.X = self.to_padded(oao_coeff, 2)
-            self.g_ao = self.to_padded(int2e_ao, 4)
+            self.h_ao = None if int1e_ao is None else self.to_padded(int1e_ao, 2)
+            self.X = None if oao_coeff is None else self.to_padded(oao_coeff, 2)
+            self.g_ao = None if int2e_ao is None else self.to_padded(int2e_ao, 4)
         self._ws = {}
         self._cache_key = None
         self._cache_val = None
@@ -100,6 +114,24 @@ class HotPathEngine:
             self._ws[key] = None
             buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             self._ws[key] = buf
+        return buf
+
+    def stage_in(self, key, host_tensor):
+        """Host -> device through a reused pinned buffer (asynchronous on the current stream)."""
+        buf = self._ws.get(("pin_in", key))
+        if buf is None or buf.shape != host_tensor.shape:
+            buf = torch.empty(host_tensor.shape, dtype=F64, pin_memory=True)
+            self._ws[("pin_in", key)] = buf
+        buf.copy_(host_tensor)
+        return buf.to(self.device, non_blocking=True)
+
+    def stage_out(self, key, dev_tensor):
+        """Device -> reused pinned host buffer (asynchronous; caller synchronises the stream)."""
+        buf = self._ws.get(("pin_out", key))
+        if buf is None or buf.shape != dev_tensor.shape:
+            buf = torch.empty(dev_tensor.shape, dtype=F64, pin_memory=True)
+            self._ws[("pin_out", key)] = buf
+        buf.copy_(dev_tensor, non_blocking=True)
         return buf
 
     def release_workspaces(self):
@@ -251,28 +283,62 @@ class HotPathEngine:
                                                       _p(g1), _p(g2), self.stream), "fock_gradient_vjp")
         return g1, g2
 
-    def hessian(self, h, g, F, d1, d2, out=None):
-        """(nk, nk) Hessian for ONE evaluation (h, g, F are single padded tensors)."""
-        nk = self.nk
+    def hessian(self, h, g, F, d1, d2, out=None, pair_l=None, pair_r=None):
+        """(nk, nk) Hessian for ONE evaluation (h, g, F are single padded tensors); the rotation
+        pairs default to the engine's non-redundant ones."""
+        pl = self.pair_l if pair_l is None else pair_l
+        pr = self.pair_r if pair_r is None else pair_r
+        nk = int(pl.numel())
         H = out if out is not None else torch.empty(nk, nk, dtype=F64, device=self.device)
         if nk == 0:
             return H
         nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_HESSIAN, self.N, self.ld, self.nI, 1)
         ws = self.workspace("hess", nbytes)
         self._check(self.lib.oo_hessian_f64(_p(h), _p(g), _p(F), _p(d1), _p(d2), self.no, self.na, self.N,
-                                            self.ld, _p(self.pair_l), _p(self.pair_r), nk, _p(H), _p(ws),
+                                            self.ld, _p(pl), _p(pr), nk, _p(H), _p(ws),
                                             nbytes, self.stream), "hessian")
         return H
 
+    def full_rdms(self, d1, d2):
+        """Dense full-space RDMs (reference full_rdms, oo_energy.py:342-379): (N,N), (N,N,N,N)."""
+        N = self.N
+        one = torch.empty(N, N, dtype=F64, device=self.device)
+        two = torch.empty(N, N, N, N, dtype=F64, device=self.device)
+        self._check(self.lib.oo_full_rdms_f64(_p(d1), _p(d2), self.no, self.na, N, _p(one), _p(two),
+                                              self.stream), "full_rdms")
+        return one, two
+
+    def y_matrix_dense(self, int2e_mo, two_full):
+        """Reference y_matrix (oo_energy.py:381-393) for an arbitrary dense two_full."""
+        N = self.N
+        g = self.to_padded(int2e_mo, 4)
+        G = self.dev(two_full)
+        Y = torch.empty(N, N, N, N, dtype=F64, device=self.device)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_YMATRIX, N, self.ld, 0, 1)
+        ws = self.workspace("ymat", nbytes)
+        self._check(self.lib.oo_y_matrix_f64(_p(g), _p(G), N, self.ld, _p(Y), _p(ws), nbytes, self.stream),
+                    "y_matrix")
+        return Y
+
+    def matmul(self, A, B):
+        """A @ B for padded (ld, ld) device matrices on the small DMMA GEMM."""
+        ld = self.ld
+        out = torch.empty(ld, ld, dtype=F64, device=self.device)
+        self._check(self.lib.oo_dgemm_small_f64(0, 0, ld, ld, ld, 1.0, _p(A), ld, 0, _p(B), ld, 0, 0.0, 0, ld, 0,
+                                                0.0, _p(out), ld, 0, 1, self.stream), "dgemm_small")
+        return out
+
     # ------------------------------------------------------------------ whole evaluations
     def evaluate(self, oao_mo_coeff, d1, d2, kappa=None, want_hessian=True, squarings=None,
-                 H_out=None):
+                 H_out=None, transform_events=None):
         """E (B,), packed gradient (B, nk) and Hessian (B, nk, nk) at C' = X C_oao expm(-K(kappa_b)).
 
         ``oao_mo_coeff``: padded (ld, ld) or (B, ld, ld) device tensor; ``kappa``: (B, nk) or None.
         One 4-index transform per evaluation serves E, G and H (the reference repeats it
         three times: oo_energy.py:207-208, :410-411, :421-422).  Evaluations are processed
-        one at a time through the N^4 stages (one g' buffer + one workspace in HBM)."""
+        one at a time through the N^4 stages (one g' buffer + one workspace in HBM).
+        ``transform_events``: optional list that receives a (start, end) CUDA-event pair around
+        every 4-index transform (four TN-DGEMM launches) for the roofline figure."""
         Coao = oao_mo_coeff if oao_mo_coeff.dim() == 3 else oao_mo_coeff[None]
         if kappa is not None:
             kappa = self.dev(kappa).reshape(-1, self.nk)
@@ -294,7 +360,13 @@ class HotPathEngine:
             gbuf = self._cache_val[1]
             self._cache_key = self._cache_val = None
         for b in range(B):
+            if transform_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             gbuf = self.int2e_transform(C[b:b + 1], out=gbuf)
+            if transform_events is not None:
+                ev[1].record()
+                transform_events.append(ev)
             h1 = hs[b:b + 1]
             d1b = d1[b] if d1.dim() == 3 else d1
             d2b = d2[b] if d2.dim() == 5 else d2

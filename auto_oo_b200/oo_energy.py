@@ -1,0 +1,438 @@
+"""``OO_energy`` and the free functions of the reference's ``auto_oo.oo_energy`` module
+(``/root/reference/src/auto_oo/oo_energy.py:21-474``), re-implemented on top of the sm_100a
+C-ABI library (``include/oo_b200.h``) through :class:`auto_oo_b200.engine.HotPathEngine`.
+
+Interface contract: same names, argument meaning and error behaviour as the
+reference; inputs are float64 torch tensors (CPU, possibly carrying an autograd graph back to the
+circuit parameters) or numpy arrays; results come back on the device / in the array type of the
+inputs, so the reference's drivers (``NewtonStep``, ``OO_pqc.full_optimization``, the Berry-phase
+loop) run unchanged.  Every number is produced by a CUDA kernel; there is no CPU path.
+
+Differences a caller can observe, all deliberate:
+
+* one four-index transform per set of MO coefficients serves energy, gradient and Hessian
+  (the reference redoes it in each call: ``oo_energy.py:207-208, :410-411, :421-422``);
+* ``analytic_hessian`` returns an :class:`OrbitalHessian` (device resident, I-space form) instead
+  of a dense ``(N,N,N,N)`` tensor; ``full_hessian_to_matrix`` accepts it (and still accepts a dense
+  tensor), ``OrbitalHessian.dense()`` materialises the reference's rank-4 tensor on request;
+* differentiability: energy is differentiable (to any order) in the RDMs, the gradient once in the
+  RDMs -- what ``OO_pqc`` needs (``oo_pqc.py:86-123``).  Nothing is differentiable in ``kappa`` or
+  the MO coefficients (no driver needs it; the reference's own analytic-vs-autograd tests are
+  replayed against the CPU oracle in ``tests/``).
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import torch
+
+from .engine import HotPathEngine, F64
+from .utils.newton_raphson import NewtonStep
+
+__all__ = [
+    "OO_energy", "OrbitalHessian", "general_4index_transform", "uniform_4index_transform",
+    "int1e_transform", "int2e_transform", "mo_ao_to_mo_oao", "vector_to_skew_symmetric",
+    "skew_symmetric_to_vector", "non_redundant_indices",
+]
+
+
+# --------------------------------------------------------------------------------------
+# array plumbing
+# --------------------------------------------------------------------------------------
+def _like(result, template):
+    """Return the device tensor ``result`` in the container type / device of ``template``."""
+    if torch.is_tensor(template):
+        return result.to(device=template.device, dtype=template.dtype if template.is_floating_point() else F64)
+    return result.cpu().numpy()
+
+
+def _as_tensor(x):
+    return x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x, dtype=np.float64))
+
+
+# --------------------------------------------------------------------------------------
+# free functions                                               (reference oo_energy.py:21-118)
+# --------------------------------------------------------------------------------------
+def general_4index_transform(M, C0, C1, C2, C3):
+    """``M'_ijkl = sum_pqrs C0_pi C1_qj C2_rk C3_sl M_pqrs`` (reference ``oo_energy.py:21-30``).
+
+    Four quarter transforms on FP64 tensor cores (``oo_int2e_transform_f64``)."""
+    Mt = _as_tensor(M)
+    n = Mt.shape[0]
+    eng = HotPathEngine.for_tensors(n)
+    g = eng.to_padded(Mt, 4)
+    Cs = [eng.to_padded(_as_tensor(c), 2) for c in (C0, C1, C2, C3)]
+    out = eng.from_padded(eng.int2e_transform(*Cs, g_ao=g), 4)[0]
+    return _like(out, M)
+
+
+def uniform_4index_transform(M, C):
+    """Reference ``oo_energy.py:33-41``."""
+    return general_4index_transform(M, C, C, C, C)
+
+
+def int1e_transform(int1e_ao, mo_coeff):
+    """``C^T h C`` (reference ``oo_energy.py:44-46``)."""
+    h = _as_tensor(int1e_ao)
+    eng = HotPathEngine.for_tensors(h.shape[0])
+    out = eng.from_padded(eng.int1e_transform(eng.to_padded(_as_tensor(mo_coeff), 2),
+                                              h_ao=eng.to_padded(h, 2)), 2)[0]
+    return _like(out, int1e_ao)
+
+
+def int2e_transform(int2e_ao, mo_coeff):
+    """Reference ``oo_energy.py:49-51``."""
+    return uniform_4index_transform(int2e_ao, mo_coeff)
+
+
+def mo_ao_to_mo_oao(mo_coeff, overlap):
+    """``S^{1/2} C`` for numpy arrays (reference ``oo_energy.py:54-60``).  Initialisation-time
+    helper on N x N host arrays; kept on the host like the reference's numpy implementation."""
+    w, v = np.linalg.eigh(np.asarray(overlap))
+    return (v * np.sqrt(w)) @ v.T @ np.asarray(mo_coeff)
+
+
+def vector_to_skew_symmetric(vector):
+    """Pack a vector into the strict lower triangle (``np.tril_indices`` order) of a skew matrix:
+    ``[1..6] -> [[0,-1,-2,-4],[1,0,-3,-5],[2,3,0,-6],[4,5,6,0]]`` (reference ``oo_energy.py:63-87``).
+    Pure index bookkeeping on the caller's array type (differentiable for torch)."""
+    n = int(np.sqrt(8 * vector.shape[0] + 1) + 1) // 2
+    rows, cols = np.tril_indices(n, k=-1)
+    if torch.is_tensor(vector):
+        r = torch.as_tensor(rows, device=vector.device)
+        c = torch.as_tensor(cols, device=vector.device)
+        out = torch.zeros((n, n), dtype=vector.dtype, device=vector.device)
+        out = out.index_put((r, c), vector)
+        return out.index_put((c, r), -vector)
+    vector = np.asarray(vector)
+    out = np.zeros((n, n), dtype=vector.dtype)
+    out[rows, cols] = vector
+    out[cols, rows] = -vector
+    return out
+
+
+def skew_symmetric_to_vector(kappa_matrix):
+    """Reference ``oo_energy.py:90-94``."""
+    rows, cols = np.tril_indices(kappa_matrix.shape[0], k=-1)
+    return kappa_matrix[rows, cols]
+
+
+def non_redundant_indices(occ_idx, act_idx, virt_idx, freeze_active):
+    """Positions in the tril vector of the rotations that are not occ-occ, virt-virt or (when
+    ``freeze_active``) act-act (reference ``oo_energy.py:97-118``)."""
+    no, na, nv = len(occ_idx), len(act_idx), len(virt_idx)
+    nao = no + na + nv
+    cls = np.full(nao, -1)
+    cls[np.asarray(occ_idx, dtype=int)] = 0
+    cls[np.asarray(act_idx, dtype=int)] = 1
+    cls[np.asarray(virt_idx, dtype=int)] = 2
+    rows, cols = np.tril_indices(nao, -1)
+    same = cls[rows] == cls[cols]
+    redundant = same & ((cls[rows] == 0) | (cls[rows] == 2) | ((cls[rows] == 1) & bool(freeze_active)))
+    params_idx = np.nonzero(~redundant)[0].astype(int)
+    n_kappa = no * na + na * nv + no * nv + (0 if freeze_active else na * (na - 1) // 2)
+    assert n_kappa == len(params_idx)
+    return params_idx
+
+
+# --------------------------------------------------------------------------------------
+# autograd bridges: E and G are affine in the RDMs
+# --------------------------------------------------------------------------------------
+class _EnergyFn(torch.autograd.Function):
+    """E = c0 + <c1, gamma> + <c2, Gamma> with the dot products done by ``oo_energy_f64``;
+    dE/dgamma = c1, dE/dGamma = c2."""
+
+    @staticmethod
+    def forward(ctx, one_rdm, two_rdm, eng, c0, c1, c2):
+        E = eng.energy(c0, c1, c2, eng.dev(one_rdm), eng.dev(two_rdm))[0]
+        ctx.c1 = c1[0].to(one_rdm.device)
+        ctx.c2 = c2[0].to(two_rdm.device)
+        return E.to(one_rdm.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return grad_out * ctx.c1, grad_out * ctx.c2, None, None, None, None
+
+
+class _GradientFn(torch.autograd.Function):
+    """G = 2 (F - F^T) by ``oo_fock_gradient_f64``; the adjoint w.r.t. (gamma, Gamma) by
+    ``oo_fock_gradient_vjp_f64``."""
+
+    @staticmethod
+    def forward(ctx, one_rdm, two_rdm, eng, h, g):
+        FI, FA, F, G, _ = eng.fock_gradient(h, g, eng.dev(one_rdm), eng.dev(two_rdm), want_vector=False)
+        ctx.eng, ctx.g, ctx.FI = eng, g, FI
+        ctx.dev1, ctx.dev2 = one_rdm.device, two_rdm.device
+        return eng.from_padded(G, 2)[0].to(one_rdm.device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gbar):
+        eng = ctx.eng
+        g1, g2 = eng.fock_gradient_vjp(ctx.g[0], ctx.FI[0], eng.to_padded(gbar, 2))
+        return g1.to(ctx.dev1), g2.to(ctx.dev2), None, None, None
+
+
+class OrbitalHessian:
+    """Device-resident orbital Hessian in the I-space form (``T`` and ``F``):
+    what ``analytic_hessian`` returns instead of the reference's dense ``(N,N,N,N)`` tensor."""
+
+    def __init__(self, eng, h, g, F, one_rdm, two_rdm, like):
+        self._eng, self._h, self._g, self._F = eng, h, g, F
+        self._d1, self._d2 = eng.dev(one_rdm), eng.dev(two_rdm)
+        self._like = like
+        self.shape = (eng.N,) * 4
+
+    def matrix(self, pair_l=None, pair_r=None):
+        """``H[l_j, r_j, l_k, r_k]`` for the engine's non-redundant pairs (or the given ones)."""
+        eng = self._eng
+        return eng.hessian(self._h[0], self._g[0], self._F[0], self._d1, self._d2,
+                           pair_l=pair_l, pair_r=pair_r)
+
+    def dense(self):
+        """The reference's rank-4 tensor ``H[p,q,r,s]`` (``oo_energy.py:311-340``); O(N^4) memory."""
+        N = self._eng.N
+        idx = torch.arange(N, device=self._eng.device, dtype=torch.int32)
+        pl = idx.repeat_interleave(N).contiguous()
+        pr = idx.repeat(N).contiguous()
+        return _like(self.matrix(pl, pr).reshape(N, N, N, N), self._like)
+
+
+# --------------------------------------------------------------------------------------
+# OO_energy                                                  (reference oo_energy.py:121-474)
+# --------------------------------------------------------------------------------------
+class OO_energy:
+    """Orbital-optimised energy for any given RDMs, with analytic orbital gradient and Hessian
+    (reference ``oo_energy.py:121-171``).  ``mol`` is duck-typed: ``int1e_ao, int2e_ao, overlap,
+    oao_coeff, nuc, nao, get_active_space_idx`` (+ ``run_rhf``/``hf.mo_coeff`` when
+    ``oao_mo_coeff`` is None)."""
+
+    def __init__(self, mol, ncas, nelecas, oao_mo_coeff=None, freeze_active=False, interface='torch',
+                 device=None):
+        if interface != 'torch':
+            raise ValueError("auto_oo_b200 implements the torch interface only (no JAX/XLA dispatch)")
+        if oao_mo_coeff is None:
+            mol.run_rhf()
+            oao_mo_coeff = mo_ao_to_mo_oao(mol.hf.mo_coeff, mol.overlap)
+        self.oao_mo_coeff = _as_tensor(oao_mo_coeff).detach().clone().to(F64)
+        self.interface = interface
+
+        self.overlap = mol.overlap
+        self.nuc = mol.nuc
+        self.nao = mol.nao
+        self.ncas = ncas
+        self.nelecas = nelecas
+        self.occ_idx, self.act_idx, self.virt_idx = mol.get_active_space_idx(ncas, nelecas)
+        no, na = len(self.occ_idx), len(self.act_idx)
+        if not (np.array_equal(self.occ_idx, np.arange(no))
+                and np.array_equal(self.act_idx, no + np.arange(na))
+                and np.array_equal(self.virt_idx, np.arange(no + na, self.nao))):
+            raise ValueError("orbital classes must be the contiguous ranges occ|act|virt "
+                             "(what Moldata_pyscf.get_active_space_idx returns)")
+        self.params_idx = non_redundant_indices(self.occ_idx, self.act_idx, self.virt_idx, freeze_active)
+        self.n_kappa = len(self.params_idx)
+
+        # integrals go to HBM once (padded layout); host copies are kept as the public attributes
+        self.int1e_ao = _as_tensor(mol.int1e_ao)
+        self.int2e_ao = _as_tensor(mol.int2e_ao)
+        self.oao_coeff = _as_tensor(mol.oao_coeff)
+        self.engine = HotPathEngine(self.int1e_ao, self.int2e_ao, self.oao_coeff, self.nuc, self.nao,
+                                    no, na, self.params_idx, device=device)
+
+    # ------------------------------------------------------------------ orbitals
+    @property
+    def mo_coeff(self):
+        """AO->MO coefficients ``X C_oao``; follows writes to ``oao_mo_coeff`` (``oo_energy.py:173-176``)."""
+        eng = self.engine
+        C = eng.mo_coeff(eng.to_padded(self.oao_mo_coeff, 2))
+        return _like(eng.from_padded(C, 2)[0], self.oao_mo_coeff)
+
+    def kappa_vector_to_matrix(self, kappa):
+        """Reference ``oo_energy.py:213-219``."""
+        kappa = _as_tensor(kappa)
+        full = torch.zeros(self.nao * (self.nao - 1) // 2, dtype=kappa.dtype, device=kappa.device)
+        full = full.index_put((torch.as_tensor(self.params_idx, device=kappa.device),), kappa)
+        return vector_to_skew_symmetric(full)
+
+    def kappa_matrix_to_vector(self, kappa_matrix):
+        """Reference ``oo_energy.py:221-224``."""
+        return skew_symmetric_to_vector(kappa_matrix)[self.params_idx]
+
+    def kappa_to_mo_coeff(self, kappa):
+        """``expm(-K(kappa))`` (reference ``oo_energy.py:226-230``) by ``oo_kappa_rotation_f64``."""
+        eng = self.engine
+        U = eng.rotation(_as_tensor(kappa).detach().reshape(1, -1))
+        return _like(eng.from_padded(U, 2)[0], kappa)
+
+    def get_transformed_mo(self, mo_coeff, kappa):
+        """``mo_coeff @ expm(-K)`` (reference ``oo_energy.py:232-236``)."""
+        eng = self.engine
+        U = eng.rotation(_as_tensor(kappa).detach().reshape(1, -1))
+        out = eng.matmul(eng.to_padded(_as_tensor(mo_coeff), 2), U[0])
+        return _like(eng.from_padded(out[None], 2)[0], mo_coeff)
+
+    # ------------------------------------------------------------------ energy
+    def _mo_integrals(self, mo_coeff):
+        eng = self.engine
+        return eng.mo_integrals(eng.to_padded(_as_tensor(mo_coeff).detach(), 2))
+
+    def get_active_integrals(self, mo_coeff):
+        """``(c0, c1, c2)`` of the active-space Hamiltonian in chemist notation
+        (reference ``oo_energy.py:204-211``, ``utils/active_space.py:177-212``)."""
+        h, g = self._mo_integrals(mo_coeff)
+        c0, c1, c2 = self.engine.active_hamiltonian(h, g)
+        return _like(c0[0], mo_coeff), _like(c1[0], mo_coeff), _like(c2[0], mo_coeff)
+
+    def energy_from_mo_coeff(self, mo_coeff, one_rdm, two_rdm):
+        """Reference ``oo_energy.py:178-197``.  0-d tensor, differentiable in the RDMs."""
+        h, g = self._mo_integrals(mo_coeff)
+        c0, c1, c2 = self.engine.active_hamiltonian(h, g)
+        one, two = _as_tensor(one_rdm), _as_tensor(two_rdm)
+        return _EnergyFn.apply(one, two, self.engine, c0, c1, c2)
+
+    def energy_from_kappa(self, kappa, one_rdm, two_rdm):
+        """Energy at ``C' = C expm(-K(kappa))`` (reference ``oo_energy.py:199-202``)."""
+        eng = self.engine
+        U = eng.rotation(_as_tensor(kappa).detach().reshape(1, -1))
+        C = eng.mo_coeff(eng.to_padded(self.oao_mo_coeff, 2), U)
+        h, g = eng.mo_integrals(C)
+        c0, c1, c2 = eng.active_hamiltonian(h, g)
+        return _EnergyFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), eng, c0, c1, c2)
+
+    # ------------------------------------------------------------------ Fock matrices / gradient
+    def _padded_integrals(self, int1e_mo, int2e_mo):
+        eng = self.engine
+        return eng.to_padded(_as_tensor(int1e_mo), 2)[None], eng.to_padded(_as_tensor(int2e_mo), 4)[None]
+
+    def fock_core(self, int1e_mo, int2e_mo):
+        """``F^I`` (reference ``oo_energy.py:272-284``)."""
+        h, g = self._padded_integrals(int1e_mo, int2e_mo)
+        d1 = torch.zeros(self.ncas, self.ncas, dtype=F64, device=self.engine.device)
+        d2 = torch.zeros((self.ncas,) * 4, dtype=F64, device=self.engine.device)
+        FI = self.engine.fock_gradient(h, g, d1, d2, want_matrix=False, want_vector=False)[0]
+        return _like(self.engine.from_padded(FI, 2)[0], int1e_mo)
+
+    def fock_active(self, int2e_mo, one_rdm):
+        """``F^A`` (reference ``oo_energy.py:286-298``)."""
+        eng = self.engine
+        g = eng.to_padded(_as_tensor(int2e_mo), 4)[None]
+        h = torch.zeros(1, eng.ld, eng.ld, dtype=F64, device=eng.device)
+        d2 = torch.zeros((self.ncas,) * 4, dtype=F64, device=eng.device)
+        FA = eng.fock_gradient(h, g, eng.dev(one_rdm), d2, want_matrix=False, want_vector=False)[1]
+        return _like(eng.from_padded(FA, 2)[0], int2e_mo)
+
+    def fock_generalized(self, int1e_mo, int2e_mo, one_rdm, two_rdm):
+        """Generalized Fock matrix (reference ``oo_energy.py:238-270``)."""
+        h, g = self._padded_integrals(int1e_mo, int2e_mo)
+        eng = self.engine
+        F = eng.fock_gradient(h, g, eng.dev(one_rdm), eng.dev(two_rdm), want_matrix=False, want_vector=False)[2]
+        return _like(eng.from_padded(F, 2)[0], int1e_mo)
+
+    def analytic_gradient_from_integrals(self, int1e_mo, int2e_mo, one_rdm, two_rdm):
+        """``G = 2 (F - F^T)`` (reference ``oo_energy.py:300-309``)."""
+        h, g = self._padded_integrals(int1e_mo, int2e_mo)
+        return _GradientFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, h, g)
+
+    def analytic_gradient(self, one_rdm, two_rdm, mo_coeff=None):
+        """Reference ``oo_energy.py:404-413``; differentiable in the RDMs."""
+        h, g = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
+        return _GradientFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, h, g)
+
+    # ------------------------------------------------------------------ Hessian
+    def full_rdms(self, one_rdm, two_rdm):
+        """RDMs embedded in the full orbital space (reference ``oo_energy.py:342-379``).  Dense
+        N^2 / N^4 buffers exactly as the reference defines them; the Hessian kernels never build
+        these (they are zero outside occ+act), the method exists for API parity."""
+        eng = self.engine
+        d1, d2 = eng.full_rdms(eng.dev(one_rdm), eng.dev(two_rdm))
+        return d1.cpu().numpy(), d2.cpu().numpy()
+
+    def y_matrix(self, int2e_mo, two_full):
+        """Reference ``oo_energy.py:381-393`` for arbitrary dense ``two_full``: three
+        ``N^2 x N^2 x N^2`` contractions on the TN-DGEMM kernel."""
+        eng = self.engine
+        out = eng.y_matrix_dense(_as_tensor(int2e_mo), _as_tensor(two_full))
+        return _like(out, int2e_mo)
+
+    def analytic_hessian_from_integrals(self, int1e_mo, int2e_mo, one_rdm, two_rdm):
+        """Reference ``oo_energy.py:311-340``; returns an :class:`OrbitalHessian`."""
+        h, g = self._padded_integrals(int1e_mo, int2e_mo)
+        return self._hessian(h, g, one_rdm, two_rdm, int1e_mo)
+
+    def analytic_hessian(self, one_rdm, two_rdm, mo_coeff=None):
+        """Reference ``oo_energy.py:415-424``; returns an :class:`OrbitalHessian`."""
+        h, g = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
+        return self._hessian(h, g, one_rdm, two_rdm, _as_tensor(one_rdm))
+
+    def _hessian(self, h, g, one_rdm, two_rdm, like):
+        eng = self.engine
+        d1, d2 = eng.dev(one_rdm), eng.dev(two_rdm)
+        F = eng.fock_gradient(h, g, d1, d2, want_matrix=False, want_vector=False)[2]
+        return OrbitalHessian(eng, h, g, F, d1, d2, like)
+
+    def full_hessian_to_matrix(self, full_hess):
+        """``(N,N,N,N)`` -> ``(n_kappa, n_kappa)`` (reference ``oo_energy.py:395-402``).  Accepts the
+        :class:`OrbitalHessian` of ``analytic_hessian`` (fused assembly on device) or any dense
+        rank-4 array (plain gather, as in the reference)."""
+        if isinstance(full_hess, OrbitalHessian):
+            return _like(full_hess.matrix(), full_hess._like)
+        rows, cols = np.tril_indices(self.nao, k=-1)
+        part = full_hess[rows, cols, :, :][:, rows, cols]
+        return part[self.params_idx, :][:, self.params_idx]
+
+    # ------------------------------------------------------------------ batched evaluation
+    def energy_gradient_hessian(self, kappa, one_rdm, two_rdm, want_hessian=True):
+        """``E``, packed gradient and Hessian matrix at ``C expm(-K(kappa_b))`` for a batch of
+        rotations ``kappa (B, n_kappa)`` -- the three reference calls ``energy_from_kappa``,
+        ``kappa_matrix_to_vector(analytic_gradient(mo_coeff=C'))`` and
+        ``full_hessian_to_matrix(analytic_hessian(mo_coeff=C'))`` fused so that one four-index
+        transform serves all three.  Host tensors in (staged through pinned memory), host tensors
+        out: ``(B,)``, ``(B, n_kappa)``, ``(B, n_kappa, n_kappa)``; CUDA tensors in -> CUDA out."""
+        eng = self.engine
+        kappa = _as_tensor(kappa).detach().reshape(-1, self.n_kappa)
+        one, two = _as_tensor(one_rdm).detach(), _as_tensor(two_rdm).detach()
+        on_host = kappa.device.type == "cpu"
+        if on_host:
+            kd = eng.stage_in("kappa", kappa)
+            d1 = eng.stage_in("rdm1", one)
+            d2 = eng.stage_in("rdm2", two)
+        else:
+            kd, d1, d2 = kappa, one, two
+        E, G, H = eng.evaluate(eng.to_padded(self.oao_mo_coeff, 2), d1, d2, kappa=kd,
+                               want_hessian=want_hessian)
+        if not on_host:
+            return E, G, H
+        out = (eng.stage_out("E", E), eng.stage_out("G", G), eng.stage_out("H", H) if want_hessian else None)
+        torch.cuda.current_stream(eng.device).synchronize()
+        return out
+
+    # ------------------------------------------------------------------ driver
+    def orbital_optimization(self, one_rdm, two_rdm, conv_tol=1e-8, max_iterations=100, verbose=0,
+                             **kwargs):
+        """Damped-Newton orbital optimisation at fixed RDMs; mutates ``oao_mo_coeff`` and returns
+        the energy trajectory (reference ``oo_energy.py:426-474``: re-base after every step,
+        convergence tested only for ``n > 1``, per-iteration line printed unless ``verbose`` is None)."""
+        objective_fn = partial(self.energy_from_kappa, one_rdm=one_rdm, two_rdm=two_rdm)
+        opt = NewtonStep(verbose=verbose, **kwargs)
+        energy_l = []
+        if verbose:
+            energy = self.energy_from_mo_coeff(self.mo_coeff, one_rdm, two_rdm).item()
+            print(f"Starting energy: {energy:.12f}")
+        one = _as_tensor(one_rdm)
+        for n in range(max_iterations):
+            kappa = torch.zeros(self.n_kappa, dtype=F64, device=one.device)
+            gradient = self.kappa_matrix_to_vector(self.analytic_gradient(one_rdm, two_rdm))
+            hessian = self.full_hessian_to_matrix(self.analytic_hessian(one_rdm, two_rdm))
+            kappa, lowest_eigenvalue = opt.damped_newton_step(objective_fn, (kappa,), gradient, hessian)
+            self.oao_mo_coeff = self.get_transformed_mo(self.oao_mo_coeff, kappa)
+            energy = self.energy_from_mo_coeff(self.mo_coeff, one_rdm, two_rdm).item()
+            energy_l.append(energy)
+            if verbose is not None:
+                print(f"iter = {n:03}, energy = {energy:.12f}")
+            if n > 1 and abs(energy_l[-1] - energy_l[-2]) < conv_tol:
+                if verbose:
+                    print("Orbital optimization finished.")
+                    print("E_fin =", energy_l[-1])
+                break
+        return energy_l

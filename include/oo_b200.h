@@ -49,12 +49,14 @@ enum {
     OO_WS_ROTATION   = 1,      /* oo_kappa_rotation_f64                            */
     OO_WS_INT2E      = 2,      /* oo_int2e_transform_f64                           */
     OO_WS_HESSIAN    = 3,      /* oo_hessian_f64                                   */
-    OO_WS_INT1E      = 4       /* oo_int1e_transform_f64 / oo_mo_coeff_f64         */
+    OO_WS_INT1E      = 4,      /* oo_int1e_transform_f64 / oo_mo_coeff_f64         */
+    OO_WS_YMATRIX    = 5       /* oo_y_matrix_f64                                  */
 };
 
 int         oo_abi_version(void);
 const char *oo_error_string(int code);
 int         oo_last_cuda_error(void);                 /* cudaError_t of the last OO_ERR_CUDA */
+unsigned long long oo_launch_count(void);             /* kernels launched by this library so far */
 int         oo_device_info(int *sm_count, int *cc_major, int *cc_minor);
 size_t      oo_workspace_bytes(int which, int N, int ld, int nI, int batch);
 
@@ -170,6 +172,18 @@ int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
                    int no, int na, int N, int ld,
                    const int32_t *pair_l, const int32_t *pair_r, int nk,
                    double *H, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- API-parity helpers (not on the hot path) ------------------------------
+ * Dense full-space RDMs exactly as full_rdms defines them (oo_energy.py:342-379):
+ * one_full N x N, two_full N^4 (dense, no padding).                               */
+int oo_full_rdms_f64(const double *gamma, const double *Gamma, int no, int na, int N,
+                     double *one_full, double *two_full, void *stream);
+
+/* Y_pqrs = sum_mn [(G_pmrn + G_pmnr) g_qmns + G_prmn g_qsmn] for an ARBITRARY dense
+ * two_full G (N^4, no padding) -- y_matrix, oo_energy.py:381-393.  g_mo is padded
+ * (ld^4); Y is dense N^4.  ws: oo_workspace_bytes(OO_WS_YMATRIX, N, ld, 0, 1).       */
+int oo_y_matrix_f64(const double *g_mo, const double *two_full, int N, int ld, double *Y,
+                    void *ws, size_t ws_bytes, void *stream);
 
 /* ---- layout helpers ----------------------------------------------------------
  * zero-padded copy between a dense N^rank tensor and its ld^rank padded image

@@ -95,6 +95,18 @@ def kappa_to_skew(kappa, params_idx, nao):
     return unpack_skew(full)
 
 
+
+def kappa_to_skew_diff(kappa, params_idx, nao):
+    """Same map as :func:`kappa_to_skew`, written out-of-place so autograd can differentiate
+    through it (used only by the analytic-vs-autograd tests)."""
+    rows, cols = tril_pairs(nao)
+    pidx = np.asarray(params_idx, dtype=int)
+    L = torch.as_tensor(rows[pidx], dtype=torch.long)
+    R = torch.as_tensor(cols[pidx], dtype=torch.long)
+    out = torch.zeros((nao, nao), dtype=DT)
+    out = out.index_put((L, R), kappa)
+    return out.index_put((R, L), -kappa)
+
 def skew_to_kappa(mat, params_idx):
     """oo_energy.py:221-224."""
     return pack_skew(mat)[torch.as_tensor(np.asarray(params_idx), dtype=torch.long)]

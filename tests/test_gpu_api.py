@@ -1,0 +1,205 @@
+"""GPU: the reference-facing Python API (OO_energy / OO_pqc / free functions) on the CUDA path,
+written the way the reference's own tests are (test/test_oo_energy.py, test/test_oo_pqc.py) and
+checked against the verbatim reference's stored outputs and the CPU oracle."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_CASES, SMALL_CASES, GOLDEN, TOL_E, TOL_GH, load_case
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+
+
+def make_oo(c, cls=None, **kw):
+    import auto_oo_b200
+    cls = cls or auto_oo_b200.OO_energy
+    return cls(c.mol(), c.ncas, c.nelecas, oao_mo_coeff=c.oao_mo_coeff, freeze_active=c.freeze, **kw)
+
+
+def test_free_functions_known_answers():
+    # reference test/test_oo_energy.py:188-231
+    import auto_oo_b200.oo_energy as m
+    v = torch.arange(1., 7., dtype=F64)
+    K = m.vector_to_skew_symmetric(v)
+    assert torch.equal(K, torch.tensor([[0, -1, -2, -4], [1, 0, -3, -5], [2, 3, 0, -6], [4, 5, 6, 0]], dtype=F64))
+    assert torch.equal(m.skew_symmetric_to_vector(K), v)
+    assert list(m.non_redundant_indices([0, 1], [2, 3], [4, 5], False)) == list(range(1, 14))
+    assert list(m.non_redundant_indices([0, 1], [2, 3], [4, 5], True)) == [1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13]
+
+
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_int_transforms_accept_numpy_and_torch(kind):
+    # reference test_int_transforms (test/test_oo_energy.py:105-185) feeds numpy and torch inputs
+    import auto_oo_b200 as pkg
+    c = load_case("n13_cas22")
+    conv = (lambda x: np.asarray(x)) if kind == "numpy" else (lambda x: torch.as_tensor(np.asarray(x)))
+    C = conv(c.ref["mo_coeff_rot"])
+    h = pkg.int1e_transform(conv(c.int1e_ao), C)
+    g = pkg.int2e_transform(conv(c.int2e_ao), C)
+    assert type(h) is type(C) and type(g) is type(C)
+    assert np.abs(np.asarray(h) - c.ref["int1e_mo"]).max() < 1e-11
+    assert np.abs(np.asarray(g) - c.ref["int2e_mo"]).max() < 1e-11
+    d = np.load(os.path.join(GOLDEN, "general_4index_n6.npz"))
+    out = pkg.general_4index_transform(*[conv(d[k]) for k in ("M", "C0", "C1", "C2", "C3")])
+    assert np.abs(np.asarray(out) - d["out"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_oo_energy_matches_reference(name):
+    c = load_case(name)
+    oo = make_oo(c)
+    r = c.ref
+    assert oo.n_kappa == len(r["params_idx"]) and np.array_equal(oo.params_idx, r["params_idx"])
+    U = oo.kappa_to_mo_coeff(c.kappa)
+    assert U.device.type == "cpu" and np.abs(U.numpy() - r["U"]).max() < 1e-13
+    Cp = oo.get_transformed_mo(oo.mo_coeff, c.kappa)
+    assert np.abs(Cp.numpy() - r["mo_coeff_rot"]).max() < 1e-12
+    c0, c1, c2 = oo.get_active_integrals(Cp)
+    assert abs(float(c0) - float(r["c0"])) < TOL_E
+    assert np.abs(c1.numpy() - r["c1"]).max() < 1e-11 and np.abs(c2.numpy() - r["c2"]).max() < 1e-11
+    E = oo.energy_from_kappa(c.kappa, c.one_rdm, c.two_rdm)
+    assert E.dim() == 0 and abs(E.item() - float(r["E"])) < TOL_E
+    assert abs(oo.energy_from_mo_coeff(oo.mo_coeff, c.one_rdm, c.two_rdm).item() - float(r["E0"])) < TOL_E
+    G = oo.kappa_matrix_to_vector(oo.analytic_gradient(c.one_rdm, c.two_rdm, mo_coeff=Cp))
+    assert np.abs(G.numpy() - r["G"]).max() < TOL_GH
+    G0 = oo.kappa_matrix_to_vector(oo.analytic_gradient(c.one_rdm, c.two_rdm))
+    assert np.abs(G0.numpy() - r["G0"]).max() < TOL_GH
+    H = oo.full_hessian_to_matrix(oo.analytic_hessian(c.one_rdm, c.two_rdm, mo_coeff=Cp))
+    assert np.abs(H.numpy() - r["H"]).max() < TOL_GH
+    assert (H - H.T).abs().max().item() < 1e-9
+
+
+@pytest.mark.parametrize("name", ["n7_cas44", "n8_nocore", "n13_cas22"])
+def test_dense_hessian_fock_and_rdm_helpers(name):
+    from oracle import oo_oracle as orc
+    c = load_case(name)
+    oo = make_oo(c)
+    p = c.oracle()
+    h, g = p.mo_integrals(c.kappa)
+    Hfull = oo.analytic_hessian_from_integrals(h, g, c.one_rdm, c.two_rdm).dense()
+    ref = orc.hessian_full(h, g, c.one_rdm, c.two_rdm, p.occ_idx, p.act_idx)
+    assert (Hfull - ref).abs().max().item() < TOL_GH
+    # a dense rank-4 tensor is still accepted by full_hessian_to_matrix (reference :395-402)
+    assert np.abs(oo.full_hessian_to_matrix(ref).numpy() - c.ref["H"]).max() < TOL_GH
+    assert (oo.fock_core(h, g) - orc.fock_core(h, g, p.occ_idx)).abs().max().item() < 1e-10
+    assert (oo.fock_active(g, c.one_rdm) - orc.fock_active(g, c.one_rdm, p.act_idx)).abs().max().item() < 1e-10
+    Fg = oo.fock_generalized(h, g, c.one_rdm, c.two_rdm)
+    assert (Fg - orc.fock_generalized(h, g, c.one_rdm, c.two_rdm, p.occ_idx, p.act_idx)).abs().max().item() < 1e-10
+    Gm = oo.analytic_gradient_from_integrals(h, g, c.one_rdm, c.two_rdm)
+    assert (Gm - orc.gradient_matrix(h, g, c.one_rdm, c.two_rdm, p.occ_idx, p.act_idx)).abs().max().item() < 1e-10
+    one_full, two_full = oo.full_rdms(c.one_rdm, c.two_rdm)
+    r1, r2 = orc.full_rdms(c.one_rdm, c.two_rdm, c.nao, p.occ_idx, p.act_idx)
+    assert isinstance(one_full, np.ndarray)
+    assert np.array_equal(one_full, r1.numpy()) and np.array_equal(two_full, r2.numpy())
+    Y = oo.y_matrix(g, r2)
+    assert (Y - orc.y_matrix(g, r2)).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_orbital_optimization_follows_reference_trajectory(name):
+    """Same Newton-Raphson trajectory as the verbatim reference (oo_energy.py:426-474)."""
+    c = load_case(name)
+    oo = make_oo(c)
+    with contextlib.redirect_stdout(io.StringIO()):
+        traj = oo.orbital_optimization(c.one_rdm, c.two_rdm, conv_tol=1e-10, max_iterations=8, verbose=0)
+    ref = c.ref["nr_energies"]
+    assert len(traj) == len(ref)
+    assert np.abs(np.asarray(traj) - ref).max() < 1e-8
+    assert abs(traj[-1] - ref[-1]) < 1e-8
+    C = oo.oao_mo_coeff.numpy()
+    assert np.abs(C.T @ C - np.eye(c.nao)).max() < 1e-12
+
+
+def test_hf_like_rdms_are_a_fixed_point_of_nothing_breaking():
+    """gamma = diag(2,..,0), Gamma of a closed-shell determinant: E must not increase under NR
+    (reference test_orbital_optimization, test/test_oo_energy.py:317-412)."""
+    c = load_case("n13_cas22")
+    oo = make_oo(c)
+    one = torch.diag(torch.tensor([2.0, 0.0], dtype=F64))
+    two = torch.zeros(2, 2, 2, 2, dtype=F64)
+    two[0, 0, 0, 0] = 2.0
+    e0 = oo.energy_from_mo_coeff(oo.mo_coeff, one, two).item()
+    with contextlib.redirect_stdout(io.StringIO()):
+        traj = oo.orbital_optimization(one, two, max_iterations=6)
+    assert all(b <= a + 1e-10 for a, b in zip([e0] + traj[:-1], traj))
+
+
+def test_energy_and_gradient_are_differentiable_in_the_rdms():
+    from oracle import oo_oracle as orc
+    c = load_case("n11_cas43")
+    oo = make_oo(c)
+    p = c.oracle()
+    one = c.one_rdm.clone().requires_grad_(True)
+    two = c.two_rdm.clone().requires_grad_(True)
+    E = oo.energy_from_kappa(c.kappa, one, two)
+    d1, d2 = torch.autograd.grad(E, (one, two))
+    c0, c1, c2 = p.active_integrals(c.kappa)
+    assert (d1 - c1).abs().max().item() < 1e-11 and (d2 - c2).abs().max().item() < 1e-11
+    Cp = p.rotated_mo(c.kappa)
+    G = oo.kappa_matrix_to_vector(oo.analytic_gradient(one, two, mo_coeff=Cp))
+    w = torch.linspace(-1, 1, G.numel(), dtype=F64)
+    g1, g2 = torch.autograd.grad((G * w).sum(), (one, two))
+    one_r = c.one_rdm.clone().requires_grad_(True)
+    two_r = c.two_rdm.clone().requires_grad_(True)
+    h, g = p.mo_integrals(c.kappa)
+    Gr = orc.skew_to_kappa(orc.gradient_matrix(h, g, one_r, two_r, p.occ_idx, p.act_idx), p.params_idx)
+    r1, r2 = torch.autograd.grad((Gr * w).sum(), (one_r, two_r))
+    assert (g1 - r1).abs().max().item() < 1e-10 and (g2 - r2).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("name,freeze", [("n7_cas44", False), ("n13_cas22", True)])
+def test_oo_pqc_full_derivatives(name, freeze):
+    """All five gradient / Hessian blocks against autograd of E(theta, kappa) on the CPU oracle
+    (reference test_full_derivatives, test/test_oo_pqc.py:38-148)."""
+    import auto_oo_b200
+    from auto_oo_b200.synthetic import CIVectorCircuit
+    from oracle import oo_oracle as orc
+    c = load_case(name)
+    circ = CIVectorCircuit(c.ncas, c.nelecas, n_theta=2, seed=3)
+    oo = auto_oo_b200.OO_pqc(circ, c.mol(), c.ncas, c.nelecas, oao_mo_coeff=c.oao_mo_coeff, freeze_active=freeze)
+    theta = torch.tensor([0.8324, 0.2490], dtype=F64)
+    p = orc.OracleProblem(c.int1e_ao, c.int2e_ao, c.oao_coeff, c.oao_mo_coeff, c.nuc, c.nelec, c.ncas,
+                          c.nelecas, freeze)
+    nt, nk = 2, p.n_kappa
+
+    def energy(x):
+        th, k = x[:nt], x[nt:]
+        one, two = circ.get_rdms(th)
+        C = p.mo_coeff @ torch.linalg.matrix_exp(-orc.kappa_to_skew_diff(k, p.params_idx, c.nao))
+        hh, gg = orc.transform_1e(p.h_ao, C), orc.transform_2e(p.g_ao, C)
+        c0, c1, c2 = orc.hamiltonian_coefficients(p.nuc, hh, gg, p.occ_idx, p.act_idx)
+        return orc.energy_from_coefficients(c0, c1, c2, one, two)
+
+    x0 = torch.cat((theta, torch.zeros(nk, dtype=F64)))
+    g_ref = torch.autograd.functional.jacobian(energy, x0)
+    h_ref = torch.autograd.functional.hessian(energy, x0)
+    grad = oo.full_gradient(theta)
+    hess = oo.full_hessian(theta)
+    assert grad.shape == (nt + nk,) and hess.shape == (nt + nk, nt + nk)
+    assert (grad - g_ref).abs().max().item() < 1e-9
+    assert (hess - h_ref).abs().max().item() < 1e-8
+    assert (oo.circuit_gradient(theta) - g_ref[:nt]).abs().max().item() < 1e-9
+    assert (oo.orbital_circuit_hessian(theta) - h_ref[nt:, :nt]).abs().max().item() < 1e-8
+    e = oo.energy_from_parameters(theta, torch.zeros(nk, dtype=F64)).item()
+    assert abs(e - energy(x0).item()) < TOL_E
+
+
+def test_oo_pqc_full_optimization_converges():
+    import auto_oo_b200
+    from auto_oo_b200.synthetic import CIVectorCircuit
+    c = load_case("n7_cas44")
+    circ = CIVectorCircuit(c.ncas, c.nelecas, n_theta=3, seed=1)
+    oo = auto_oo_b200.OO_pqc(circ, c.mol(), c.ncas, c.nelecas, oao_mo_coeff=c.oao_mo_coeff)
+    with contextlib.redirect_stdout(io.StringIO()):
+        energy_l, theta_l, kappa_l, coeff_l, eig_l = oo.full_optimization(
+            circ.init_zeros(), max_iterations=25, conv_tol=1e-10, verbose=0)
+    assert all(b <= a + 1e-9 for a, b in zip(energy_l[:-1], energy_l[1:]))
+    assert abs(energy_l[-1] - energy_l[-2]) < 1e-8
+    g = oo.full_gradient(theta_l[-1])
+    assert g.abs().max().item() < 1e-5
+    assert len(theta_l) == len(kappa_l) == len(coeff_l) == len(eig_l) == len(energy_l)

@@ -1,0 +1,255 @@
+"""GPU: every kernel group of liboo_b200.so, called through the C ABI (via HotPathEngine's
+ctypes calls), against the CPU oracle and the golden outputs of the verbatim reference.
+Tolerances: energy 1e-10 Ha; gradient/Hessian/matrix elements 1e-8 (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_CASES, SMALL_CASES, GOLDEN, TOL_E, TOL_GH, load_case
+
+pytestmark = pytest.mark.gpu
+
+F64 = torch.float64
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from auto_oo_b200 import _lib
+    return _lib.load()
+
+
+def engine_for(c):
+    from auto_oo_b200.engine import HotPathEngine
+    p = c.oracle()
+    eng = HotPathEngine(c.int1e_ao, c.int2e_ao, c.oao_coeff, c.nuc, c.nao, len(p.occ_idx), c.ncas,
+                        p.params_idx)
+    return eng, p
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------ dense building blocks
+@pytest.mark.parametrize("M,N,K,batch", [
+    (64, 64, 64, 1), (130, 7, 9, 1), (257, 33, 50, 1), (1000, 114, 114, 1), (343, 8, 8, 3),
+    (28 ** 3, 28, 28, 2), (100, 484, 201, 1), (576, 12996 // 4, 1153, 1),
+])
+def test_dgemm_tn(lib, M, N, K, batch):
+    gen = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    lda, ldb, ldc = M + (M & 1), N + (N & 1), N + (N & 1)
+    At = torch.randn(batch, K, lda, dtype=F64, device="cuda", generator=gen)
+    B = torch.randn(batch, K, ldb, dtype=F64, device="cuda", generator=gen)
+    C = torch.full((batch, M, ldc), float("nan"), dtype=F64, device="cuda")
+    rc = lib.oo_dgemm_tn_f64(At.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, lda, ldb, ldc, batch,
+                             K * lda, K * ldb, M * ldc, _stream())
+    assert rc == 0
+    ref = torch.matmul(At[:, :, :M].transpose(1, 2).cpu(), B[:, :, :N].cpu())
+    err = (C[:, :, :N].cpu() - ref).abs().max().item()
+    assert err < 1e-12 * K * 10, err
+
+
+def test_dgemm_tn_shared_operands(lib):
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K, batch = 200, 20, 20, 4
+    At = torch.randn(K, M, dtype=F64, device="cuda", generator=gen)
+    B = torch.randn(batch, K, N, dtype=F64, device="cuda", generator=gen)
+    C = torch.empty(batch, M, N, dtype=F64, device="cuda")
+    assert lib.oo_dgemm_tn_f64(At.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, M, N, N, batch,
+                               0, K * N, M * N, _stream()) == 0
+    ref = torch.matmul(At.T.cpu()[None], B.cpu())
+    assert (C.cpu() - ref).abs().max().item() < 1e-11
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_dgemm_small_epilogue(lib, tA, tB):
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K, batch = 45, 37, 29, 3
+    A = torch.randn(batch, *((K, M) if tA else (M, K)), dtype=F64, device="cuda", generator=gen)
+    B = torch.randn(batch, *((N, K) if tB else (K, N)), dtype=F64, device="cuda", generator=gen)
+    E = torch.randn(batch, M, N, dtype=F64, device="cuda", generator=gen)
+    D = torch.empty(batch, M, N, dtype=F64, device="cuda")
+    rc = lib.oo_dgemm_small_f64(tA, tB, M, N, K, 1.5, A.data_ptr(), A.shape[2], A[0].numel(),
+                                B.data_ptr(), B.shape[2], B[0].numel(), -0.5, E.data_ptr(), N, M * N,
+                                2.0, D.data_ptr(), N, M * N, batch, _stream())
+    assert rc == 0
+    opA = A.transpose(1, 2) if tA else A
+    opB = B.transpose(1, 2) if tB else B
+    ref = 1.5 * torch.matmul(opA.cpu(), opB.cpu()) - 0.5 * E.cpu() + 2.0 * torch.eye(M, N, dtype=F64)
+    assert (D.cpu() - ref).abs().max().item() < 1e-12
+
+
+def test_pad_copy_roundtrip(lib):
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for rank in (2, 4):
+        N, ld, b = 7, 8, 2
+        x = torch.randn((b,) + (N,) * rank, dtype=F64, device="cuda", generator=gen)
+        p = torch.full((b,) + (ld,) * rank, float("nan"), dtype=F64, device="cuda")
+        y = torch.empty_like(x)
+        assert lib.oo_pad_copy_f64(x.data_ptr(), p.data_ptr(), N, ld, rank, b, 1, _stream()) == 0
+        assert lib.oo_pad_copy_f64(p.data_ptr(), y.data_ptr(), N, ld, rank, b, 0, _stream()) == 0
+        assert torch.equal(x, y)
+        sl = (slice(None),) + (slice(0, N),) * rank
+        assert torch.equal(p[sl], x)
+        assert float(p.sum()) == pytest.approx(float(x.sum()), rel=1e-12)   # padding is exactly zero
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_rotation_matches_reference(name):
+    c = load_case(name)
+    eng, p = engine_for(c)
+    U = eng.from_padded(eng.rotation(c.kappa[None]), 2)[0].cpu().numpy()
+    assert np.abs(U - c.ref["U"]).max() < 1e-13
+    assert np.abs(U.T @ U - np.eye(c.nao)).max() < 1e-13
+    Cp = eng.from_padded(eng.mo_coeff(eng.to_padded(c.oao_mo_coeff, 2), eng.rotation(c.kappa[None])), 2)
+    assert np.abs(Cp[0].cpu().numpy() - c.ref["mo_coeff_rot"]).max() < 1e-12
+
+
+def test_rotation_batched_large_norm():
+    from oracle import oo_oracle as orc
+    c = load_case("n13_bigkappa")
+    eng, p = engine_for(c)
+    gen = torch.Generator().manual_seed(1)
+    kap = torch.randn(5, p.n_kappa, dtype=F64, generator=gen) * torch.tensor([0.0, 0.01, 0.3, 1.0, 3.0])[:, None]
+    U = eng.from_padded(eng.rotation(kap), 2).cpu()
+    for b in range(5):
+        ref = orc.rotation_from_kappa(kap[b], p.params_idx, c.nao)
+        assert (U[b] - ref).abs().max().item() < 2e-13
+
+
+def test_expm_general_matrix(lib):
+    gen = torch.Generator().manual_seed(2)
+    N, ld, B = 9, 10, 3
+    A = torch.randn(B, N, N, dtype=F64, generator=gen) * 0.4
+    Ap = torch.zeros(B, ld, ld, dtype=F64)
+    Ap[:, :N, :N] = A
+    Ap = Ap.cuda()
+    U = torch.empty_like(Ap)
+    s = max(0, int(np.ceil(np.log2(A.abs().sum(1).max().item() / 0.95))))
+    nbytes = lib.oo_workspace_bytes(1, N, ld, 0, B)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    assert lib.oo_expm_f64(Ap.data_ptr(), -1.0, N, ld, B, s, U.data_ptr(), ws.data_ptr(), nbytes, _stream()) == 0
+    ref = torch.linalg.matrix_exp(-A)
+    assert (U.cpu()[:, :N, :N] - ref).abs().max().item() < 1e-12
+
+
+# ------------------------------------------------------------------ K2
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_integral_transforms_match_reference(name):
+    c = load_case(name)
+    eng, p = engine_for(c)
+    Cp = eng.to_padded(c.ref["mo_coeff_rot"], 2)
+    h = eng.from_padded(eng.int1e_transform(Cp), 2)[0].cpu().numpy()
+    g = eng.from_padded(eng.int2e_transform(Cp), 4)[0].cpu().numpy()
+    assert np.abs(h - c.ref["int1e_mo"]).max() < 1e-11
+    assert np.abs(g - c.ref["int2e_mo"]).max() < 1e-11
+
+
+def test_general_4index_four_matrices():
+    from auto_oo_b200.engine import HotPathEngine
+    d = np.load(os.path.join(GOLDEN, "general_4index_n6.npz"))
+    eng = HotPathEngine(np.zeros((6, 6)), d["M"], np.eye(6), 0.0, 6, 0, 6, [0])
+    Cs = [eng.to_padded(d[k], 2) for k in ("C0", "C1", "C2", "C3")]
+    out = eng.from_padded(eng.int2e_transform(*Cs), 4)[0].cpu().numpy()
+    assert np.abs(out - d["out"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", ["n28_cas66", "n43_cas34"])
+def test_int2e_transform_vs_oracle_and_identity(name):
+    from oracle import oo_oracle as orc
+    c = load_case(name)
+    eng, p = engine_for(c)
+    Cp = eng.to_padded(c.ref["mo_coeff_rot"], 2)
+    g = eng.from_padded(eng.int2e_transform(Cp), 4)[0].cpu()
+    ref = orc.transform_2e(c.int2e_ao, c.ref["mo_coeff_rot"])
+    assert (g - ref).abs().max().item() < 1e-10
+    ident = eng.to_padded(np.eye(c.nao), 2)
+    g_id = eng.from_padded(eng.int2e_transform(ident), 4)[0].cpu().numpy()
+    assert np.array_equal(g_id, np.asarray(c.int2e_ao))     # exact: sums of x*1 and x*0
+
+
+def test_int2e_transform_batched_kappa_sweep():
+    from oracle import oo_oracle as orc
+    c = load_case("n11_cas43")
+    eng, p = engine_for(c)
+    gen = torch.Generator().manual_seed(4)
+    kap = torch.randn(3, p.n_kappa, dtype=F64, generator=gen) * 0.1
+    C = eng.mo_coeff(eng.to_padded(c.oao_mo_coeff, 2), eng.rotation(kap))
+    g = eng.from_padded(eng.int2e_transform(C), 4).cpu()
+    for b in range(3):
+        ref = orc.transform_2e(c.int2e_ao, p.rotated_mo(kap[b]))
+        assert (g[b] - ref).abs().max().item() < 1e-11
+
+
+# ------------------------------------------------------------------ K3 / K4
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_full_evaluation_matches_reference(name):
+    c = load_case(name)
+    eng, p = engine_for(c)
+    E, G, H = eng.evaluate(eng.to_padded(c.oao_mo_coeff, 2), c.one_rdm, c.two_rdm, kappa=c.kappa[None])
+    assert abs(E.item() - float(c.ref["E"])) < TOL_E
+    assert np.abs(G[0].cpu().numpy() - c.ref["G"]).max() < TOL_GH
+    assert np.abs(H[0].cpu().numpy() - c.ref["H"]).max() < TOL_GH
+    E0, G0, _ = eng.evaluate(eng.to_padded(c.oao_mo_coeff, 2), c.one_rdm, c.two_rdm, want_hessian=False)
+    assert abs(E0.item() - float(c.ref["E0"])) < TOL_E
+    assert np.abs(G0[0].cpu().numpy() - c.ref["G0"]).max() < TOL_GH
+
+
+@pytest.mark.parametrize("name", ["n7_cas44", "n8_nocore", "n11_cas43", "n28_cas66"])
+def test_active_hamiltonian_and_fock_stages(name):
+    from oracle import oo_oracle as orc
+    c = load_case(name)
+    eng, p = engine_for(c)
+    Cp = eng.to_padded(c.ref["mo_coeff_rot"], 2)
+    h, g = eng.mo_integrals(Cp)
+    c0, c1, c2 = eng.active_hamiltonian(h, g)
+    assert abs(c0.item() - float(c.ref["c0"])) < TOL_E
+    assert np.abs(c1[0].cpu().numpy() - c.ref["c1"]).max() < 1e-11
+    assert np.abs(c2[0].cpu().numpy() - c.ref["c2"]).max() < 1e-11
+    d1, d2 = eng.dev(c.one_rdm), eng.dev(c.two_rdm)
+    FI, FA, F, Gm, gv = eng.fock_gradient(h, g, d1, d2)
+    ho, go = p.mo_integrals(c.kappa)
+    for got, ref in ((FI, orc.fock_core(ho, go, p.occ_idx)),
+                     (FA, orc.fock_active(go, c.one_rdm, p.act_idx)),
+                     (F, orc.fock_generalized(ho, go, c.one_rdm, c.two_rdm, p.occ_idx, p.act_idx)),
+                     (Gm, orc.gradient_matrix(ho, go, c.one_rdm, c.two_rdm, p.occ_idx, p.act_idx))):
+        assert (eng.from_padded(got, 2)[0].cpu() - ref).abs().max().item() < 1e-10
+    assert np.abs(gv[0].cpu().numpy() - c.ref["G"]).max() < TOL_GH
+
+
+@pytest.mark.parametrize("name", ["n7_cas44", "n11_cas43"])
+def test_gradient_vjp_matches_autograd(name):
+    """Adjoint of (gamma, Gamma) -> G (what jacobian(orbital_gradient, theta) needs, oo_pqc.py:113-123)."""
+    from oracle import oo_oracle as orc
+    c = load_case(name)
+    eng, p = engine_for(c)
+    h, g = eng.mo_integrals(eng.to_padded(c.ref["mo_coeff_rot"], 2))
+    d1, d2 = eng.dev(c.one_rdm), eng.dev(c.two_rdm)
+    FI, FA, F, Gm, gv = eng.fock_gradient(h, g, d1, d2)
+    gen = torch.Generator().manual_seed(8)
+    Gbar = torch.randn(c.nao, c.nao, dtype=F64, generator=gen)
+    g1, g2 = eng.fock_gradient_vjp(g[0], FI[0], eng.to_padded(Gbar, 2))
+    ho, go = p.mo_integrals(c.kappa)
+    one = c.one_rdm.clone().requires_grad_(True)
+    two = c.two_rdm.clone().requires_grad_(True)
+    Gref = orc.gradient_matrix(ho, go, one, two, p.occ_idx, p.act_idx)
+    r1, r2 = torch.autograd.grad((Gref * Gbar).sum(), (one, two))
+    assert (g1.cpu() - r1).abs().max().item() < 1e-10
+    assert (g2.cpu() - r2).abs().max().item() < 1e-10
+
+
+def test_batched_evaluation_equals_single():
+    c = load_case("n13_cas22")
+    eng, p = engine_for(c)
+    gen = torch.Generator().manual_seed(6)
+    kap = torch.randn(4, p.n_kappa, dtype=F64, generator=gen) * 0.05
+    Coao = eng.to_padded(c.oao_mo_coeff, 2)
+    E, G, H = eng.evaluate(Coao, c.one_rdm, c.two_rdm, kappa=kap)
+    for b in range(4):
+        e, gvec, hm = p.evaluate(c.one_rdm, c.two_rdm, kap[b])
+        assert abs(E[b].item() - e.item()) < TOL_E
+        assert (G[b].cpu() - gvec).abs().max().item() < TOL_GH
+        assert (H[b].cpu() - hm).abs().max().item() < TOL_GH

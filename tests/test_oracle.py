@@ -1,0 +1,111 @@
+"""CPU: pin the oracle (oracle/oo_oracle.py) against (1) the reference's own known-answer
+tests and (2) outputs of the verbatim reference stored in tests/golden (made by
+oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oo_oracle as orc
+from helpers import ALL_CASES, SMALL_CASES, GOLDEN, TOL_E, TOL_GH, load_case
+
+
+def test_vector_to_skew_symmetric_known_answer():
+    # reference test/test_oo_energy.py:188-213
+    v = torch.arange(1.0, 7.0, dtype=torch.float64)
+    K = orc.unpack_skew(v)
+    expect = torch.tensor([[0, -1, -2, -4], [1, 0, -3, -5], [2, 3, 0, -6], [4, 5, 6, 0]], dtype=torch.float64)
+    assert torch.equal(K, expect)
+    assert torch.equal(orc.pack_skew(K), v)
+
+
+@pytest.mark.parametrize("occ,act,virt,freeze,expect", [
+    # reference test/test_oo_energy.py:216-231
+    ([0, 1], [2, 3], [4, 5], False, [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]),
+    ([0, 1], [2, 3], [4, 5], True, [1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13]),
+])
+def test_non_redundant_indices_known_answer(occ, act, virt, freeze, expect):
+    assert list(orc.non_redundant_indices(occ, act, virt, freeze)) == expect
+
+
+def test_non_redundant_counts():
+    for (no, na, nv) in [(0, 3, 5), (3, 4, 0), (2, 2, 2), (6, 4, 24)]:
+        occ, act, virt = np.arange(no), no + np.arange(na), no + na + np.arange(nv)
+        for freeze in (False, True):
+            idx = orc.non_redundant_indices(occ, act, virt, freeze)
+            assert len(idx) == no * na + na * nv + no * nv + (0 if freeze else na * (na - 1) // 2)
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_oracle_matches_reference_outputs(name):
+    c = load_case(name)
+    p = c.oracle()
+    r = c.ref
+    assert np.array_equal(p.params_idx, r["params_idx"])
+    U = orc.rotation_from_kappa(c.kappa, p.params_idx, c.nao)
+    assert np.abs(U.numpy() - r["U"]).max() < 1e-14
+    assert np.abs(p.rotated_mo(c.kappa).numpy() - r["mo_coeff_rot"]).max() < 1e-13
+    c0, c1, c2 = p.active_integrals(c.kappa)
+    assert abs(float(c0) - float(r["c0"])) < TOL_E
+    assert np.abs(c1.numpy() - r["c1"]).max() < 1e-11
+    assert np.abs(c2.numpy() - r["c2"]).max() < 1e-11
+    assert abs(p.energy(c.one_rdm, c.two_rdm, c.kappa).item() - float(r["E"])) < TOL_E
+    assert abs(p.energy(c.one_rdm, c.two_rdm).item() - float(r["E0"])) < TOL_E
+    assert np.abs(p.gradient(c.one_rdm, c.two_rdm, c.kappa).numpy() - r["G"]).max() < TOL_GH
+    assert np.abs(p.gradient(c.one_rdm, c.two_rdm).numpy() - r["G0"]).max() < TOL_GH
+    # the dense N^6 form is the reference's algorithm; keep it to the sizes that finish in seconds
+    H = p.hessian(c.one_rdm, c.two_rdm, c.kappa, ispace=c.nao > 13)
+    assert np.abs(H.numpy() - r["H"]).max() < TOL_GH
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_ispace_hessian_equals_dense_form(name):
+    c = load_case(name)
+    p = c.oracle()
+    Hd = p.hessian(c.one_rdm, c.two_rdm, c.kappa, ispace=False)
+    Hi = p.hessian(c.one_rdm, c.two_rdm, c.kappa, ispace=True)
+    assert (Hd - Hi).abs().max().item() < 1e-11
+    assert (Hd - Hd.T).abs().max().item() < 1e-10
+    assert np.abs(Hi.numpy() - c.ref["H"]).max() < TOL_GH
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_transforms_match_reference(name):
+    c = load_case(name)
+    Cp = torch.as_tensor(c.ref["mo_coeff_rot"])
+    assert np.abs(orc.transform_1e(c.int1e_ao, Cp).numpy() - c.ref["int1e_mo"]).max() < 1e-12
+    assert np.abs(orc.transform_2e(c.int2e_ao, Cp).numpy() - c.ref["int2e_mo"]).max() < 1e-12
+
+
+def test_general_4index_transform():
+    d = np.load(os.path.join(GOLDEN, "general_4index_n6.npz"))
+    out = orc.transform_4index(d["M"], d["C0"], d["C1"], d["C2"], d["C3"])
+    assert np.abs(out.numpy() - d["out"]).max() < 1e-12
+    explicit = np.einsum('pi,qj,rk,sl,pqrs->ijkl', d["C0"], d["C1"], d["C2"], d["C3"], d["M"])
+    assert np.abs(out.numpy() - explicit).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", ["n7_cas44", "n13_cas22"])
+def test_analytic_derivatives_equal_autograd(name):
+    """The reference's own strategy (test/test_oo_energy.py:415-971): analytic G/H at kappa=0
+    against autograd of energy_from_kappa -- proves the fixtures obey the symmetry preconditions."""
+    c = load_case(name)
+    p = c.oracle()
+
+    def energy(k):
+        C = p.mo_coeff @ torch.linalg.matrix_exp(-orc.kappa_to_skew_diff(k, p.params_idx, c.nao))
+        h, g = orc.transform_1e(p.h_ao, C), orc.transform_2e(p.g_ao, C)
+        c0, c1, c2 = orc.hamiltonian_coefficients(p.nuc, h, g, p.occ_idx, p.act_idx)
+        return orc.energy_from_coefficients(c0, c1, c2, c.one_rdm, c.two_rdm)
+
+    k0 = torch.zeros(p.n_kappa, dtype=torch.float64)
+    g_auto = torch.autograd.functional.jacobian(energy, k0)
+    h_auto = torch.autograd.functional.hessian(energy, k0)
+    assert (g_auto - p.gradient(c.one_rdm, c.two_rdm)).abs().max().item() < 1e-10
+    assert (h_auto - p.hessian(c.one_rdm, c.two_rdm)).abs().max().item() < 1e-9
+
+
+def test_odd_core_electrons_raises():
+    with pytest.raises(ValueError):
+        orc.active_space_idx(7, 9, 4, 4)
