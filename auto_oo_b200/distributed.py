@@ -1,0 +1,205 @@
+"""Multi-GPU sharding of the hot path on one NVLink/NVSwitch box (one process per GPU,
+``torch.distributed``).
+
+1. :func:`shard_range` / :func:`sharded_evaluations` -- independent evaluations (a kappa sweep, the
+   geometries of a Berry loop): contiguous slices of the batch per rank, integrals replicated,
+   no data-path collective; results are all-gathered only if the caller wants them on every rank.
+
+2. :class:`SlabTransform` -- ONE four-index transform (reference ``oo_energy.py:21-30``) whose N^4
+   tensor is sharded over the ranks, for bases that do not fit a single GPU.  Every quarter is
+   the rotating TN-GEMM of ``csrc/api.cu`` (``Out[(rest), new] = sum_lead In[lead,(rest)] C[lead,new]``);
+   what differs is which index is distributed and the one exchange step:
+
+   * ``mode="reduce_scatter"`` (the decomposition named in BASELINE.json): rank ``r`` holds the slab
+     ``g[p in P_r, :, :, :]`` of the LEADING AO index.  Quarter 1 gives partial sums over ``p in P_r``
+     for every destination block of the new index ``i``; chunk ``d`` (``i in I_d``) is summed onto rank
+     ``d`` (NCCL ``reduce_scatter``: N^4 doubles leave every rank).  Quarters 2-4 are local.
+   * ``mode="all_to_all"``: rank ``r`` holds ``g[:, :, (r s) in RS_r]`` (a slab of the TRAILING pair).
+     Quarters 1-2 need no communication (the contracted indices p, q are complete on every rank);
+     one ``all_to_all`` re-shards ``[(rs)_loc, i, j] -> [(rs), i_loc, j]`` (N^4/G doubles leave every
+     rank, and every element is summed on one rank in the single-GPU order => bit-identical results),
+     then quarters 3-4 are local.
+
+   Both end with ``g'[i in I_r, :, :, :]`` on rank ``r``.  Per-destination GEMMs make every exchanged
+   chunk contiguous, so no pack/unpack pass exists; chunk ``d+1`` is computed while chunk ``d`` is in
+   flight (communication on NCCL's own stream, ``async_op=True``).
+
+The GEMM is injectable so the orchestration is testable on CPU with the ``gloo`` backend
+(``tests/test_distributed_cpu.py``); the default is the sm_100a kernel ``oo_dgemm_tn_f64``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+F64 = torch.float64
+
+
+# --------------------------------------------------------------------------------------
+# independent evaluations
+# --------------------------------------------------------------------------------------
+def shard_range(n_items, world_size, rank):
+    """Contiguous, balanced slice ``[lo, hi)`` of ``n_items`` for ``rank`` (first ``n % world``
+    ranks get one more)."""
+    base, extra = divmod(int(n_items), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sharded_evaluations(evaluate, kappas, group=None, gather=True):
+    """Run ``evaluate(kappa_slice) -> tuple of tensors with leading batch dim`` on this rank's
+    slice of ``kappas (B, n_kappa)``; with ``gather`` every rank receives the full-batch results
+    (``all_gather`` of equal-size padded slices)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = kappas.shape[0]
+    lo, hi = shard_range(B, world, rank)
+    local = evaluate(kappas[lo:hi])
+    if not gather or world == 1:
+        return local
+    width = -(-B // world)
+    outs = []
+    for t in local:
+        pad = torch.zeros((width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: hi - lo] = t
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        parts = []
+        for r in range(world):
+            a, b = shard_range(B, world, r)
+            parts.append(bufs[r][: b - a])
+        outs.append(torch.cat(parts, dim=0))
+    return tuple(outs)
+
+
+# --------------------------------------------------------------------------------------
+# slab-parallel four-index transform
+# --------------------------------------------------------------------------------------
+def _cuda_gemm_tn(At, B, out):
+    """out[m, n] = sum_k At[k, m] B[k, n] on the FP64 tensor-core kernel (device tensors)."""
+    from . import _lib
+    lib = _lib.load()
+    K, M = At.shape
+    N = B.shape[1]
+    rc = lib.oo_dgemm_tn_f64(At.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, At.stride(0), B.stride(0),
+                             out.stride(0), 1, 0, 0, 0, torch.cuda.current_stream(At.device).cuda_stream)
+    _lib.check(rc, "dgemm_tn")
+    return out
+
+
+def torch_gemm_tn(At, B, out):
+    """Same contract on torch ops -- for the CPU/gloo tests of the orchestration only."""
+    torch.matmul(At.T, B, out=out)
+    return out
+
+
+class SlabTransform:
+    """Distributed ``general_4index_transform`` over the ranks of ``group``.
+
+    ``n`` orbitals (even, or pre-padded), ``mode`` as in the module docstring.  ``slab_shape()``
+    tells the caller which slab of the AO tensor this rank must hold; ``__call__(g_slab, C0..C3)``
+    returns ``g'[i in I_r, :, :, :]`` (``out_range()``)."""
+
+    def __init__(self, n, mode="reduce_scatter", group=None, gemm=None):
+        assert mode in ("reduce_scatter", "all_to_all")
+        self.n, self.mode, self.group = int(n), mode, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.gemm = gemm or _cuda_gemm_tn
+        if mode == "all_to_all":
+            # equal splits keep all_to_all_single simple: n^2 trailing pairs and n leading indices
+            assert (self.n * self.n) % self.world == 0 and self.n % self.world == 0, \
+                "all_to_all mode needs world_size | n"
+        else:
+            assert self.n % self.world == 0, "reduce_scatter mode needs world_size | n"
+        self.blk = self.n // self.world                 # |I_d| for every destination
+
+    # ---- which part of g_ao each rank holds
+    def in_range(self):
+        """reduce_scatter: range of the leading index p; all_to_all: range of the flat (r s) pair."""
+        if self.mode == "reduce_scatter":
+            return shard_range(self.n, self.world, self.rank)
+        return shard_range(self.n * self.n, self.world, self.rank)
+
+    def slab_shape(self):
+        lo, hi = self.in_range()
+        n = self.n
+        return (hi - lo, n, n, n) if self.mode == "reduce_scatter" else (n, n, hi - lo)
+
+    def take_slab(self, g_full):
+        """Cut this rank's slab out of a full (n,n,n,n) tensor (tests / small cases)."""
+        lo, hi = self.in_range()
+        n = self.n
+        if self.mode == "reduce_scatter":
+            return g_full[lo:hi].contiguous()
+        return g_full.reshape(n, n, n * n)[:, :, lo:hi].contiguous()
+
+    def out_range(self):
+        return shard_range(self.n, self.world, self.rank)
+
+    # ---- the transform
+    def __call__(self, g_slab, C0, C1, C2, C3):
+        if self.mode == "reduce_scatter":
+            t1 = self._quarter1_reduce_scatter(g_slab, C0)
+            rest = (C1, C2, C3)
+        else:
+            t1 = self._quarters12_all_to_all(g_slab, C0, C1)
+            rest = (C2, C3)
+        # t1 is [lead, (rest...)] with the distributed index somewhere in the middle; every
+        # remaining quarter contracts the leading index against a full C and appends the new one.
+        cur = t1
+        for C in rest:
+            lead = cur.shape[0]
+            m = cur.numel() // lead
+            out = torch.empty(m, self.n, dtype=F64, device=cur.device)
+            self.gemm(cur.reshape(lead, m), C, out)
+            cur = out.reshape(self.n, -1)                 # next leading index is the slowest of `out`
+        return cur.reshape(self.blk, self.n, self.n, self.n)
+
+    def _quarter1_reduce_scatter(self, g_slab, C0):
+        n, W, blk = self.n, self.world, self.blk
+        lo, hi = self.in_range()
+        At = g_slab.reshape(hi - lo, n * n * n)                      # [p_loc, (q r s)]
+        mine = torch.empty(n * n * n, blk, dtype=F64, device=g_slab.device)
+        if W == 1:
+            self.gemm(At, C0, mine)
+            return mine.reshape(n, n * n * blk)
+        bufs = [torch.empty_like(mine) for _ in range(2)]
+        pending = []
+        for d in range(W):
+            buf = bufs[d % 2]
+            if len(pending) >= 2:                                    # the buffer we are about to reuse
+                pending.pop(0).wait()
+            Cd = C0[lo:hi, d * blk:(d + 1) * blk].contiguous()       # [p_loc, i in I_d]
+            self.gemm(At, Cd, buf)
+            # sum of chunk d over all ranks lands on rank d: a reduce-scatter issued chunk by chunk
+            # so that chunk d+1 is computed while chunk d is on the wire
+            pending.append(dist.reduce(buf, dst=self._global_rank(d), op=dist.ReduceOp.SUM,
+                                       group=self.group, async_op=True))
+            if d == self.rank:
+                keep = buf
+                bufs[d % 2] = torch.empty_like(mine)                 # do not overwrite the result chunk
+        for w in pending:
+            w.wait()
+        return keep.reshape(n, n * n * blk)                          # [q, (r s i_loc)]
+
+    def _quarters12_all_to_all(self, g_slab, C0, C1):
+        n, W, blk = self.n, self.world, self.blk
+        lo, hi = self.in_range()
+        nrs = hi - lo
+        At = g_slab.reshape(n, n * nrs)                              # [p, (q rs_loc)]
+        send = torch.empty(W, nrs, blk, n, dtype=F64, device=g_slab.device)   # chunk d: [rs_loc, i in I_d, j]
+        t1 = torch.empty(n * nrs, blk, dtype=F64, device=g_slab.device)
+        for d in range(W):
+            self.gemm(At, C0[:, d * blk:(d + 1) * blk].contiguous(), t1)      # [(q rs_loc), i_d]
+            self.gemm(t1.reshape(n, nrs * blk), C1, send[d].reshape(nrs * blk, n))   # [(rs_loc i_d), j]
+        if W == 1:
+            return send[0].reshape(n, n * blk * n)
+        recv = torch.empty_like(send)                                 # chunk s: [rs in RS_s, i_loc, j]
+        dist.all_to_all_single(recv.reshape(-1), send.reshape(-1), group=self.group)
+        return recv.reshape(n, n * blk * n)                          # [r, (s i_loc j)]
+
+    def _global_rank(self, group_rank):
+        if self.group is None:
+            return group_rank
+        return dist.get_global_rank(self.group, group_rank)

@@ -253,3 +253,22 @@ def test_batched_evaluation_equals_single():
         assert abs(E[b].item() - e.item()) < TOL_E
         assert (G[b].cpu() - gvec).abs().max().item() < TOL_GH
         assert (H[b].cpu() - hm).abs().max().item() < TOL_GH
+
+
+# ------------------------------------------------------------------ multi-GPU orchestration on the CUDA GEMM
+@pytest.mark.parametrize("mode", ["reduce_scatter", "all_to_all"])
+def test_slab_transform_world1_on_cuda_gemm(mode):
+    """world_size 1: the slab-parallel driver on the sm_100a GEMM must reproduce the single-GPU
+    transform (the world_size 2 exchange is covered on CPU/gloo and by tools/slab_transform_check.py)."""
+    from auto_oo_b200.distributed import SlabTransform
+    from auto_oo_b200.engine import HotPathEngine
+    n = 12
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    g = torch.randn(n, n, n, n, dtype=F64, device="cuda", generator=gen)
+    Cs = [torch.randn(n, n, dtype=F64, device="cuda", generator=gen) for _ in range(4)]
+    ref = HotPathEngine.for_tensors(n).int2e_transform(*Cs, g_ao=g)[0]
+    st = SlabTransform(n, mode=mode)
+    out = st(st.take_slab(g), *Cs)
+    assert torch.equal(out, ref)          # same kernel, same summation order: bit-identical
+    cpu = torch.einsum('pi,qj,rk,sl,pqrs->ijkl', *[c.cpu() for c in Cs], g.cpu())
+    assert (out.cpu() - cpu).abs().max().item() < 1e-10
