@@ -19,6 +19,7 @@ _ptr = C.c_void_p
 _size = C.c_size_t
 
 OO_WS_ROTATION, OO_WS_INT2E, OO_WS_HESSIAN, OO_WS_INT1E, OO_WS_YMATRIX = 1, 2, 3, 4, 5
+OO_WS_CLASS_TRANSFORM, OO_WS_CLASS_BUFFER, OO_WS_CLASS_HESSIAN = 6, 7, 8
 
 # name -> (restype, argtypes); mirrors include/oo_b200.h one to one
 _SIGNATURES = {
@@ -47,6 +48,15 @@ _SIGNATURES = {
     "oo_fock_gradient_vjp_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "oo_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32,
                               _ptr, _ptr, _size, _ptr]),
+    "oo_transpose_f64": (_i32, [_ptr, _ptr, _i64, _i64, _ptr]),
+    "oo_class_transform_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_class_active_hamiltonian_f64": (_i32, [_ptr, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr,
+                                               _ptr, _ptr]),
+    "oo_class_fock_gradient_f64": (_i32, [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
+                                          _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "oo_class_fock_gradient_vjp_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
+    "oo_class_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32,
+                                    _ptr, _ptr, _size, _ptr]),
     "oo_full_rdms_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "oo_y_matrix_f64": (_i32, [_ptr, _ptr, _i32, _i32, _ptr, _ptr, _size, _ptr]),
     "oo_pad_copy_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr]),

@@ -136,6 +136,42 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
     return r;
 }
 
+// ---- views of the transformed two-electron integrals ----------------------------
+// Every contraction of the hot path touches g' only through two access patterns with at
+// least two indices m, n in I = occ + act:
+//   coul(a,b,m,n) = g'[a,b,m,n]     (Coulomb class  (ab|mn))
+//   exch(a,m,n,b) = g'[a,m,n,b]     (exchange class (am|nb))
+// FullView reads them from the complete ld^4 tensor of the four-index transform;
+// ClassView from the two class tensors of the partial transform (classes.cu):
+//   J[m,n,a,b] = g'[a,b,m,n],  K[n,m,a,b] = g'[a,m,n,b],  each [nIp][nIp][ld][ld].
+struct FullView {
+    const double *g;
+    int ld;
+    int64_t batch_stride;
+    __device__ __forceinline__ FullView at(int b) const { return {g + (int64_t)b * batch_stride, ld, batch_stride}; }
+    __device__ __forceinline__ double coul(int a, int b, int m, int n) const {
+        return g[(((int64_t)a * ld + b) * ld + m) * ld + n];
+    }
+    __device__ __forceinline__ double exch(int a, int m, int n, int b) const {
+        return g[(((int64_t)a * ld + m) * ld + n) * ld + b];
+    }
+};
+
+struct ClassView {
+    const double *K, *J;      // K first: the Hessian's B operand is [K rows; J rows; h row]
+    int ld, nIp;
+    int64_t batch_stride;
+    __device__ __forceinline__ ClassView at(int b) const {
+        return {K + (int64_t)b * batch_stride, J + (int64_t)b * batch_stride, ld, nIp, batch_stride};
+    }
+    __device__ __forceinline__ double coul(int a, int b, int m, int n) const {
+        return J[(((int64_t)m * nIp + n) * ld + a) * ld + b];
+    }
+    __device__ __forceinline__ double exch(int a, int m, int n, int b) const {
+        return K[(((int64_t)n * nIp + m) * ld + a) * ld + b];
+    }
+};
+
 // ---- host: TMA descriptor encode (driver entry point fetched at run time) -----
 int encode_tmap_3d_f64(CUtensorMap *map, const void *base, uint64_t dim0, uint64_t dim1,
                        uint64_t dim2, uint64_t stride1_elems, uint64_t stride2_elems,

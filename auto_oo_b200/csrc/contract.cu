@@ -20,14 +20,15 @@ __device__ __forceinline__ int64_t idx4(int p, int q, int r, int s, int ld) {
 
 // ---------------------------------------------------------------- active Hamiltonian
 // grid (1 + na*na + ceil(na^4/256), batch).  block 0: c0; blocks 1..na^2: c1[t,u]; rest: c2.
+template <class GV>
 __global__ void __launch_bounds__(256)
-active_hamiltonian_kernel(const double *__restrict__ h, const double *__restrict__ g, int no, int na,
+active_hamiltonian_kernel(const double *__restrict__ h, int64_t h_stride, const GV gv, int no, int na,
                           int ld, double e_nuc, double *__restrict__ c0, double *__restrict__ c1,
                           double *__restrict__ c2) {
     __shared__ double scratch[32];
     const int b = blockIdx.y;
-    const double *hb = h + (int64_t)b * ld * ld;
-    const double *gb = g + (int64_t)b * ld * ld * ld * ld;
+    const double *hb = h + (int64_t)b * h_stride;
+    const GV gb = gv.at(b);
     const int na2 = na * na;
     const int64_t na4 = (int64_t)na2 * na2;
     const int blk = blockIdx.x;
@@ -36,7 +37,7 @@ active_hamiltonian_kernel(const double *__restrict__ h, const double *__restrict
         double s = 0.0;
         for (int e = threadIdx.x; e < no * no; e += blockDim.x) {
             const int i = e / no, j = e % no;
-            s += 2.0 * gb[idx4(i, i, j, j, ld)] - gb[idx4(i, j, j, i, ld)];
+            s += 2.0 * gb.coul(i, i, j, j) - gb.exch(i, j, j, i);
             if (j == 0) s += 2.0 * hb[(int64_t)i * ld + i];
         }
         s = block_sum(s, scratch);
@@ -46,7 +47,7 @@ active_hamiltonian_kernel(const double *__restrict__ h, const double *__restrict
         const int T = no + t, U = no + u;
         double s = 0.0;
         for (int i = threadIdx.x; i < no; i += blockDim.x)
-            s += 2.0 * gb[idx4(T, U, i, i, ld)] - gb[idx4(T, i, i, U, ld)];
+            s += 2.0 * gb.coul(T, U, i, i) - gb.exch(T, i, i, U);
         s = block_sum(s, scratch);
         if (threadIdx.x == 0) c1[(int64_t)b * na2 + t * na + u] = s + hb[(int64_t)T * ld + U];
     } else {
@@ -54,7 +55,7 @@ active_hamiltonian_kernel(const double *__restrict__ h, const double *__restrict
         if (e < na4) {
             const int w = (int)(e % na), v = (int)((e / na) % na), u = (int)((e / na2) % na),
                       t = (int)(e / ((int64_t)na2 * na));
-            c2[(int64_t)b * na4 + e] = 0.5 * gb[idx4(no + t, no + u, no + v, no + w, ld)];
+            c2[(int64_t)b * na4 + e] = 0.5 * gb.coul(no + t, no + u, no + v, no + w);
         }
     }
 }
@@ -80,8 +81,9 @@ energy_kernel(const double *__restrict__ c0, const double *__restrict__ c1, cons
 
 // ---------------------------------------------------------------- F^I and F^A
 // one warp per (m, n); lanes split the i / (v,w) sums.  grid (ceil(ld*ld/8), batch), 256 threads.
+template <class GV>
 __global__ void __launch_bounds__(256)
-fock_core_active_kernel(const double *__restrict__ h, const double *__restrict__ g,
+fock_core_active_kernel(const double *__restrict__ h, int64_t h_stride, const GV gv,
                         const double *__restrict__ d1, int64_t sd1, int no, int na, int N, int ld,
                         double *__restrict__ FI, double *__restrict__ FA) {
     extern __shared__ double s_d1[];   // gamma (na*na)
@@ -96,19 +98,15 @@ fock_core_active_kernel(const double *__restrict__ h, const double *__restrict__
     const int64_t mat = (int64_t)ld * ld;
     double fi = 0.0, fa = 0.0;
     if (m < N && n < N) {
-        const double *gb = g + (int64_t)b * mat * mat;
-        const double *g_mn = gb + ((int64_t)m * ld + n) * mat;   // g[m,n,:,:]
-        const double *g_m = gb + (int64_t)m * ld * mat;          // g[m,:,:,:]
-        for (int i = lane; i < no; i += 32)
-            fi += 2.0 * g_mn[(int64_t)i * ld + i] - g_m[((int64_t)i * ld + i) * ld + n];
+        const GV gb = gv.at(b);
+        for (int i = lane; i < no; i += 32) fi += 2.0 * gb.coul(m, n, i, i) - gb.exch(m, i, i, n);
         for (int e = lane; e < na * na; e += 32) {
             const int v = e / na, w = e % na;
-            fa += s_d1[e] * (g_mn[(int64_t)(no + v) * ld + (no + w)]
-                             - 0.5 * g_m[((int64_t)(no + w) * ld + (no + v)) * ld + n]);
+            fa += s_d1[e] * (gb.coul(m, n, no + v, no + w) - 0.5 * gb.exch(m, no + w, no + v, n));
         }
         fi = warp_sum(fi);
         fa = warp_sum(fa);
-        fi += h[(int64_t)b * mat + (int64_t)m * ld + n];
+        fi += h[(int64_t)b * h_stride + (int64_t)m * ld + n];
     }
     if (lane == 0) {
         FI[(int64_t)b * mat + pair] = fi;
@@ -121,8 +119,9 @@ fock_core_active_kernel(const double *__restrict__ h, const double *__restrict__
 //   F[i,n] = 2 (FI[n,i] + FA[n,i])                       i in occ
 //   F[v,n] = sum_w FI[n,w] d1[v,w] + sum_wxy d2[v,w,x,y] g[n,w,x,y]    v in act
 //   F[a,n] = 0                                           a in virt / padding
+template <class GV>
 __global__ void __launch_bounds__(256)
-fock_general_kernel(const double *__restrict__ g, const double *__restrict__ FI,
+fock_general_kernel(const GV gv, const double *__restrict__ FI,
                     const double *__restrict__ FA, const double *__restrict__ d1, int64_t sd1,
                     const double *__restrict__ d2, int64_t sd2, int no, int na, int N, int ld,
                     double *__restrict__ F) {
@@ -136,10 +135,10 @@ fock_general_kernel(const double *__restrict__ g, const double *__restrict__ FI,
         for (int r = threadIdx.x; r < ld; r += blockDim.x) Fb[(int64_t)r * ld + n] = 0.0;
         return;
     }
-    const double *gn = g + (int64_t)b * mat * mat + (int64_t)n * ld * mat;   // g[n,:,:,:]
+    const GV gb = gv.at(b);
     for (int e = threadIdx.x; e < na3; e += blockDim.x) {
         const int w = e / na2, x = (e / na) % na, y = e % na;
-        s_g[e] = gn[((int64_t)(no + w) * ld + (no + x)) * ld + (no + y)];
+        s_g[e] = gb.coul(n, no + w, no + x, no + y);
     }
     __syncthreads();
     for (int r = threadIdx.x; r < ld; r += blockDim.x) {
@@ -187,8 +186,9 @@ __global__ void gradient_pack_kernel(const double *__restrict__ F, const int32_t
 // Fbar = 2 (Gbar - Gbar^T).
 //  blocks [0, na^2):  gbar1[v,w] = sum_{i,n} Fbar[i,n] 2 (g[n,i,v,w] - g[n,w,v,i]/2) + sum_n Fbar[v,n] FI[n,w]
 //  blocks [na^2, na^2 + na^4): gbar2[v,w,x,y] = sum_n Fbar[v,n] g[n,w,x,y]
+template <class GV>
 __global__ void __launch_bounds__(128)
-fock_gradient_vjp_kernel(const double *__restrict__ g, const double *__restrict__ FI,
+fock_gradient_vjp_kernel(const GV g, const double *__restrict__ FI,
                          const double *__restrict__ Gbar, int no, int na, int N, int ld,
                          double *__restrict__ gbar1, double *__restrict__ gbar2) {
     __shared__ double scratch[32];
@@ -204,8 +204,7 @@ fock_gradient_vjp_kernel(const double *__restrict__ g, const double *__restrict_
         double s = 0.0;
         for (int e = threadIdx.x; e < no * N; e += blockDim.x) {
             const int i = e / N, n = e % N;
-            const double *gn = g + (int64_t)n * ld * mat;
-            s += fbar(i, n) * 2.0 * (gn[((int64_t)i * ld + V) * ld + W] - 0.5 * gn[((int64_t)W * ld + V) * ld + i]);
+            s += fbar(i, n) * 2.0 * (g.coul(n, i, V, W) - 0.5 * g.exch(n, W, V, i));
         }
         for (int n = threadIdx.x; n < N; n += blockDim.x) s += fbar(V, n) * FI[(int64_t)n * ld + W];
         s = block_sum(s, scratch);
@@ -216,7 +215,7 @@ fock_gradient_vjp_kernel(const double *__restrict__ g, const double *__restrict_
                   v = (int)(e / ((int64_t)na2 * na));
         double s = 0.0;
         for (int n = threadIdx.x; n < N; n += blockDim.x)
-            s += fbar(no + v, n) * g[(int64_t)n * ld * mat + ((int64_t)(no + w) * ld + (no + x)) * ld + (no + y)];
+            s += fbar(no + v, n) * g.coul(n, no + w, no + x, no + y);
         s = block_sum(s, scratch);
         if (threadIdx.x == 0) gbar2[e] = s;
     }
@@ -263,14 +262,16 @@ __global__ void pad_copy_kernel(const double *__restrict__ src, double *__restri
 
 }  // namespace
 
-int active_hamiltonian(const double *h, const double *g, int no, int na, int N, int ld, int batch,
-                       double e_nuc, double *c0, double *c1, double *c2, cudaStream_t stream) {
-    OO_REQUIRE(h && g && c0 && c1 && c2);
+template <class GV>
+static int active_hamiltonian_t(const double *h, int64_t h_stride, const GV &gv, int no, int na, int N,
+                                int ld, int batch, double e_nuc, double *c0, double *c1, double *c2,
+                                cudaStream_t stream) {
+    OO_REQUIRE(h && c0 && c1 && c2);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && batch > 0);
     if (batch > 65535) return OO_ERR_UNSUPPORTED;
     const int64_t na4 = (int64_t)na * na * na * na;
     dim3 grid((unsigned)(1 + na * na + ceil_div(na4, 256)), (unsigned)batch);
-    active_hamiltonian_kernel<<<grid, 256, 0, stream>>>(h, g, no, na, ld, e_nuc, c0, c1, c2);
+    active_hamiltonian_kernel<GV><<<grid, 256, 0, stream>>>(h, h_stride, gv, no, na, ld, e_nuc, c0, c1, c2);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -283,11 +284,12 @@ int energy(const double *c0, const double *c1, const double *c2, const double *d
     return OO_OK;
 }
 
-int fock_gradient(const double *h, const double *g, const double *d1, int64_t sd1, const double *d2,
-                  int64_t sd2, int no, int na, int N, int ld, int batch, const int32_t *pl,
-                  const int32_t *pr, int nk, double *FI, double *FA, double *F, double *Gmat,
-                  double *gvec, cudaStream_t stream) {
-    OO_REQUIRE(h && g && d1 && d2 && FI && FA && F);
+template <class GV>
+static int fock_gradient_t(const double *h, int64_t h_stride, const GV &gv, const double *d1, int64_t sd1,
+                           const double *d2, int64_t sd2, int no, int na, int N, int ld, int batch,
+                           const int32_t *pl, const int32_t *pr, int nk, double *FI, double *FA, double *F,
+                           double *Gmat, double *gvec, cudaStream_t stream) {
+    OO_REQUIRE(h && d1 && d2 && FI && FA && F);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && batch > 0);
     OO_REQUIRE(!gvec || nk == 0 || (pl && pr));
     if (batch > 65535) return OO_ERR_UNSUPPORTED;
@@ -296,12 +298,12 @@ int fock_gradient(const double *h, const double *g, const double *d1, int64_t sd
     if (sm1 > 48 * 1024 || sm3 > 48 * 1024) return OO_ERR_UNSUPPORTED;   // na <= 18
     {
         dim3 grid((unsigned)ceil_div((int64_t)ld * ld, 8), (unsigned)batch);
-        fock_core_active_kernel<<<grid, 256, sm1, stream>>>(h, g, d1, sd1, no, na, N, ld, FI, FA);
+        fock_core_active_kernel<GV><<<grid, 256, sm1, stream>>>(h, h_stride, gv, d1, sd1, no, na, N, ld, FI, FA);
         OO_LAUNCH_CHECK();
     }
     {
         dim3 grid((unsigned)ld, (unsigned)batch);
-        fock_general_kernel<<<grid, 256, sm3, stream>>>(g, FI, FA, d1, sd1, d2, sd2, no, na, N, ld, F);
+        fock_general_kernel<GV><<<grid, 256, sm3, stream>>>(gv, FI, FA, d1, sd1, d2, sd2, no, na, N, ld, F);
         OO_LAUNCH_CHECK();
     }
     if (Gmat) {
@@ -318,15 +320,77 @@ int fock_gradient(const double *h, const double *g, const double *d1, int64_t sd
     return OO_OK;
 }
 
-int fock_gradient_vjp(const double *g, const double *FI, const double *Gbar, int no, int na, int N,
-                      int ld, double *gbar1, double *gbar2, cudaStream_t stream) {
-    OO_REQUIRE(g && FI && Gbar && gbar1 && gbar2);
+template <class GV>
+static int fock_gradient_vjp_t(const GV &gv, const double *FI, const double *Gbar, int no, int na, int N,
+                               int ld, double *gbar1, double *gbar2, cudaStream_t stream) {
+    OO_REQUIRE(FI && Gbar && gbar1 && gbar2);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N);
     const int64_t blocks = (int64_t)na * na + (int64_t)na * na * na * na;
     if (blocks > 0x7fffffffll) return OO_ERR_UNSUPPORTED;
-    fock_gradient_vjp_kernel<<<(unsigned)blocks, 128, 0, stream>>>(g, FI, Gbar, no, na, N, ld, gbar1, gbar2);
+    fock_gradient_vjp_kernel<GV><<<(unsigned)blocks, 128, 0, stream>>>(gv, FI, Gbar, no, na, N, ld, gbar1, gbar2);
     OO_LAUNCH_CHECK();
     return OO_OK;
+}
+
+static inline FullView full_view(const double *g, int ld) {
+    return FullView{g, ld, (int64_t)ld * ld * ld * ld};
+}
+
+// class tensors live in one buffer per evaluation: [K rows nIp^2][J rows nIp^2][h' row], rows of ld^2
+static inline int64_t class_rows(int nIp) { return 2 * (int64_t)nIp * nIp + 1; }
+static inline ClassView class_view(const double *cls, int ld, int nIp) {
+    const int64_t mat = (int64_t)ld * ld;
+    return ClassView{cls, cls + (int64_t)nIp * nIp * mat, ld, nIp, class_rows(nIp) * mat};
+}
+static inline const double *class_h(const double *cls, int ld, int nIp) {
+    return cls + 2 * (int64_t)nIp * nIp * ld * ld;
+}
+
+int active_hamiltonian(const double *h, const double *g, int no, int na, int N, int ld, int batch,
+                       double e_nuc, double *c0, double *c1, double *c2, cudaStream_t stream) {
+    OO_REQUIRE(g);
+    return active_hamiltonian_t(h, (int64_t)ld * ld, full_view(g, ld), no, na, N, ld, batch, e_nuc, c0, c1, c2,
+                                stream);
+}
+
+int fock_gradient(const double *h, const double *g, const double *d1, int64_t sd1, const double *d2,
+                  int64_t sd2, int no, int na, int N, int ld, int batch, const int32_t *pl,
+                  const int32_t *pr, int nk, double *FI, double *FA, double *F, double *Gmat,
+                  double *gvec, cudaStream_t stream) {
+    OO_REQUIRE(g);
+    return fock_gradient_t(h, (int64_t)ld * ld, full_view(g, ld), d1, sd1, d2, sd2, no, na, N, ld, batch, pl, pr,
+                           nk, FI, FA, F, Gmat, gvec, stream);
+}
+
+int fock_gradient_vjp(const double *g, const double *FI, const double *Gbar, int no, int na, int N,
+                      int ld, double *gbar1, double *gbar2, cudaStream_t stream) {
+    OO_REQUIRE(g);
+    return fock_gradient_vjp_t(full_view(g, ld), FI, Gbar, no, na, N, ld, gbar1, gbar2, stream);
+}
+
+// ---- the same contractions on the class tensors of the partial transform (classes.cu)
+int class_active_hamiltonian(const double *cls, int no, int na, int N, int ld, int nIp, int batch,
+                             double e_nuc, double *c0, double *c1, double *c2, cudaStream_t stream) {
+    OO_REQUIRE(cls && nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
+    const ClassView v = class_view(cls, ld, nIp);
+    return active_hamiltonian_t(class_h(cls, ld, nIp), v.batch_stride, v, no, na, N, ld, batch, e_nuc, c0, c1,
+                                c2, stream);
+}
+
+int class_fock_gradient(const double *cls, const double *d1, int64_t sd1, const double *d2, int64_t sd2,
+                        int no, int na, int N, int ld, int nIp, int batch, const int32_t *pl,
+                        const int32_t *pr, int nk, double *FI, double *FA, double *F, double *Gmat,
+                        double *gvec, cudaStream_t stream) {
+    OO_REQUIRE(cls && nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
+    const ClassView v = class_view(cls, ld, nIp);
+    return fock_gradient_t(class_h(cls, ld, nIp), v.batch_stride, v, d1, sd1, d2, sd2, no, na, N, ld, batch, pl,
+                           pr, nk, FI, FA, F, Gmat, gvec, stream);
+}
+
+int class_fock_gradient_vjp(const double *cls, const double *FI, const double *Gbar, int no, int na, int N,
+                            int ld, int nIp, double *gbar1, double *gbar2, cudaStream_t stream) {
+    OO_REQUIRE(cls && nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
+    return fock_gradient_vjp_t(class_view(cls, ld, nIp), FI, Gbar, no, na, N, ld, gbar1, gbar2, stream);
 }
 
 int pad_copy(const double *src, double *dst, int N, int ld, int rank, int batch, int to_padded,
@@ -376,5 +440,27 @@ int oo_fock_gradient_vjp_f64(const double *g_mo, const double *FI, const double 
 int oo_pad_copy_f64(const double *src, double *dst, int N, int ld, int rank, int batch, int to_padded,
                     void *stream) {
     return oo::pad_copy(src, dst, N, ld, rank, batch, to_padded, (cudaStream_t)stream);
+}
+}
+
+extern "C" {
+
+int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp, int batch,
+                                    double e_nuc, double *c0, double *c1, double *c2, void *stream) {
+    return oo::class_active_hamiltonian(cls, no, na, N, ld, nIp, batch, e_nuc, c0, c1, c2,
+                                        (cudaStream_t)stream);
+}
+
+int oo_class_fock_gradient_f64(const double *cls, const double *gamma, int64_t stride_rdm1,
+                               const double *Gamma, int64_t stride_rdm2, int no, int na, int N, int ld,
+                               int nIp, int batch, const int32_t *pair_l, const int32_t *pair_r, int nk,
+                               double *FI, double *FA, double *F, double *Gmat, double *gvec, void *stream) {
+    return oo::class_fock_gradient(cls, gamma, stride_rdm1, Gamma, stride_rdm2, no, na, N, ld, nIp, batch,
+                                   pair_l, pair_r, nk, FI, FA, F, Gmat, gvec, (cudaStream_t)stream);
+}
+
+int oo_class_fock_gradient_vjp_f64(const double *cls, const double *FI, const double *Gbar, int no, int na,
+                                   int N, int ld, int nIp, double *gbar1, double *gbar2, void *stream) {
+    return oo::class_fock_gradient_vjp(cls, FI, Gbar, no, na, N, ld, nIp, gbar1, gbar2, (cudaStream_t)stream);
 }
 }

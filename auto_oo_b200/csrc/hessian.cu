@@ -64,7 +64,10 @@ __device__ __forceinline__ double gf2(const RdmView &r, int p, int q, int s, int
 }
 
 // At rows: [0,nI^2) exchange-type, [nI^2, 2nI^2) Coulomb-type, 2nI^2: one-body.  lda >= nI^2 (even).
-__global__ void hess_build_at_kernel(RdmView rdm, int nI, int64_t lda, double *__restrict__ At) {
+// nI here is the ROW STRIDE of the I-space (nI for the full-tensor path, nIp for the class path;
+// gf1/gf2 return 0 for indices beyond occ+act).  swap_exch: exchange rows are ordered (n,m)
+// instead of (m,n) -- the order in which classes.cu stores K[n,m,a,b].
+__global__ void hess_build_at_kernel(RdmView rdm, int nI, int swap_exch, int64_t lda, double *__restrict__ At) {
     const int nI2 = nI * nI;
     const int64_t total = (int64_t)(2 * nI2 + 1) * lda;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -75,7 +78,8 @@ __global__ void hess_build_at_kernel(RdmView rdm, int nI, int64_t lda, double *_
         if (col < nI2) {
             const int p = col / nI, r = col % nI;
             if (k < nI2) {
-                const int m = (int)(k / nI), n = (int)(k % nI);
+                const int k1 = (int)(k / nI), k2 = (int)(k % nI);
+                const int m = swap_exch ? k2 : k1, n = swap_exch ? k1 : k2;
                 v = 2.0 * (gf2(rdm, p, m, r, n) + gf2(rdm, p, m, n, r));
             } else if (k < 2 * nI2) {
                 const int kk = (int)(k - nI2);
@@ -116,25 +120,25 @@ __global__ void hess_gather_b_kernel(const double *__restrict__ h, const double 
 }
 
 __device__ __forceinline__ double hess_x(const double *__restrict__ T, const double *__restrict__ F,
-                                         int nI, int ld, int a, int b, int c, int d) {
-    // X(a,b,c,d) = -(F_ac + F_ca) delta_bd + [a,c in I] T[(a c),(b d)]
+                                         int nI, int nIs, int ld, int a, int b, int c, int d) {
+    // X(a,b,c,d) = -(F_ac + F_ca) delta_bd + [a,c in I] T[(a c),(b d)]   (T rows: a * nIs + c)
     double v = 0.0;
     if (b == d) v = -(F[(int64_t)a * ld + c] + F[(int64_t)c * ld + a]);
-    if (a < nI && c < nI) v += T[((int64_t)a * nI + c) * ld * ld + (int64_t)b * ld + d];
+    if (a < nI && c < nI) v += T[((int64_t)a * nIs + c) * ld * ld + (int64_t)b * ld + d];
     return v;
 }
 
 __global__ void __launch_bounds__(256)
 hess_assemble_kernel(const double *__restrict__ T, const double *__restrict__ F,
                      const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int nI,
-                     int ld, double *__restrict__ H) {
+                     int nIs, int ld, double *__restrict__ H) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (k >= nk) return;
     const int p = pl[j], q = pr[j];
     const int r = pl[k], s = pr[k];
-    const double v = hess_x(T, F, nI, ld, p, q, r, s) - hess_x(T, F, nI, ld, p, q, s, r)
-                   - hess_x(T, F, nI, ld, q, p, r, s) + hess_x(T, F, nI, ld, q, p, s, r);
+    const double v = hess_x(T, F, nI, nIs, ld, p, q, r, s) - hess_x(T, F, nI, nIs, ld, p, q, s, r)
+                   - hess_x(T, F, nI, nIs, ld, q, p, r, s) + hess_x(T, F, nI, nIs, ld, q, p, s, r);
     H[(int64_t)j * nk + k] = v;
 }
 
@@ -228,7 +232,7 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     {
         int64_t blocks = ceil_div(L.krows * L.lda, 256);
         if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-        hess_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nI, L.lda, At);
+        hess_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nI, 0, L.lda, At);
         OO_LAUNCH_CHECK();
     }
     {
@@ -242,9 +246,41 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     {
         if (nk > 65535) return OO_ERR_UNSUPPORTED;
         dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-        hess_assemble_kernel<<<grid, 256, 0, stream>>>(T, F, pl, pr, nk, nI, ld, H);
+        hess_assemble_kernel<<<grid, 256, 0, stream>>>(T, F, pl, pr, nk, nI, nI, ld, H);
         OO_LAUNCH_CHECK();
     }
+    return OO_OK;
+}
+
+// Hessian from the class buffer of classes.cu: cls = [K rows; J rows; h' row] IS the B operand.
+size_t class_hessian_ws_bytes(int ld, int nIp) {
+    const HessLayout L = hess_layout(ld, nIp);
+    return L.off_b + (L.total - L.off_t);          // At + T (no gathered B)
+}
+
+int class_hessian(const double *cls, const double *F, const double *d1, const double *d2, int no, int na,
+                  int N, int ld, int nIp, const int32_t *pl, const int32_t *pr, int nk, double *H, void *ws,
+                  size_t ws_bytes, cudaStream_t stream) {
+    OO_REQUIRE(cls && F && d1 && d2 && H && ws && pl && pr);
+    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0);
+    OO_REQUIRE(nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
+    if (ws_bytes < class_hessian_ws_bytes(ld, nIp)) return OO_ERR_WORKSPACE;
+    if (nk > 65535) return OO_ERR_UNSUPPORTED;
+    const HessLayout L = hess_layout(ld, nIp);
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    double *At = reinterpret_cast<double *>(w);
+    double *T = reinterpret_cast<double *>(w + L.off_b);
+    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld;
+    RdmView rdm{d1, d2, no, na};
+    int64_t blocks = ceil_div(L.krows * L.lda, 256);
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    hess_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nIp, 1, L.lda, At);
+    OO_LAUNCH_CHECK();
+    int rc = dgemm_tn(At, cls, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
+    hess_assemble_kernel<<<grid, 256, 0, stream>>>(T, F, pl, pr, nk, no + na, nIp, ld, H);
+    OO_LAUNCH_CHECK();
     return OO_OK;
 }
 
@@ -309,4 +345,12 @@ extern "C" int oo_full_rdms_f64(const double *gamma, const double *Gamma, int no
 extern "C" int oo_y_matrix_f64(const double *g_mo, const double *two_full, int N, int ld, double *Y,
                                void *ws, size_t ws_bytes, void *stream) {
     return oo::y_matrix(g_mo, two_full, N, ld, Y, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma,
+                                    const double *Gamma, int no, int na, int N, int ld, int nIp,
+                                    const int32_t *pair_l, const int32_t *pair_r, int nk, double *H,
+                                    void *ws, size_t ws_bytes, void *stream) {
+    return oo::class_hessian(cls, F, gamma, Gamma, no, na, N, ld, nIp, pair_l, pair_r, nk, H, ws, ws_bytes,
+                             (cudaStream_t)stream);
 }

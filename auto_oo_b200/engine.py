@@ -33,6 +33,36 @@ def tril_pair_table(nao, params_idx):
     return rows[pidx].astype(np.int32), cols[pidx].astype(np.int32)
 
 
+class MOIntegrals:
+    """Transformed integrals of ONE set of MO coefficients on the device, in either representation:
+    ``kind="full"`` -- (h', g') with the complete ld^4 tensor of the four-index transform, or
+    ``kind="class"`` -- the class buffer [K; J; h'] of the partial transform.  Both give the same
+    numbers to every consumer (energy, Fock matrices, gradient, adjoint, Hessian)."""
+
+    def __init__(self, eng, kind, h=None, g=None, cls=None):
+        self.eng, self.kind, self.h, self.g, self.cls = eng, kind, h, g, cls
+
+    def active_hamiltonian(self):
+        if self.kind == "class":
+            return self.eng.class_active_hamiltonian(self.cls)
+        return self.eng.active_hamiltonian(self.h, self.g)
+
+    def fock_gradient(self, d1, d2, want_matrix=True, want_vector=True):
+        if self.kind == "class":
+            return self.eng.class_fock_gradient(self.cls, d1, d2, want_matrix, want_vector)
+        return self.eng.fock_gradient(self.h, self.g, d1, d2, want_matrix, want_vector)
+
+    def fock_gradient_vjp(self, FI, Gbar):
+        if self.kind == "class":
+            return self.eng.class_fock_gradient_vjp(self.cls, FI[0], Gbar)
+        return self.eng.fock_gradient_vjp(self.g[0], FI[0], Gbar)
+
+    def hessian(self, F, d1, d2, pair_l=None, pair_r=None):
+        if self.kind == "class":
+            return self.eng.class_hessian(self.cls, F[0], d1, d2, pair_l=pair_l, pair_r=pair_r)
+        return self.eng.hessian(self.h[0], self.g[0], F[0], d1, d2, pair_l=pair_l, pair_r=pair_r)
+
+
 class HotPathEngine:
     _tensor_engines = {}
 
@@ -66,9 +96,13 @@ class HotPathEngine:
             self.h_ao = None if int1e_ao is None else self.to_padded(int1e_ao, 2)
             self.X = None if oao_coeff is None else self.to_padded(oao_coeff, 2)
             self.g_ao = None if int2e_ao is None else self.to_padded(int2e_ao, 4)
+        self.nIp = pad_even(self.nI)                   # class index padded to even (TMA strides)
+        self.g_pairT = None                            # g_ao[p,q,r,s] stored as [r,s,p,q]; built on first use
         self._ws = {}
         self._cache_key = None
         self._cache_val = None
+        self._ccache_key = None
+        self._ccache_val = None
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -217,6 +251,14 @@ class HotPathEngine:
                                                     _p(out), _p(ws), nbytes, self.stream), "int2e_transform")
         return out
 
+    def integrals(self, C, kind="class"):
+        """:class:`MOIntegrals` for one padded C (ld, ld), cached by the value of C."""
+        if kind == "class":
+            cls = self.class_integrals_cached(C)
+            return MOIntegrals(self, "class", cls=cls)
+        h, g = self.mo_integrals(C)
+        return MOIntegrals(self, "full", h=h, g=g)
+
     def mo_integrals(self, C):
         """(h', g') for padded C (B, ld, ld); the last single-matrix result is cached by value."""
         C = C if C.dim() == 3 else C[None]
@@ -232,6 +274,97 @@ class HotPathEngine:
         if C.shape[0] == 1:
             self._cache_key, self._cache_val = C.clone(), (h, g)
         return h, g
+
+    # ------------------------------------------------------------------ class (partial-transform) path
+    def pair_transposed_eri(self):
+        """g_pairT[r,s,p,q] = g_ao[p,q,r,s] (one HBM-bound transpose, once per problem)."""
+        if self.g_pairT is None:
+            ld2 = self.ld * self.ld
+            out = torch.empty_like(self.g_ao)
+            self._check(self.lib.oo_transpose_f64(_p(self.g_ao), _p(out), ld2, ld2, self.stream), "transpose")
+            self.g_pairT = out
+        return self.g_pairT
+
+    def drop_full_eri(self):
+        """Free g_ao (and the full-transform buffers) once g_pairT exists: the class path needs only
+        the pair-transposed copy.  The full four-index transform API then needs ``g_ao=`` again."""
+        self.pair_transposed_eri()
+        self.g_ao = None
+        self._cache_key = self._cache_val = None
+        self._ws.pop("i2e", None)
+
+    def class_integrals(self, C, out=None):
+        """Class buffer [K rows; J rows; h' row] (2 nIp^2 + 1, ld, ld) for ONE padded C (ld, ld)."""
+        C = C.reshape(self.ld, self.ld)
+        ld, nIp = self.ld, self.nIp
+        rows = 2 * nIp * nIp + 1
+        cls = out if out is not None else torch.empty(rows, ld, ld, dtype=F64, device=self.device)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, 1)
+        ws = self.workspace("cls", nbytes)
+        self._check(self.lib.oo_class_transform_f64(_p(self.pair_transposed_eri()), _p(C), self.N, ld, nIp,
+                                                    _p(cls), _p(ws), nbytes, self.stream), "class_transform")
+        nb1 = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, ld, 0, 1)
+        ws1 = self.workspace("i1e", nb1)
+        self._check(self.lib.oo_int1e_transform_f64(_p(self.h_ao), _p(C), 0, self.N, ld, 1, _p(cls[rows - 1]),
+                                                    _p(ws1), nb1, self.stream), "int1e_transform")
+        return cls
+
+    def class_integrals_cached(self, C):
+        """As class_integrals, but the last result is cached by the value of C."""
+        C = C.reshape(self.ld, self.ld)
+        if self._ccache_key is not None and torch.equal(self._ccache_key, C):
+            return self._ccache_val
+        buf = self._ccache_val
+        self._ccache_key = self._ccache_val = None
+        cls = self.class_integrals(C, out=buf)
+        self._ccache_key, self._ccache_val = C.clone(), cls
+        return cls
+
+    def class_active_hamiltonian(self, cls):
+        na = self.na
+        c0 = torch.empty(1, dtype=F64, device=self.device)
+        c1 = torch.empty(1, na, na, dtype=F64, device=self.device)
+        c2 = torch.empty(1, na, na, na, na, dtype=F64, device=self.device)
+        self._check(self.lib.oo_class_active_hamiltonian_f64(_p(cls), self.no, na, self.N, self.ld, self.nIp, 1,
+                                                             self.nuc, _p(c0), _p(c1), _p(c2), self.stream),
+                    "class_active_hamiltonian")
+        return c0, c1, c2
+
+    def class_fock_gradient(self, cls, d1, d2, want_matrix=True, want_vector=True):
+        ld = self.ld
+        FI = torch.empty(1, ld, ld, dtype=F64, device=self.device)
+        FA = torch.empty_like(FI)
+        F = torch.empty_like(FI)
+        G = torch.empty_like(FI) if want_matrix else None
+        gv = torch.empty(1, self.nk, dtype=F64, device=self.device) if want_vector else None
+        self._check(self.lib.oo_class_fock_gradient_f64(_p(cls), _p(d1), 0, _p(d2), 0, self.no, self.na, self.N,
+                                                        ld, self.nIp, 1, _p(self.pair_l), _p(self.pair_r),
+                                                        self.nk, _p(FI), _p(FA), _p(F), _p(G), _p(gv),
+                                                        self.stream), "class_fock_gradient")
+        return FI, FA, F, G, gv
+
+    def class_fock_gradient_vjp(self, cls, FI, Gbar):
+        na = self.na
+        g1 = torch.empty(na, na, dtype=F64, device=self.device)
+        g2 = torch.empty(na, na, na, na, dtype=F64, device=self.device)
+        self._check(self.lib.oo_class_fock_gradient_vjp_f64(_p(cls), _p(FI), _p(Gbar), self.no, na, self.N,
+                                                            self.ld, self.nIp, _p(g1), _p(g2), self.stream),
+                    "class_fock_gradient_vjp")
+        return g1, g2
+
+    def class_hessian(self, cls, F, d1, d2, out=None, pair_l=None, pair_r=None):
+        pl = self.pair_l if pair_l is None else pair_l
+        pr = self.pair_r if pair_r is None else pair_r
+        nk = int(pl.numel())
+        H = out if out is not None else torch.empty(nk, nk, dtype=F64, device=self.device)
+        if nk == 0:
+            return H
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.N, self.ld, self.nI, 1)
+        ws = self.workspace("chess", nbytes)
+        self._check(self.lib.oo_class_hessian_f64(_p(cls), _p(F), _p(d1), _p(d2), self.no, self.na, self.N,
+                                                  self.ld, self.nIp, _p(pl), _p(pr), nk, _p(H), _p(ws), nbytes,
+                                                  self.stream), "class_hessian")
+        return H
 
     # ------------------------------------------------------------------ K3
     def active_hamiltonian(self, h, g):
@@ -330,12 +463,14 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ whole evaluations
     def evaluate(self, oao_mo_coeff, d1, d2, kappa=None, want_hessian=True, squarings=None,
-                 H_out=None, transform_events=None):
+                 H_out=None, transform_events=None, path="class"):
         """E (B,), packed gradient (B, nk) and Hessian (B, nk, nk) at C' = X C_oao expm(-K(kappa_b)).
 
         ``oao_mo_coeff``: padded (ld, ld) or (B, ld, ld) device tensor; ``kappa``: (B, nk) or None.
         One 4-index transform per evaluation serves E, G and H (the reference repeats it
-        three times: oo_energy.py:207-208, :410-411, :421-422).  Evaluations are processed
+        three times: oo_energy.py:207-208, :410-411, :421-422).  ``path="class"`` computes only the
+        J/K integral classes E, G and H read (partial transform); ``path="full"`` the complete
+        four-index transform.  Evaluations are processed
         one at a time through the N^4 stages (one g' buffer + one workspace in HBM).
         ``transform_events``: optional list that receives a (start, end) CUDA-event pair around
         every 4-index transform (four TN-DGEMM launches) for the roofline figure."""
@@ -354,6 +489,27 @@ class HotPathEngine:
         H = None
         if want_hessian:
             H = H_out if H_out is not None else torch.empty(B, self.nk, self.nk, dtype=F64, device=self.device)
+        if path == "class":
+            cbuf = self._ccache_val
+            self._ccache_key = self._ccache_val = None
+            for b in range(B):
+                if transform_events is not None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                cbuf = self.class_integrals(C[b], out=cbuf)
+                if transform_events is not None:
+                    ev[1].record()
+                    transform_events.append(ev)
+                d1b = d1[b] if d1.dim() == 3 else d1
+                d2b = d2[b] if d2.dim() == 5 else d2
+                c0, c1, c2 = self.class_active_hamiltonian(cbuf)
+                E[b:b + 1] = self.energy(c0, c1, c2, d1b, d2b)
+                FI, FA, F, _, gv = self.class_fock_gradient(cbuf, d1b, d2b, want_matrix=False)
+                G[b] = gv[0]
+                if want_hessian:
+                    self.class_hessian(cbuf, F[0], d1b, d2b, out=H[b])
+            self._ccache_val = cbuf                     # keep the buffer (not the key) for reuse
+            return E, G, H
         hs = self.int1e_transform(C)
         gbuf = None
         if self._cache_val is not None:

@@ -160,9 +160,9 @@ class _GradientFn(torch.autograd.Function):
     ``oo_fock_gradient_vjp_f64``."""
 
     @staticmethod
-    def forward(ctx, one_rdm, two_rdm, eng, h, g):
-        FI, FA, F, G, _ = eng.fock_gradient(h, g, eng.dev(one_rdm), eng.dev(two_rdm), want_vector=False)
-        ctx.eng, ctx.g, ctx.FI = eng, g, FI
+    def forward(ctx, one_rdm, two_rdm, eng, ints):
+        FI, FA, F, G, _ = ints.fock_gradient(eng.dev(one_rdm), eng.dev(two_rdm), want_vector=False)
+        ctx.eng, ctx.ints, ctx.FI = eng, ints, FI
         ctx.dev1, ctx.dev2 = one_rdm.device, two_rdm.device
         return eng.from_padded(G, 2)[0].to(one_rdm.device)
 
@@ -170,25 +170,23 @@ class _GradientFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gbar):
         eng = ctx.eng
-        g1, g2 = eng.fock_gradient_vjp(ctx.g[0], ctx.FI[0], eng.to_padded(gbar, 2))
-        return g1.to(ctx.dev1), g2.to(ctx.dev2), None, None, None
+        g1, g2 = ctx.ints.fock_gradient_vjp(ctx.FI, eng.to_padded(gbar, 2))
+        return g1.to(ctx.dev1), g2.to(ctx.dev2), None, None
 
 
 class OrbitalHessian:
     """Device-resident orbital Hessian in the I-space form (``T`` and ``F``):
     what ``analytic_hessian`` returns instead of the reference's dense ``(N,N,N,N)`` tensor."""
 
-    def __init__(self, eng, h, g, F, one_rdm, two_rdm, like):
-        self._eng, self._h, self._g, self._F = eng, h, g, F
+    def __init__(self, eng, ints, F, one_rdm, two_rdm, like):
+        self._eng, self._ints, self._F = eng, ints, F
         self._d1, self._d2 = eng.dev(one_rdm), eng.dev(two_rdm)
         self._like = like
         self.shape = (eng.N,) * 4
 
     def matrix(self, pair_l=None, pair_r=None):
         """``H[l_j, r_j, l_k, r_k]`` for the engine's non-redundant pairs (or the given ones)."""
-        eng = self._eng
-        return eng.hessian(self._h[0], self._g[0], self._F[0], self._d1, self._d2,
-                           pair_l=pair_l, pair_r=pair_r)
+        return self._ints.hessian(self._F, self._d1, self._d2, pair_l=pair_l, pair_r=pair_r)
 
     def dense(self):
         """The reference's rank-4 tensor ``H[p,q,r,s]`` (``oo_energy.py:311-340``); O(N^4) memory."""
@@ -209,7 +207,12 @@ class OO_energy:
     ``oao_mo_coeff`` is None)."""
 
     def __init__(self, mol, ncas, nelecas, oao_mo_coeff=None, freeze_active=False, interface='torch',
-                 device=None):
+                 device=None, integral_path="class"):
+        """``integral_path``: ``"class"`` (default) transforms only the J/K integral classes that
+        energy, gradient and Hessian read; ``"full"`` runs the complete four-index transform for
+        every set of MO coefficients, as the reference does."""
+        assert integral_path in ("class", "full")
+        self.integral_path = integral_path
         if interface != 'torch':
             raise ValueError("auto_oo_b200 implements the torch interface only (no JAX/XLA dispatch)")
         if oao_mo_coeff is None:
@@ -274,20 +277,19 @@ class OO_energy:
 
     # ------------------------------------------------------------------ energy
     def _mo_integrals(self, mo_coeff):
+        """Transformed integrals at ``mo_coeff`` (class representation, cached by value)."""
         eng = self.engine
-        return eng.mo_integrals(eng.to_padded(_as_tensor(mo_coeff).detach(), 2))
+        return eng.integrals(eng.to_padded(_as_tensor(mo_coeff).detach(), 2), kind=self.integral_path)
 
     def get_active_integrals(self, mo_coeff):
         """``(c0, c1, c2)`` of the active-space Hamiltonian in chemist notation
         (reference ``oo_energy.py:204-211``, ``utils/active_space.py:177-212``)."""
-        h, g = self._mo_integrals(mo_coeff)
-        c0, c1, c2 = self.engine.active_hamiltonian(h, g)
+        c0, c1, c2 = self._mo_integrals(mo_coeff).active_hamiltonian()
         return _like(c0[0], mo_coeff), _like(c1[0], mo_coeff), _like(c2[0], mo_coeff)
 
     def energy_from_mo_coeff(self, mo_coeff, one_rdm, two_rdm):
         """Reference ``oo_energy.py:178-197``.  0-d tensor, differentiable in the RDMs."""
-        h, g = self._mo_integrals(mo_coeff)
-        c0, c1, c2 = self.engine.active_hamiltonian(h, g)
+        c0, c1, c2 = self._mo_integrals(mo_coeff).active_hamiltonian()
         one, two = _as_tensor(one_rdm), _as_tensor(two_rdm)
         return _EnergyFn.apply(one, two, self.engine, c0, c1, c2)
 
@@ -296,14 +298,19 @@ class OO_energy:
         eng = self.engine
         U = eng.rotation(_as_tensor(kappa).detach().reshape(1, -1))
         C = eng.mo_coeff(eng.to_padded(self.oao_mo_coeff, 2), U)
-        h, g = eng.mo_integrals(C)
-        c0, c1, c2 = eng.active_hamiltonian(h, g)
+        c0, c1, c2 = eng.integrals(C[0], kind=self.integral_path).active_hamiltonian()
         return _EnergyFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), eng, c0, c1, c2)
 
     # ------------------------------------------------------------------ Fock matrices / gradient
     def _padded_integrals(self, int1e_mo, int2e_mo):
         eng = self.engine
         return eng.to_padded(_as_tensor(int1e_mo), 2)[None], eng.to_padded(_as_tensor(int2e_mo), 4)[None]
+
+    def _given_integrals(self, int1e_mo, int2e_mo):
+        """Caller-supplied dense MO integrals (the ``*_from_integrals`` methods)."""
+        from .engine import MOIntegrals
+        h, g = self._padded_integrals(int1e_mo, int2e_mo)
+        return MOIntegrals(self.engine, "full", h=h, g=g)
 
     def fock_core(self, int1e_mo, int2e_mo):
         """``F^I`` (reference ``oo_energy.py:272-284``)."""
@@ -331,13 +338,13 @@ class OO_energy:
 
     def analytic_gradient_from_integrals(self, int1e_mo, int2e_mo, one_rdm, two_rdm):
         """``G = 2 (F - F^T)`` (reference ``oo_energy.py:300-309``)."""
-        h, g = self._padded_integrals(int1e_mo, int2e_mo)
-        return _GradientFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, h, g)
+        ints = self._given_integrals(int1e_mo, int2e_mo)
+        return _GradientFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, ints)
 
     def analytic_gradient(self, one_rdm, two_rdm, mo_coeff=None):
         """Reference ``oo_energy.py:404-413``; differentiable in the RDMs."""
-        h, g = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
-        return _GradientFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, h, g)
+        ints = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
+        return _GradientFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, ints)
 
     # ------------------------------------------------------------------ Hessian
     def full_rdms(self, one_rdm, two_rdm):
@@ -357,19 +364,18 @@ class OO_energy:
 
     def analytic_hessian_from_integrals(self, int1e_mo, int2e_mo, one_rdm, two_rdm):
         """Reference ``oo_energy.py:311-340``; returns an :class:`OrbitalHessian`."""
-        h, g = self._padded_integrals(int1e_mo, int2e_mo)
-        return self._hessian(h, g, one_rdm, two_rdm, int1e_mo)
+        return self._hessian(self._given_integrals(int1e_mo, int2e_mo), one_rdm, two_rdm, int1e_mo)
 
     def analytic_hessian(self, one_rdm, two_rdm, mo_coeff=None):
         """Reference ``oo_energy.py:415-424``; returns an :class:`OrbitalHessian`."""
-        h, g = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
-        return self._hessian(h, g, one_rdm, two_rdm, _as_tensor(one_rdm))
+        ints = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
+        return self._hessian(ints, one_rdm, two_rdm, _as_tensor(one_rdm))
 
-    def _hessian(self, h, g, one_rdm, two_rdm, like):
+    def _hessian(self, ints, one_rdm, two_rdm, like):
         eng = self.engine
         d1, d2 = eng.dev(one_rdm), eng.dev(two_rdm)
-        F = eng.fock_gradient(h, g, d1, d2, want_matrix=False, want_vector=False)[2]
-        return OrbitalHessian(eng, h, g, F, d1, d2, like)
+        F = ints.fock_gradient(d1, d2, want_matrix=False, want_vector=False)[2]
+        return OrbitalHessian(eng, ints, F, d1, d2, like)
 
     def full_hessian_to_matrix(self, full_hess):
         """``(N,N,N,N)`` -> ``(n_kappa, n_kappa)`` (reference ``oo_energy.py:395-402``).  Accepts the
@@ -400,7 +406,7 @@ class OO_energy:
         else:
             kd, d1, d2 = kappa, one, two
         E, G, H = eng.evaluate(eng.to_padded(self.oao_mo_coeff, 2), d1, d2, kappa=kd,
-                               want_hessian=want_hessian)
+                               want_hessian=want_hessian, path=self.integral_path)
         if not on_host:
             return E, G, H
         out = (eng.stage_out("E", E), eng.stage_out("G", G), eng.stage_out("H", H) if want_hessian else None)

@@ -50,7 +50,10 @@ enum {
     OO_WS_INT2E      = 2,      /* oo_int2e_transform_f64                           */
     OO_WS_HESSIAN    = 3,      /* oo_hessian_f64                                   */
     OO_WS_INT1E      = 4,      /* oo_int1e_transform_f64 / oo_mo_coeff_f64         */
-    OO_WS_YMATRIX    = 5       /* oo_y_matrix_f64                                  */
+    OO_WS_YMATRIX    = 5,      /* oo_y_matrix_f64                                  */
+    OO_WS_CLASS_TRANSFORM = 6, /* oo_class_transform_f64 (nI = no+na)              */
+    OO_WS_CLASS_BUFFER    = 7, /* size of the class buffer `cls` (x batch)         */
+    OO_WS_CLASS_HESSIAN   = 8  /* oo_class_hessian_f64                             */
 };
 
 int         oo_abi_version(void);
@@ -172,6 +175,38 @@ int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
                    int no, int na, int N, int ld,
                    const int32_t *pair_l, const int32_t *pair_r, int nk,
                    double *H, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- partial ("class") transform path -------------------------------------------
+ * Energy, gradient and the I-space Hessian read g' only through two classes with two
+ * indices in I = occ+act:  J[m,n,a,b] = g'[a,b,m,n]  and  K[n,m,a,b] = g'[a,m,n,b]
+ * (m,n < nIp = nI rounded up to even; a,b general).  oo_class_transform_f64 computes just
+ * these (2 N^4 nI + 12 N^3 nI^2 flop instead of 8 N^5) with the same TN-DGEMM kernel, from
+ * the PAIR-TRANSPOSED AO tensor g_pairT[r,s,p,q] = g[p,q,r,s] (oo_transpose_f64 on the
+ * ld^2 x ld^2 matrix, once per problem; no symmetry of g is assumed).  Replaces, for the
+ * callers of oo_energy.py:204-211, :404-424, the int2e_transform of oo_energy.py:49-51.
+ * `cls` = [K rows (nIp^2) ; J rows (nIp^2) ; h' row], rows of ld^2 doubles
+ * (oo_workspace_bytes(OO_WS_CLASS_BUFFER, N, ld, nI, batch)); the caller writes h' = C^T h C
+ * into the last row with oo_int1e_transform_f64.  The oo_class_* entry points below are the
+ * class-buffer forms of oo_active_hamiltonian_f64 / oo_fock_gradient_f64 /
+ * oo_fock_gradient_vjp_f64 / oo_hessian_f64 (same outputs, same reference lines).      */
+int oo_transpose_f64(const double *src, double *dst, int64_t rows, int64_t cols, void *stream);
+int oo_class_transform_f64(const double *g_pairT, const double *C, int N, int ld, int nIp,
+                           double *cls, void *ws, size_t ws_bytes, void *stream);
+int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp,
+                                    int batch, double e_nuc, double *c0, double *c1, double *c2,
+                                    void *stream);
+int oo_class_fock_gradient_f64(const double *cls, const double *gamma, int64_t stride_rdm1,
+                               const double *Gamma, int64_t stride_rdm2, int no, int na, int N,
+                               int ld, int nIp, int batch, const int32_t *pair_l,
+                               const int32_t *pair_r, int nk, double *FI, double *FA, double *F,
+                               double *Gmat, double *gvec, void *stream);
+int oo_class_fock_gradient_vjp_f64(const double *cls, const double *FI, const double *Gbar, int no,
+                                   int na, int N, int ld, int nIp, double *gbar1, double *gbar2,
+                                   void *stream);
+int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma,
+                         const double *Gamma, int no, int na, int N, int ld, int nIp,
+                         const int32_t *pair_l, const int32_t *pair_r, int nk, double *H,
+                         void *ws, size_t ws_bytes, void *stream);
 
 /* ---- API-parity helpers (not on the hot path) ------------------------------
  * Dense full-space RDMs exactly as full_rdms defines them (oo_energy.py:342-379):

@@ -49,10 +49,11 @@ def test_int_transforms_accept_numpy_and_torch(kind):
     assert np.abs(np.asarray(out) - d["out"]).max() < 1e-11
 
 
+@pytest.mark.parametrize("path", ["class", "full"])
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_oo_energy_matches_reference(name):
+def test_oo_energy_matches_reference(name, path):
     c = load_case(name)
-    oo = make_oo(c)
+    oo = make_oo(c, integral_path=path)
     r = c.ref
     assert oo.n_kappa == len(r["params_idx"]) and np.array_equal(oo.params_idx, r["params_idx"])
     U = oo.kappa_to_mo_coeff(c.kappa)

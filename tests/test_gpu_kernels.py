@@ -185,15 +185,18 @@ def test_int2e_transform_batched_kappa_sweep():
 
 
 # ------------------------------------------------------------------ K3 / K4
+@pytest.mark.parametrize("path", ["class", "full"])
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_full_evaluation_matches_reference(name):
+def test_full_evaluation_matches_reference(name, path):
     c = load_case(name)
     eng, p = engine_for(c)
-    E, G, H = eng.evaluate(eng.to_padded(c.oao_mo_coeff, 2), c.one_rdm, c.two_rdm, kappa=c.kappa[None])
+    E, G, H = eng.evaluate(eng.to_padded(c.oao_mo_coeff, 2), c.one_rdm, c.two_rdm, kappa=c.kappa[None],
+                           path=path)
     assert abs(E.item() - float(c.ref["E"])) < TOL_E
     assert np.abs(G[0].cpu().numpy() - c.ref["G"]).max() < TOL_GH
     assert np.abs(H[0].cpu().numpy() - c.ref["H"]).max() < TOL_GH
-    E0, G0, _ = eng.evaluate(eng.to_padded(c.oao_mo_coeff, 2), c.one_rdm, c.two_rdm, want_hessian=False)
+    E0, G0, _ = eng.evaluate(eng.to_padded(c.oao_mo_coeff, 2), c.one_rdm, c.two_rdm, want_hessian=False,
+                             path=path)
     assert abs(E0.item() - float(c.ref["E0"])) < TOL_E
     assert np.abs(G0[0].cpu().numpy() - c.ref["G0"]).max() < TOL_GH
 
@@ -239,6 +242,59 @@ def test_gradient_vjp_matches_autograd(name):
     r1, r2 = torch.autograd.grad((Gref * Gbar).sum(), (one, two))
     assert (g1.cpu() - r1).abs().max().item() < 1e-10
     assert (g2.cpu() - r2).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["n7_cas44", "n8_nocore", "n13_cas22", "n28_cas66"])
+def test_class_transform_equals_slices_of_full_transform(name):
+    """J[m,n,a,b] = g'[a,b,m,n], K[n,m,a,b] = g'[a,m,n,b] and the h' row of the class buffer."""
+    c = load_case(name)
+    eng, p = engine_for(c)
+    Cp = eng.to_padded(c.ref["mo_coeff_rot"], 2)
+    cls = eng.class_integrals(Cp).cpu()
+    g = eng.from_padded(eng.int2e_transform(Cp), 4)[0].cpu()
+    h = eng.from_padded(eng.int1e_transform(Cp), 2)[0].cpu()
+    N, nI, nIp = c.nao, eng.nI, eng.nIp
+    K = cls[:nIp * nIp].reshape(nIp, nIp, eng.ld, eng.ld)[:nI, :nI, :N, :N]
+    J = cls[nIp * nIp:2 * nIp * nIp].reshape(nIp, nIp, eng.ld, eng.ld)[:nI, :nI, :N, :N]
+    assert (J - g[:, :, :nI, :nI].permute(2, 3, 0, 1)).abs().max().item() < 1e-11
+    assert (K - g[:, :nI, :nI, :].permute(2, 1, 0, 3)).abs().max().item() < 1e-11
+    assert (cls[-1][:N, :N] - h).abs().max().item() < 1e-12
+    if eng.ld > N:                                       # zero padding survives
+        assert cls[:, N:, :].abs().max().item() == 0.0 and cls[:, :, N:].abs().max().item() == 0.0
+
+
+def test_transpose_kernel(lib):
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(100, 37, dtype=F64, device="cuda", generator=gen)
+    y = torch.empty(37, 100, dtype=F64, device="cuda")
+    assert lib.oo_transpose_f64(x.data_ptr(), y.data_ptr(), 100, 37, _stream()) == 0
+    assert torch.equal(y, x.T)
+
+
+@pytest.mark.parametrize("name", ["n7_cas44", "n11_cas43"])
+def test_class_path_stages_and_vjp(name):
+    from oracle import oo_oracle as orc
+    c = load_case(name)
+    eng, p = engine_for(c)
+    ints = eng.integrals(eng.to_padded(c.ref["mo_coeff_rot"], 2), kind="class")
+    c0, c1, c2 = ints.active_hamiltonian()
+    assert abs(c0.item() - float(c.ref["c0"])) < TOL_E
+    assert np.abs(c1[0].cpu().numpy() - c.ref["c1"]).max() < 1e-11
+    assert np.abs(c2[0].cpu().numpy() - c.ref["c2"]).max() < 1e-11
+    d1, d2 = eng.dev(c.one_rdm), eng.dev(c.two_rdm)
+    FI, FA, F, Gm, gv = ints.fock_gradient(d1, d2)
+    ho, go = p.mo_integrals(c.kappa)
+    for got, ref in ((FI, orc.fock_core(ho, go, p.occ_idx)), (FA, orc.fock_active(go, c.one_rdm, p.act_idx)),
+                     (F, orc.fock_generalized(ho, go, c.one_rdm, c.two_rdm, p.occ_idx, p.act_idx))):
+        assert (eng.from_padded(got, 2)[0].cpu() - ref).abs().max().item() < 1e-10
+    gen = torch.Generator().manual_seed(8)
+    Gbar = torch.randn(c.nao, c.nao, dtype=F64, generator=gen)
+    g1, g2 = ints.fock_gradient_vjp(FI, eng.to_padded(Gbar, 2))
+    one = c.one_rdm.clone().requires_grad_(True)
+    two = c.two_rdm.clone().requires_grad_(True)
+    Gref = orc.gradient_matrix(ho, go, one, two, p.occ_idx, p.act_idx)
+    r1, r2 = torch.autograd.grad((Gref * Gbar).sum(), (one, two))
+    assert (g1.cpu() - r1).abs().max().item() < 1e-10 and (g2.cpu() - r2).abs().max().item() < 1e-10
 
 
 def test_batched_evaluation_equals_single():
