@@ -27,6 +27,7 @@ _SIGNATURES = {
     "oo_error_string": (C.c_char_p, [_i32]),
     "oo_last_cuda_error": (_i32, []),
     "oo_launch_count": (C.c_ulonglong, []),
+    "oo_set_option": (_i32, [_i32, _i32]),
     "oo_device_info": (_i32, [C.POINTER(_i32)] * 3),
     "oo_workspace_bytes": (_size, [_i32, _i32, _i32, _i32, _i32]),
     "oo_dgemm_tn_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i32,

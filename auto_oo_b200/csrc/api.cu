@@ -18,7 +18,8 @@ size_t hessian_ws_bytes(int ld, int nI);
 size_t y_matrix_ws_bytes(int ld, int N);
 size_t class_transform_ws_bytes(int ld, int nIp);
 size_t class_buffer_bytes(int ld, int nIp);
-size_t class_hessian_ws_bytes(int ld, int nIp);
+size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na);
+extern int g_hessian_dense;
 
 int sm_count() {
     static int cached = 0;
@@ -116,6 +117,14 @@ int oo_last_cuda_error(void) { return oo::g_last_cuda_error; }
 
 unsigned long long oo_launch_count(void) { return oo::g_launch_count; }
 
+int oo_set_option(int key, int value) {
+    if (key == OO_OPT_HESSIAN_DENSE) {
+        oo::g_hessian_dense = value ? 1 : 0;
+        return OO_OK;
+    }
+    return OO_ERR_INVALID_ARG;
+}
+
 int oo_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     int dev = 0;
     cudaDeviceProp prop;
@@ -138,7 +147,8 @@ size_t oo_workspace_bytes(int which, int N, int ld, int nI, int batch) {
         case OO_WS_YMATRIX: return oo::y_matrix_ws_bytes(ld, N);
         case OO_WS_CLASS_TRANSFORM: return oo::class_transform_ws_bytes(ld, nI + (nI & 1));
         case OO_WS_CLASS_BUFFER: return (size_t)batch * oo::class_buffer_bytes(ld, nI + (nI & 1));
-        case OO_WS_CLASS_HESSIAN: return oo::class_hessian_ws_bytes(ld, nI + (nI & 1));
+        case OO_WS_CLASS_HESSIAN:   /* batch carries na here (the sparse layout depends on no, na) */
+            return oo::class_hessian_ws_bytes(ld, nI + (nI & 1), nI - batch, batch);
         default: return 0;
     }
 }

@@ -234,7 +234,8 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
 
 //                     BM   BN  BK WGM WGN STAGES
 using TnWide = TnCfg<128, 128, 16, 2, 4, 4>;   // N > 64 : warp tile 64x32
-using TnMid = TnCfg<256, 64, 16, 4, 2, 4>;     // N in (32, 64]
+using TnMid = TnCfg<256, 64, 16, 4, 2, 4>;     // N in (48, 64]
+using TnMid48 = TnCfg<256, 48, 16, 8, 1, 4>;   // N in (32, 48] : warp tile 32x48 (class index nIp = 44 at N=256)
 using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (16, 32] : warp tile 32x32
 using TnSlim = TnCfg<256, 16, 16, 8, 1, 4>;    // N <= 16 : warp tile 32x16
 
@@ -250,8 +251,10 @@ int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N,
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
     if (N > 64)
         return launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
-    if (N > 32)
+    if (N > 48)
         return launch_tn<TnMid>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+    if (N > 32)
+        return launch_tn<TnMid48>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
     if (N > 16)
         return launch_tn<TnNarrow>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
     return launch_tn<TnSlim>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);

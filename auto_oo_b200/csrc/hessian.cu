@@ -67,6 +67,27 @@ __device__ __forceinline__ double gf2(const RdmView &r, int p, int q, int s, int
 // nI here is the ROW STRIDE of the I-space (nI for the full-tensor path, nIp for the class path;
 // gf1/gf2 return 0 for indices beyond occ+act).  swap_exch: exchange rows are ordered (n,m)
 // instead of (m,n) -- the order in which classes.cu stores K[n,m,a,b].
+// At[k, (p r)]: k < nI^2 exchange row (m,n) -- or (n,m) when swap_exch --, k < 2 nI^2 Coulomb row (m,n),
+// k = 2 nI^2 the one-body row.  `mn` receives the (m, n) the row stands for (-1 for the one-body row).
+__device__ __forceinline__ double at_value(const RdmView &rdm, int nI, int swap_exch, int64_t k, int p, int r,
+                                           int &m, int &n) {
+    const int nI2 = nI * nI;
+    if (k < nI2) {
+        const int k1 = (int)(k / nI), k2 = (int)(k % nI);
+        m = swap_exch ? k2 : k1;
+        n = swap_exch ? k1 : k2;
+        return 2.0 * (gf2(rdm, p, m, r, n) + gf2(rdm, p, m, n, r));
+    }
+    if (k < 2 * nI2) {
+        const int kk = (int)(k - nI2);
+        m = kk / nI;
+        n = kk % nI;
+        return 2.0 * gf2(rdm, p, r, m, n);
+    }
+    m = n = -1;
+    return 2.0 * gf1(rdm, p, r);
+}
+
 __global__ void hess_build_at_kernel(RdmView rdm, int nI, int swap_exch, int64_t lda, double *__restrict__ At) {
     const int nI2 = nI * nI;
     const int64_t total = (int64_t)(2 * nI2 + 1) * lda;
@@ -75,21 +96,142 @@ __global__ void hess_build_at_kernel(RdmView rdm, int nI, int swap_exch, int64_t
         const int64_t k = i / lda;
         const int col = (int)(i % lda);
         double v = 0.0;
-        if (col < nI2) {
-            const int p = col / nI, r = col % nI;
-            if (k < nI2) {
-                const int k1 = (int)(k / nI), k2 = (int)(k % nI);
-                const int m = swap_exch ? k2 : k1, n = swap_exch ? k1 : k2;
-                v = 2.0 * (gf2(rdm, p, m, r, n) + gf2(rdm, p, m, n, r));
-            } else if (k < 2 * nI2) {
-                const int kk = (int)(k - nI2);
-                const int m = kk / nI, n = kk % nI;
-                v = 2.0 * gf2(rdm, p, r, m, n);
-            } else {
-                v = 2.0 * gf1(rdm, p, r);
-            }
-        }
+        int m, n;
+        if (col < nI2) v = at_value(rdm, nI, swap_exch, k, col / nI, col % nI, m, n);
         At[i] = v;
+    }
+}
+
+// ---- sparse form of At (class path) ----------------------------------------------------------
+// The full-space 2-RDM is a dense na^4 block plus Kronecker-delta core blocks (full_rdms,
+// oo_energy.py:356-379), so At is dense only for (p,r) act-act x (m,n) act-act (+ the one-body
+// row) and has O(na) entries per column elsewhere.  T = At^T B is therefore evaluated as
+//   T_aa[(v w), :]  = dense GEMM over the 2 na^2 + 1 act-act rows of B          (4 na^4 N^2 flop)
+//   T[(p r), :]    (+)= sum over the remaining non-zeros  val * B[k, :]          (L2-bound SpMM)
+// Both are generated from the same at_value() as the dense route, in increasing k (deterministic).
+__device__ __forceinline__ bool in_dense_block(int no, int nI, int p, int r, int m, int n) {
+    if (p < no || r < no) return false;
+    if (m < 0) return true;                               // one-body row
+    return m >= no && n >= no && m < nI && n < nI;
+}
+
+// one warp per column (p r) of At: ELL list (k, val) of its non-zeros outside the dense block
+__global__ void __launch_bounds__(256)
+hess_sparse_build_kernel(RdmView rdm, int nIs, int swap_exch, int width, int *__restrict__ cnt,
+                         int *__restrict__ idx, double *__restrict__ val, int *__restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= nIs * nIs) return;
+    const int p = col / nIs, r = col % nIs;
+    const int nI = rdm.no + rdm.na;
+    int base = 0;
+    if (p < nI && r < nI) {
+        const int64_t krows = 2 * (int64_t)nIs * nIs + 1;
+        for (int64_t k0 = 0; k0 < krows; k0 += 32) {
+            const int64_t k = k0 + lane;
+            double v = 0.0;
+            if (k < krows) {
+                int m, n;
+                v = at_value(rdm, nIs, swap_exch, k, p, r, m, n);
+                if (in_dense_block(rdm.no, nI, p, r, m, n)) v = 0.0;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, v != 0.0);
+            if (v != 0.0) {
+                const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                if (pos < width) {
+                    idx[(int64_t)col * width + pos] = (int)k;
+                    val[(int64_t)col * width + pos] = v;
+                } else {
+                    *overflow = 1;
+                }
+            }
+            base += __popc(mask);
+        }
+    }
+    if (lane == 0) cnt[col] = base < width ? base : width;
+}
+
+// dense block operands: rows k' = [exchange act pairs | Coulomb act pairs | one-body]
+//   Atc[k', (v w)] and Bc[k', :] = the matching row of the class buffer
+__global__ void hess_dense_at_kernel(RdmView rdm, int nIs, int swap_exch, int64_t lda, double *__restrict__ Atc) {
+    const int na = rdm.na, no = rdm.no, na2 = na * na;
+    const int64_t total = (int64_t)(2 * na2 + 1) * lda;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(i / lda), col = (int)(i % lda);
+        double v = 0.0;
+        if (col < na2) {
+            const int p = no + col / na, r = no + col % na;
+            int64_t k;
+            if (kc < 2 * na2) {
+                const int a = no + (kc % na2) / na, b = no + (kc % na2) % na;   // the two act indices, row-major
+                k = (kc < na2 ? 0 : (int64_t)nIs * nIs) + (int64_t)a * nIs + b;
+            } else {
+                k = 2 * (int64_t)nIs * nIs;
+            }
+            int m, n;
+            v = at_value(rdm, nIs, swap_exch, k, p, r, m, n);
+        }
+        Atc[i] = v;
+    }
+}
+
+__global__ void hess_dense_b_kernel(const double *__restrict__ cls, int no, int na, int nIs, int64_t mat,
+                                    double *__restrict__ Bc) {
+    const int kc = blockIdx.y, na2 = na * na;
+    int64_t k;
+    if (kc < 2 * na2) {
+        const int a = no + (kc % na2) / na, b = no + (kc % na2) % na;
+        k = (kc < na2 ? 0 : (int64_t)nIs * nIs) + (int64_t)a * nIs + b;
+    } else {
+        k = 2 * (int64_t)nIs * nIs;
+    }
+    const double2 *src = reinterpret_cast<const double2 *>(cls + k * mat);
+    double2 *dst = reinterpret_cast<double2 *>(Bc + (int64_t)kc * mat);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mat / 2;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// T[(p r), c] (= or +=) sum_e val[e] * B[idx[e], c].   grid (columns (p r), column tiles of 512);
+// consecutive CTAs share a column tile of B, which therefore stays in L2.
+__global__ void __launch_bounds__(256)
+hess_spmm_kernel(const double *__restrict__ B, const int *__restrict__ cnt, const int *__restrict__ idx,
+                 const double *__restrict__ val, int width, int no, int na, int nIs, int64_t mat,
+                 double *__restrict__ T, double *__restrict__ Taa) {
+    const int col = blockIdx.x;
+    const int p = col / nIs, r = col % nIs, nI = no + na;
+    if (p >= nI || r >= nI) return;
+    const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2;
+    if (c >= mat) return;
+    const int n = cnt[col];
+    const int *ix = idx + (int64_t)col * width;
+    const double *vl = val + (int64_t)col * width;
+    double2 acc = make_double2(0.0, 0.0);
+    int e = 0;
+    for (; e + 4 <= n; e += 4) {
+        double2 b0 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c);
+        double2 b1 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 1] * mat + c);
+        double2 b2 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 2] * mat + c);
+        double2 b3 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 3] * mat + c);
+        const double v0 = vl[e], v1 = vl[e + 1], v2 = vl[e + 2], v3 = vl[e + 3];
+        acc.x = fma(v0, b0.x, acc.x); acc.y = fma(v0, b0.y, acc.y);
+        acc.x = fma(v1, b1.x, acc.x); acc.y = fma(v1, b1.y, acc.y);
+        acc.x = fma(v2, b2.x, acc.x); acc.y = fma(v2, b2.y, acc.y);
+        acc.x = fma(v3, b3.x, acc.x); acc.y = fma(v3, b3.y, acc.y);
+    }
+    for (; e < n; ++e) {
+        const double2 b0 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c);
+        const double v0 = vl[e];
+        acc.x = fma(v0, b0.x, acc.x); acc.y = fma(v0, b0.y, acc.y);
+    }
+    if (p >= no && r >= no) {
+        double2 *o = reinterpret_cast<double2 *>(Taa + ((int64_t)(p - no) * na + (r - no)) * mat + c);
+        double2 t = *o;
+        t.x += acc.x; t.y += acc.y;
+        *o = t;
+    } else {
+        *reinterpret_cast<double2 *>(T + (int64_t)col * mat + c) = acc;
     }
 }
 
@@ -119,26 +261,38 @@ __global__ void hess_gather_b_kernel(const double *__restrict__ h, const double 
     }
 }
 
-__device__ __forceinline__ double hess_x(const double *__restrict__ T, const double *__restrict__ F,
-                                         int nI, int nIs, int ld, int a, int b, int c, int d) {
-    // X(a,b,c,d) = -(F_ac + F_ca) delta_bd + [a,c in I] T[(a c),(b d)]   (T rows: a * nIs + c)
+struct TView {
+    const double *T;     // rows (a c) -> a * nIs + c
+    const double *Taa;   // optional: act-act rows (a - no) * na + (c - no); null = everything in T
+    int nI, nIs, no, na;
+};
+
+__device__ __forceinline__ double hess_x(const TView &tv, const double *__restrict__ F, int ld, int a, int b,
+                                         int c, int d) {
+    // X(a,b,c,d) = -(F_ac + F_ca) delta_bd + [a,c in I] T[(a c),(b d)]
     double v = 0.0;
     if (b == d) v = -(F[(int64_t)a * ld + c] + F[(int64_t)c * ld + a]);
-    if (a < nI && c < nI) v += T[((int64_t)a * nIs + c) * ld * ld + (int64_t)b * ld + d];
+    if (a < tv.nI && c < tv.nI) {
+        const int64_t off = (int64_t)b * ld + d;
+        if (tv.Taa && a >= tv.no && c >= tv.no)
+            v += tv.Taa[((int64_t)(a - tv.no) * tv.na + (c - tv.no)) * ld * ld + off];
+        else
+            v += tv.T[((int64_t)a * tv.nIs + c) * ld * ld + off];
+    }
     return v;
 }
 
 __global__ void __launch_bounds__(256)
-hess_assemble_kernel(const double *__restrict__ T, const double *__restrict__ F,
-                     const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int nI,
-                     int nIs, int ld, double *__restrict__ H) {
+hess_assemble_kernel(const TView tv, const double *__restrict__ F,
+                     const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int ld,
+                     double *__restrict__ H) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (k >= nk) return;
     const int p = pl[j], q = pr[j];
     const int r = pl[k], s = pr[k];
-    const double v = hess_x(T, F, nI, nIs, ld, p, q, r, s) - hess_x(T, F, nI, nIs, ld, p, q, s, r)
-                   - hess_x(T, F, nI, nIs, ld, q, p, r, s) + hess_x(T, F, nI, nIs, ld, q, p, s, r);
+    const double v = hess_x(tv, F, ld, p, q, r, s) - hess_x(tv, F, ld, p, q, s, r)
+                   - hess_x(tv, F, ld, q, p, r, s) + hess_x(tv, F, ld, q, p, s, r);
     H[(int64_t)j * nk + k] = v;
 }
 
@@ -246,16 +400,67 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     {
         if (nk > 65535) return OO_ERR_UNSUPPORTED;
         dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-        hess_assemble_kernel<<<grid, 256, 0, stream>>>(T, F, pl, pr, nk, nI, nI, ld, H);
+        hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, nullptr, nI, nI, no, na}, F, pl, pr, nk, ld, H);
         OO_LAUNCH_CHECK();
     }
     return OO_OK;
 }
 
 // Hessian from the class buffer of classes.cu: cls = [K rows; J rows; h' row] IS the B operand.
-size_t class_hessian_ws_bytes(int ld, int nIp) {
+int g_hessian_dense = 0;     // oo_set_option(OO_OPT_HESSIAN_DENSE): 1 = one dense GEMM over all of At
+
+struct ClassHessLayout {
+    int width;                       // ELL width of the sparse part
+    int64_t lda_c, krows_c;          // dense act-act block
+    size_t off_cnt, off_idx, off_val, off_flag, off_atc, off_bc, off_taa, off_t, total;
+};
+
+static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na) {
+    ClassHessLayout L;
+    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld, na2 = (int64_t)na * na;
+    L.width = 2 * na * na + 2 * (no + na) + 8;
+    L.lda_c = (na2 + 1) & ~1ll;
+    L.krows_c = 2 * na2 + 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+    L.off_cnt = take((size_t)nI2 * sizeof(int));
+    L.off_idx = take((size_t)nI2 * L.width * sizeof(int));
+    L.off_val = take((size_t)nI2 * L.width * sizeof(double));
+    L.off_flag = take(sizeof(int));
+    L.off_atc = take((size_t)L.krows_c * L.lda_c * sizeof(double));
+    L.off_bc = take((size_t)L.krows_c * mat * sizeof(double));
+    L.off_taa = take((size_t)na2 * mat * sizeof(double));
+    L.off_t = take((size_t)nI2 * mat * sizeof(double));
+    L.total = off;
+    return L;
+}
+
+size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na) {
+    const HessLayout D = hess_layout(ld, nIp);
+    const size_t dense = D.off_b + (D.total - D.off_t);          // At + T (no gathered B)
+    const size_t sparse = class_hess_layout(ld, nIp, no, na).total;
+    return dense > sparse ? dense : sparse;
+}
+
+static int class_hessian_dense(const double *cls, const double *F, const RdmView &rdm, int ld, int nIp,
+                               const int32_t *pl, const int32_t *pr, int nk, double *H, void *ws,
+                               cudaStream_t stream) {
     const HessLayout L = hess_layout(ld, nIp);
-    return L.off_b + (L.total - L.off_t);          // At + T (no gathered B)
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    double *At = reinterpret_cast<double *>(w);
+    double *T = reinterpret_cast<double *>(w + L.off_b);
+    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld;
+    int64_t blocks = ceil_div(L.krows * L.lda, 256);
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    hess_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nIp, 1, L.lda, At);
+    OO_LAUNCH_CHECK();
+    int rc = dgemm_tn(At, cls, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
+    hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na}, F,
+                                                   pl, pr, nk, ld, H);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
 }
 
 int class_hessian(const double *cls, const double *F, const double *d1, const double *d2, int no, int na,
@@ -264,22 +469,47 @@ int class_hessian(const double *cls, const double *F, const double *d1, const do
     OO_REQUIRE(cls && F && d1 && d2 && H && ws && pl && pr);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0);
     OO_REQUIRE(nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
-    if (ws_bytes < class_hessian_ws_bytes(ld, nIp)) return OO_ERR_WORKSPACE;
+    if (ws_bytes < class_hessian_ws_bytes(ld, nIp, no, na)) return OO_ERR_WORKSPACE;
     if (nk > 65535) return OO_ERR_UNSUPPORTED;
-    const HessLayout L = hess_layout(ld, nIp);
-    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
-    double *At = reinterpret_cast<double *>(w);
-    double *T = reinterpret_cast<double *>(w + L.off_b);
-    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld;
     RdmView rdm{d1, d2, no, na};
-    int64_t blocks = ceil_div(L.krows * L.lda, 256);
-    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-    hess_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nIp, 1, L.lda, At);
+    if (g_hessian_dense) return class_hessian_dense(cls, F, rdm, ld, nIp, pl, pr, nk, H, ws, stream);
+
+    const ClassHessLayout L = class_hess_layout(ld, nIp, no, na);
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    int *cnt = reinterpret_cast<int *>(w + L.off_cnt);
+    int *idx = reinterpret_cast<int *>(w + L.off_idx);
+    double *val = reinterpret_cast<double *>(w + L.off_val);
+    int *flag = reinterpret_cast<int *>(w + L.off_flag);
+    double *Atc = reinterpret_cast<double *>(w + L.off_atc);
+    double *Bc = reinterpret_cast<double *>(w + L.off_bc);
+    double *Taa = reinterpret_cast<double *>(w + L.off_taa);
+    double *T = reinterpret_cast<double *>(w + L.off_t);
+    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld, na2 = (int64_t)na * na;
+
+    // sparse structure of At outside the act-act block
+    hess_sparse_build_kernel<<<(unsigned)ceil_div(nI2, 8), 256, 0, stream>>>(rdm, nIp, 1, L.width, cnt, idx, val,
+                                                                            flag);
     OO_LAUNCH_CHECK();
-    int rc = dgemm_tn(At, cls, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
-    if (rc) return rc;
+    // dense act-act block: Taa = Atc^T Bc
+    {
+        int64_t blocks = ceil_div(L.krows_c * L.lda_c, 256);
+        hess_dense_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nIp, 1, L.lda_c, Atc);
+        OO_LAUNCH_CHECK();
+        int64_t bx = ceil_div(mat / 2, 256);
+        if (bx > 64) bx = 64;
+        hess_dense_b_kernel<<<dim3((unsigned)bx, (unsigned)L.krows_c), 256, 0, stream>>>(cls, no, na, nIp, mat, Bc);
+        OO_LAUNCH_CHECK();
+        int rc = dgemm_tn(Atc, Bc, Taa, na2, mat, L.krows_c, L.lda_c, mat, mat, 1, 0, 0, 0, stream);
+        if (rc) return rc;
+    }
+    // sparse remainder (accumulates into Taa for act-act columns)
+    {
+        dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256));
+        hess_spmm_kernel<<<grid, 256, 0, stream>>>(cls, cnt, idx, val, L.width, no, na, nIp, mat, T, Taa);
+        OO_LAUNCH_CHECK();
+    }
     dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-    hess_assemble_kernel<<<grid, 256, 0, stream>>>(T, F, pl, pr, nk, no + na, nIp, ld, H);
+    hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, Taa, no + na, nIp, no, na}, F, pl, pr, nk, ld, H);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }

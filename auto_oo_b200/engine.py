@@ -359,7 +359,7 @@ class HotPathEngine:
         H = out if out is not None else torch.empty(nk, nk, dtype=F64, device=self.device)
         if nk == 0:
             return H
-        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.N, self.ld, self.nI, 1)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.N, self.ld, self.nI, self.na)
         ws = self.workspace("chess", nbytes)
         self._check(self.lib.oo_class_hessian_f64(_p(cls), _p(F), _p(d1), _p(d2), self.no, self.na, self.N,
                                                   self.ld, self.nIp, _p(pl), _p(pr), nk, _p(H), _p(ws), nbytes,

@@ -259,6 +259,7 @@ def main():
     n_transforms = len(events)
     E_full, G_full = E_full.clone(), G_full.clone()
     h_diag_full = H.diagonal(dim1=1, dim2=2).sum().item()
+    oo.int2e_ao = None
     eng.drop_full_eri()                                   # keep only the pair-transposed ERI copy
     torch.cuda.empty_cache()
 

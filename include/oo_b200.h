@@ -53,13 +53,20 @@ enum {
     OO_WS_YMATRIX    = 5,      /* oo_y_matrix_f64                                  */
     OO_WS_CLASS_TRANSFORM = 6, /* oo_class_transform_f64 (nI = no+na)              */
     OO_WS_CLASS_BUFFER    = 7, /* size of the class buffer `cls` (x batch)         */
-    OO_WS_CLASS_HESSIAN   = 8  /* oo_class_hessian_f64                             */
+    OO_WS_CLASS_HESSIAN   = 8  /* oo_class_hessian_f64: pass nI = no+na and batch = na */
 };
 
 int         oo_abi_version(void);
 const char *oo_error_string(int code);
 int         oo_last_cuda_error(void);                 /* cudaError_t of the last OO_ERR_CUDA */
 unsigned long long oo_launch_count(void);             /* kernels launched by this library so far */
+
+/* process-wide switches (A/B timing and tests) */
+enum {
+    OO_OPT_HESSIAN_DENSE = 1   /* 1: oo_class_hessian_f64 uses one dense GEMM over all of At instead of
+                                  the dense act-act block + sparse remainder (same numbers)          */
+};
+int         oo_set_option(int key, int value);
 int         oo_device_info(int *sm_count, int *cc_major, int *cc_minor);
 size_t      oo_workspace_bytes(int which, int N, int ld, int nI, int batch);
 

@@ -328,3 +328,23 @@ def test_slab_transform_world1_on_cuda_gemm(mode):
     assert torch.equal(out, ref)          # same kernel, same summation order: bit-identical
     cpu = torch.einsum('pi,qj,rk,sl,pqrs->ijkl', *[c.cpu() for c in Cs], g.cpu())
     assert (out.cpu() - cpu).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["n7_cas44", "n7_cas44_frozen", "n8_nocore", "n11_cas43", "n28_cas66", "n34_cas44"])
+def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
+    """oo_class_hessian_f64: dense act-act block + sparse remainder (default) against the single
+    dense GEMM over all of At (OO_OPT_HESSIAN_DENSE), and both against the verbatim reference."""
+    c = load_case(name)
+    eng, p = engine_for(c)
+    ints = eng.integrals(eng.to_padded(c.ref["mo_coeff_rot"], 2), kind="class")
+    d1, d2 = eng.dev(c.one_rdm), eng.dev(c.two_rdm)
+    F = ints.fock_gradient(d1, d2, want_matrix=False, want_vector=False)[2]
+    Hs = ints.hessian(F, d1, d2).clone()
+    try:
+        assert lib.oo_set_option(1, 1) == 0
+        Hd = ints.hessian(F, d1, d2).clone()
+    finally:
+        lib.oo_set_option(1, 0)
+    assert (Hs - Hd).abs().max().item() < 1e-11
+    assert np.abs(Hs.cpu().numpy() - c.ref["H"]).max() < TOL_GH
+    assert np.abs(Hd.cpu().numpy() - c.ref["H"]).max() < TOL_GH
