@@ -32,6 +32,8 @@ _SIGNATURES = {
     "oo_workspace_bytes": (_size, [_i32, _i32, _i32, _i32, _i32]),
     "oo_dgemm_tn_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
                                _i64, _i64, _i64, _ptr]),
+    "oo_dgemm_tn_swap02_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64,
+                                      _ptr]),
     "oo_dgemm_small_f64": (_i32, [_i32, _i32, _i32, _i32, _i32, _f64, _ptr, _i32, _i64, _ptr, _i32,
                                   _i64, _f64, _ptr, _i32, _i64, _f64, _ptr, _i32, _i64, _i32, _ptr]),
     "oo_kappa_rotation_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,

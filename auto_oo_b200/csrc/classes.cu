@@ -13,7 +13,7 @@
 //   J:  Q2        X[p,q,m,n]   = sum_s T1[s,(p q m)] C[s,n]
 //       Q3        X'[q,m,n,a]  = sum_p X[p,(q m n)]  C[p,a]
 //       Q4        J[m,n,a,b]   = sum_q X'[q,(m n a)] C[q,b]
-//   K:  swap      T1t[q,p,s,m] = T1[s,p,q,m]                       (HBM-bound copy)
+//   K:  swap      T1t[q,p,s,m] = T1[s,p,q,m]                       (second store in Q1's epilogue)
 //       K2        X[p,s,n,m]   = sum_q T1t[q,(p s n)] C[q,m]
 //       K3        X'[s,n,m,a]  = sum_p X[p,(s n m)]   C[p,a]
 //       K4        K[n,m,a,b]   = sum_s X'[s,(n m a)]  C[s,b]
@@ -26,6 +26,8 @@ namespace oo {
 int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
              int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
              int64_t strideC, cudaStream_t stream);
+int dgemm_tn_swap02(const double *At, const double *B, double *C, double *C2, int d0, int d1, int d2,
+                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, cudaStream_t stream);
 
 namespace {
 
@@ -97,12 +99,11 @@ int class_transform(const double *gp, const double *C, int N, int ld, int nIp, d
     int rc;
 #define Q(in, out, M, Ncols) \
     if ((rc = dgemm_tn((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), 1, 0, 0, 0, stream))) return rc
-    Q(gp, T1, ld3, nIp);              // [s,p,q,m]
+    // Q1 writes T1[s,p,q,m] and its (s <-> q) swapped copy T1t[q,p,s,m] from the same accumulators
+    if ((rc = dgemm_tn_swap02(gp, C, T1, T1t, ld, ld, ld, nIp, ld, ld3, ld, nIp, stream))) return rc;
     Q(T1, X, ld2 * nIp, nIp);         // [p,q,m,n]
     Q(X, Xp, ld * nI2, ld);           // [q,m,n,a]
     Q(Xp, Jout, nI2 * ld, ld);        // [m,n,a,b]
-    swap02_kernel<<<dim3((unsigned)ld, (unsigned)ld), 256, 0, stream>>>(T1, T1t, ld, ld, ld, nIp);
-    OO_LAUNCH_CHECK();
     Q(T1t, X, ld2 * nIp, nIp);        // [p,s,n,m]
     Q(X, Xp, ld * nI2, ld);           // [s,n,m,a]
     Q(Xp, Kout, nI2 * ld, ld);        // [n,m,a,b]

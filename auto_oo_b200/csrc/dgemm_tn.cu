@@ -23,8 +23,9 @@ namespace oo {
 template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_>
 struct TnCfg {
     static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_;
-    static constexpr int NCW = WGM * WGN;            // consumer warps
-    static constexpr int THREADS = (NCW + 1) * 32;   // + 1 producer warp
+    static constexpr int NCW = WGM * WGN;            // consumer warps (two warpgroups)
+    static constexpr int THREADS = (NCW + 4) * 32;   // + one producer warpgroup (its first warp issues TMA)
+    static_assert(NCW == 8, "register re-allocation below assumes 2 consumer warpgroups + 1 producer warpgroup");
     static constexpr int WTM = BM / WGM, WTN = BN / WGN;
     static constexpr int MT = WTM / 8, NT = WTN / 8;
     static constexpr int CHUNK_BYTES = BK * 128;     // one TMA box: [BK][16 doubles]
@@ -39,14 +40,25 @@ struct TnCfg {
 
 struct TnArgs {
     double *C;
+    // optional second copy of the result with rows permuted (a b c) -> (c b a), M = d0*d1*d2
+    // (classes.cu: T1[s,p,q,m] and T1t[q,p,s,m] from the same accumulators, no separate swap pass)
+    double *C2;
+    int d0, d1, d2;
     int64_t M, N;
     int64_t ldc, strideC;
     int kblocks;
     int tiles_m, tiles_n, batch;
     int a_batched, b_batched;
+    // Always 0, but opaque to the compiler: ANDed with bits of every fragment a consumer loaded from
+    // a stage and added to the address of that stage's "empty" arrive.  The arrive thus has a true
+    // register dependency on the LDS results, so it cannot be issued while a shared-memory load of
+    // the stage is still in flight (an in-flight LDS is NOT ordered against the TMA refill that the
+    // arrive releases; without this, ptxas schedules the arrive ahead of the last loads' consumers
+    // and a stage was seen overwritten under a pending read).
+    uint32_t zero;
 };
 
-template <class Cfg>
+template <class Cfg, bool DUAL>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const TnArgs args) {
@@ -74,9 +86,14 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int tiles_per_batch = args.tiles_m * args.tiles_n;
     const int64_t total_tiles = (int64_t)tiles_per_batch * args.batch;
 
-    if (warp == Cfg::NCW) {
+    // Register re-allocation (setmaxnreg): the CTA starts with 168 registers per thread (384 threads,
+    // three warps per SM sub-partition); the producer warpgroup gives most of its share back and the
+    // two consumer warpgroups grow to 232, which holds the 128 accumulator registers of the 64x32 /
+    // 32x48 warp tiles plus fragments and addressing without spilling.
+    if (warp >= Cfg::NCW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (warp == Cfg::NCW && lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -106,6 +123,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ===================== DMMA consumers =====================
         const int g = lane >> 2, t = lane & 3;
         const int wm = warp / Cfg::WGN, wn = warp % Cfg::WGN;
@@ -122,25 +140,25 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const uint32_t a_warp_off = (uint32_t)(wm * Cfg::WTM / 16) * Cfg::CHUNK_BYTES;
         const uint32_t b_warp_off = Cfg::A_BYTES + (uint32_t)(wn * Cfg::WTN / 16) * Cfg::CHUNK_BYTES;
 
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int b = (int)(tile / tiles_per_batch);
-            const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
-            const int m0 = (rem / args.tiles_n) * Cfg::BM;
-            const int n0 = (rem % args.tiles_n) * Cfg::BN;
-
+        // registers are the scarce resource here (3 warps share one SM sub-partition's file: 168 per
+        // thread): one running k-block counter carries both the ring slot and its phase, and the
+        // tile coordinates are re-derived in the epilogue instead of living across the k loop.
+        static_assert((Cfg::STAGES & (Cfg::STAGES - 1)) == 0, "STAGES must be a power of two");
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < (uint32_t)total_tiles; tile += gridDim.x) {
             double acc[Cfg::MT][Cfg::NT][2];
 #pragma unroll
             for (int mi = 0; mi < Cfg::MT; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < Cfg::NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-            for (int kb = 0; kb < args.kblocks; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+            for (int kb = 0; kb < args.kblocks; ++kb, ++it) {
+                const uint32_t stage = it & (Cfg::STAGES - 1);
+                mbar_wait(&full_bar[stage], (it / Cfg::STAGES) & 1u);
                 const uint32_t sbase = smem_base + stage * Cfg::STAGE_BYTES;
                 const uint32_t abase = sbase + a_warp_off;
                 const uint32_t bbase = sbase + b_warp_off;
+                uint32_t loaded = 0;   // XOR of the high words of everything read from this stage
 #pragma unroll
                 for (int kk = 0; kk < Cfg::BK / 8; ++kk) {
 #pragma unroll
@@ -153,35 +171,48 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         for (int ni = 0; ni < Cfg::NT; ++ni)
                             bf[ni] = lds_f64(bbase + (ni >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[ni & 1][j]);
 #pragma unroll
+                        for (int mi = 0; mi < Cfg::MT; ++mi) loaded ^= (uint32_t)__double2hiint(a[mi]);
+#pragma unroll
+                        for (int ni = 0; ni < Cfg::NT; ++ni) loaded ^= (uint32_t)__double2hiint(bf[ni]);
+#pragma unroll
                         for (int mi = 0; mi < Cfg::MT; ++mi)
 #pragma unroll
                             for (int ni = 0; ni < Cfg::NT; ++ni)
                                 dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[stage]);
-                if (++stage == Cfg::STAGES) {
-                    stage = 0;
-                    phase ^= 1u;
-                }
+                // release the stage only once every load from it has landed in registers (see TnArgs::zero)
+                if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[stage]) + (loaded & args.zero));
             }
 
             // epilogue: registers -> global (16-byte stores, rows of 64 B per MMA tile)
+            const int b = (int)(tile / (uint32_t)tiles_per_batch);
+            const int rem = (int)(tile - (uint32_t)b * (uint32_t)tiles_per_batch);
+            const int m0 = (rem / args.tiles_n) * Cfg::BM;
+            const int n0 = (rem % args.tiles_n) * Cfg::BN;
             double *Cb = args.C + (int64_t)b * args.strideC;
 #pragma unroll
             for (int mi = 0; mi < Cfg::MT; ++mi) {
                 const int64_t row = (int64_t)m0 + wm * Cfg::WTM + mi * 8 + g;
                 if (row < args.M) {
                     double *crow = Cb + row * args.ldc;
+                    double *crow2 = nullptr;
+                    if (DUAL) {
+                        const int c = (int)(row % args.d2);
+                        const int64_t ab = row / args.d2;
+                        const int bq = (int)(ab % args.d1), a = (int)(ab / args.d1);
+                        crow2 = args.C2 + (((int64_t)c * args.d1 + bq) * args.d0 + a) * args.ldc;
+                    }
 #pragma unroll
                     for (int ni = 0; ni < Cfg::NT; ++ni) {
                         const int64_t col = (int64_t)n0 + wn * Cfg::WTN + ni * 8 + 2 * t;
                         if (col + 1 < args.N) {
-                            *reinterpret_cast<double2 *>(crow + col) =
-                                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                            const double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                            *reinterpret_cast<double2 *>(crow + col) = v;
+                            if (DUAL) *reinterpret_cast<double2 *>(crow2 + col) = v;
                         } else if (col < args.N) {
                             crow[col] = acc[mi][ni][0];
+                            if (DUAL) crow2[col] = acc[mi][ni][0];
                         }
                     }
                 }
@@ -190,10 +221,15 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
 }
 
+struct TnDual {
+    double *C2 = nullptr;
+    int d0 = 0, d1 = 0, d2 = 0;
+};
+
 template <class Cfg>
 static int launch_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
                      int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA,
-                     int64_t strideB, int64_t strideC, cudaStream_t stream) {
+                     int64_t strideB, int64_t strideC, cudaStream_t stream, const TnDual &dual = TnDual()) {
     CUtensorMap mapA, mapB;
     const int a_batched = (batch > 1 && strideA != 0);
     const int b_batched = (batch > 1 && strideB != 0);
@@ -207,6 +243,10 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
 
     TnArgs args;
     args.C = C;
+    args.C2 = dual.C2;
+    args.d0 = dual.d0;
+    args.d1 = dual.d1;
+    args.d2 = dual.d2;
     args.M = M;
     args.N = N;
     args.ldc = ldc;
@@ -217,17 +257,24 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     args.batch = batch;
     args.a_batched = a_batched;
     args.b_batched = b_batched;
+    args.zero = 0;
 
     static bool attr_set = false;
     if (!attr_set) {
-        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg>,
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    dgemm_tn_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    if (dual.C2)
+        dgemm_tn_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    else
+        dgemm_tn_kernel<Cfg, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -239,9 +286,9 @@ using TnMid48 = TnCfg<256, 48, 16, 8, 1, 4>;   // N in (32, 48] : warp tile 32x4
 using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (16, 32] : warp tile 32x32
 using TnSlim = TnCfg<256, 16, 16, 8, 1, 4>;    // N <= 16 : warp tile 32x16
 
-int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
-             int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
-             int64_t strideC, cudaStream_t stream) {
+static int dgemm_tn_impl(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
+                         int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
+                         int64_t strideC, cudaStream_t stream, const TnDual &dual) {
     OO_REQUIRE(At && B && C);
     OO_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0);
     OO_REQUIRE(lda >= M && ldb >= N && ldc >= N);
@@ -250,14 +297,32 @@ int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N,
     OO_REQUIRE(((uintptr_t)At % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0);
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
     if (N > 64)
-        return launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+        return launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 48)
-        return launch_tn<TnMid>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+        return launch_tn<TnMid>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 32)
-        return launch_tn<TnMid48>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+        return launch_tn<TnMid48>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 16)
-        return launch_tn<TnNarrow>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
-    return launch_tn<TnSlim>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream);
+        return launch_tn<TnNarrow>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
+    return launch_tn<TnSlim>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
+}
+
+int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
+             int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
+             int64_t strideC, cudaStream_t stream) {
+    return dgemm_tn_impl(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, TnDual());
+}
+
+// C[(a b c), n] and C2[(c b a), n] from one pass (M = d0*d1*d2, same ldc for both)
+int dgemm_tn_swap02(const double *At, const double *B, double *C, double *C2, int d0, int d1, int d2,
+                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, cudaStream_t stream) {
+    OO_REQUIRE(C2 && d0 > 0 && d1 > 0 && d2 > 0);
+    TnDual dual;
+    dual.C2 = C2;
+    dual.d0 = d0;
+    dual.d1 = d1;
+    dual.d2 = d2;
+    return dgemm_tn_impl(At, B, C, (int64_t)d0 * d1 * d2, N, K, lda, ldb, ldc, 1, 0, 0, 0, stream, dual);
 }
 
 }  // namespace oo
@@ -267,4 +332,10 @@ extern "C" int oo_dgemm_tn_f64(const double *At, const double *B, double *C, int
                                int64_t strideA, int64_t strideB, int64_t strideC, void *stream) {
     return oo::dgemm_tn(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC,
                         (cudaStream_t)stream);
+}
+
+extern "C" int oo_dgemm_tn_swap02_f64(const double *At, const double *B, double *C, double *C2, int d0,
+                                      int d1, int d2, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                      int64_t ldc, void *stream) {
+    return oo::dgemm_tn_swap02(At, B, C, C2, d0, d1, d2, N, K, lda, ldb, ldc, (cudaStream_t)stream);
 }

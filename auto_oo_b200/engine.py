@@ -159,6 +159,19 @@ class HotPathEngine:
         buf.copy_(host_tensor)
         return buf.to(self.device, non_blocking=True)
 
+    def pinned(self, key, shape):
+        buf = self._ws.get(("pin_out", key))
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(tuple(shape), dtype=F64, pin_memory=True)
+            self._ws[("pin_out", key)] = buf
+        return buf
+
+    def copy_stream(self):
+        st = self._ws.get("copy_stream")
+        if st is None:
+            st = self._ws["copy_stream"] = torch.cuda.Stream(self.device)
+        return st
+
     def stage_out(self, key, dev_tensor):
         """Device -> reused pinned host buffer (asynchronous; caller synchronises the stream)."""
         buf = self._ws.get(("pin_out", key))
@@ -166,6 +179,15 @@ class HotPathEngine:
             buf = torch.empty(dev_tensor.shape, dtype=F64, pin_memory=True)
             self._ws[("pin_out", key)] = buf
         buf.copy_(dev_tensor, non_blocking=True)
+        return buf
+
+    def workspace_tensor(self, key, shape):
+        """Reused float64 device buffer of the given shape."""
+        buf = self._ws.get(("t", key))
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            self._ws[("t", key)] = None
+            buf = torch.empty(tuple(shape), dtype=F64, device=self.device)
+            self._ws[("t", key)] = buf
         return buf
 
     def release_workspaces(self):
@@ -463,7 +485,7 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ whole evaluations
     def evaluate(self, oao_mo_coeff, d1, d2, kappa=None, want_hessian=True, squarings=None,
-                 H_out=None, transform_events=None, path="class"):
+                 H_out=None, transform_events=None, path="class", on_result=None):
         """E (B,), packed gradient (B, nk) and Hessian (B, nk, nk) at C' = X C_oao expm(-K(kappa_b)).
 
         ``oao_mo_coeff``: padded (ld, ld) or (B, ld, ld) device tensor; ``kappa``: (B, nk) or None.
@@ -473,7 +495,9 @@ class HotPathEngine:
         four-index transform.  Evaluations are processed
         one at a time through the N^4 stages (one g' buffer + one workspace in HBM).
         ``transform_events``: optional list that receives a (start, end) CUDA-event pair around
-        every 4-index transform (four TN-DGEMM launches) for the roofline figure."""
+        every 4-index transform (four TN-DGEMM launches) for the roofline figure.
+        ``on_result(b)`` is called after the kernels of evaluation ``b`` are enqueued (used to start
+        the device->host copy of its Hessian while evaluation ``b+1`` computes)."""
         Coao = oao_mo_coeff if oao_mo_coeff.dim() == 3 else oao_mo_coeff[None]
         if kappa is not None:
             kappa = self.dev(kappa).reshape(-1, self.nk)
@@ -508,6 +532,8 @@ class HotPathEngine:
                 G[b] = gv[0]
                 if want_hessian:
                     self.class_hessian(cbuf, F[0], d1b, d2b, out=H[b])
+                if on_result is not None:
+                    on_result(b)
             self._ccache_val = cbuf                     # keep the buffer (not the key) for reuse
             return E, G, H
         hs = self.int1e_transform(C)
@@ -532,4 +558,6 @@ class HotPathEngine:
             G[b] = gv[0]
             if want_hessian:
                 self.hessian(h1[0], gbuf[0], F[0], d1b, d2b, out=H[b])
+            if on_result is not None:
+                on_result(b)
         return E, G, H

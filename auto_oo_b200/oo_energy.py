@@ -405,12 +405,30 @@ class OO_energy:
             d2 = eng.stage_in("rdm2", two)
         else:
             kd, d1, d2 = kappa, one, two
-        E, G, H = eng.evaluate(eng.to_padded(self.oao_mo_coeff, 2), d1, d2, kappa=kd,
-                               want_hessian=want_hessian, path=self.integral_path)
+        Coao = eng.to_padded(self.oao_mo_coeff, 2)
         if not on_host:
-            return E, G, H
-        out = (eng.stage_out("E", E), eng.stage_out("G", G), eng.stage_out("H", H) if want_hessian else None)
-        torch.cuda.current_stream(eng.device).synchronize()
+            return eng.evaluate(Coao, d1, d2, kappa=kd, want_hessian=want_hessian, path=self.integral_path)
+        # host results: the Hessian of evaluation b travels to pinned host memory on a copy stream
+        # while evaluation b+1 computes
+        B, nk = kd.shape[0], self.n_kappa
+        H_dev = eng.workspace_tensor("H_batch", (B, nk, nk)) if want_hessian else None
+        H_host = eng.pinned("H", (B, nk, nk)) if want_hessian else None
+        main = torch.cuda.current_stream(eng.device)
+        side = eng.copy_stream()
+
+        def ship(b):
+            if want_hessian:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    H_host[b].copy_(H_dev[b], non_blocking=True)
+
+        E, G, _ = eng.evaluate(Coao, d1, d2, kappa=kd, want_hessian=want_hessian, path=self.integral_path,
+                               H_out=H_dev, on_result=ship)
+        out = (eng.stage_out("E", E), eng.stage_out("G", G), H_host)
+        main.synchronize()
+        side.synchronize()
         return out
 
     # ------------------------------------------------------------------ driver

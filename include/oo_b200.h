@@ -81,6 +81,12 @@ int oo_dgemm_tn_f64(const double *At, const double *B, double *C,
                     int batch, int64_t strideA, int64_t strideB, int64_t strideC,
                     void *stream);
 
+/* same product with M = d0*d1*d2 rows (a b c), additionally storing the rows in the order
+ * (c b a) into C2 (same ldc): the first quarter of the class transform needs both layouts.   */
+int oo_dgemm_tn_swap02_f64(const double *At, const double *B, double *C, double *C2,
+                           int d0, int d1, int d2, int64_t N, int64_t K,
+                           int64_t lda, int64_t ldb, int64_t ldc, void *stream);
+
 /* general small batched product with fused epilogue (expm, C^T h C, X C U):
  * D[b] = alpha * op(A[b]) op(B[b]) + beta * E[b] + gamma * I ; op = transpose if trans* != 0;
  * E may be NULL (beta ignored) and may alias D.                                 */

@@ -348,3 +348,36 @@ def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
     assert (Hs - Hd).abs().max().item() < 1e-11
     assert np.abs(Hs.cpu().numpy() - c.ref["H"]).max() < TOL_GH
     assert np.abs(Hd.cpu().numpy() - c.ref["H"]).max() < TOL_GH
+
+
+@pytest.mark.parametrize("nao,nelec,ncas,nelecas", [(64, 64, 4, 4), (70, 100, 6, 6), (56, 36, 4, 4)])
+def test_class_transform_with_wide_class_index(nao, nelec, ncas, nelecas):
+    """Class index nIp in (16, 64]: exercises the 32/48/64-wide GEMM tiles and the dual-store epilogue
+    (small fixtures only reach the 16-wide tile).  Class tensors must equal slices of the full transform,
+    and E / G / H of both paths must agree."""
+    from auto_oo_b200.engine import HotPathEngine
+    from auto_oo_b200.synthetic import SyntheticMol, random_rdms, random_kappa
+    from oracle import oo_oracle as orc
+    mol = SyntheticMol(nao, nelec, seed=11)
+    occ, act, virt = mol.get_active_space_idx(ncas, nelecas)
+    pidx = orc.non_redundant_indices(occ, act, virt, False)
+    eng = HotPathEngine(mol.int1e_ao, mol.int2e_ao, mol.oao_coeff, mol.nuc, nao, len(occ), ncas, pidx)
+    one, two = random_rdms(ncas, nelecas, seed=2)
+    kap = random_kappa(len(pidx), seed=2, scale=0.05)[None]
+    Coao = eng.to_padded(mol.random_oao_mo_coeff, 2)
+    C = eng.mo_coeff(Coao, eng.rotation(kap))
+    cls = eng.class_integrals(C[0])
+    g = eng.int2e_transform(C)[0]
+    nI, nIp, ld = eng.nI, eng.nIp, eng.ld
+    K = cls[:nIp * nIp].reshape(nIp, nIp, ld, ld)[:nI, :nI]
+    J = cls[nIp * nIp:2 * nIp * nIp].reshape(nIp, nIp, ld, ld)[:nI, :nI]
+    assert (J - g[:, :, :nI, :nI].permute(2, 3, 0, 1)).abs().max().item() < 1e-10
+    assert (K - g[:, :nI, :nI, :].permute(2, 1, 0, 3)).abs().max().item() < 1e-10
+    Ec, Gc, Hc = eng.evaluate(Coao, one, two, kappa=kap, path="class")
+    Ef, Gf, Hf = eng.evaluate(Coao, one, two, kappa=kap, path="full")
+    assert abs(Ec.item() - Ef.item()) < TOL_E
+    assert (Gc - Gf).abs().max().item() < TOL_GH and (Hc - Hf).abs().max().item() < TOL_GH
+    prob = orc.OracleProblem(mol.int1e_ao, mol.int2e_ao, mol.oao_coeff, mol.random_oao_mo_coeff, mol.nuc,
+                             nelec, ncas, nelecas, False)
+    assert abs(Ec.item() - prob.energy(one, two, kap[0]).item()) < TOL_E
+    assert (Gc[0].cpu() - prob.gradient(one, two, kap[0])).abs().max().item() < TOL_GH
