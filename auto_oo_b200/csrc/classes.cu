@@ -27,7 +27,8 @@ int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N,
              int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
              int64_t strideC, cudaStream_t stream);
 int dgemm_tn_swap02(const double *At, const double *B, double *C, double *C2, int d0, int d1, int d2,
-                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, cudaStream_t stream);
+                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA,
+                    int64_t strideB, int64_t strideC, cudaStream_t stream);
 
 namespace {
 
@@ -75,38 +76,45 @@ int transpose(const double *src, double *dst, int64_t rows, int64_t cols, cudaSt
     return OO_OK;
 }
 
-size_t class_transform_ws_bytes(int ld, int nIp) {
+size_t class_transform_ws_bytes(int ld, int nIp, int batch) {
     const size_t ld2 = (size_t)ld * ld;
-    return (2 * ld2 * ld * nIp + 2 * ld2 * nIp * nIp) * sizeof(double);
+    return (size_t)batch * (2 * ld2 * ld * nIp + 2 * ld2 * nIp * nIp) * sizeof(double);
 }
 
 size_t class_buffer_bytes(int ld, int nIp) {
     return (size_t)(2 * (size_t)nIp * nIp + 1) * ld * ld * sizeof(double);
 }
 
-int class_transform(const double *gp, const double *C, int N, int ld, int nIp, double *cls, void *ws,
-                    size_t ws_bytes, cudaStream_t stream) {
+// batch evaluations at once: C[b] (strideC, 0 = shared), gp[b] (strideG, 0 = shared AO integrals),
+// cls[b] contiguous class buffers.  Every step is one batched TN-GEMM launch.
+int class_transform(const double *gp, int64_t strideG, const double *C, int64_t strideC, int N, int ld,
+                    int nIp, int batch, double *cls, void *ws, size_t ws_bytes, cudaStream_t stream) {
     OO_REQUIRE(gp && C && cls && ws);
-    OO_REQUIRE(N > 0 && ld >= N && (ld % 2) == 0 && nIp > 0 && (nIp % 2) == 0 && nIp <= ld);
-    if (ws_bytes < class_transform_ws_bytes(ld, nIp)) return OO_ERR_WORKSPACE;
+    OO_REQUIRE(N > 0 && ld >= N && (ld % 2) == 0 && nIp > 0 && (nIp % 2) == 0 && nIp <= ld && batch > 0);
+    if (ws_bytes < class_transform_ws_bytes(ld, nIp, batch)) return OO_ERR_WORKSPACE;
     if (ld > 65535) return OO_ERR_UNSUPPORTED;
     const int64_t ld2 = (int64_t)ld * ld, ld3 = ld2 * ld, nI2 = (int64_t)nIp * nIp;
+    const int64_t sT1 = ld3 * nIp, sX = ld2 * nI2, sCls = (2 * nI2 + 1) * ld2;
     double *T1 = reinterpret_cast<double *>(ws);
-    double *T1t = T1 + ld3 * nIp;
-    double *X = T1t + ld3 * nIp;
-    double *Xp = X + ld2 * nI2;
+    double *T1t = T1 + (int64_t)batch * sT1;
+    double *X = T1t + (int64_t)batch * sT1;
+    double *Xp = X + (int64_t)batch * sX;
     double *Kout = cls, *Jout = cls + nI2 * ld2;
     int rc;
-#define Q(in, out, M, Ncols) \
-    if ((rc = dgemm_tn((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), 1, 0, 0, 0, stream))) return rc
+#define Q(in, sIn, out, sOut, M, Ncols)                                                                  \
+    if ((rc = dgemm_tn((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), batch, (sIn), strideC, (sOut), \
+                       stream)))                                                                         \
+    return rc
     // Q1 writes T1[s,p,q,m] and its (s <-> q) swapped copy T1t[q,p,s,m] from the same accumulators
-    if ((rc = dgemm_tn_swap02(gp, C, T1, T1t, ld, ld, ld, nIp, ld, ld3, ld, nIp, stream))) return rc;
-    Q(T1, X, ld2 * nIp, nIp);         // [p,q,m,n]
-    Q(X, Xp, ld * nI2, ld);           // [q,m,n,a]
-    Q(Xp, Jout, nI2 * ld, ld);        // [m,n,a,b]
-    Q(T1t, X, ld2 * nIp, nIp);        // [p,s,n,m]
-    Q(X, Xp, ld * nI2, ld);           // [s,n,m,a]
-    Q(Xp, Kout, nI2 * ld, ld);        // [n,m,a,b]
+    if ((rc = dgemm_tn_swap02(gp, C, T1, T1t, ld, ld, ld, nIp, ld, ld3, ld, nIp, batch, strideG, strideC, sT1,
+                              stream)))
+        return rc;
+    Q(T1, sT1, X, sX, ld2 * nIp, nIp);         // [p,q,m,n]
+    Q(X, sX, Xp, sX, ld * nI2, ld);            // [q,m,n,a]
+    Q(Xp, sX, Jout, sCls, nI2 * ld, ld);       // [m,n,a,b]
+    Q(T1t, sT1, X, sX, ld2 * nIp, nIp);        // [p,s,n,m]
+    Q(X, sX, Xp, sX, ld * nI2, ld);            // [s,n,m,a]
+    Q(Xp, sX, Kout, sCls, nI2 * ld, ld);       // [n,m,a,b]
 #undef Q
     return OO_OK;
 }
@@ -119,8 +127,9 @@ int oo_transpose_f64(const double *src, double *dst, int64_t rows, int64_t cols,
     return oo::transpose(src, dst, rows, cols, (cudaStream_t)stream);
 }
 
-int oo_class_transform_f64(const double *g_pairT, const double *C, int N, int ld, int nIp, double *cls,
-                           void *ws, size_t ws_bytes, void *stream) {
-    return oo::class_transform(g_pairT, C, N, ld, nIp, cls, ws, ws_bytes, (cudaStream_t)stream);
+int oo_class_transform_f64(const double *g_pairT, int64_t strideG, const double *C, int64_t strideC, int N,
+                           int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes, void *stream) {
+    return oo::class_transform(g_pairT, strideG, C, strideC, N, ld, nIp, batch, cls, ws, ws_bytes,
+                               (cudaStream_t)stream);
 }
 }

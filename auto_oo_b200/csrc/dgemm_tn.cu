@@ -201,7 +201,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         const int c = (int)(row % args.d2);
                         const int64_t ab = row / args.d2;
                         const int bq = (int)(ab % args.d1), a = (int)(ab / args.d1);
-                        crow2 = args.C2 + (((int64_t)c * args.d1 + bq) * args.d0 + a) * args.ldc;
+                        crow2 = args.C2 + (int64_t)b * args.strideC + (((int64_t)c * args.d1 + bq) * args.d0 + a) * args.ldc;
                     }
 #pragma unroll
                     for (int ni = 0; ni < Cfg::NT; ++ni) {
@@ -313,16 +313,18 @@ int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N,
     return dgemm_tn_impl(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, TnDual());
 }
 
-// C[(a b c), n] and C2[(c b a), n] from one pass (M = d0*d1*d2, same ldc for both)
+// C[(a b c), n] and C2[(c b a), n] from one pass (M = d0*d1*d2, same ldc and batch stride for both)
 int dgemm_tn_swap02(const double *At, const double *B, double *C, double *C2, int d0, int d1, int d2,
-                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, cudaStream_t stream) {
+                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA,
+                    int64_t strideB, int64_t strideC, cudaStream_t stream) {
     OO_REQUIRE(C2 && d0 > 0 && d1 > 0 && d2 > 0);
     TnDual dual;
     dual.C2 = C2;
     dual.d0 = d0;
     dual.d1 = d1;
     dual.d2 = d2;
-    return dgemm_tn_impl(At, B, C, (int64_t)d0 * d1 * d2, N, K, lda, ldb, ldc, 1, 0, 0, 0, stream, dual);
+    return dgemm_tn_impl(At, B, C, (int64_t)d0 * d1 * d2, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC,
+                         stream, dual);
 }
 
 }  // namespace oo
@@ -337,5 +339,5 @@ extern "C" int oo_dgemm_tn_f64(const double *At, const double *B, double *C, int
 extern "C" int oo_dgemm_tn_swap02_f64(const double *At, const double *B, double *C, double *C2, int d0,
                                       int d1, int d2, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                       int64_t ldc, void *stream) {
-    return oo::dgemm_tn_swap02(At, B, C, C2, d0, d1, d2, N, K, lda, ldb, ldc, (cudaStream_t)stream);
+    return oo::dgemm_tn_swap02(At, B, C, C2, d0, d1, d2, N, K, lda, ldb, ldc, 1, 0, 0, 0, (cudaStream_t)stream);
 }

@@ -117,11 +117,17 @@ __device__ __forceinline__ bool in_dense_block(int no, int nI, int p, int r, int
 
 // one warp per column (p r) of At: ELL list (k, val) of its non-zeros outside the dense block
 __global__ void __launch_bounds__(256)
-hess_sparse_build_kernel(RdmView rdm, int nIs, int swap_exch, int width, int *__restrict__ cnt,
-                         int *__restrict__ idx, double *__restrict__ val, int *__restrict__ overflow) {
+hess_sparse_build_kernel(RdmView rdm0, int64_t sd1, int64_t sd2, int nIs, int swap_exch, int width,
+                         int *__restrict__ cnt, int *__restrict__ idx, double *__restrict__ val,
+                         int *__restrict__ overflow) {
     const int lane = threadIdx.x & 31;
     const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (col >= nIs * nIs) return;
+    // blockIdx.y = which set of RDMs (one ELL table per set)
+    const RdmView rdm{rdm0.d1 + blockIdx.y * sd1, rdm0.d2 + blockIdx.y * sd2, rdm0.no, rdm0.na};
+    cnt += (int64_t)blockIdx.y * nIs * nIs;
+    idx += (int64_t)blockIdx.y * nIs * nIs * width;
+    val += (int64_t)blockIdx.y * nIs * nIs * width;
     const int p = col / nIs, r = col % nIs;
     const int nI = rdm.no + rdm.na;
     int base = 0;
@@ -153,9 +159,12 @@ hess_sparse_build_kernel(RdmView rdm, int nIs, int swap_exch, int width, int *__
 
 // dense block operands: rows k' = [exchange act pairs | Coulomb act pairs | one-body]
 //   Atc[k', (v w)] and Bc[k', :] = the matching row of the class buffer
-__global__ void hess_dense_at_kernel(RdmView rdm, int nIs, int swap_exch, int64_t lda, double *__restrict__ Atc) {
+__global__ void hess_dense_at_kernel(RdmView rdm0, int64_t sd1, int64_t sd2, int nIs, int swap_exch, int64_t lda,
+                                     double *__restrict__ Atc) {
+    const RdmView rdm{rdm0.d1 + blockIdx.y * sd1, rdm0.d2 + blockIdx.y * sd2, rdm0.no, rdm0.na};
     const int na = rdm.na, no = rdm.no, na2 = na * na;
     const int64_t total = (int64_t)(2 * na2 + 1) * lda;
+    Atc += (int64_t)blockIdx.y * total;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int kc = (int)(i / lda), col = (int)(i % lda);
@@ -176,9 +185,11 @@ __global__ void hess_dense_at_kernel(RdmView rdm, int nIs, int swap_exch, int64_
     }
 }
 
-__global__ void hess_dense_b_kernel(const double *__restrict__ cls, int no, int na, int nIs, int64_t mat,
-                                    double *__restrict__ Bc) {
+__global__ void hess_dense_b_kernel(const double *__restrict__ cls, int64_t cls_stride, int no, int na, int nIs,
+                                    int64_t mat, double *__restrict__ Bc) {
     const int kc = blockIdx.y, na2 = na * na;
+    cls += (int64_t)blockIdx.z * cls_stride;
+    Bc += (int64_t)blockIdx.z * (2 * na2 + 1) * mat;
     int64_t k;
     if (kc < 2 * na2) {
         const int a = no + (kc % na2) / na, b = no + (kc % na2) % na;
@@ -196,12 +207,23 @@ __global__ void hess_dense_b_kernel(const double *__restrict__ cls, int no, int 
 // T[(p r), c] (= or +=) sum_e val[e] * B[idx[e], c].   grid (columns (p r), column tiles of 512);
 // consecutive CTAs share a column tile of B, which therefore stays in L2.
 __global__ void __launch_bounds__(256)
-hess_spmm_kernel(const double *__restrict__ B, const int *__restrict__ cnt, const int *__restrict__ idx,
-                 const double *__restrict__ val, int width, int no, int na, int nIs, int64_t mat,
-                 double *__restrict__ T, double *__restrict__ Taa) {
+hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__restrict__ cnt,
+                 const int *__restrict__ idx, const double *__restrict__ val, int rdm_batched, int width, int no,
+                 int na, int nIs, int64_t mat, double *__restrict__ T, double *__restrict__ Taa) {
     const int col = blockIdx.x;
     const int p = col / nIs, r = col % nIs, nI = no + na;
     if (p >= nI || r >= nI) return;
+    {
+        const int64_t bz = blockIdx.z, nI2 = (int64_t)nIs * nIs;
+        B += bz * b_stride;
+        T += bz * nI2 * mat;
+        Taa += bz * (int64_t)na * na * mat;
+        if (rdm_batched) {
+            cnt += bz * nI2;
+            idx += bz * nI2 * width;
+            val += bz * nI2 * width;
+        }
+    }
     const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2;
     if (c >= mat) return;
     const int n = cnt[col];
@@ -265,6 +287,7 @@ struct TView {
     const double *T;     // rows (a c) -> a * nIs + c
     const double *Taa;   // optional: act-act rows (a - no) * na + (c - no); null = everything in T
     int nI, nIs, no, na;
+    int64_t t_stride, taa_stride, f_stride, h_stride;   // per-evaluation strides (blockIdx.z)
 };
 
 __device__ __forceinline__ double hess_x(const TView &tv, const double *__restrict__ F, int ld, int a, int b,
@@ -283,12 +306,16 @@ __device__ __forceinline__ double hess_x(const TView &tv, const double *__restri
 }
 
 __global__ void __launch_bounds__(256)
-hess_assemble_kernel(const TView tv, const double *__restrict__ F,
+hess_assemble_kernel(TView tv, const double *__restrict__ F,
                      const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int ld,
                      double *__restrict__ H) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (k >= nk) return;
+    tv.T += blockIdx.z * tv.t_stride;
+    if (tv.Taa) tv.Taa += blockIdx.z * tv.taa_stride;
+    F += blockIdx.z * tv.f_stride;
+    H += blockIdx.z * tv.h_stride;
     const int p = pl[j], q = pr[j];
     const int r = pl[k], s = pr[k];
     const double v = hess_x(tv, F, ld, p, q, r, s) - hess_x(tv, F, ld, p, q, s, r)
@@ -400,7 +427,7 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     {
         if (nk > 65535) return OO_ERR_UNSUPPORTED;
         dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-        hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, nullptr, nI, nI, no, na}, F, pl, pr, nk, ld, H);
+        hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, nullptr, nI, nI, no, na, 0, 0, 0, 0}, F, pl, pr, nk, ld, H);
         OO_LAUNCH_CHECK();
     }
     return OO_OK;
@@ -415,7 +442,7 @@ struct ClassHessLayout {
     size_t off_cnt, off_idx, off_val, off_flag, off_atc, off_bc, off_taa, off_t, total;
 };
 
-static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na) {
+static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na, int batch) {
     ClassHessLayout L;
     const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld, na2 = (int64_t)na * na;
     L.width = 2 * na * na + 2 * (no + na) + 8;
@@ -423,22 +450,22 @@ static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na) {
     L.krows_c = 2 * na2 + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
-    L.off_cnt = take((size_t)nI2 * sizeof(int));
-    L.off_idx = take((size_t)nI2 * L.width * sizeof(int));
-    L.off_val = take((size_t)nI2 * L.width * sizeof(double));
+    L.off_cnt = take((size_t)batch * nI2 * sizeof(int));
+    L.off_idx = take((size_t)batch * nI2 * L.width * sizeof(int));
+    L.off_val = take((size_t)batch * nI2 * L.width * sizeof(double));
     L.off_flag = take(sizeof(int));
-    L.off_atc = take((size_t)L.krows_c * L.lda_c * sizeof(double));
-    L.off_bc = take((size_t)L.krows_c * mat * sizeof(double));
-    L.off_taa = take((size_t)na2 * mat * sizeof(double));
-    L.off_t = take((size_t)nI2 * mat * sizeof(double));
+    L.off_atc = take((size_t)batch * L.krows_c * L.lda_c * sizeof(double));
+    L.off_bc = take((size_t)batch * L.krows_c * mat * sizeof(double));
+    L.off_taa = take((size_t)batch * na2 * mat * sizeof(double));
+    L.off_t = take((size_t)batch * nI2 * mat * sizeof(double));
     L.total = off;
     return L;
 }
 
-size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na) {
+size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch) {
     const HessLayout D = hess_layout(ld, nIp);
-    const size_t dense = D.off_b + (D.total - D.off_t);          // At + T (no gathered B)
-    const size_t sparse = class_hess_layout(ld, nIp, no, na).total;
+    const size_t dense = D.off_b + (D.total - D.off_t);          // At + T (no gathered B); batch 1 only
+    const size_t sparse = class_hess_layout(ld, nIp, no, na, batch).total;
     return dense > sparse ? dense : sparse;
 }
 
@@ -457,24 +484,38 @@ static int class_hessian_dense(const double *cls, const double *F, const RdmView
     int rc = dgemm_tn(At, cls, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
     if (rc) return rc;
     dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-    hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na}, F,
-                                                   pl, pr, nk, ld, H);
+    hess_assemble_kernel<<<grid, 256, 0, stream>>>(
+        TView{T, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na, 0, 0, 0, 0}, F, pl, pr, nk, ld, H);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
 
-int class_hessian(const double *cls, const double *F, const double *d1, const double *d2, int no, int na,
-                  int N, int ld, int nIp, const int32_t *pl, const int32_t *pr, int nk, double *H, void *ws,
-                  size_t ws_bytes, cudaStream_t stream) {
+// batch evaluations: cls[b] (class buffers, contiguous), F[b] (ld^2), H[b] (nk^2); RDMs shared
+// (stride 0) or per evaluation.
+int class_hessian(const double *cls, const double *F, const double *d1, int64_t sd1, const double *d2,
+                  int64_t sd2, int no, int na, int N, int ld, int nIp, int batch, const int32_t *pl,
+                  const int32_t *pr, int nk, double *H, void *ws, size_t ws_bytes, cudaStream_t stream) {
     OO_REQUIRE(cls && F && d1 && d2 && H && ws && pl && pr);
-    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0);
+    OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0 && batch > 0);
     OO_REQUIRE(nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
-    if (ws_bytes < class_hessian_ws_bytes(ld, nIp, no, na)) return OO_ERR_WORKSPACE;
-    if (nk > 65535) return OO_ERR_UNSUPPORTED;
+    const int rdm_batched = (batch > 1 && (sd1 != 0 || sd2 != 0)) ? 1 : 0;
+    const int nsets = rdm_batched ? batch : 1;
+    if (ws_bytes < class_hessian_ws_bytes(ld, nIp, no, na, batch)) return OO_ERR_WORKSPACE;
+    if (nk > 65535 || batch > 65535) return OO_ERR_UNSUPPORTED;
     RdmView rdm{d1, d2, no, na};
-    if (g_hessian_dense) return class_hessian_dense(cls, F, rdm, ld, nIp, pl, pr, nk, H, ws, stream);
+    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld, na2 = (int64_t)na * na;
+    const int64_t cls_stride = (2 * nI2 + 1) * mat;
+    if (g_hessian_dense) {
+        for (int b = 0; b < batch; ++b) {
+            RdmView rb{d1 + b * sd1, d2 + b * sd2, no, na};
+            int rc = class_hessian_dense(cls + b * cls_stride, F + b * mat, rb, ld, nIp, pl, pr, nk,
+                                         H + (int64_t)b * nk * nk, ws, stream);
+            if (rc) return rc;
+        }
+        return OO_OK;
+    }
 
-    const ClassHessLayout L = class_hess_layout(ld, nIp, no, na);
+    const ClassHessLayout L = class_hess_layout(ld, nIp, no, na, batch);
     uint8_t *w = reinterpret_cast<uint8_t *>(ws);
     int *cnt = reinterpret_cast<int *>(w + L.off_cnt);
     int *idx = reinterpret_cast<int *>(w + L.off_idx);
@@ -484,32 +525,36 @@ int class_hessian(const double *cls, const double *F, const double *d1, const do
     double *Bc = reinterpret_cast<double *>(w + L.off_bc);
     double *Taa = reinterpret_cast<double *>(w + L.off_taa);
     double *T = reinterpret_cast<double *>(w + L.off_t);
-    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld, na2 = (int64_t)na * na;
 
-    // sparse structure of At outside the act-act block
-    hess_sparse_build_kernel<<<(unsigned)ceil_div(nI2, 8), 256, 0, stream>>>(rdm, nIp, 1, L.width, cnt, idx, val,
-                                                                            flag);
+    // sparse structure of At outside the act-act block (one table per set of RDMs)
+    hess_sparse_build_kernel<<<dim3((unsigned)ceil_div(nI2, 8), (unsigned)nsets), 256, 0, stream>>>(
+        rdm, sd1, sd2, nIp, 1, L.width, cnt, idx, val, flag);
     OO_LAUNCH_CHECK();
-    // dense act-act block: Taa = Atc^T Bc
+    // dense act-act block: Taa[b] = Atc^T Bc[b]
     {
         int64_t blocks = ceil_div(L.krows_c * L.lda_c, 256);
-        hess_dense_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nIp, 1, L.lda_c, Atc);
+        hess_dense_at_kernel<<<dim3((unsigned)blocks, (unsigned)nsets), 256, 0, stream>>>(rdm, sd1, sd2, nIp, 1,
+                                                                                         L.lda_c, Atc);
         OO_LAUNCH_CHECK();
         int64_t bx = ceil_div(mat / 2, 256);
         if (bx > 64) bx = 64;
-        hess_dense_b_kernel<<<dim3((unsigned)bx, (unsigned)L.krows_c), 256, 0, stream>>>(cls, no, na, nIp, mat, Bc);
+        hess_dense_b_kernel<<<dim3((unsigned)bx, (unsigned)L.krows_c, (unsigned)batch), 256, 0, stream>>>(
+            cls, cls_stride, no, na, nIp, mat, Bc);
         OO_LAUNCH_CHECK();
-        int rc = dgemm_tn(Atc, Bc, Taa, na2, mat, L.krows_c, L.lda_c, mat, mat, 1, 0, 0, 0, stream);
+        int rc = dgemm_tn(Atc, Bc, Taa, na2, mat, L.krows_c, L.lda_c, mat, mat, batch,
+                          rdm_batched ? L.krows_c * L.lda_c : 0, L.krows_c * mat, na2 * mat, stream);
         if (rc) return rc;
     }
     // sparse remainder (accumulates into Taa for act-act columns)
     {
-        dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256));
-        hess_spmm_kernel<<<grid, 256, 0, stream>>>(cls, cnt, idx, val, L.width, no, na, nIp, mat, T, Taa);
+        dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256), (unsigned)batch);
+        hess_spmm_kernel<<<grid, 256, 0, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no, na,
+                                                   nIp, mat, T, Taa);
         OO_LAUNCH_CHECK();
     }
-    dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-    hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, Taa, no + na, nIp, no, na}, F, pl, pr, nk, ld, H);
+    dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk, (unsigned)batch);
+    hess_assemble_kernel<<<grid, 256, 0, stream>>>(
+        TView{T, Taa, no + na, nIp, no, na, nI2 * mat, na2 * mat, mat, (int64_t)nk * nk}, F, pl, pr, nk, ld, H);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -578,9 +623,10 @@ extern "C" int oo_y_matrix_f64(const double *g_mo, const double *two_full, int N
 }
 
 extern "C" int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma,
-                                    const double *Gamma, int no, int na, int N, int ld, int nIp,
-                                    const int32_t *pair_l, const int32_t *pair_r, int nk, double *H,
-                                    void *ws, size_t ws_bytes, void *stream) {
-    return oo::class_hessian(cls, F, gamma, Gamma, no, na, N, ld, nIp, pair_l, pair_r, nk, H, ws, ws_bytes,
-                             (cudaStream_t)stream);
+                                    int64_t stride_rdm1, const double *Gamma, int64_t stride_rdm2, int no,
+                                    int na, int N, int ld, int nIp, int batch, const int32_t *pair_l,
+                                    const int32_t *pair_r, int nk, double *H, void *ws, size_t ws_bytes,
+                                    void *stream) {
+    return oo::class_hessian(cls, F, gamma, stride_rdm1, Gamma, stride_rdm2, no, na, N, ld, nIp, batch, pair_l,
+                             pair_r, nk, H, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -54,12 +54,12 @@ class MOIntegrals:
 
     def fock_gradient_vjp(self, FI, Gbar):
         if self.kind == "class":
-            return self.eng.class_fock_gradient_vjp(self.cls, FI[0], Gbar)
+            return self.eng.class_fock_gradient_vjp(self.cls[0], FI[0], Gbar)
         return self.eng.fock_gradient_vjp(self.g[0], FI[0], Gbar)
 
     def hessian(self, F, d1, d2, pair_l=None, pair_r=None):
         if self.kind == "class":
-            return self.eng.class_hessian(self.cls, F[0], d1, d2, pair_l=pair_l, pair_r=pair_r)
+            return self.eng.class_hessian(self.cls, F, d1, d2, pair_l=pair_l, pair_r=pair_r)[0]
         return self.eng.hessian(self.h[0], self.g[0], F[0], d1, d2, pair_l=pair_l, pair_r=pair_r)
 
 
@@ -315,25 +315,33 @@ class HotPathEngine:
         self._cache_key = self._cache_val = None
         self._ws.pop("i2e", None)
 
+    def class_rows(self):
+        return 2 * self.nIp * self.nIp + 1
+
     def class_integrals(self, C, out=None):
-        """Class buffer [K rows; J rows; h' row] (2 nIp^2 + 1, ld, ld) for ONE padded C (ld, ld)."""
-        C = C.reshape(self.ld, self.ld)
-        ld, nIp = self.ld, self.nIp
-        rows = 2 * nIp * nIp + 1
-        cls = out if out is not None else torch.empty(rows, ld, ld, dtype=F64, device=self.device)
-        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, 1)
+        """Class buffers [K rows; J rows; h' row] for padded C (ld, ld) or (B, ld, ld):
+        returns (B, 2 nIp^2 + 1, ld, ld); every GEMM step is one batched launch."""
+        C = C.reshape(-1, self.ld, self.ld)
+        B, ld, nIp, rows = C.shape[0], self.ld, self.nIp, self.class_rows()
+        cls = out if out is not None and out.shape[0] == B else torch.empty(B, rows, ld, ld, dtype=F64,
+                                                                           device=self.device)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, B)
         ws = self.workspace("cls", nbytes)
-        self._check(self.lib.oo_class_transform_f64(_p(self.pair_transposed_eri()), _p(C), self.N, ld, nIp,
-                                                    _p(cls), _p(ws), nbytes, self.stream), "class_transform")
-        nb1 = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, ld, 0, 1)
-        ws1 = self.workspace("i1e", nb1)
-        self._check(self.lib.oo_int1e_transform_f64(_p(self.h_ao), _p(C), 0, self.N, ld, 1, _p(cls[rows - 1]),
-                                                    _p(ws1), nb1, self.stream), "int1e_transform")
+        self._check(self.lib.oo_class_transform_f64(_p(self.pair_transposed_eri()), 0, _p(C), ld * ld if B > 1 else 0,
+                                                    self.N, ld, nIp, B, _p(cls), _p(ws), nbytes, self.stream),
+                    "class_transform")
+        if B == 1:                                           # h' = C^T h C straight into the last row
+            nb1 = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, ld, 0, 1)
+            ws1 = self.workspace("i1e", nb1)
+            self._check(self.lib.oo_int1e_transform_f64(_p(self.h_ao), _p(C), 0, self.N, ld, 1, _p(cls[0, rows - 1]),
+                                                        _p(ws1), nb1, self.stream), "int1e_transform")
+        else:                                                # batched: dense scratch, then a strided device copy
+            cls[:, rows - 1].copy_(self.int1e_transform(C))
         return cls
 
     def class_integrals_cached(self, C):
-        """As class_integrals, but the last result is cached by the value of C."""
-        C = C.reshape(self.ld, self.ld)
+        """As class_integrals for ONE C, but the last result is cached by the value of C."""
+        C = C.reshape(1, self.ld, self.ld)
         if self._ccache_key is not None and torch.equal(self._ccache_key, C):
             return self._ccache_val
         buf = self._ccache_val
@@ -343,24 +351,25 @@ class HotPathEngine:
         return cls
 
     def class_active_hamiltonian(self, cls):
-        na = self.na
-        c0 = torch.empty(1, dtype=F64, device=self.device)
-        c1 = torch.empty(1, na, na, dtype=F64, device=self.device)
-        c2 = torch.empty(1, na, na, na, na, dtype=F64, device=self.device)
-        self._check(self.lib.oo_class_active_hamiltonian_f64(_p(cls), self.no, na, self.N, self.ld, self.nIp, 1,
+        na, B = self.na, cls.shape[0]
+        c0 = torch.empty(B, dtype=F64, device=self.device)
+        c1 = torch.empty(B, na, na, dtype=F64, device=self.device)
+        c2 = torch.empty(B, na, na, na, na, dtype=F64, device=self.device)
+        self._check(self.lib.oo_class_active_hamiltonian_f64(_p(cls), self.no, na, self.N, self.ld, self.nIp, B,
                                                              self.nuc, _p(c0), _p(c1), _p(c2), self.stream),
                     "class_active_hamiltonian")
         return c0, c1, c2
 
     def class_fock_gradient(self, cls, d1, d2, want_matrix=True, want_vector=True):
-        ld = self.ld
-        FI = torch.empty(1, ld, ld, dtype=F64, device=self.device)
+        ld, B = self.ld, cls.shape[0]
+        s1, s2 = self._rdm_strides(d1, d2, B)
+        FI = torch.empty(B, ld, ld, dtype=F64, device=self.device)
         FA = torch.empty_like(FI)
         F = torch.empty_like(FI)
         G = torch.empty_like(FI) if want_matrix else None
-        gv = torch.empty(1, self.nk, dtype=F64, device=self.device) if want_vector else None
-        self._check(self.lib.oo_class_fock_gradient_f64(_p(cls), _p(d1), 0, _p(d2), 0, self.no, self.na, self.N,
-                                                        ld, self.nIp, 1, _p(self.pair_l), _p(self.pair_r),
+        gv = torch.empty(B, self.nk, dtype=F64, device=self.device) if want_vector else None
+        self._check(self.lib.oo_class_fock_gradient_f64(_p(cls), _p(d1), s1, _p(d2), s2, self.no, self.na, self.N,
+                                                        ld, self.nIp, B, _p(self.pair_l), _p(self.pair_r),
                                                         self.nk, _p(FI), _p(FA), _p(F), _p(G), _p(gv),
                                                         self.stream), "class_fock_gradient")
         return FI, FA, F, G, gv
@@ -375,18 +384,29 @@ class HotPathEngine:
         return g1, g2
 
     def class_hessian(self, cls, F, d1, d2, out=None, pair_l=None, pair_r=None):
+        """Hessians (B, nk, nk) of the B evaluations in cls (B, rows, ld, ld), F (B, ld, ld)."""
         pl = self.pair_l if pair_l is None else pair_l
         pr = self.pair_r if pair_r is None else pair_r
         nk = int(pl.numel())
-        H = out if out is not None else torch.empty(nk, nk, dtype=F64, device=self.device)
+        B = cls.shape[0]
+        H = out if out is not None else torch.empty(B, nk, nk, dtype=F64, device=self.device)
         if nk == 0:
             return H
-        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.N, self.ld, self.nI, self.na)
+        s1, s2 = self._rdm_strides(d1, d2, B)
+        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.na, self.ld, self.nI, B)
         ws = self.workspace("chess", nbytes)
-        self._check(self.lib.oo_class_hessian_f64(_p(cls), _p(F), _p(d1), _p(d2), self.no, self.na, self.N,
-                                                  self.ld, self.nIp, _p(pl), _p(pr), nk, _p(H), _p(ws), nbytes,
+        self._check(self.lib.oo_class_hessian_f64(_p(cls), _p(F), _p(d1), s1, _p(d2), s2, self.no, self.na, self.N,
+                                                  self.ld, self.nIp, B, _p(pl), _p(pr), nk, _p(H), _p(ws), nbytes,
                                                   self.stream), "class_hessian")
         return H
+
+    def class_chunk(self, B):
+        """How many evaluations the class path processes per batched launch: as many as keep the
+        transform + Hessian workspaces under ~8 GB (always at least one)."""
+        per = (self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, self.ld, self.nI, 1)
+               + self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.na, self.ld, self.nI, 1)
+               + self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_BUFFER, self.N, self.ld, self.nI, 1))
+        return int(max(1, min(B, (8 << 30) // max(per, 1))))
 
     # ------------------------------------------------------------------ K3
     def active_hamiltonian(self, h, g):
@@ -514,27 +534,30 @@ class HotPathEngine:
         if want_hessian:
             H = H_out if H_out is not None else torch.empty(B, self.nk, self.nk, dtype=F64, device=self.device)
         if path == "class":
+            chunk = self.class_chunk(B)
             cbuf = self._ccache_val
             self._ccache_key = self._ccache_val = None
-            for b in range(B):
+            for lo in range(0, B, chunk):
+                hi = min(B, lo + chunk)
                 if transform_events is not None:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record()
-                cbuf = self.class_integrals(C[b], out=cbuf)
+                cbuf = self.class_integrals(C[lo:hi], out=cbuf)
                 if transform_events is not None:
                     ev[1].record()
                     transform_events.append(ev)
-                d1b = d1[b] if d1.dim() == 3 else d1
-                d2b = d2[b] if d2.dim() == 5 else d2
+                d1b = d1[lo:hi] if d1.dim() == 3 else d1
+                d2b = d2[lo:hi] if d2.dim() == 5 else d2
                 c0, c1, c2 = self.class_active_hamiltonian(cbuf)
-                E[b:b + 1] = self.energy(c0, c1, c2, d1b, d2b)
+                E[lo:hi] = self.energy(c0, c1, c2, d1b, d2b)
                 FI, FA, F, _, gv = self.class_fock_gradient(cbuf, d1b, d2b, want_matrix=False)
-                G[b] = gv[0]
+                G[lo:hi] = gv
                 if want_hessian:
-                    self.class_hessian(cbuf, F[0], d1b, d2b, out=H[b])
+                    self.class_hessian(cbuf, F, d1b, d2b, out=H[lo:hi])
                 if on_result is not None:
-                    on_result(b)
-            self._ccache_val = cbuf                     # keep the buffer (not the key) for reuse
+                    for b in range(lo, hi):
+                        on_result(b)
+            self._ccache_val = cbuf if cbuf.shape[0] == 1 else None     # keep a single-evaluation buffer for reuse
             return E, G, H
         hs = self.int1e_transform(C)
         gbuf = None

@@ -53,7 +53,7 @@ enum {
     OO_WS_YMATRIX    = 5,      /* oo_y_matrix_f64                                  */
     OO_WS_CLASS_TRANSFORM = 6, /* oo_class_transform_f64 (nI = no+na)              */
     OO_WS_CLASS_BUFFER    = 7, /* size of the class buffer `cls` (x batch)         */
-    OO_WS_CLASS_HESSIAN   = 8  /* oo_class_hessian_f64: pass nI = no+na and batch = na */
+    OO_WS_CLASS_HESSIAN   = 8  /* oo_class_hessian_f64: pass N = na (!), nI = no+na, batch */
 };
 
 int         oo_abi_version(void);
@@ -203,8 +203,9 @@ int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
  * class-buffer forms of oo_active_hamiltonian_f64 / oo_fock_gradient_f64 /
  * oo_fock_gradient_vjp_f64 / oo_hessian_f64 (same outputs, same reference lines).      */
 int oo_transpose_f64(const double *src, double *dst, int64_t rows, int64_t cols, void *stream);
-int oo_class_transform_f64(const double *g_pairT, const double *C, int N, int ld, int nIp,
-                           double *cls, void *ws, size_t ws_bytes, void *stream);
+int oo_class_transform_f64(const double *g_pairT, int64_t strideG, const double *C, int64_t strideC,
+                           int N, int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
+                           void *stream);   /* stride 0 = shared over the batch; cls[b] contiguous */
 int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp,
                                     int batch, double e_nuc, double *c0, double *c1, double *c2,
                                     void *stream);
@@ -216,10 +217,11 @@ int oo_class_fock_gradient_f64(const double *cls, const double *gamma, int64_t s
 int oo_class_fock_gradient_vjp_f64(const double *cls, const double *FI, const double *Gbar, int no,
                                    int na, int N, int ld, int nIp, double *gbar1, double *gbar2,
                                    void *stream);
-int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma,
-                         const double *Gamma, int no, int na, int N, int ld, int nIp,
-                         const int32_t *pair_l, const int32_t *pair_r, int nk, double *H,
-                         void *ws, size_t ws_bytes, void *stream);
+int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma, int64_t stride_rdm1,
+                         const double *Gamma, int64_t stride_rdm2, int no, int na, int N, int ld,
+                         int nIp, int batch, const int32_t *pair_l, const int32_t *pair_r, int nk,
+                         double *H, void *ws, size_t ws_bytes, void *stream);
+                         /* batched: cls[b], F[b] (ld^2), H[b] (nk^2) contiguous per evaluation */
 
 /* ---- API-parity helpers (not on the hot path) ------------------------------
  * Dense full-space RDMs exactly as full_rdms defines them (oo_energy.py:342-379):

@@ -250,7 +250,7 @@ def test_class_transform_equals_slices_of_full_transform(name):
     c = load_case(name)
     eng, p = engine_for(c)
     Cp = eng.to_padded(c.ref["mo_coeff_rot"], 2)
-    cls = eng.class_integrals(Cp).cpu()
+    cls = eng.class_integrals(Cp)[0].cpu()
     g = eng.from_padded(eng.int2e_transform(Cp), 4)[0].cpu()
     h = eng.from_padded(eng.int1e_transform(Cp), 2)[0].cpu()
     N, nI, nIp = c.nao, eng.nI, eng.nIp
@@ -295,6 +295,29 @@ def test_class_path_stages_and_vjp(name):
     Gref = orc.gradient_matrix(ho, go, one, two, p.occ_idx, p.act_idx)
     r1, r2 = torch.autograd.grad((Gref * Gbar).sum(), (one, two))
     assert (g1.cpu() - r1).abs().max().item() < 1e-10 and (g2.cpu() - r2).abs().max().item() < 1e-10
+
+
+def test_batched_class_path_matches_per_evaluation_results():
+    """kappa batch through the batched launches (class path) == one evaluation at a time, and per-evaluation
+    RDMs (stride != 0) are honoured."""
+    c = load_case("n11_cas43")
+    eng, p = engine_for(c)
+    gen = torch.Generator().manual_seed(12)
+    B = 5
+    kap = torch.randn(B, p.n_kappa, dtype=F64, generator=gen) * 0.1
+    one = c.one_rdm[None] + 0.01 * torch.randn(B, c.ncas, c.ncas, dtype=F64, generator=gen)
+    one = 0.5 * (one + one.transpose(1, 2))
+    two = c.two_rdm[None].repeat(B, 1, 1, 1, 1) * torch.linspace(0.8, 1.2, B, dtype=F64)[:, None, None, None, None]
+    Coao = eng.to_padded(c.oao_mo_coeff, 2)
+    E, G, H = eng.evaluate(Coao, one, two, kappa=kap, path="class")
+    for b in range(B):
+        e1, g1, h1 = eng.evaluate(Coao, one[b], two[b], kappa=kap[b:b + 1], path="class")
+        assert abs(E[b].item() - e1.item()) < 1e-12
+        assert (G[b] - g1[0]).abs().max().item() < 1e-12 and (H[b] - h1[0]).abs().max().item() < 1e-12
+        e, gvec, hm = p.evaluate(one[b], two[b], kap[b])
+        assert abs(E[b].item() - e.item()) < TOL_E
+        assert (G[b].cpu() - gvec).abs().max().item() < TOL_GH
+        assert (H[b].cpu() - hm).abs().max().item() < TOL_GH
 
 
 def test_batched_evaluation_equals_single():
@@ -366,7 +389,7 @@ def test_class_transform_with_wide_class_index(nao, nelec, ncas, nelecas):
     kap = random_kappa(len(pidx), seed=2, scale=0.05)[None]
     Coao = eng.to_padded(mol.random_oao_mo_coeff, 2)
     C = eng.mo_coeff(Coao, eng.rotation(kap))
-    cls = eng.class_integrals(C[0])
+    cls = eng.class_integrals(C[0])[0]
     g = eng.int2e_transform(C)[0]
     nI, nIp, ld = eng.nI, eng.nIp, eng.ld
     K = cls[:nIp * nIp].reshape(nIp, nIp, ld, ld)[:nI, :nI]
