@@ -20,7 +20,15 @@
      rank, and every element is summed on one rank in the single-GPU order => bit-identical results),
      then quarters 3-4 are local.
 
-   Both end with ``g'[i in I_r, :, :, :]`` on rank ``r``.  Per-destination GEMMs make every exchanged
+   * ``mode="p2p"``: same decomposition as ``all_to_all``, but there is no separate exchange pass:
+     the output pointer of the quarter-2 GEMM for destination ``d`` is rank ``d``'s receive buffer
+     mapped into this process (``torch.distributed._symmetric_memory``, NVLink peer mapping), so the
+     TN-GEMM's epilogue stores travel over NVLink tile by tile while the tensor pipe works on the
+     next tile -- compute and the all-to-all are ONE kernel launch per destination, bracketed by two
+     stream-ordered symmetric-memory barriers.  Destinations are visited in a rank-staggered order
+     so that no two ranks write to the same peer at the same time.
+
+   All end with ``g'[i in I_r, :, :, :]`` on rank ``r``.  Per-destination GEMMs make every exchanged
    chunk contiguous, so no pack/unpack pass exists; chunk ``d+1`` is computed while chunk ``d`` is in
    flight (communication on NCCL's own stream, ``async_op=True``).
 
@@ -101,12 +109,13 @@ class SlabTransform:
     returns ``g'[i in I_r, :, :, :]`` (``out_range()``)."""
 
     def __init__(self, n, mode="reduce_scatter", group=None, gemm=None):
-        assert mode in ("reduce_scatter", "all_to_all")
+        assert mode in ("reduce_scatter", "all_to_all", "p2p")
         self.n, self.mode, self.group = int(n), mode, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.gemm = gemm or _cuda_gemm_tn
-        if mode == "all_to_all":
+        self._symm = {}
+        if mode in ("all_to_all", "p2p"):
             # equal splits keep all_to_all_single simple: n^2 trailing pairs and n leading indices
             assert (self.n * self.n) % self.world == 0 and self.n % self.world == 0, \
                 "all_to_all mode needs world_size | n"
@@ -142,6 +151,9 @@ class SlabTransform:
         if self.mode == "reduce_scatter":
             t1 = self._quarter1_reduce_scatter(g_slab, C0)
             rest = (C1, C2, C3)
+        elif self.mode == "p2p" and self.world > 1:
+            t1 = self._quarters12_p2p(g_slab, C0, C1)
+            rest = (C2, C3)
         else:
             t1 = self._quarters12_all_to_all(g_slab, C0, C1)
             rest = (C2, C3)
@@ -198,6 +210,35 @@ class SlabTransform:
         recv = torch.empty_like(send)                                 # chunk s: [rs in RS_s, i_loc, j]
         dist.all_to_all_single(recv.reshape(-1), send.reshape(-1), group=self.group)
         return recv.reshape(n, n * blk * n)                          # [r, (s i_loc j)]
+
+    def _symmetric_recv(self, shape, device):
+        """Receive buffer of this rank, peer-mapped on every rank (allocated once per shape)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        key = tuple(shape)
+        if key not in self._symm:
+            buf = symm_mem.empty(shape, dtype=F64, device=device)
+            group = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, group)
+            self._symm[key] = (buf, hdl)
+        return self._symm[key]
+
+    def _quarters12_p2p(self, g_slab, C0, C1):
+        n, W, blk = self.n, self.world, self.blk
+        lo, hi = self.in_range()
+        nrs = hi - lo
+        shape = (W, nrs, blk, n)                                        # chunk s: [rs in RS_s, i_loc, j]
+        recv, hdl = self._symmetric_recv(shape, g_slab.device)
+        At = g_slab.reshape(n, n * nrs)                                 # [p, (q rs_loc)]
+        t1 = torch.empty(n * nrs, blk, dtype=F64, device=g_slab.device)
+        hdl.barrier()                                                   # peers are done reading their recv buffers
+        for step in range(W):
+            d = (self.rank + step) % W                                  # staggered: one writer per peer at a time
+            self.gemm(At, C0[:, d * blk:(d + 1) * blk].contiguous(), t1)        # [(q rs_loc), i_d]
+            peer = hdl.get_buffer(d, shape, F64)                        # rank d's receive buffer, mapped here
+            # quarter 2 for destination d: the GEMM epilogue writes straight into peer memory
+            self.gemm(t1.reshape(n, nrs * blk), C1, peer[self.rank].reshape(nrs * blk, n))
+        hdl.barrier()                                                   # every rank's stores have landed
+        return recv.reshape(n, n * blk * n)                             # [r, (s i_loc j)]
 
     def _global_rank(self, group_rank):
         if self.group is None:
