@@ -208,3 +208,16 @@ def test_oo_pqc_full_optimization_converges():
     g = oo.full_gradient(theta_l[-1])
     assert g.abs().max().item() < 1e-5
     assert len(theta_l) == len(kappa_l) == len(coeff_l) == len(eig_l) == len(energy_l)
+
+
+def test_device_resident_newton_raphson():
+    """CUDA tensors in -> CUDA tensors out: the whole orbital optimisation (G, H, eigh, line search)
+    stays on the device and follows the host-tensor trajectory."""
+    c = load_case("n7_cas44")
+    oo_h, oo_d = make_oo(c), make_oo(c)
+    with contextlib.redirect_stdout(io.StringIO()):
+        th = oo_h.orbital_optimization(c.one_rdm, c.two_rdm, max_iterations=5)
+        td = oo_d.orbital_optimization(c.one_rdm.cuda(), c.two_rdm.cuda(), max_iterations=5)
+    assert np.abs(np.asarray(th[:3]) - np.asarray(td[:3])).max() < 1e-8
+    g = oo_d.kappa_matrix_to_vector(oo_d.analytic_gradient(c.one_rdm.cuda(), c.two_rdm.cuda()))
+    assert g.device.type == "cuda"

@@ -109,3 +109,26 @@ def test_analytic_derivatives_equal_autograd(name):
 def test_odd_core_electrons_raises():
     with pytest.raises(ValueError):
         orc.active_space_idx(7, 9, 4, 4)
+
+
+@pytest.mark.parametrize("no,na", [(0, 3), (1, 2), (3, 4), (6, 4), (4, 6), (10, 3), (18, 6)])
+def test_hessian_sparse_row_bound(no, na):
+    """The CUDA Hessian stores the non-dense part of At in ELL rows of width 2 na^2 + 2 (no+na) + 8
+    (csrc/hessian.cu, class_hess_layout).  Count the structural non-zeros of the reference's full-space
+    2-RDM (full_rdms, oo_energy.py:342-379) outside the act-act block and check the bound."""
+    gen = torch.Generator().manual_seed(0)
+    one = torch.rand(na, na, dtype=torch.float64, generator=gen) + 0.5          # no accidental zeros
+    two = torch.rand(na, na, na, na, dtype=torch.float64, generator=gen) + 0.5
+    ni = no + na
+    occ, act = np.arange(no), no + np.arange(na)
+    d1, d2 = orc.full_rdms(one, two, ni, occ, act)
+    a1 = (d2.permute(0, 2, 1, 3) + d2.permute(0, 3, 1, 2)) != 0     # [(p r),(m n)]
+    a2 = d2 != 0                                                    # [(p r),(m n)] = G_prmn
+    worst = 0
+    for p in range(ni):
+        for r in range(ni):
+            nnz = int(a1[p, r].sum()) + int(a2[p, r].sum()) + int(d1[p, r] != 0)
+            if p >= no and r >= no:                                  # dense block handled by the GEMM
+                nnz -= int(a1[p, r][no:, no:].sum()) + int(a2[p, r][no:, no:].sum()) + int(d1[p, r] != 0)
+            worst = max(worst, nnz)
+    assert worst <= 2 * na * na + 2 * ni + 8, worst
