@@ -39,11 +39,11 @@ _SIGNATURES = {
     "oo_kappa_rotation_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
                                      _size, _ptr]),
     "oo_expm_f64": (_i32, [_ptr, _f64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
-    "oo_mo_coeff_f64": (_i32, [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
-    "oo_int1e_transform_f64": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_mo_coeff_f64": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_int1e_transform_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
     "oo_int2e_transform_f64": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32,
                                       _ptr, _ptr, _size, _ptr]),
-    "oo_active_hamiltonian_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr,
+    "oo_active_hamiltonian_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr, _ptr,
                                          _ptr, _ptr]),
     "oo_energy_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _ptr, _ptr]),
     "oo_fock_gradient_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32,
@@ -53,7 +53,7 @@ _SIGNATURES = {
                               _ptr, _ptr, _size, _ptr]),
     "oo_transpose_f64": (_i32, [_ptr, _ptr, _i64, _i64, _ptr]),
     "oo_class_transform_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
-    "oo_class_active_hamiltonian_f64": (_i32, [_ptr, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr,
+    "oo_class_active_hamiltonian_f64": (_i32, [_ptr, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr, _ptr,
                                                _ptr, _ptr]),
     "oo_class_fock_gradient_f64": (_i32, [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                                           _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),

@@ -52,19 +52,6 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict
     }
 }
 
-// dst[c][b][a][v] = src[a][b][c][v]  (vectors of V doubles stay contiguous)
-__global__ void __launch_bounds__(256) swap02_kernel(const double *__restrict__ src, double *__restrict__ dst,
-                                                     int A, int B, int C, int V) {
-    // one CTA per (c, b): copies the A vectors src[a][b][c][:] -> dst[c][b][a][:]
-    const int c = blockIdx.x, b = blockIdx.y;
-    const int64_t total = (int64_t)A * V;
-    double *out = dst + ((int64_t)c * B + b) * total;
-    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-        const int a = (int)(i / V), v = (int)(i % V);
-        out[i] = src[(((int64_t)a * B + b) * C + c) * V + v];
-    }
-}
-
 }  // namespace
 
 int transpose(const double *src, double *dst, int64_t rows, int64_t cols, cudaStream_t stream) {

@@ -14,16 +14,13 @@
 namespace oo {
 namespace {
 
-__device__ __forceinline__ int64_t idx4(int p, int q, int r, int s, int ld) {
-    return (((int64_t)p * ld + q) * ld + r) * ld + s;
-}
-
 // ---------------------------------------------------------------- active Hamiltonian
 // grid (1 + na*na + ceil(na^4/256), batch).  block 0: c0; blocks 1..na^2: c1[t,u]; rest: c2.
 template <class GV>
 __global__ void __launch_bounds__(256)
 active_hamiltonian_kernel(const double *__restrict__ h, int64_t h_stride, const GV gv, int no, int na,
-                          int ld, double e_nuc, double *__restrict__ c0, double *__restrict__ c1,
+                          int ld, double e_nuc, const double *__restrict__ e_nuc_b, double *__restrict__ c0,
+                          double *__restrict__ c1,
                           double *__restrict__ c2) {
     __shared__ double scratch[32];
     const int b = blockIdx.y;
@@ -41,7 +38,7 @@ active_hamiltonian_kernel(const double *__restrict__ h, int64_t h_stride, const 
             if (j == 0) s += 2.0 * hb[(int64_t)i * ld + i];
         }
         s = block_sum(s, scratch);
-        if (threadIdx.x == 0) c0[b] = s + e_nuc;
+        if (threadIdx.x == 0) c0[b] = s + (e_nuc_b ? e_nuc_b[b] : e_nuc);
     } else if (blk <= na2) {
         const int t = (blk - 1) / na, u = (blk - 1) % na;
         const int T = no + t, U = no + u;
@@ -193,7 +190,6 @@ fock_gradient_vjp_kernel(const GV g, const double *__restrict__ FI,
                          double *__restrict__ gbar1, double *__restrict__ gbar2) {
     __shared__ double scratch[32];
     const int na2 = na * na;
-    const int64_t mat = (int64_t)ld * ld;
     auto fbar = [&](int p, int q) {
         return 2.0 * (Gbar[(int64_t)p * ld + q] - Gbar[(int64_t)q * ld + p]);
     };
@@ -264,14 +260,15 @@ __global__ void pad_copy_kernel(const double *__restrict__ src, double *__restri
 
 template <class GV>
 static int active_hamiltonian_t(const double *h, int64_t h_stride, const GV &gv, int no, int na, int N,
-                                int ld, int batch, double e_nuc, double *c0, double *c1, double *c2,
+                                int ld, int batch, double e_nuc, const double *e_nuc_b, double *c0, double *c1,
+                                double *c2,
                                 cudaStream_t stream) {
     OO_REQUIRE(h && c0 && c1 && c2);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && batch > 0);
     if (batch > 65535) return OO_ERR_UNSUPPORTED;
     const int64_t na4 = (int64_t)na * na * na * na;
     dim3 grid((unsigned)(1 + na * na + ceil_div(na4, 256)), (unsigned)batch);
-    active_hamiltonian_kernel<GV><<<grid, 256, 0, stream>>>(h, h_stride, gv, no, na, ld, e_nuc, c0, c1, c2);
+    active_hamiltonian_kernel<GV><<<grid, 256, 0, stream>>>(h, h_stride, gv, no, na, ld, e_nuc, e_nuc_b, c0, c1, c2);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -347,10 +344,11 @@ static inline const double *class_h(const double *cls, int ld, int nIp) {
 }
 
 int active_hamiltonian(const double *h, const double *g, int no, int na, int N, int ld, int batch,
-                       double e_nuc, double *c0, double *c1, double *c2, cudaStream_t stream) {
+                       double e_nuc, const double *e_nuc_b, double *c0, double *c1, double *c2,
+                       cudaStream_t stream) {
     OO_REQUIRE(g);
-    return active_hamiltonian_t(h, (int64_t)ld * ld, full_view(g, ld), no, na, N, ld, batch, e_nuc, c0, c1, c2,
-                                stream);
+    return active_hamiltonian_t(h, (int64_t)ld * ld, full_view(g, ld), no, na, N, ld, batch, e_nuc, e_nuc_b, c0,
+                                c1, c2, stream);
 }
 
 int fock_gradient(const double *h, const double *g, const double *d1, int64_t sd1, const double *d2,
@@ -370,11 +368,12 @@ int fock_gradient_vjp(const double *g, const double *FI, const double *Gbar, int
 
 // ---- the same contractions on the class tensors of the partial transform (classes.cu)
 int class_active_hamiltonian(const double *cls, int no, int na, int N, int ld, int nIp, int batch,
-                             double e_nuc, double *c0, double *c1, double *c2, cudaStream_t stream) {
+                             double e_nuc, const double *e_nuc_b, double *c0, double *c1, double *c2,
+                             cudaStream_t stream) {
     OO_REQUIRE(cls && nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
     const ClassView v = class_view(cls, ld, nIp);
-    return active_hamiltonian_t(class_h(cls, ld, nIp), v.batch_stride, v, no, na, N, ld, batch, e_nuc, c0, c1,
-                                c2, stream);
+    return active_hamiltonian_t(class_h(cls, ld, nIp), v.batch_stride, v, no, na, N, ld, batch, e_nuc, e_nuc_b,
+                                c0, c1, c2, stream);
 }
 
 int class_fock_gradient(const double *cls, const double *d1, int64_t sd1, const double *d2, int64_t sd2,
@@ -411,9 +410,9 @@ int pad_copy(const double *src, double *dst, int N, int ld, int rank, int batch,
 extern "C" {
 
 int oo_active_hamiltonian_f64(const double *h_mo, const double *g_mo, int no, int na, int N, int ld,
-                              int batch, double e_nuc, double *c0, double *c1, double *c2,
-                              void *stream) {
-    return oo::active_hamiltonian(h_mo, g_mo, no, na, N, ld, batch, e_nuc, c0, c1, c2,
+                              int batch, double e_nuc, const double *e_nuc_batch, double *c0, double *c1,
+                              double *c2, void *stream) {
+    return oo::active_hamiltonian(h_mo, g_mo, no, na, N, ld, batch, e_nuc, e_nuc_batch, c0, c1, c2,
                                   (cudaStream_t)stream);
 }
 
@@ -446,8 +445,9 @@ int oo_pad_copy_f64(const double *src, double *dst, int N, int ld, int rank, int
 extern "C" {
 
 int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp, int batch,
-                                    double e_nuc, double *c0, double *c1, double *c2, void *stream) {
-    return oo::class_active_hamiltonian(cls, no, na, N, ld, nIp, batch, e_nuc, c0, c1, c2,
+                                    double e_nuc, const double *e_nuc_batch, double *c0, double *c1,
+                                    double *c2, void *stream) {
+    return oo::class_active_hamiltonian(cls, no, na, N, ld, nIp, batch, e_nuc, e_nuc_batch, c0, c1, c2,
                                         (cudaStream_t)stream);
 }
 

@@ -35,6 +35,7 @@ struct TnCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
     static_assert(WTM % 16 == 0 && WTN % 16 == 0, "warp tile must cover whole 16-wide chunks");
     static_assert(BK % 8 == 0, "BK must be a multiple of 8");
+    static_assert((BK / 4) % 2 == 0, "the substep double buffer assumes an even number of substeps per k-block");
     static_assert(CHUNK_BYTES % 1024 == 0, "chunks must keep the 1024B swizzle alignment");
 };
 
@@ -152,37 +153,57 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                 for (int ni = 0; ni < Cfg::NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-            for (int kb = 0; kb < args.kblocks; ++kb, ++it) {
+            // Software pipeline over the SUBSTEPS (4 k values each: kk = 8-row swizzle atom, j = k parity):
+            // the fragments of substep s+1 -- or of the next k-block's first substep, after waiting for
+            // its stage -- are requested before the DMMAs of substep s are issued, so shared-memory
+            // latency hides behind MT*NT tensor instructions even across k-block boundaries.
+            constexpr int SUB = Cfg::BK / 4;            // substeps per k-block
+            double a[2][Cfg::MT], bf[2][Cfg::NT];
+            uint32_t loaded = 0, loaded_next = 0;       // XOR of the high words read from the current / next stage
+            auto load_frags = [&](int buf, uint32_t st, int sub, uint32_t &lx) {
+                const uint32_t sbase = smem_base + st * Cfg::STAGE_BYTES;
+                const uint32_t abase = sbase + a_warp_off, bbase = sbase + b_warp_off;
+                const int kk = sub >> 1, j = sub & 1;
+#pragma unroll
+                for (int mi = 0; mi < Cfg::MT; ++mi)
+                    a[buf][mi] = lds_f64(abase + (mi >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[mi & 1][j]);
+#pragma unroll
+                for (int ni = 0; ni < Cfg::NT; ++ni)
+                    bf[buf][ni] = lds_f64(bbase + (ni >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[ni & 1][j]);
+#ifndef OO_TN_DIAG_NO_RELEASE_DEPENDENCY   /* diagnostic builds only: measures what the dependency costs */
+#pragma unroll
+                for (int mi = 0; mi < Cfg::MT; ++mi) lx ^= (uint32_t)__double2hiint(a[buf][mi]);
+#pragma unroll
+                for (int ni = 0; ni < Cfg::NT; ++ni) lx ^= (uint32_t)__double2hiint(bf[buf][ni]);
+#endif
+            };
+            {
                 const uint32_t stage = it & (Cfg::STAGES - 1);
                 mbar_wait(&full_bar[stage], (it / Cfg::STAGES) & 1u);
-                const uint32_t sbase = smem_base + stage * Cfg::STAGE_BYTES;
-                const uint32_t abase = sbase + a_warp_off;
-                const uint32_t bbase = sbase + b_warp_off;
-                uint32_t loaded = 0;   // XOR of the high words of everything read from this stage
+                load_frags(0, stage, 0, loaded);
+            }
+            for (int kb = 0; kb < args.kblocks; ++kb, ++it) {
+                const uint32_t stage = it & (Cfg::STAGES - 1);
 #pragma unroll
-                for (int kk = 0; kk < Cfg::BK / 8; ++kk) {
+                for (int sub = 0; sub < SUB; ++sub) {
+                    const int cur = sub & 1, nxt = cur ^ 1;
+                    if (sub + 1 < SUB) {
+                        load_frags(nxt, stage, sub + 1, loaded);
+                    } else if (kb + 1 < args.kblocks) {
+                        const uint32_t nstage = (it + 1) & (Cfg::STAGES - 1);
+                        mbar_wait(&full_bar[nstage], ((it + 1) / Cfg::STAGES) & 1u);
+                        load_frags(nxt, nstage, 0, loaded_next);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        double a[Cfg::MT], bf[Cfg::NT];
-#pragma unroll
-                        for (int mi = 0; mi < Cfg::MT; ++mi)
-                            a[mi] = lds_f64(abase + (mi >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[mi & 1][j]);
+                    for (int mi = 0; mi < Cfg::MT; ++mi)
 #pragma unroll
                         for (int ni = 0; ni < Cfg::NT; ++ni)
-                            bf[ni] = lds_f64(bbase + (ni >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[ni & 1][j]);
-#pragma unroll
-                        for (int mi = 0; mi < Cfg::MT; ++mi) loaded ^= (uint32_t)__double2hiint(a[mi]);
-#pragma unroll
-                        for (int ni = 0; ni < Cfg::NT; ++ni) loaded ^= (uint32_t)__double2hiint(bf[ni]);
-#pragma unroll
-                        for (int mi = 0; mi < Cfg::MT; ++mi)
-#pragma unroll
-                            for (int ni = 0; ni < Cfg::NT; ++ni)
-                                dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
-                    }
+                            dmma884(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], bf[cur][ni]);
                 }
                 // release the stage only once every load from it has landed in registers (see TnArgs::zero)
                 if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[stage]) + (loaded & args.zero));
+                loaded = loaded_next;
+                loaded_next = 0;
             }
 
             // epilogue: registers -> global (16-byte stores, rows of 64 B per MMA tile)

@@ -155,13 +155,14 @@ int expm_general(const double *Ain, double sign, int N, int ld, int batch, int s
 
 size_t int1e_ws_bytes(int ld, int batch) { return (size_t)batch * ld * ld * sizeof(double); }
 
-int mo_coeff(const double *X, const double *Coao, int64_t strideCoao, const double *U, int64_t strideU,
-             int N, int ld, int batch, double *Cout, void *ws, size_t ws_bytes, cudaStream_t stream) {
+int mo_coeff(const double *X, int64_t strideX, const double *Coao, int64_t strideCoao, const double *U,
+             int64_t strideU, int N, int ld, int batch, double *Cout, void *ws, size_t ws_bytes,
+             cudaStream_t stream) {
     OO_REQUIRE(X && Coao && Cout);
     OO_REQUIRE(N > 0 && ld >= N && batch > 0);
     const int64_t mat = (int64_t)ld * ld;
     if (!U)
-        return dgemm_small(0, 0, ld, ld, ld, 1.0, X, ld, 0, Coao, ld, strideCoao, 0.0, nullptr, ld, 0, 0.0,
+        return dgemm_small(0, 0, ld, ld, ld, 1.0, X, ld, strideX, Coao, ld, strideCoao, 0.0, nullptr, ld, 0, 0.0,
                            Cout, ld, mat, batch, stream, 0);
     OO_REQUIRE(ws);
     if (ws_bytes < int1e_ws_bytes(ld, batch)) return OO_ERR_WORKSPACE;
@@ -169,19 +170,19 @@ int mo_coeff(const double *X, const double *Coao, int64_t strideCoao, const doub
     int rc = dgemm_small(0, 0, ld, ld, ld, 1.0, Coao, ld, strideCoao, U, ld, strideU, 0.0, nullptr, ld, 0,
                          0.0, T, ld, mat, batch, stream, 0);
     if (rc) return rc;
-    return dgemm_small(0, 0, ld, ld, ld, 1.0, X, ld, 0, T, ld, mat, 0.0, nullptr, ld, 0, 0.0, Cout, ld,
+    return dgemm_small(0, 0, ld, ld, ld, 1.0, X, ld, strideX, T, ld, mat, 0.0, nullptr, ld, 0, 0.0, Cout, ld,
                        mat, batch, stream, 0);
 }
 
-int int1e_transform(const double *h, const double *C, int64_t strideC, int N, int ld, int batch,
-                    double *hmo, void *ws, size_t ws_bytes, cudaStream_t stream) {
+int int1e_transform(const double *h, int64_t stride_h, const double *C, int64_t strideC, int N, int ld,
+                    int batch, double *hmo, void *ws, size_t ws_bytes, cudaStream_t stream) {
     OO_REQUIRE(h && C && hmo && ws);
     OO_REQUIRE(N > 0 && ld >= N && batch > 0);
     if (ws_bytes < int1e_ws_bytes(ld, batch)) return OO_ERR_WORKSPACE;
     const int64_t mat = (int64_t)ld * ld;
     double *T = reinterpret_cast<double *>(ws);
     // T = h C ; h' = C^T T
-    int rc = dgemm_small(0, 0, ld, ld, ld, 1.0, h, ld, 0, C, ld, strideC, 0.0, nullptr, ld, 0, 0.0, T, ld,
+    int rc = dgemm_small(0, 0, ld, ld, ld, 1.0, h, ld, stride_h, C, ld, strideC, 0.0, nullptr, ld, 0, 0.0, T, ld,
                          mat, batch, stream, 0);
     if (rc) return rc;
     return dgemm_small(1, 0, ld, ld, ld, 1.0, C, ld, strideC, T, ld, mat, 0.0, nullptr, ld, 0, 0.0, hmo,
@@ -204,16 +205,16 @@ int oo_expm_f64(const double *A, double sign, int N, int ld, int batch, int squa
     return oo::expm_general(A, sign, N, ld, batch, squarings, U, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int oo_mo_coeff_f64(const double *X, const double *Coao, int64_t strideCoao, const double *U,
+int oo_mo_coeff_f64(const double *X, int64_t strideX, const double *Coao, int64_t strideCoao, const double *U,
                     int64_t strideU, int N, int ld, int batch, double *Cout, void *ws, size_t ws_bytes,
                     void *stream) {
-    return oo::mo_coeff(X, Coao, strideCoao, U, strideU, N, ld, batch, Cout, ws, ws_bytes,
+    return oo::mo_coeff(X, strideX, Coao, strideCoao, U, strideU, N, ld, batch, Cout, ws, ws_bytes,
                         (cudaStream_t)stream);
 }
 
-int oo_int1e_transform_f64(const double *h_ao, const double *C, int64_t strideC, int N, int ld,
-                           int batch, double *h_mo, void *ws, size_t ws_bytes, void *stream) {
-    return oo::int1e_transform(h_ao, C, strideC, N, ld, batch, h_mo, ws, ws_bytes,
+int oo_int1e_transform_f64(const double *h_ao, int64_t stride_h, const double *C, int64_t strideC, int N,
+                           int ld, int batch, double *h_mo, void *ws, size_t ws_bytes, void *stream) {
+    return oo::int1e_transform(h_ao, stride_h, C, strideC, N, ld, batch, h_mo, ws, ws_bytes,
                                (cudaStream_t)stream);
 }
 }

@@ -78,7 +78,11 @@ class HotPathEngine:
             cls._tensor_engines[key] = cls(None, None, None, 0.0, nao, 0, max(1, min(2, int(nao))), [], device=dev)
         return cls._tensor_engines[key]
 
-    def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None):
+    def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None,
+                 n_geometries=0):
+        """``n_geometries`` > 0: ``int1e_ao (G,N,N)``, ``int2e_ao (G,N,N,N,N)``, ``oao_coeff (G,N,N)``,
+        ``nuc (G,)`` hold one molecule geometry each (same orbital classes); evaluation ``b`` of a
+        batch then uses geometry ``b`` (class path only)."""
         if not torch.cuda.is_available():
             raise _lib.OOError("auto_oo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -87,15 +91,18 @@ class HotPathEngine:
         self.ld = pad_even(self.N)
         self.no, self.na = int(no), int(na)
         self.nI = self.no + self.na
-        self.nuc = float(nuc)
+        self.n_geom = int(n_geometries)
+        G = self.n_geom if self.n_geom > 0 else None
+        self.nuc = float(nuc) if G is None else 0.0
         pl, pr = tril_pair_table(self.N, params_idx)
         self.nk = len(pl)
         self.pair_l = torch.as_tensor(pl, device=self.device)
         self.pair_r = torch.as_tensor(pr, device=self.device)
         with torch.cuda.device(self.device):
-            self.h_ao = None if int1e_ao is None else self.to_padded(int1e_ao, 2)
-            self.X = None if oao_coeff is None else self.to_padded(oao_coeff, 2)
-            self.g_ao = None if int2e_ao is None else self.to_padded(int2e_ao, 4)
+            self.h_ao = None if int1e_ao is None else self.to_padded(int1e_ao, 2, batch=G)
+            self.X = None if oao_coeff is None else self.to_padded(oao_coeff, 2, batch=G)
+            self.g_ao = None if int2e_ao is None else self.to_padded(int2e_ao, 4, batch=G)
+            self.nuc_dev = None if G is None else self.dev(np.asarray(nuc, dtype=np.float64).reshape(G))
         self.nIp = pad_even(self.nI)                   # class index padded to even (TMA strides)
         self.g_pairT = None                            # g_ao[p,q,r,s] stored as [r,s,p,q]; built on first use
         self._ws = {}
@@ -230,29 +237,35 @@ class HotPathEngine:
         return U
 
     def mo_coeff(self, oao_mo_coeff, U=None):
-        """C' = X C_oao U  (padded, batched over U)."""
+        """C' = X C_oao U  (padded, batched over U; one X per evaluation for geometry batches)."""
         Coao = oao_mo_coeff if oao_mo_coeff.dim() == 3 else oao_mo_coeff[None]
         B = max(Coao.shape[0], 1 if U is None else U.shape[0])
+        if self.n_geom:
+            assert B == self.n_geom, "a geometry batch evaluates exactly one rotation per geometry"
         out = torch.empty(B, self.ld, self.ld, dtype=F64, device=self.device)
         nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, self.ld, 0, B)
         ws = self.workspace("i1e", nbytes)
         mat = self.ld * self.ld
         sC = mat if Coao.shape[0] > 1 else 0
         sU = 0 if U is None or U.shape[0] == 1 else mat
-        self._check(self.lib.oo_mo_coeff_f64(_p(self.X), _p(Coao), sC, _p(U), sU, self.N, self.ld, B,
+        self._check(self.lib.oo_mo_coeff_f64(_p(self.X), mat if self.n_geom > 1 else 0, _p(Coao), sC, _p(U), sU,
+                                             self.N, self.ld, B,
                                              _p(out), _p(ws), nbytes, self.stream), "mo_coeff")
         return out
 
     # ------------------------------------------------------------------ K2
-    def int1e_transform(self, C, h_ao=None):
+    def int1e_transform(self, C, h_ao=None, geo=(0, None)):
         C = C if C.dim() == 3 else C[None]
         B = C.shape[0]
         out = torch.empty(B, self.ld, self.ld, dtype=F64, device=self.device)
         nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, self.ld, 0, B)
         ws = self.workspace("i1e", nbytes)
         mat = self.ld * self.ld
-        h = self.h_ao if h_ao is None else h_ao
-        self._check(self.lib.oo_int1e_transform_f64(_p(h), _p(C), mat if B > 1 else 0, self.N, self.ld, B,
+        if h_ao is None:
+            h, sh = self._geo(self.h_ao, geo[0], geo[0] + B)
+        else:
+            h, sh = h_ao, 0
+        self._check(self.lib.oo_int1e_transform_f64(_p(h), sh, _p(C), mat if B > 1 else 0, self.N, self.ld, B,
                                                     _p(out), _p(ws), nbytes, self.stream), "int1e_transform")
         return out
 
@@ -303,9 +316,19 @@ class HotPathEngine:
         if self.g_pairT is None:
             ld2 = self.ld * self.ld
             out = torch.empty_like(self.g_ao)
-            self._check(self.lib.oo_transpose_f64(_p(self.g_ao), _p(out), ld2, ld2, self.stream), "transpose")
+            src, dst = self.g_ao.reshape(-1, ld2, ld2), out.reshape(-1, ld2, ld2)
+            for i in range(src.shape[0]):
+                self._check(self.lib.oo_transpose_f64(_p(src[i]), _p(dst[i]), ld2, ld2, self.stream), "transpose")
             self.g_pairT = out
         return self.g_pairT
+
+    def _geo(self, t, lo, hi):
+        """(tensor, per-evaluation stride) of a per-problem / per-geometry resident tensor for the
+        evaluations [lo, hi) of a batch."""
+        if self.n_geom == 0:
+            return t, 0
+        sl = t[lo:hi]
+        return sl, (sl[0].numel() if hi - lo > 1 else 0)
 
     def drop_full_eri(self):
         """Free g_ao (and the full-transform buffers) once g_pairT exists: the class path needs only
@@ -318,7 +341,7 @@ class HotPathEngine:
     def class_rows(self):
         return 2 * self.nIp * self.nIp + 1
 
-    def class_integrals(self, C, out=None):
+    def class_integrals(self, C, out=None, geo_lo=0):
         """Class buffers [K rows; J rows; h' row] for padded C (ld, ld) or (B, ld, ld):
         returns (B, 2 nIp^2 + 1, ld, ld); every GEMM step is one batched launch."""
         C = C.reshape(-1, self.ld, self.ld)
@@ -327,16 +350,18 @@ class HotPathEngine:
                                                                            device=self.device)
         nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, B)
         ws = self.workspace("cls", nbytes)
-        self._check(self.lib.oo_class_transform_f64(_p(self.pair_transposed_eri()), 0, _p(C), ld * ld if B > 1 else 0,
+        gp, sg = self._geo(self.pair_transposed_eri(), geo_lo, geo_lo + B)
+        self._check(self.lib.oo_class_transform_f64(_p(gp), sg, _p(C), ld * ld if B > 1 else 0,
                                                     self.N, ld, nIp, B, _p(cls), _p(ws), nbytes, self.stream),
                     "class_transform")
         if B == 1:                                           # h' = C^T h C straight into the last row
             nb1 = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, ld, 0, 1)
             ws1 = self.workspace("i1e", nb1)
-            self._check(self.lib.oo_int1e_transform_f64(_p(self.h_ao), _p(C), 0, self.N, ld, 1, _p(cls[0, rows - 1]),
+            h1, _ = self._geo(self.h_ao, geo_lo, geo_lo + 1)
+            self._check(self.lib.oo_int1e_transform_f64(_p(h1), 0, _p(C), 0, self.N, ld, 1, _p(cls[0, rows - 1]),
                                                         _p(ws1), nb1, self.stream), "int1e_transform")
         else:                                                # batched: dense scratch, then a strided device copy
-            cls[:, rows - 1].copy_(self.int1e_transform(C))
+            cls[:, rows - 1].copy_(self.int1e_transform(C, geo=(geo_lo, None)))
         return cls
 
     def class_integrals_cached(self, C):
@@ -350,13 +375,15 @@ class HotPathEngine:
         self._ccache_key, self._ccache_val = C.clone(), cls
         return cls
 
-    def class_active_hamiltonian(self, cls):
+    def class_active_hamiltonian(self, cls, geo_lo=0):
         na, B = self.na, cls.shape[0]
+        nuc_b = None if self.n_geom == 0 else self.nuc_dev[geo_lo:geo_lo + B]
         c0 = torch.empty(B, dtype=F64, device=self.device)
         c1 = torch.empty(B, na, na, dtype=F64, device=self.device)
         c2 = torch.empty(B, na, na, na, na, dtype=F64, device=self.device)
         self._check(self.lib.oo_class_active_hamiltonian_f64(_p(cls), self.no, na, self.N, self.ld, self.nIp, B,
-                                                             self.nuc, _p(c0), _p(c1), _p(c2), self.stream),
+                                                             self.nuc, _p(nuc_b), _p(c0), _p(c1), _p(c2),
+                                                             self.stream),
                     "class_active_hamiltonian")
         return c0, c1, c2
 
@@ -415,7 +442,7 @@ class HotPathEngine:
         c1 = torch.empty(B, na, na, dtype=F64, device=self.device)
         c2 = torch.empty(B, na, na, na, na, dtype=F64, device=self.device)
         self._check(self.lib.oo_active_hamiltonian_f64(_p(h), _p(g), self.no, na, self.N, self.ld, B,
-                                                       self.nuc, _p(c0), _p(c1), _p(c2), self.stream),
+                                                       self.nuc, None, _p(c0), _p(c1), _p(c2), self.stream),
                     "active_hamiltonian")
         return c0, c1, c2
 
@@ -533,6 +560,7 @@ class HotPathEngine:
         H = None
         if want_hessian:
             H = H_out if H_out is not None else torch.empty(B, self.nk, self.nk, dtype=F64, device=self.device)
+        assert path == "class" or self.n_geom == 0, "geometry batches use the class path"
         if path == "class":
             chunk = self.class_chunk(B)
             cbuf = self._ccache_val
@@ -542,13 +570,13 @@ class HotPathEngine:
                 if transform_events is not None:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record()
-                cbuf = self.class_integrals(C[lo:hi], out=cbuf)
+                cbuf = self.class_integrals(C[lo:hi], out=cbuf, geo_lo=lo)
                 if transform_events is not None:
                     ev[1].record()
                     transform_events.append(ev)
                 d1b = d1[lo:hi] if d1.dim() == 3 else d1
                 d2b = d2[lo:hi] if d2.dim() == 5 else d2
-                c0, c1, c2 = self.class_active_hamiltonian(cbuf)
+                c0, c1, c2 = self.class_active_hamiltonian(cbuf, geo_lo=lo)
                 E[lo:hi] = self.energy(c0, c1, c2, d1b, d2b)
                 FI, FA, F, _, gv = self.class_fock_gradient(cbuf, d1b, d2b, want_matrix=False)
                 G[lo:hi] = gv

@@ -31,7 +31,7 @@ from .engine import HotPathEngine, F64
 from .utils.newton_raphson import NewtonStep
 
 __all__ = [
-    "OO_energy", "OrbitalHessian", "general_4index_transform", "uniform_4index_transform",
+    "OO_energy", "OO_energy_geometries", "OrbitalHessian", "general_4index_transform", "uniform_4index_transform",
     "int1e_transform", "int2e_transform", "mo_ao_to_mo_oao", "vector_to_skew_symmetric",
     "skew_symmetric_to_vector", "non_redundant_indices",
 ]
@@ -460,3 +460,54 @@ class OO_energy:
                     print("E_fin =", energy_l[-1])
                 break
         return energy_l
+
+
+class OO_energy_geometries:
+    """Many molecular geometries of one system (same basis size, same active space) evaluated
+    together -- the shape of the Berry-phase loop (``examples/Tutorial_Berry_phase.ipynb`` cell 22:
+    one ``Moldata_pyscf`` / ``OO_pqc`` per geometry, each needing energy, orbital gradient and
+    Hessian at its own integrals).  Every stage is ONE batched launch over the geometries.
+
+    ``mols``: sequence of duck-typed ``Moldata_pyscf`` objects; ``oao_mo_coeff``: ``(G, N, N)`` (or
+    one ``(N, N)`` matrix used for all).  ``energy_gradient_hessian(kappa, one_rdm, two_rdm)`` takes
+    ``kappa (G, n_kappa)`` and RDMs shared ``(na,na)/(na^4)`` or per geometry ``(G, ...)``."""
+
+    def __init__(self, mols, ncas, nelecas, oao_mo_coeff, freeze_active=False, device=None):
+        mols = list(mols)
+        assert len(mols) > 0
+        self.nao = mols[0].nao
+        assert all(m.nao == self.nao for m in mols), "all geometries must share the basis size"
+        self.ncas, self.nelecas = ncas, nelecas
+        self.occ_idx, self.act_idx, self.virt_idx = mols[0].get_active_space_idx(ncas, nelecas)
+        self.params_idx = non_redundant_indices(self.occ_idx, self.act_idx, self.virt_idx, freeze_active)
+        self.n_kappa = len(self.params_idx)
+        self.n_geometries = G = len(mols)
+        stack = lambda name: torch.stack([_as_tensor(getattr(m, name)) for m in mols])
+        self.engine = HotPathEngine(stack("int1e_ao"), stack("int2e_ao"), stack("oao_coeff"),
+                                    np.array([m.nuc for m in mols], dtype=np.float64), self.nao,
+                                    len(self.occ_idx), len(self.act_idx), self.params_idx, device=device,
+                                    n_geometries=G)
+        self.engine.drop_full_eri()                       # only the pair-transposed copy is needed
+        C = _as_tensor(oao_mo_coeff).detach().to(F64)
+        self.oao_mo_coeff = C if C.dim() == 3 else C[None].repeat(G, 1, 1)
+        assert self.oao_mo_coeff.shape[0] == G
+
+    def energy_gradient_hessian(self, kappa, one_rdm, two_rdm, want_hessian=True):
+        """``(E (G,), gradient (G, n_kappa), Hessian (G, n_kappa, n_kappa))`` at
+        ``C_g expm(-K(kappa_g))`` for every geometry ``g``; results on the device of ``kappa``."""
+        eng = self.engine
+        kappa = _as_tensor(kappa).detach().reshape(self.n_geometries, self.n_kappa)
+        Coao = eng.to_padded(self.oao_mo_coeff, 2, batch=self.n_geometries)
+        E, G, H = eng.evaluate(Coao, eng.dev(one_rdm), eng.dev(two_rdm), kappa=eng.dev(kappa),
+                               want_hessian=want_hessian, path="class")
+        if kappa.device.type == "cpu":
+            return E.cpu(), G.cpu(), (H.cpu() if want_hessian else None)
+        return E, G, H
+
+    def rotate(self, kappa):
+        """``C_g <- C_g expm(-K(kappa_g))`` for every geometry (the re-basing step of the loop)."""
+        eng = self.engine
+        U = eng.rotation(_as_tensor(kappa).detach().reshape(self.n_geometries, self.n_kappa))
+        Coao = eng.to_padded(self.oao_mo_coeff, 2, batch=self.n_geometries)
+        new = torch.stack([eng.matmul(Coao[g], U[g]) for g in range(self.n_geometries)])
+        self.oao_mo_coeff = eng.from_padded(new, 2).to(self.oao_mo_coeff.device)

@@ -114,15 +114,16 @@ int oo_expm_f64(const double *A, double sign, int N, int ld, int batch, int squa
 
 /* ---- K1 epilogue / K2a ------------------------------------------------------
  * C'[b] = X * Coao[b] * U[b]          (oo_energy.py:173-176 mo_coeff, :201/:235)
- * strideCoao / strideU = 0 shares the matrix across the batch; U may be NULL.   */
-int oo_mo_coeff_f64(const double *X, const double *Coao, int64_t strideCoao,
+ * strideX / strideCoao / strideU = 0 shares the matrix across the batch (strideX != 0:
+ * one orthogonaliser per geometry); U may be NULL.                               */
+int oo_mo_coeff_f64(const double *X, int64_t strideX, const double *Coao, int64_t strideCoao,
                     const double *U, int64_t strideU, int N, int ld, int batch,
                     double *Cout, void *ws, size_t ws_bytes, void *stream);
 
 /* h'[b] = C[b]^T h C[b]               (oo_energy.py:44-46 int1e_transform)      */
-int oo_int1e_transform_f64(const double *h_ao, const double *C, int64_t strideC,
+int oo_int1e_transform_f64(const double *h_ao, int64_t stride_h, const double *C, int64_t strideC,
                            int N, int ld, int batch, double *h_mo,
-                           void *ws, size_t ws_bytes, void *stream);
+                           void *ws, size_t ws_bytes, void *stream);   /* stride_h != 0: h per geometry */
 
 /* ---- K2b: four-index transform ---------------------------------------------
  * g'[i,j,k,l] = sum_pqrs C0[p,i] C1[q,j] C2[r,k] C3[s,l] g[p,q,r,s]
@@ -144,8 +145,9 @@ int oo_int2e_transform_f64(const double *g_ao, int64_t strideG,
  * replaces utils/active_space.py:111-174 and :177-212.
  * c0[b], c1[b][na*na], c2[b][na^4] (dense, no padding).                          */
 int oo_active_hamiltonian_f64(const double *h_mo, const double *g_mo, int no, int na,
-                              int N, int ld, int batch, double e_nuc,
+                              int N, int ld, int batch, double e_nuc, const double *e_nuc_batch,
                               double *c0, double *c1, double *c2, void *stream);
+                              /* e_nuc_batch (device, batch doubles) overrides e_nuc when not NULL */
 
 /* E[b] = c0[b] + <c1[b],gamma[b]> + <c2[b],Gamma[b]>   (oo_energy.py:194-197)
  * stride_rdm1/2 = 0 shares the RDMs across the batch.                            */
@@ -207,8 +209,8 @@ int oo_class_transform_f64(const double *g_pairT, int64_t strideG, const double 
                            int N, int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
                            void *stream);   /* stride 0 = shared over the batch; cls[b] contiguous */
 int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp,
-                                    int batch, double e_nuc, double *c0, double *c1, double *c2,
-                                    void *stream);
+                                    int batch, double e_nuc, const double *e_nuc_batch, double *c0,
+                                    double *c1, double *c2, void *stream);
 int oo_class_fock_gradient_f64(const double *cls, const double *gamma, int64_t stride_rdm1,
                                const double *Gamma, int64_t stride_rdm2, int no, int na, int N,
                                int ld, int nIp, int batch, const int32_t *pair_l,
