@@ -301,6 +301,15 @@ class OO_energy:
         c0, c1, c2 = eng.integrals(C[0], kind=self.integral_path).active_hamiltonian()
         return _EnergyFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), eng, c0, c1, c2)
 
+    def energies_from_kappas(self, kappas, one_rdm, two_rdm):
+        """``energy_from_kappa`` for a batch ``kappas (B, n_kappa)`` in one pass (batched launches);
+        returns ``(B,)`` on the device of ``kappas``.  Used by the speculative line search."""
+        eng = self.engine
+        kappas = _as_tensor(kappas).detach().reshape(-1, self.n_kappa)
+        E, _, _ = eng.evaluate(eng.to_padded(self.oao_mo_coeff, 2), eng.dev(one_rdm), eng.dev(two_rdm),
+                               kappa=eng.dev(kappas), want_hessian=False, path=self.integral_path)
+        return E.to(kappas.device)
+
     # ------------------------------------------------------------------ Fock matrices / gradient
     def _padded_integrals(self, int1e_mo, int2e_mo):
         eng = self.engine
@@ -438,6 +447,9 @@ class OO_energy:
         the energy trajectory (reference ``oo_energy.py:426-474``: re-base after every step,
         convergence tested only for ``n > 1``, per-iteration line printed unless ``verbose`` is None)."""
         objective_fn = partial(self.energy_from_kappa, one_rdm=one_rdm, two_rdm=two_rdm)
+        # batched form for NewtonStep(speculate=k): a list of (kappa,) tuples -> energies
+        objective_fn.batched = lambda plist: self.energies_from_kappas(
+            torch.stack([_as_tensor(p[0]) for p in plist]), one_rdm, two_rdm)
         opt = NewtonStep(verbose=verbose, **kwargs)
         energy_l = []
         if verbose:

@@ -79,3 +79,30 @@ def test_log_barrier_line_search():
         x, _ = opt.damped_newton_step(f, (x,), g, h)
         assert abs(x.item()) < 1.0
     assert torch.autograd.functional.jacobian(f, x).abs().item() < 1e-8
+
+
+def test_speculative_line_search_equals_sequential():
+    """speculate=k evaluates k step lengths per batched call but must accept the same step.
+    f = sum sqrt(1 + x^2): the pure Newton step -x^3 overshoots for |x| > 1, so the search must damp."""
+    def f(x):
+        return torch.sum(torch.sqrt(1.0 + x ** 2))
+
+    calls = []
+
+    def batched(plist):
+        calls.append(len(plist))
+        return torch.stack([f(p[0]) for p in plist])
+
+    f.batched = batched
+    x_seq = torch.tensor([3.0, -2.0, 1.5], dtype=torch.float64)
+    x_spec = x_seq.clone()
+    for _ in range(10):
+        g = torch.autograd.functional.jacobian(f, x_seq)
+        h = torch.autograd.functional.hessian(f, x_seq)
+        x_seq, _ = NewtonStep(verbose=0).damped_newton_step(f, (x_seq,), g, h)
+        g = torch.autograd.functional.jacobian(f, x_spec)
+        h = torch.autograd.functional.hessian(f, x_spec)
+        x_spec, _ = NewtonStep(verbose=0, speculate=4).damped_newton_step(f, (x_spec,), g, h)
+        assert torch.equal(x_seq, x_spec)
+    assert calls and max(calls) <= 4
+    assert x_seq.abs().max().item() < 1e-6
