@@ -55,6 +55,56 @@ def case_inputs(name, nao, nelec, ncas, nelecas, freeze, kscale, rdm_kind, seed)
     return mol, one.detach(), two.detach()
 
 
+def reference_case(ref, mol, nelec, ncas, nelecas, freeze, C_oao, kappa_of, one, two, store, seed=0,
+                   trajectory=False):
+    """Run the verbatim reference on one problem; returns ``(fixture dict, oracle-vs-reference diffs)``.
+    ``kappa_of(n_kappa)`` supplies the rotation once the reference has counted the parameters."""
+    nao = mol.nao
+    oo = ref.oo_energy.OO_energy(mol, ncas, nelecas, oao_mo_coeff=C_oao,
+                                 freeze_active=freeze, interface='torch')
+    kappa = kappa_of(oo.n_kappa)
+    U = oo.kappa_to_mo_coeff(kappa)
+    Cp = oo.mo_coeff @ U
+    c0, c1, c2 = oo.get_active_integrals(Cp)
+    E = oo.energy_from_kappa(kappa, one, two)
+    G = oo.kappa_matrix_to_vector(oo.analytic_gradient(one, two, mo_coeff=Cp))
+    H = oo.full_hessian_to_matrix(oo.analytic_hessian(one, two, mo_coeff=Cp))
+    E0 = oo.energy_from_mo_coeff(oo.mo_coeff, one, two)
+    G0 = oo.kappa_matrix_to_vector(oo.analytic_gradient(one, two))
+
+    out = dict(
+        shape=np.array([nao, nelec, ncas, nelecas, int(freeze)]), seed=np.array(seed),
+        kappa=kappa.numpy(), one_rdm=one.numpy(), two_rdm=two.numpy(),
+        params_idx=np.asarray(oo.params_idx), U=U.numpy(), mo_coeff_rot=Cp.numpy(),
+        c0=np.asarray(float(c0)), c1=c1.numpy(), c2=c2.numpy(),
+        E=np.asarray(E.item()), G=G.numpy(), H=H.numpy(),
+        E0=np.asarray(E0.item()), G0=G0.numpy(),
+        checksum=np.array([float(np.sum(mol.int1e_ao)), float(np.sum(mol.int2e_ao)),
+                           float(np.sum(mol.oao_coeff)), float(np.sum(np.asarray(C_oao)))]),
+    )
+    if store:
+        out.update(int1e_ao=mol.int1e_ao, int2e_ao=mol.int2e_ao, overlap=mol.overlap,
+                   oao_coeff=mol.oao_coeff, oao_mo_coeff=np.asarray(C_oao), nuc=np.asarray(mol.nuc),
+                   int1e_mo=ref.oo_energy.int1e_transform(oo.int1e_ao, Cp).numpy(),
+                   int2e_mo=ref.oo_energy.int2e_transform(oo.int2e_ao, Cp).numpy())
+    if trajectory:
+        # orbital-only Newton-Raphson trajectory (oo_energy.py:426-474), fresh object
+        oo2 = ref.oo_energy.OO_energy(mol, ncas, nelecas, oao_mo_coeff=C_oao,
+                                      freeze_active=freeze, interface='torch')
+        with contextlib.redirect_stdout(io.StringIO()):
+            traj = oo2.orbital_optimization(one, two, conv_tol=1e-10, max_iterations=8, verbose=0)
+        out.update(nr_energies=np.asarray(traj), nr_oao_mo_coeff=oo2.oao_mo_coeff.numpy())
+
+    # oracle cross-check
+    prob = orc.OracleProblem(mol.int1e_ao, mol.int2e_ao, mol.oao_coeff, C_oao, mol.nuc,
+                             nelec, ncas, nelecas, freeze)
+    eo, go, ho = prob.evaluate(one, two, kappa)
+    hi = prob.hessian(one, two, kappa, ispace=True)
+    d = (abs(eo.item() - E.item()), (go - G).abs().max().item(), (ho - H).abs().max().item(),
+         (hi - H).abs().max().item())
+    return out, d, oo.n_kappa
+
+
 def main():
     ref = load_reference()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -62,52 +112,12 @@ def main():
     worst = 0.0
     for seed, (name, nao, nelec, ncas, nelecas, freeze, kscale, rdm_kind, store) in enumerate(CASES):
         mol, one, two = case_inputs(name, nao, nelec, ncas, nelecas, freeze, kscale, rdm_kind, seed)
-        C_oao = mol.random_oao_mo_coeff
-        oo = ref.oo_energy.OO_energy(mol, ncas, nelecas, oao_mo_coeff=C_oao,
-                                     freeze_active=freeze, interface='torch')
-        kappa = random_kappa(oo.n_kappa, seed=seed, scale=kscale)
-        U = oo.kappa_to_mo_coeff(kappa)
-        Cp = oo.mo_coeff @ U
-        c0, c1, c2 = oo.get_active_integrals(Cp)
-        E = oo.energy_from_kappa(kappa, one, two)
-        G = oo.kappa_matrix_to_vector(oo.analytic_gradient(one, two, mo_coeff=Cp))
-        H = oo.full_hessian_to_matrix(oo.analytic_hessian(one, two, mo_coeff=Cp))
-        E0 = oo.energy_from_mo_coeff(oo.mo_coeff, one, two)
-        G0 = oo.kappa_matrix_to_vector(oo.analytic_gradient(one, two))
-
-        out = dict(
-            shape=np.array([nao, nelec, ncas, nelecas, int(freeze)]), seed=np.array(seed),
-            kappa=kappa.numpy(), one_rdm=one.numpy(), two_rdm=two.numpy(),
-            params_idx=np.asarray(oo.params_idx), U=U.numpy(), mo_coeff_rot=Cp.numpy(),
-            c0=np.asarray(float(c0)), c1=c1.numpy(), c2=c2.numpy(),
-            E=np.asarray(E.item()), G=G.numpy(), H=H.numpy(),
-            E0=np.asarray(E0.item()), G0=G0.numpy(),
-            checksum=np.array([float(np.sum(mol.int1e_ao)), float(np.sum(mol.int2e_ao)),
-                               float(np.sum(mol.oao_coeff)), float(np.sum(C_oao))]),
-        )
-        if store:
-            out.update(int1e_ao=mol.int1e_ao, int2e_ao=mol.int2e_ao, overlap=mol.overlap,
-                       oao_coeff=mol.oao_coeff, oao_mo_coeff=C_oao, nuc=np.asarray(mol.nuc),
-                       int1e_mo=ref.oo_energy.int1e_transform(oo.int1e_ao, Cp).numpy(),
-                       int2e_mo=ref.oo_energy.int2e_transform(oo.int2e_ao, Cp).numpy())
-        if nao <= 13:
-            # orbital-only Newton-Raphson trajectory (oo_energy.py:426-474), fresh object
-            oo2 = ref.oo_energy.OO_energy(mol, ncas, nelecas, oao_mo_coeff=C_oao,
-                                          freeze_active=freeze, interface='torch')
-            with contextlib.redirect_stdout(io.StringIO()):
-                traj = oo2.orbital_optimization(one, two, conv_tol=1e-10, max_iterations=8, verbose=0)
-            out.update(nr_energies=np.asarray(traj), nr_oao_mo_coeff=oo2.oao_mo_coeff.numpy())
+        out, d, nk = reference_case(ref, mol, nelec, ncas, nelecas, freeze, mol.random_oao_mo_coeff,
+                                    lambda n: random_kappa(n, seed=seed, scale=kscale), one, two, store,
+                                    seed=seed, trajectory=nao <= 13)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
-
-        # oracle cross-check
-        prob = orc.OracleProblem(mol.int1e_ao, mol.int2e_ao, mol.oao_coeff, C_oao, mol.nuc,
-                                 nelec, ncas, nelecas, freeze)
-        eo, go, ho = prob.evaluate(one, two, kappa)
-        hi = prob.hessian(one, two, kappa, ispace=True)
-        d = (abs(eo.item() - E.item()), (go - G).abs().max().item(), (ho - H).abs().max().item(),
-             (hi - H).abs().max().item())
         worst = max(worst, *d)
-        print(f"{name:18s} N={nao:3d} nk={oo.n_kappa:4d} E={E.item():+.10f} "
+        print(f"{name:18s} N={nao:3d} nk={nk:4d} E={float(out['E']):+.10f} "
               f"|dE|={d[0]:.1e} |dG|={d[1]:.1e} |dH|={d[2]:.1e} |dH_ispace|={d[3]:.1e}")
 
     # general (non-symmetric) 4-index transform with four different matrices

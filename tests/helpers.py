@@ -9,7 +9,10 @@ from auto_oo_b200.synthetic import SyntheticMol
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-SMALL_CASES = ["n7_cas44", "n7_cas44_frozen", "n8_nocore", "n11_cas43", "n13_cas22", "n13_bigkappa"]
+# real molecules (STO-3G integrals rebuilt by oracle/gto_sto3g.py, outputs by the verbatim reference,
+# oracle/make_molecular_golden.py): formaldimine at the reference's two test geometries, water (config 1)
+MOL_CASES = ["mol_ch2nh_sto3g_cas22", "mol_ch2nh_sto3g_cas44", "mol_h2o_sto3g_cas44"]
+SMALL_CASES = ["n7_cas44", "n7_cas44_frozen", "n8_nocore", "n11_cas43", "n13_cas22", "n13_bigkappa"] + MOL_CASES
 SEEDED_CASES = ["n28_cas66", "n34_cas44", "n43_cas34"]
 ALL_CASES = SMALL_CASES + SEEDED_CASES
 

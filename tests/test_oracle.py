@@ -86,7 +86,7 @@ def test_general_4index_transform():
     assert np.abs(out.numpy() - explicit).max() < 1e-11
 
 
-@pytest.mark.parametrize("name", ["n7_cas44", "n13_cas22"])
+@pytest.mark.parametrize("name", ["n7_cas44", "n13_cas22", "mol_ch2nh_sto3g_cas22", "mol_h2o_sto3g_cas44"])
 def test_analytic_derivatives_equal_autograd(name):
     """The reference's own strategy (test/test_oo_energy.py:415-971): analytic G/H at kappa=0
     against autograd of energy_from_kappa -- proves the fixtures obey the symmetry preconditions."""
