@@ -19,7 +19,7 @@ _ptr = C.c_void_p
 _size = C.c_size_t
 
 OO_WS_ROTATION, OO_WS_INT2E, OO_WS_HESSIAN, OO_WS_INT1E, OO_WS_YMATRIX = 1, 2, 3, 4, 5
-OO_WS_CLASS_TRANSFORM, OO_WS_CLASS_BUFFER, OO_WS_CLASS_HESSIAN = 6, 7, 8
+OO_WS_CLASS_TRANSFORM, OO_WS_CLASS_BUFFER, OO_WS_CLASS_HESSIAN, OO_WS_CLASS_TRANSFORM_SYM = 6, 7, 8, 9
 
 # name -> (restype, argtypes); mirrors include/oo_b200.h one to one
 _SIGNATURES = {
@@ -53,6 +53,10 @@ _SIGNATURES = {
                               _ptr, _ptr, _size, _ptr]),
     "oo_transpose_f64": (_i32, [_ptr, _ptr, _i64, _i64, _ptr]),
     "oo_class_transform_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_eri_symmetry_defect_f64": (_i32, [_ptr, _i32, _ptr, _ptr]),
+    "oo_pair_ld": (_i64, [_i32]),
+    "oo_pack_eri_pairs_f64": (_i32, [_ptr, _ptr, _i32, _ptr]),
+    "oo_class_transform_sym_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
     "oo_class_active_hamiltonian_f64": (_i32, [_ptr, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr, _ptr,
                                                _ptr, _ptr]),
     "oo_class_fock_gradient_f64": (_i32, [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32,

@@ -18,6 +18,7 @@ size_t hessian_ws_bytes(int ld, int nI);
 size_t y_matrix_ws_bytes(int ld, int N);
 size_t class_transform_ws_bytes(int ld, int nIp, int batch);
 size_t class_buffer_bytes(int ld, int nIp);
+size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch);
 size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch);
 extern int g_hessian_dense;
 
@@ -146,6 +147,7 @@ size_t oo_workspace_bytes(int which, int N, int ld, int nI, int batch) {
         case OO_WS_INT1E: return oo::int1e_ws_bytes(ld, batch);
         case OO_WS_YMATRIX: return oo::y_matrix_ws_bytes(ld, N);
         case OO_WS_CLASS_TRANSFORM: return oo::class_transform_ws_bytes(ld, nI + (nI & 1), batch);
+        case OO_WS_CLASS_TRANSFORM_SYM: return oo::class_transform_sym_ws_bytes(ld, nI + (nI & 1), batch);
         case OO_WS_CLASS_BUFFER: return (size_t)batch * oo::class_buffer_bytes(ld, nI + (nI & 1));
         case OO_WS_CLASS_HESSIAN:   /* N carries na here (the sparse layout depends on no, na, not on N) */
             return oo::class_hessian_ws_bytes(ld, nI + (nI & 1), nI - N, N, batch);

@@ -29,6 +29,10 @@ int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N,
 int dgemm_tn_swap02(const double *At, const double *B, double *C, double *C2, int d0, int d1, int d2,
                     int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA,
                     int64_t strideB, int64_t strideC, cudaStream_t stream);
+int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C2, int d0, int dorb, int dP,
+                         int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int batch,
+                         int64_t strideA, int64_t strideB, int64_t strideC, int64_t strideC2,
+                         cudaStream_t stream);
 
 namespace {
 
@@ -106,12 +110,271 @@ int class_transform(const double *gp, int64_t strideG, const double *C, int64_t 
     return OO_OK;
 }
 
+
+// =====================================================================================
+// Symmetric variant.  Real AO integrals have the 8-fold symmetry (pq|rs) = (qp|rs) = (rs|pq);
+// eri_symmetry_defect measures it and the host selects this path only when the defect is
+// round-off.  Then
+//   * the AO tensor is kept with the LAST pair packed, gpk[r,s,pq] = g[r,s,p,q], p >= q
+//     (half the HBM of g_pairT, which equals g itself), and Q1 runs over packed pairs only:
+//       Q1   T1[s,pq,m] = sum_r gpk[r,(s pq)] C[r,m]              N^4 nI flop (half of the general Q1)
+//     its epilogue also writes the unpacked, pair-first copy T1t[q,p,s,m] = T1t[p,q,s,m] for K;
+//   * J[m,n,a,b] = J[n,m,a,b] and K[n,m,a,b] = K[m,n,b,a]: only class pairs m >= n go through
+//     the last two quarters (packed pair index mn), and one HBM-bound pass expands them into
+//     the class buffer.
+//       J:  Q2   X[pq,m,n]    = sum_s T1[s,(pq m)] C[s,n]
+//           pack Xf[p,q,mn]   = X[tri(p,q),m,n]                     (pair index unpacked, class pair packed)
+//           Q3   X'[q,mn,a]   = sum_p Xf[p,(q mn)] C[p,a]
+//           Q4   Jp[mn,a,b]   = sum_q X'[q,(mn a)] C[q,b]
+//       K:  K2   X2[p,s,m,n]  = sum_q T1t[q,(p s m)] C[q,n]
+//           pack X2p[p,s,mn]  = X2[p,s,m,n]
+//           K3   X3[s,mn,a]   = sum_p X2p[p,(s mn)] C[p,a]
+//           K4   Kp[mn,a,b]   = sum_s X3[s,(mn a)] C[s,b]           = g'[a,n,m,b]
+//       expand   J[m,n] = J[n,m] = Jp[mn];  K[m,n] = Kp[mn],  K[n,m] = Kp[mn]^T
+// Total 2 N^4 nI / 2 + ~7 N^3 nI^2 flop: 4.2e11 at N=256, nI=44 instead of 7.7e11.
+namespace {
+
+__host__ __device__ inline int64_t tri_count(int n) { return (int64_t)n * (n + 1) / 2; }
+
+__device__ __forceinline__ void tri_decode(int pq, int &p, int &q) {
+    p = (int)((sqrt(8.0 * pq + 1.0) - 1.0) * 0.5);
+    while ((p + 1) * (p + 2) / 2 <= pq) ++p;
+    while (p * (p + 1) / 2 > pq) --p;
+    q = pq - p * (p + 1) / 2;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// defect[0] = max |g[p,q,r,s] - g[q,p,r,s]|, defect[1] = max |g[p,q,r,s] - g[r,s,p,q]|, defect[2] = max |g|
+// g viewed as a (ld^2 x ld^2) matrix; 32x32 tiles, the mirrored tile read transposed through smem.
+__global__ void __launch_bounds__(256) eri_defect_kernel(const double *__restrict__ g, int ld,
+                                                         double *__restrict__ defect) {
+    __shared__ double tile[32][33];
+    __shared__ double red[32];
+    const int64_t ld2 = (int64_t)ld * ld;
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {      // mirrored tile: rows c0.., cols r0..
+        const int64_t r = c0 + j, c = r0 + tx;
+        tile[j][tx] = (r < ld2 && c < ld2) ? g[r * ld2 + c] : 0.0;
+    }
+    __syncthreads();
+    double d_pq = 0.0, d_pair = 0.0, amax = 0.0;
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t r = r0 + j, c = c0 + tx;
+        if (r < ld2 && c < ld2) {
+            const double v = g[r * ld2 + c];
+            amax = fmax(amax, fabs(v));
+            d_pair = fmax(d_pair, fabs(v - tile[tx][j]));
+            const int p = (int)(r / ld), q = (int)(r % ld);
+            d_pq = fmax(d_pq, fabs(v - g[((int64_t)q * ld + p) * ld2 + c]));
+        }
+    }
+    double vals[3] = {d_pq, d_pair, amax};
+    for (int k = 0; k < 3; ++k) {
+        double v = vals[k];
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if (tx == 0) red[ty] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            for (int w = 0; w < 8; ++w) m = fmax(m, red[w]);
+            atomic_max_nonneg(&defect[k], m);
+        }
+    }
+}
+
+// gpk[(r s), pq] = g[(r s), p, q] for p >= q < ld; pq in [npair, ldp) zero.  One CTA per (r,s) row.
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const double *__restrict__ g, double *__restrict__ gpk,
+                                                         int ld, int64_t ldp) {
+    const int64_t row = blockIdx.x;
+    const double *src = g + row * (int64_t)ld * ld;
+    double *dst = gpk + row * ldp;
+    const int npair = (int)tri_count(ld);
+    for (int pq = threadIdx.x; pq < ldp; pq += blockDim.x) {
+        double v = 0.0;
+        if (pq < npair) {
+            int p, q;
+            tri_decode(pq, p, q);
+            v = src[(int64_t)p * ld + q];
+        }
+        dst[pq] = v;
+    }
+}
+
+// dst[b][row][mn] = src[b][srow][m*nIp + n], m >= n, mn = m(m+1)/2 + n (zero for mn >= npI);
+// srow = row (identity) or, with tri_rows, row = (p,q) of ld x ld and srow = tri(max,min).
+__global__ void __launch_bounds__(128) pack_class_pairs_kernel(const double *__restrict__ src,
+                                                               double *__restrict__ dst, int ld, int nIp,
+                                                               int npIp, int tri_rows, int64_t src_stride,
+                                                               int64_t dst_stride) {
+    const int64_t row = blockIdx.x;
+    const int b = blockIdx.y;
+    int64_t srow = row;
+    if (tri_rows) {
+        const int p = (int)(row / ld), q = (int)(row % ld);
+        const int hi = p > q ? p : q, lo = p > q ? q : p;
+        srow = tri_count(hi) + lo;
+    }
+    const double *s = src + b * src_stride + srow * (int64_t)nIp * nIp;
+    double *d = dst + b * dst_stride + row * (int64_t)npIp;
+    const int npI = (int)tri_count(nIp);
+    for (int mn = threadIdx.x; mn < npIp; mn += blockDim.x) {
+        double v = 0.0;
+        if (mn < npI) {
+            int m, n;
+            tri_decode(mn, m, n);
+            v = s[m * nIp + n];
+        }
+        d[mn] = v;
+    }
+}
+
+// cls J rows: J[m,n,:,:] = J[n,m,:,:] = Jp[mn,:,:];  K rows: K[m,n,:,:] = Kp[mn,:,:], K[n,m,:,:] = Kp[mn,:,:]^T.
+// grid (ld/32, ld/32, npI * batch); 32x32 tiles (the transposed copy goes through padded smem).
+__global__ void __launch_bounds__(256) expand_class_kernel(const double *__restrict__ Jp,
+                                                           const double *__restrict__ Kp, double *__restrict__ cls,
+                                                           int ld, int nIp, int npI, int64_t pk_stride,
+                                                           int64_t cls_stride) {
+    __shared__ double tile[32][33];
+    const int mn = blockIdx.z % npI, b = blockIdx.z / npI;
+    int m, n;
+    tri_decode(mn, m, n);
+    const int64_t ld2 = (int64_t)ld * ld;
+    const double *jp = Jp + b * pk_stride + (int64_t)mn * ld2;
+    const double *kp = Kp + b * pk_stride + (int64_t)mn * ld2;
+    double *Kc = cls + b * cls_stride;
+    double *Jc = Kc + (int64_t)nIp * nIp * ld2;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t row_mn = (int64_t)m * nIp + n, row_nm = (int64_t)n * nIp + m;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + tx;
+        if (r < ld && c < ld) {
+            const double vj = jp[(int64_t)r * ld + c], vk = kp[(int64_t)r * ld + c];
+            Jc[row_mn * ld2 + (int64_t)r * ld + c] = vj;
+            Kc[row_mn * ld2 + (int64_t)r * ld + c] = vk;
+            if (m != n) Jc[row_nm * ld2 + (int64_t)r * ld + c] = vj;
+            tile[j][tx] = vk;
+        }
+    }
+    if (m == n) return;
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + tx;          // element (r, c) of Kp -> (c, r) of K[n,m]
+        if (r < ld && c < ld) Kc[row_nm * ld2 + (int64_t)c * ld + r] = tile[tx][j];
+    }
+}
+
+}  // namespace
+
+int64_t pair_ld(int ld) {                       // packed pair count rounded up to even (TMA strides)
+    const int64_t n = tri_count(ld);
+    return n + (n & 1);
+}
+
+int eri_symmetry_defect(const double *g, int ld, double *defect3, cudaStream_t stream) {
+    OO_REQUIRE(g && defect3 && ld > 0);
+    OO_CUDA_CHECK(cudaMemsetAsync(defect3, 0, 3 * sizeof(double), stream));
+    const int64_t t = ceil_div((int64_t)ld * ld, 32);
+    if (t > 65535) return OO_ERR_UNSUPPORTED;
+    eri_defect_kernel<<<dim3((unsigned)t, (unsigned)t), 256, 0, stream>>>(g, ld, defect3);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+int pack_eri_pairs(const double *g, double *gpk, int ld, cudaStream_t stream) {
+    OO_REQUIRE(g && gpk && ld > 0 && (ld % 2) == 0);
+    const int64_t rows = (int64_t)ld * ld;
+    if (rows > 0x7fffffffll) return OO_ERR_UNSUPPORTED;
+    pack_pairs_kernel<<<(unsigned)rows, 256, 0, stream>>>(g, gpk, ld, pair_ld(ld));
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch) {
+    const size_t ld2 = (size_t)ld * ld, ldp = (size_t)pair_ld(ld), npIp = (size_t)pair_ld(nIp);
+    const size_t t1 = (size_t)ld * ldp * nIp, t1t = ld2 * ld * nIp;
+    const size_t x = ld2 * nIp * nIp;                 // >= ldp * nIp^2 (Q2 output) as well
+    const size_t xp = ld2 * npIp;
+    return (size_t)batch * (t1 + t1t + x + 4 * xp) * sizeof(double);
+}
+
+int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int64_t strideC, int N, int ld,
+                        int nIp, int batch, double *cls, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    OO_REQUIRE(gpk && C && cls && ws);
+    OO_REQUIRE(N > 0 && ld >= N && (ld % 2) == 0 && nIp > 0 && (nIp % 2) == 0 && nIp <= ld && batch > 0);
+    if (ws_bytes < class_transform_sym_ws_bytes(ld, nIp, batch)) return OO_ERR_WORKSPACE;
+    if (ld > 65535) return OO_ERR_UNSUPPORTED;
+    const int64_t ld2 = (int64_t)ld * ld, ldp = pair_ld(ld), nI2 = (int64_t)nIp * nIp;
+    const int64_t npI = tri_count(nIp), npIp = pair_ld(nIp);
+    const int64_t sT1 = (int64_t)ld * ldp * nIp, sT1t = ld2 * ld * nIp, sX = ld2 * nI2, sXp = ld2 * npIp;
+    const int64_t sCls = (2 * nI2 + 1) * ld2;
+    if (npI * batch > 65535) return OO_ERR_UNSUPPORTED;
+    double *T1 = reinterpret_cast<double *>(ws);
+    double *T1t = T1 + (int64_t)batch * sT1;
+    double *X = T1t + (int64_t)batch * sT1t;
+    double *P0 = X + (int64_t)batch * sX;         // packed-class-pair buffers
+    double *P1 = P0 + (int64_t)batch * sXp;
+    double *Jp = P1 + (int64_t)batch * sXp;
+    double *Kp = Jp + (int64_t)batch * sXp;
+    int rc;
+#define Q(in, sIn, out, sOut, M, Ncols)                                                                  \
+    if ((rc = dgemm_tn((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), batch, (sIn), strideC, (sOut), \
+                       stream)))                                                                         \
+    return rc
+    // Q1: rows (s, pq); the epilogue also writes T1t[q,p,s,m] and T1t[p,q,s,m]
+    if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp, batch,
+                                   strideG, strideC, sT1, sT1t, stream)))
+        return rc;
+    const dim3 pgrid((unsigned)ld2, (unsigned)batch);
+    // ---- J
+    Q(T1, sT1, X, sX, ldp * nIp, nIp);                                   // X[pq,m,n]
+    pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 1, sX, sXp);   // Xf[p,q,mn]
+    OO_LAUNCH_CHECK();
+    Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X'[q,mn,a]
+    Q(P1, sXp, Jp, sXp, npIp * ld, ld);                                  // Jp[mn,a,b]
+    // ---- K
+    Q(T1t, sT1t, X, sX, ld2 * nIp, nIp);                                 // X2[p,s,m,n]
+    pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 0, sX, sXp);   // X2p[p,s,mn]
+    OO_LAUNCH_CHECK();
+    Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X3[s,mn,a]
+    Q(P1, sXp, Kp, sXp, npIp * ld, ld);                                  // Kp[mn,a,b]
+#undef Q
+    const unsigned t = (unsigned)ceil_div(ld, 32);
+    expand_class_kernel<<<dim3(t, t, (unsigned)(npI * batch)), 256, 0, stream>>>(Jp, Kp, cls, ld, nIp, (int)npI,
+                                                                                 sXp, sCls);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
 }  // namespace oo
 
 extern "C" {
 
 int oo_transpose_f64(const double *src, double *dst, int64_t rows, int64_t cols, void *stream) {
     return oo::transpose(src, dst, rows, cols, (cudaStream_t)stream);
+}
+
+int oo_eri_symmetry_defect_f64(const double *g_ao, int ld, double *defect3, void *stream) {
+    return oo::eri_symmetry_defect(g_ao, ld, defect3, (cudaStream_t)stream);
+}
+
+int64_t oo_pair_ld(int ld) { return ld > 0 ? oo::pair_ld(ld) : 0; }
+
+int oo_pack_eri_pairs_f64(const double *g_ao, double *g_packed, int ld, void *stream) {
+    return oo::pack_eri_pairs(g_ao, g_packed, ld, (cudaStream_t)stream);
+}
+
+int oo_class_transform_sym_f64(const double *g_packed, int64_t strideG, const double *C, int64_t strideC, int N,
+                               int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
+                               void *stream) {
+    return oo::class_transform_sym(g_packed, strideG, C, strideC, N, ld, nIp, batch, cls, ws, ws_bytes,
+                                   (cudaStream_t)stream);
 }
 
 int oo_class_transform_f64(const double *g_pairT, int64_t strideG, const double *C, int64_t strideC, int N,

@@ -43,10 +43,12 @@ struct TnArgs {
     double *C;
     // optional second copy of the result with rows permuted (a b c) -> (c b a), M = d0*d1*d2
     // (classes.cu: T1[s,p,q,m] and T1t[q,p,s,m] from the same accumulators, no separate swap pass)
+    // or (mode 2, symmetric class transform) rows (a, pq) with pq = p(p+1)/2 + q a packed lower-triangular
+    // pair of d1 orbitals (d2 = padded pair count): C2 receives the value at rows (q p a) AND (p q a)
     double *C2;
     int d0, d1, d2;
     int64_t M, N;
-    int64_t ldc, strideC;
+    int64_t ldc, strideC, strideC2;
     int kblocks;
     int tiles_m, tiles_n, batch;
     int a_batched, b_batched;
@@ -59,7 +61,8 @@ struct TnArgs {
     uint32_t zero;
 };
 
-template <class Cfg, bool DUAL>
+// DUAL: 0 = plain store, 1 = second store with rows (a b c) -> (c b a), 2 = packed-pair unpack (see TnArgs)
+template <class Cfg, int DUAL>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const TnArgs args) {
@@ -217,12 +220,25 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int64_t row = (int64_t)m0 + wm * Cfg::WTM + mi * 8 + g;
                 if (row < args.M) {
                     double *crow = Cb + row * args.ldc;
-                    double *crow2 = nullptr;
-                    if (DUAL) {
+                    double *crow2 = nullptr, *crow3 = nullptr;
+                    if (DUAL == 1) {
                         const int c = (int)(row % args.d2);
                         const int64_t ab = row / args.d2;
                         const int bq = (int)(ab % args.d1), a = (int)(ab / args.d1);
-                        crow2 = args.C2 + (int64_t)b * args.strideC + (((int64_t)c * args.d1 + bq) * args.d0 + a) * args.ldc;
+                        crow2 = args.C2 + (int64_t)b * args.strideC2 + (((int64_t)c * args.d1 + bq) * args.d0 + a) * args.ldc;
+                    }
+                    if (DUAL == 2) {
+                        const int pq = (int)(row % args.d2);
+                        const int a = (int)(row / args.d2);
+                        int p = (int)((sqrt(8.0 * pq + 1.0) - 1.0) * 0.5);
+                        while ((p + 1) * (p + 2) / 2 <= pq) ++p;
+                        while (p * (p + 1) / 2 > pq) --p;
+                        const int q = pq - p * (p + 1) / 2;
+                        if (p < args.d1) {                     // (padding of the pair index: nothing to unpack)
+                            double *base2 = args.C2 + (int64_t)b * args.strideC2;
+                            crow2 = base2 + (((int64_t)q * args.d1 + p) * args.d0 + a) * args.ldc;
+                            crow3 = base2 + (((int64_t)p * args.d1 + q) * args.d0 + a) * args.ldc;
+                        }
                     }
 #pragma unroll
                     for (int ni = 0; ni < Cfg::NT; ++ni) {
@@ -230,10 +246,15 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         if (col + 1 < args.N) {
                             const double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                             *reinterpret_cast<double2 *>(crow + col) = v;
-                            if (DUAL) *reinterpret_cast<double2 *>(crow2 + col) = v;
+                            if (DUAL == 1) *reinterpret_cast<double2 *>(crow2 + col) = v;
+                            if (DUAL == 2 && crow2) {
+                                *reinterpret_cast<double2 *>(crow2 + col) = v;
+                                *reinterpret_cast<double2 *>(crow3 + col) = v;
+                            }
                         } else if (col < args.N) {
                             crow[col] = acc[mi][ni][0];
-                            if (DUAL) crow2[col] = acc[mi][ni][0];
+                            if (DUAL == 1) crow2[col] = acc[mi][ni][0];
+                            if (DUAL == 2 && crow2) crow2[col] = crow3[col] = acc[mi][ni][0];
                         }
                     }
                 }
@@ -244,7 +265,9 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
 struct TnDual {
     double *C2 = nullptr;
+    int mode = 0;               // 1 = swap02, 2 = packed-pair unpack
     int d0 = 0, d1 = 0, d2 = 0;
+    int64_t strideC2 = 0;
 };
 
 template <class Cfg>
@@ -272,6 +295,7 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     args.N = N;
     args.ldc = ldc;
     args.strideC = strideC;
+    args.strideC2 = dual.strideC2;
     args.kblocks = (int)ceil_div(K, Cfg::BK);
     args.tiles_m = (int)ceil_div(M, Cfg::BM);
     args.tiles_n = (int)ceil_div(N, Cfg::BN);
@@ -282,20 +306,25 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
 
     static bool attr_set = false;
     if (!attr_set) {
-        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, false>,
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 0>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
-        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, true>,
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 1>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    if (dual.C2)
-        dgemm_tn_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    if (dual.C2 && dual.mode == 2)
+        dgemm_tn_kernel<Cfg, 2><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    else if (dual.C2)
+        dgemm_tn_kernel<Cfg, 1><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     else
-        dgemm_tn_kernel<Cfg, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+        dgemm_tn_kernel<Cfg, 0><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -341,10 +370,32 @@ int dgemm_tn_swap02(const double *At, const double *B, double *C, double *C2, in
     OO_REQUIRE(C2 && d0 > 0 && d1 > 0 && d2 > 0);
     TnDual dual;
     dual.C2 = C2;
+    dual.mode = 1;
     dual.d0 = d0;
     dual.d1 = d1;
     dual.d2 = d2;
+    dual.strideC2 = strideC;
     return dgemm_tn_impl(At, B, C, (int64_t)d0 * d1 * d2, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC,
+                         stream, dual);
+}
+
+// Rows (a, pq): a < d0, pq < dP a packed lower-triangular pair (p >= q) of `dorb` orbitals, dP >= dorb(dorb+1)/2
+// (padding rows carry zeros).  C[(a pq), n] is stored as is; C2 receives the same value at rows (q p a) and
+// (p q a), i.e. the pair index unpacked to both orders and moved to the front (M2 = dorb*dorb*d0 rows).
+int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C2, int d0, int dorb, int dP,
+                         int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int batch,
+                         int64_t strideA, int64_t strideB, int64_t strideC, int64_t strideC2,
+                         cudaStream_t stream) {
+    OO_REQUIRE(C2 && d0 > 0 && dorb > 0 && (int64_t)dP >= (int64_t)dorb * (dorb + 1) / 2);
+    if ((int64_t)dorb * (dorb + 1) / 2 >= (1ll << 30)) return OO_ERR_UNSUPPORTED;
+    TnDual dual;
+    dual.C2 = C2;
+    dual.mode = 2;
+    dual.d0 = d0;
+    dual.d1 = dorb;
+    dual.d2 = dP;
+    dual.strideC2 = strideC2;
+    return dgemm_tn_impl(At, B, C, (int64_t)d0 * dP, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC,
                          stream, dual);
 }
 

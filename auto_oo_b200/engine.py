@@ -78,9 +78,15 @@ class HotPathEngine:
             cls._tensor_engines[key] = cls(None, None, None, 0.0, nao, 0, max(1, min(2, int(nao))), [], device=dev)
         return cls._tensor_engines[key]
 
+    # relative 8-fold-symmetry defect of the AO integrals below which the symmetric class transform is used
+    SYMMETRY_TOL = 1e-13
+
     def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None,
-                 n_geometries=0):
-        """``n_geometries`` > 0: ``int1e_ao (G,N,N)``, ``int2e_ao (G,N,N,N,N)``, ``oao_coeff (G,N,N)``,
+                 n_geometries=0, eri_symmetry="auto"):
+        """``eri_symmetry``: "auto" measures the 8-fold symmetry of ``int2e_ao`` on the device at first use and
+        takes the symmetric class transform (half the quarter-1 work, packed AO integrals) when it holds to
+        round-off, the general one otherwise; "off" always takes the general one.
+        ``n_geometries`` > 0: ``int1e_ao (G,N,N)``, ``int2e_ao (G,N,N,N,N)``, ``oao_coeff (G,N,N)``,
         ``nuc (G,)`` hold one molecule geometry each (same orbital classes); evaluation ``b`` of a
         batch then uses geometry ``b`` (class path only)."""
         if not torch.cuda.is_available():
@@ -105,6 +111,10 @@ class HotPathEngine:
             self.nuc_dev = None if G is None else self.dev(np.asarray(nuc, dtype=np.float64).reshape(G))
         self.nIp = pad_even(self.nI)                   # class index padded to even (TMA strides)
         self.g_pairT = None                            # g_ao[p,q,r,s] stored as [r,s,p,q]; built on first use
+        self.g_packed = None                           # g_ao[r,s,(p>=q)] when the integrals are 8-fold symmetric
+        self.eri_symmetry = eri_symmetry
+        self._eri_symmetric = None if eri_symmetry == "auto" else False
+        self.eri_defect = None
         self._ws = {}
         self._cache_key = None
         self._cache_val = None
@@ -322,6 +332,34 @@ class HotPathEngine:
             self.g_pairT = out
         return self.g_pairT
 
+    def eri_is_symmetric(self):
+        """True when every resident AO tensor has (pq|rs) = (qp|rs) = (rs|pq) to round-off (measured once
+        on the device; ``eri_defect`` keeps (max |g_pqrs - g_qprs|, max |g_pqrs - g_rspq|, max |g|))."""
+        if self._eri_symmetric is None:
+            g = self.g_ao.reshape(-1, self.ld ** 4)
+            worst = torch.zeros(3, dtype=F64, device=self.device)
+            d = torch.empty(3, dtype=F64, device=self.device)
+            for i in range(g.shape[0]):
+                self._check(self.lib.oo_eri_symmetry_defect_f64(_p(g[i]), self.ld, _p(d), self.stream),
+                            "eri_symmetry_defect")
+                worst = torch.maximum(worst, d)
+            dpq, dpair, amax = (float(x) for x in worst.cpu())
+            self.eri_defect = (dpq, dpair, amax)
+            self._eri_symmetric = max(dpq, dpair) <= self.SYMMETRY_TOL * max(amax, 1e-300)
+        return self._eri_symmetric
+
+    def packed_eri(self):
+        """g_packed[r,s,pq] = g_ao[r,s,p,q], p >= q (pairs of the ld padded orbitals, row padded to even)."""
+        if self.g_packed is None:
+            ldp = int(self.lib.oo_pair_ld(self.ld))
+            g = self.g_ao.reshape(-1, self.ld ** 4)
+            out = torch.empty(g.shape[0], self.ld, self.ld, ldp, dtype=F64, device=self.device)
+            for i in range(g.shape[0]):
+                self._check(self.lib.oo_pack_eri_pairs_f64(_p(g[i]), _p(out[i]), self.ld, self.stream),
+                            "pack_eri_pairs")
+            self.g_packed = out if self.n_geom else out[0]
+        return self.g_packed
+
     def _geo(self, t, lo, hi):
         """(tensor, per-evaluation stride) of a per-problem / per-geometry resident tensor for the
         evaluations [lo, hi) of a batch."""
@@ -331,9 +369,12 @@ class HotPathEngine:
         return sl, (sl[0].numel() if hi - lo > 1 else 0)
 
     def drop_full_eri(self):
-        """Free g_ao (and the full-transform buffers) once g_pairT exists: the class path needs only
-        the pair-transposed copy.  The full four-index transform API then needs ``g_ao=`` again."""
-        self.pair_transposed_eri()
+        """Free g_ao (and the full-transform buffers) once the class path's own copy exists (the packed
+        tensor for symmetric integrals, the pair-transposed one otherwise).  The full four-index transform API then needs ``g_ao=`` again."""
+        if self.eri_is_symmetric():
+            self.packed_eri()
+        else:
+            self.pair_transposed_eri()
         self.g_ao = None
         self._cache_key = self._cache_val = None
         self._ws.pop("i2e", None)
@@ -348,12 +389,20 @@ class HotPathEngine:
         B, ld, nIp, rows = C.shape[0], self.ld, self.nIp, self.class_rows()
         cls = out if out is not None and out.shape[0] == B else torch.empty(B, rows, ld, ld, dtype=F64,
                                                                            device=self.device)
-        nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, B)
-        ws = self.workspace("cls", nbytes)
-        gp, sg = self._geo(self.pair_transposed_eri(), geo_lo, geo_lo + B)
-        self._check(self.lib.oo_class_transform_f64(_p(gp), sg, _p(C), ld * ld if B > 1 else 0,
-                                                    self.N, ld, nIp, B, _p(cls), _p(ws), nbytes, self.stream),
-                    "class_transform")
+        if self.eri_is_symmetric():
+            nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM_SYM, self.N, ld, self.nI, B)
+            ws = self.workspace("cls", nbytes)
+            gp, sg = self._geo(self.packed_eri(), geo_lo, geo_lo + B)
+            self._check(self.lib.oo_class_transform_sym_f64(_p(gp), sg, _p(C), ld * ld if B > 1 else 0,
+                                                            self.N, ld, nIp, B, _p(cls), _p(ws), nbytes,
+                                                            self.stream), "class_transform_sym")
+        else:
+            nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, B)
+            ws = self.workspace("cls", nbytes)
+            gp, sg = self._geo(self.pair_transposed_eri(), geo_lo, geo_lo + B)
+            self._check(self.lib.oo_class_transform_f64(_p(gp), sg, _p(C), ld * ld if B > 1 else 0,
+                                                        self.N, ld, nIp, B, _p(cls), _p(ws), nbytes, self.stream),
+                        "class_transform")
         if B == 1:                                           # h' = C^T h C straight into the last row
             nb1 = self.lib.oo_workspace_bytes(_lib.OO_WS_INT1E, self.N, ld, 0, 1)
             ws1 = self.workspace("i1e", nb1)
@@ -430,7 +479,8 @@ class HotPathEngine:
     def class_chunk(self, B):
         """How many evaluations the class path processes per batched launch: as many as keep the
         transform + Hessian workspaces under ~8 GB (always at least one)."""
-        per = (self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, self.ld, self.nI, 1)
+        which = _lib.OO_WS_CLASS_TRANSFORM_SYM if self.eri_is_symmetric() else _lib.OO_WS_CLASS_TRANSFORM
+        per = (self.lib.oo_workspace_bytes(which, self.N, self.ld, self.nI, 1)
                + self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.na, self.ld, self.nI, 1)
                + self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_BUFFER, self.N, self.ld, self.nI, 1))
         return int(max(1, min(B, (8 << 30) // max(per, 1))))

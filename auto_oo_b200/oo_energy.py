@@ -207,10 +207,12 @@ class OO_energy:
     ``oao_mo_coeff`` is None)."""
 
     def __init__(self, mol, ncas, nelecas, oao_mo_coeff=None, freeze_active=False, interface='torch',
-                 device=None, integral_path="class"):
+                 device=None, integral_path="class", eri_symmetry="auto"):
         """``integral_path``: ``"class"`` (default) transforms only the J/K integral classes that
         energy, gradient and Hessian read; ``"full"`` runs the complete four-index transform for
-        every set of MO coefficients, as the reference does."""
+        every set of MO coefficients, as the reference does.  ``eri_symmetry``: ``"auto"`` lets the
+        class path use the 8-fold symmetry of ``int2e_ao`` when the device check finds it (real-orbital
+        integrals always have it), ``"off"`` never assumes it."""
         assert integral_path in ("class", "full")
         self.integral_path = integral_path
         if interface != 'torch':
@@ -241,7 +243,7 @@ class OO_energy:
         self.int2e_ao = _as_tensor(mol.int2e_ao)
         self.oao_coeff = _as_tensor(mol.oao_coeff)
         self.engine = HotPathEngine(self.int1e_ao, self.int2e_ao, self.oao_coeff, self.nuc, self.nao,
-                                    no, na, self.params_idx, device=device)
+                                    no, na, self.params_idx, device=device, eri_symmetry=eri_symmetry)
 
     # ------------------------------------------------------------------ orbitals
     @property
@@ -484,7 +486,8 @@ class OO_energy_geometries:
     one ``(N, N)`` matrix used for all).  ``energy_gradient_hessian(kappa, one_rdm, two_rdm)`` takes
     ``kappa (G, n_kappa)`` and RDMs shared ``(na,na)/(na^4)`` or per geometry ``(G, ...)``."""
 
-    def __init__(self, mols, ncas, nelecas, oao_mo_coeff, freeze_active=False, device=None):
+    def __init__(self, mols, ncas, nelecas, oao_mo_coeff, freeze_active=False, device=None,
+                 eri_symmetry="auto"):
         mols = list(mols)
         assert len(mols) > 0
         self.nao = mols[0].nao
@@ -498,8 +501,8 @@ class OO_energy_geometries:
         self.engine = HotPathEngine(stack("int1e_ao"), stack("int2e_ao"), stack("oao_coeff"),
                                     np.array([m.nuc for m in mols], dtype=np.float64), self.nao,
                                     len(self.occ_idx), len(self.act_idx), self.params_idx, device=device,
-                                    n_geometries=G)
-        self.engine.drop_full_eri()                       # only the pair-transposed copy is needed
+                                    n_geometries=G, eri_symmetry=eri_symmetry)
+        self.engine.drop_full_eri()                       # only the class path's copy of the integrals is needed
         C = _as_tensor(oao_mo_coeff).detach().to(F64)
         self.oao_mo_coeff = C if C.dim() == 3 else C[None].repeat(G, 1, 1)
         assert self.oao_mo_coeff.shape[0] == G

@@ -53,7 +53,8 @@ enum {
     OO_WS_YMATRIX    = 5,      /* oo_y_matrix_f64                                  */
     OO_WS_CLASS_TRANSFORM = 6, /* oo_class_transform_f64 (nI = no+na)              */
     OO_WS_CLASS_BUFFER    = 7, /* size of the class buffer `cls` (x batch)         */
-    OO_WS_CLASS_HESSIAN   = 8  /* oo_class_hessian_f64: pass N = na (!), nI = no+na, batch */
+    OO_WS_CLASS_HESSIAN   = 8, /* oo_class_hessian_f64: pass N = na (!), nI = no+na, batch */
+    OO_WS_CLASS_TRANSFORM_SYM = 9 /* oo_class_transform_sym_f64 (nI = no+na)       */
 };
 
 int         oo_abi_version(void);
@@ -208,6 +209,23 @@ int oo_transpose_f64(const double *src, double *dst, int64_t rows, int64_t cols,
 int oo_class_transform_f64(const double *g_pairT, int64_t strideG, const double *C, int64_t strideC,
                            int N, int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
                            void *stream);   /* stride 0 = shared over the batch; cls[b] contiguous */
+
+/* Symmetric variant of the class transform, for AO integrals with the 8-fold symmetry
+ * (pq|rs) = (qp|rs) = (rs|pq) that every real-orbital ERI tensor has (PySCF int2e,
+ * moldata_pyscf.py:31).  oo_eri_symmetry_defect_f64 writes defect3 = { max |g_pqrs - g_qprs|,
+ * max |g_pqrs - g_rspq|, max |g| } (device) so the caller can decide; oo_pack_eri_pairs_f64 builds
+ * g_packed[r,s,pq] = g[r,s,p,q], p >= q, pq = p(p+1)/2 + q over the ld PADDED orbitals, row length
+ * oo_pair_ld(ld) = ld(ld+1)/2 rounded up to even, padding zero (half the HBM of the full tensor).
+ * oo_class_transform_sym_f64 fills the same class buffer as oo_class_transform_f64 with
+ * N^4 nI + ~7 N^3 nI^2 flop: quarter 1 runs over packed pairs only (its epilogue unpacks the pair
+ * for the exchange class), and only class pairs m >= n go through the last two quarters
+ * (J[m,n,a,b] = J[n,m,a,b], K[n,m,a,b] = K[m,n,b,a]).  ws: OO_WS_CLASS_TRANSFORM_SYM.            */
+int     oo_eri_symmetry_defect_f64(const double *g_ao, int ld, double *defect3, void *stream);
+int64_t oo_pair_ld(int ld);
+int     oo_pack_eri_pairs_f64(const double *g_ao, double *g_packed, int ld, void *stream);
+int     oo_class_transform_sym_f64(const double *g_packed, int64_t strideG, const double *C, int64_t strideC,
+                                   int N, int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
+                                   void *stream);
 int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp,
                                     int batch, double e_nuc, const double *e_nuc_batch, double *c0,
                                     double *c1, double *c2, void *stream);

@@ -20,12 +20,16 @@ def lib():
     return _lib.load()
 
 
-def engine_for(c):
+def engine_for(c, **kw):
     from auto_oo_b200.engine import HotPathEngine
     p = c.oracle()
     eng = HotPathEngine(c.int1e_ao, c.int2e_ao, c.oao_coeff, c.nuc, c.nao, len(p.occ_idx), c.ncas,
-                        p.params_idx)
+                        p.params_idx, **kw)
     return eng, p
+
+
+# evaluation routes: the class path with / without the 8-fold ERI symmetry, and the complete transform
+ROUTES = {"class": ("class", "auto"), "class_general": ("class", "off"), "full": ("full", "auto")}
 
 
 def _stream():
@@ -185,11 +189,14 @@ def test_int2e_transform_batched_kappa_sweep():
 
 
 # ------------------------------------------------------------------ K3 / K4
-@pytest.mark.parametrize("path", ["class", "full"])
+@pytest.mark.parametrize("route", list(ROUTES))
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_full_evaluation_matches_reference(name, path):
+def test_full_evaluation_matches_reference(name, route):
     c = load_case(name)
-    eng, p = engine_for(c)
+    path, sym = ROUTES[route]
+    eng, p = engine_for(c, eri_symmetry=sym)
+    if path == "class":
+        assert eng.eri_is_symmetric() == (sym == "auto")          # every fixture is 8-fold symmetric
     E, G, H = eng.evaluate(eng.to_padded(c.oao_mo_coeff, 2), c.one_rdm, c.two_rdm, kappa=c.kappa[None],
                            path=path)
     assert abs(E.item() - float(c.ref["E"])) < TOL_E
@@ -244,11 +251,14 @@ def test_gradient_vjp_matches_autograd(name):
     assert (g2.cpu() - r2).abs().max().item() < 1e-10
 
 
-@pytest.mark.parametrize("name", ["n7_cas44", "n8_nocore", "n13_cas22", "n28_cas66"])
-def test_class_transform_equals_slices_of_full_transform(name):
-    """J[m,n,a,b] = g'[a,b,m,n], K[n,m,a,b] = g'[a,m,n,b] and the h' row of the class buffer."""
+@pytest.mark.parametrize("sym", ["auto", "off"])
+@pytest.mark.parametrize("name", ["n7_cas44", "n8_nocore", "n13_cas22", "n28_cas66", "mol_ch2nh_sto3g_cas44"])
+def test_class_transform_equals_slices_of_full_transform(name, sym):
+    """J[m,n,a,b] = g'[a,b,m,n], K[n,m,a,b] = g'[a,m,n,b] and the h' row of the class buffer, through the
+    symmetric (packed-pair) and the general class transform."""
     c = load_case(name)
-    eng, p = engine_for(c)
+    eng, p = engine_for(c, eri_symmetry=sym)
+    assert eng.eri_is_symmetric() == (sym == "auto")
     Cp = eng.to_padded(c.ref["mo_coeff_rot"], 2)
     cls = eng.class_integrals(Cp)[0].cpu()
     g = eng.from_padded(eng.int2e_transform(Cp), 4)[0].cpu()
@@ -261,6 +271,56 @@ def test_class_transform_equals_slices_of_full_transform(name):
     assert (cls[-1][:N, :N] - h).abs().max().item() < 1e-12
     if eng.ld > N:                                       # zero padding survives
         assert cls[:, N:, :].abs().max().item() == 0.0 and cls[:, :, N:].abs().max().item() == 0.0
+
+
+def test_eri_symmetry_defect_and_pair_packing(lib):
+    c = load_case("n11_cas43")
+    eng, _ = engine_for(c)
+    ld = eng.ld
+    assert eng.eri_is_symmetric() and max(eng.eri_defect[:2]) <= 1e-13 * eng.eri_defect[2]
+    assert abs(eng.eri_defect[2] - np.abs(c.int2e_ao).max()) < 1e-15
+    gp = eng.packed_eri().cpu()
+    ldp = int(lib.oo_pair_ld(ld))
+    assert gp.shape == (ld, ld, ldp) and ldp % 2 == 0 and ldp >= ld * (ld + 1) // 2
+    g = eng.g_ao.cpu()
+    rows, cols = np.tril_indices(ld)                              # p >= q, pq = p(p+1)/2 + q
+    assert torch.equal(gp[:, :, :len(rows)], g[:, :, rows, cols])
+    assert gp[:, :, len(rows):].abs().max().item() == 0.0 if ldp > len(rows) else True
+    # break each symmetry in turn: the defect reports it and the engine falls back to the general route
+    for kind in (0, 1):
+        g2 = torch.as_tensor(c.int2e_ao).clone()
+        if kind == 0:
+            g2[3, 1, 2, 5] += 1e-6                                # (pq|rs) != (qp|rs)
+        else:
+            g2[3, 1, 2, 5] += 1e-6
+            g2[1, 3, 2, 5] += 1e-6                                # pq-symmetric, but (pq|rs) != (rs|pq)
+        from auto_oo_b200.engine import HotPathEngine
+        p = c.oracle()
+        e2 = HotPathEngine(c.int1e_ao, g2, c.oao_coeff, c.nuc, c.nao, len(p.occ_idx), c.ncas, p.params_idx)
+        assert not e2.eri_is_symmetric()
+        assert abs(e2.eri_defect[kind] - 1e-6) < 1e-12
+        if kind == 1:
+            assert e2.eri_defect[0] == 0.0
+
+
+def test_asymmetric_integrals_take_the_general_class_route():
+    """No symmetry of M is assumed by the reference's transform (oo_energy.py:21-30); for a tensor without
+    the 8-fold symmetry the class path must still equal slices of the complete transform."""
+    from auto_oo_b200.engine import HotPathEngine
+    gen = torch.Generator().manual_seed(3)
+    N, no, na = 9, 2, 3
+    g = torch.randn(N, N, N, N, dtype=F64, generator=gen)
+    C = torch.randn(N, N, dtype=F64, generator=gen)
+    eng = HotPathEngine(np.eye(N), g, np.eye(N), 0.0, N, no, na, [0])
+    assert not eng.eri_is_symmetric()
+    Cp = eng.to_padded(C, 2)
+    cls = eng.class_integrals(Cp)[0].cpu()
+    gm = torch.einsum('pi,qj,rk,sl,pqrs->ijkl', C, C, C, C, g)
+    nI, nIp, ld = no + na, eng.nIp, eng.ld
+    K = cls[:nIp * nIp].reshape(nIp, nIp, ld, ld)[:nI, :nI, :N, :N]
+    J = cls[nIp * nIp:2 * nIp * nIp].reshape(nIp, nIp, ld, ld)[:nI, :nI, :N, :N]
+    assert (J - gm[:, :, :nI, :nI].permute(2, 3, 0, 1)).abs().max().item() < 1e-11
+    assert (K - gm[:, :nI, :nI, :].permute(2, 1, 0, 3)).abs().max().item() < 1e-11
 
 
 def test_transpose_kernel(lib):

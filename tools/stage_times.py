@@ -1,5 +1,6 @@
 """Per-stage device times (CUDA events) of one class-path evaluation at a config shape.
-    python tools/stage_times.py [workload] -> gpurun_out/stage_times_<workload>.json"""
+    python tools/stage_times.py [workload] [auto|off] -> gpurun_out/stage_times_<workload>[_general].json
+(second argument: eri_symmetry; "off" times the general class transform quarter by quarter)"""
 import json
 import os
 import sys
@@ -40,10 +41,11 @@ class Timer:
 
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "synthetic_n256_cas1212"
+    sym = sys.argv[2] if len(sys.argv) > 2 else "auto"
     nao, nelec, ncas, nelecas = CONFIG_SHAPES[wl]
     dev = torch.device("cuda", 0)
     mol = SyntheticMol(nao, nelec, seed=5, device=dev)
-    oo = OO_energy(mol, ncas, nelecas, oao_mo_coeff=mol.random_oao_mo_coeff, device=dev)
+    oo = OO_energy(mol, ncas, nelecas, oao_mo_coeff=mol.random_oao_mo_coeff, device=dev, eri_symmetry=sym)
     eng, lib = oo.engine, _lib.load()
     mol._int2e = mol._B = None
     oo.int2e_ao = None
@@ -56,34 +58,43 @@ def main():
     t = Timer()
     U = t("rotation(expm)", lambda: eng.rotation(kap))
     C = t("mo_coeff", lambda: eng.mo_coeff(eng.to_padded(oo.oao_mo_coeff, 2), U))[0]
-    gp = eng.pair_transposed_eri()
-    # the eight GEMMs + swap of the class transform, individually
     ld2, ld3, nI2 = ld * ld, ld ** 3, nIp * nIp
-    T1 = torch.empty(ld3 * nIp, dtype=F64, device=dev)
-    T1t = torch.empty_like(T1)
-    X = torch.empty(ld2 * nI2, dtype=F64, device=dev)
-    Xp = torch.empty_like(X)
-    cls = torch.empty(2 * nI2 + 1, ld, ld, dtype=F64, device=dev)
+    cls = torch.empty(1, 2 * nI2 + 1, ld, ld, dtype=F64, device=dev)
+    if eng.eri_is_symmetric():
+        ldp, npIp = int(lib.oo_pair_ld(ld)), int(lib.oo_pair_ld(nIp))
+        flop = 2.0 * ld * ldp * nIp * ld + 2.0 * ldp * nI2 * ld + 2.0 * ld2 * nI2 * ld + 8.0 * ld3 * npIp
+        t("class_transform_sym (all; per-kernel split: ncu launch list)", lambda: eng.class_integrals(C, out=cls),
+          flop=flop)
+    else:
+        gp = eng.pair_transposed_eri()
+        # the GEMMs of the general class transform, individually
+        T1 = torch.empty(ld3 * nIp, dtype=F64, device=dev)
+        X = torch.empty(ld2 * nI2, dtype=F64, device=dev)
+        Xp = torch.empty_like(X)
 
-    def gemm(a, out, M, Nc):
-        rc = lib.oo_dgemm_tn_f64(a.data_ptr(), C.data_ptr(), out.data_ptr(), M, Nc, ld, M, ld, Nc, 1, 0, 0, 0, st())
-        assert rc == 0
+        def gemm(a, out, M, Nc):
+            rc = lib.oo_dgemm_tn_f64(a.data_ptr(), C.data_ptr(), out.data_ptr(), M, Nc, ld, M, ld, Nc, 1, 0, 0, 0,
+                                     st())
+            assert rc == 0
 
-    t("Q1  [ld^3 x nIp x ld]", lambda: gemm(gp, T1, ld3, nIp), flop=2.0 * ld3 * nIp * ld, bytes_=8.0 * (ld ** 4 + ld3 * nIp))
-    t("Q2  [ld^2 nIp x nIp x ld]", lambda: gemm(T1, X, ld2 * nIp, nIp), flop=2.0 * ld2 * nIp * nIp * ld)
-    t("Q3  [ld nIp^2 x ld x ld]", lambda: gemm(X, Xp, ld * nI2, ld), flop=2.0 * ld * nI2 * ld * ld)
-    t("Q4  [nIp^2 ld x ld x ld]", lambda: gemm(Xp, cls[nI2:], nI2 * ld, ld), flop=2.0 * ld * nI2 * ld * ld)
-    t("class_transform (all)", lambda: eng.class_integrals(C, out=cls),
-      flop=2.0 * ld ** 4 * nIp + 12.0 * ld3 * nI2)
+        t("Q1  [ld^3 x nIp x ld]", lambda: gemm(gp, T1, ld3, nIp), flop=2.0 * ld3 * nIp * ld,
+          bytes_=8.0 * (ld ** 4 + ld3 * nIp))
+        t("Q2  [ld^2 nIp x nIp x ld]", lambda: gemm(T1, X, ld2 * nIp, nIp), flop=2.0 * ld2 * nIp * nIp * ld)
+        t("Q3  [ld nIp^2 x ld x ld]", lambda: gemm(X, Xp, ld * nI2, ld), flop=2.0 * ld * nI2 * ld * ld)
+        t("Q4  [nIp^2 ld x ld x ld]", lambda: gemm(Xp, cls[0, nI2:], nI2 * ld, ld), flop=2.0 * ld * nI2 * ld * ld)
+        del T1, X, Xp
+        t("class_transform (all)", lambda: eng.class_integrals(C, out=cls),
+          flop=2.0 * ld ** 4 * nIp + 12.0 * ld3 * nI2)
     c = t("active_hamiltonian", lambda: eng.class_active_hamiltonian(cls))
     t("energy", lambda: eng.energy(*c, one, two))
     FI, FA, F, _, gv = t("fock+gradient", lambda: eng.class_fock_gradient(cls, one, two, want_matrix=False))
     H = torch.empty(nk, nk, dtype=F64, device=dev)
-    t("hessian (At + GEMM + assemble)", lambda: eng.class_hessian(cls, F[0], one, two, out=H),
+    t("hessian (At + GEMM + assemble)", lambda: eng.class_hessian(cls, F, one, two, out=H[None]),
       flop=2.0 * nI2 * ld2 * (2 * nI2 + 1))
     t("evaluate (E+G+H)", lambda: eng.evaluate(eng.to_padded(oo.oao_mo_coeff, 2), one, two, kappa=kap, H_out=H[None]))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"stage_times_{wl}.json"), "w") as f:
+    tag = "" if eng.eri_is_symmetric() else "_general"
+    with open(os.path.join(ROOT, "gpurun_out", f"stage_times_{wl}{tag}.json"), "w") as f:
         json.dump(t.rows, f, indent=1)
 
 
