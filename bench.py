@@ -349,7 +349,10 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "nao": nao, "cas": [nelecas, ncas], "n_kappa": nk,
                    "evals_per_step_per_gpu": B,
-                   "transform": "partial J/K-class transform (2N^4 nI + 12 N^3 nI^2 flop), same E/G/H",
+                   "transform": ("symmetric J/K-class transform (packed AO pairs: N^4 nI + ~7 N^3 nI^2 flop), same E/G/H"
+                                 if eng.eri_is_symmetric() else
+                                 "general J/K-class transform (2N^4 nI + 12 N^3 nI^2 flop), same E/G/H"),
+                   "eri_symmetry_defect": eng.eri_defect,
                    "full_transform_arm": {"value": world * B * args.steps / t_full, "unit": UNIT,
                                           "transform": "full four-index (8 N^5 flop), as the reference"},
                    "l2": "inputs larger than L2 (N^4 tensors of %.1f GB)" % (nao ** 4 * 8 / 1e9)
