@@ -4,8 +4,9 @@ from .oo_energy import (OO_energy, OO_energy_geometries, OrbitalHessian, mo_ao_t
                         general_4index_transform, uniform_4index_transform, vector_to_skew_symmetric,
                         skew_symmetric_to_vector, non_redundant_indices)
 from .oo_pqc import OO_pqc
+from .rdm import StatevectorRDM, StatevectorCircuit
 from .utils.newton_raphson import NewtonStep
 
-__all__ = ["OO_energy", "OO_energy_geometries", "OO_pqc", "OrbitalHessian", "NewtonStep", "mo_ao_to_mo_oao", "int1e_transform",
+__all__ = ["OO_energy", "OO_energy_geometries", "OO_pqc", "OrbitalHessian", "NewtonStep", "StatevectorRDM", "StatevectorCircuit", "mo_ao_to_mo_oao", "int1e_transform",
            "int2e_transform", "general_4index_transform", "uniform_4index_transform",
            "vector_to_skew_symmetric", "skew_symmetric_to_vector", "non_redundant_indices"]

@@ -243,6 +243,32 @@ int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma
                          double *H, void *ws, size_t ws_bytes, void *stream);
                          /* batched: cls[b], F[b] (ld^2), H[b] (nk^2) contiguous per evaluation */
 
+/* ---- RDMs from a state vector (the producer of the hot path's gamma, Gamma) -----
+ * replaces Parameterized_circuit.get_rdms_from_state (pqc.py:192-218) with the operators of
+ * utils/active_space.py:29-83 (restricted = spin-summed): gamma_pq = Re<psi|E_pq|psi>,
+ * Gamma_pqrs = Re<psi|E_pq E_rs - delta_qr E_ps|psi>, Jordan-Wigner with qubit 0 the most significant
+ * bit of the state index, spin orbitals 2p/2p+1 (up_then_down: p/p+ncas).
+ * psi: 2^(2 ncas) amplitudes, float64 or interleaved complex128 (is_complex).
+ *  oo_rdm_excitations_f64  Phi[k][c] (transposed=0, row length oo_rdm_columns(ncas)) or Phi[c][k]
+ *                          (transposed=1) for the basis states x0 <= x < x0+nx: c = r*ncas+s -> (E_rs psi)[x],
+ *                          c = ncas^2 -> psi[x], then zero padding; rows k = [Re x-chunk ; Im x-chunk].
+ *  then  C = PhiL^T PhiR  with oo_dgemm_tn_f64 (k split over the batch argument),
+ *  oo_rdm_accumulate_f64   acc += sum_b parts[b]      (fixed order),
+ *  oo_rdm_assemble_f64     gamma_pq = C[ncas^2,(p q)], Gamma_pqrs = C[(q p),(r s)] - delta_qr gamma_ps.
+ * With PhiL from u and PhiR from v the same calls give the transition form Re<u|O|v>; its adjoint
+ *  (g1, g2, v) -> sum g1_pq E_pq v + sum g2_pqrs e_pqrs v  is
+ *  oo_rdm_operator_matrix_f64  Mext[c][(p q)]  ((ncolp) x (ncas^2 rounded up to even)),
+ *  Wt = Mext^T Phi_v^T (oo_dgemm_tn_f64 on the transposed Phi), and
+ *  oo_rdm_apply_gather_f64     w[x] = sum_pq (E_pq Wt[pq])[x]   (Wt_im NULL for a real state).        */
+int64_t oo_rdm_columns(int ncas);
+int oo_rdm_excitations_f64(const double *psi, int is_complex, int ncas, int up_then_down,
+                           int64_t x0, int64_t nx, int transposed, double *Phi, void *stream);
+int oo_rdm_accumulate_f64(const double *parts, int nparts, int64_t n, double *acc, void *stream);
+int oo_rdm_assemble_f64(const double *C, int ncas, double *one_rdm, double *two_rdm, void *stream);
+int oo_rdm_operator_matrix_f64(const double *g1, const double *g2, int ncas, double *Mext, void *stream);
+int oo_rdm_apply_gather_f64(const double *Wt_re, const double *Wt_im, int ncas, int up_then_down,
+                            double *w, void *stream);
+
 /* ---- API-parity helpers (not on the hot path) ------------------------------
  * Dense full-space RDMs exactly as full_rdms defines them (oo_energy.py:342-379):
  * one_full N x N, two_full N^4 (dense, no padding).                               */
