@@ -3,9 +3,9 @@
 // Used for the N x N products of the hot path: Pade/Newton-Schulz/squaring steps
 // of expm(-kappa) (reference oo_energy.py:226-230), C' = X C_oao U (:173-176, :201)
 // and C^T h C (:44-46).  Operands may be transposed and arbitrarily strided, so
-// tiles are staged through padded shared memory with plain loads (these products
-// are latency-bound: 2 N^3 flop on <= 256^2 outputs); the large contractions use
-// the TMA kernel in dgemm_tn.cu instead.
+// tiles are staged through padded shared memory with plain loads, register-prefetched
+// one k-block ahead (these products are latency-bound: 2 N^3 flop on <= 256^2
+// outputs); the large contractions use the TMA kernel in dgemm_tn.cu instead.
 #include "common.cuh"
 
 namespace oo {
@@ -26,9 +26,55 @@ struct SmallArgs {
     int eye_n;   // gamma * I is added on rows < eye_n only (keeps zero padding zero)
 };
 
+// One k-block of op(A) / op(B) per thread: 4 + 4 elements, fetched into registers first (all eight loads in
+// flight at once) and stored to shared memory afterwards; the next block's loads are issued before the DMMAs of
+// the current one (two smem stages, one barrier per k-block).
+struct Stage {
+    double a[TS * TK / 128], b[TS * TK / 128];
+};
+
+__device__ __forceinline__ void fetch_block(const SmallArgs &p, const double *__restrict__ A,
+                                            const double *__restrict__ B, int m0, int n0, int k0, Stage &r) {
+#pragma unroll
+    for (int i = 0; i < TS * TK / 128; ++i) {
+        const int idx = threadIdx.x + i * 128;
+        int k, f;
+        if (p.transA) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
+        const int gm = m0 + f, gk = k0 + k;
+        double v = 0.0;
+        if (gm < p.M && gk < p.K)
+            v = p.transA ? __ldg(A + (int64_t)gk * p.lda + gm) : __ldg(A + (int64_t)gm * p.lda + gk);
+        r.a[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < TS * TK / 128; ++i) {
+        const int idx = threadIdx.x + i * 128;
+        int k, f;
+        if (!p.transB) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
+        const int gn = n0 + f, gk = k0 + k;
+        double v = 0.0;
+        if (gn < p.N && gk < p.K)
+            v = p.transB ? __ldg(B + (int64_t)gn * p.ldb + gk) : __ldg(B + (int64_t)gk * p.ldb + gn);
+        r.b[i] = v;
+    }
+}
+
+__device__ __forceinline__ void store_block(const SmallArgs &p, const Stage &r, double (*sA)[SPAD],
+                                            double (*sB)[SPAD]) {
+#pragma unroll
+    for (int i = 0; i < TS * TK / 128; ++i) {
+        const int idx = threadIdx.x + i * 128;
+        int k, f;
+        if (p.transA) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
+        sA[k][f] = r.a[i];
+        if (!p.transB) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
+        sB[k][f] = r.b[i];
+    }
+}
+
 __global__ void __launch_bounds__(128) dgemm_small_kernel(const SmallArgs p) {
-    __shared__ double sA[TK][SPAD];   // sA[k][m]
-    __shared__ double sB[TK][SPAD];   // sB[k][n]
+    __shared__ double sA[2][TK][SPAD];   // sA[stage][k][m]
+    __shared__ double sB[2][TK][SPAD];   // sB[stage][k][n]
     const int b = blockIdx.z;
     const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
     const double *A = p.A + (int64_t)b * p.sA;
@@ -38,41 +84,30 @@ __global__ void __launch_bounds__(128) dgemm_small_kernel(const SmallArgs p) {
     const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
 
     double acc[2][2][2] = {};
+    Stage r;
+    fetch_block(p, A, B, m0, n0, 0, r);
+    store_block(p, r, sA[0], sB[0]);
+    __syncthreads();
+    int cur = 0;
     for (int k0 = 0; k0 < p.K; k0 += TK) {
-        // stage op(A)[m0.., k0..] as sA[k][m]
-        for (int idx = threadIdx.x; idx < TS * TK; idx += blockDim.x) {
-            int k, f;
-            if (p.transA) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
-            const int gm = m0 + f, gk = k0 + k;
-            double v = 0.0;
-            if (gm < p.M && gk < p.K)
-                v = p.transA ? A[(int64_t)gk * p.lda + gm] : A[(int64_t)gm * p.lda + gk];
-            sA[k][f] = v;
-        }
-        for (int idx = threadIdx.x; idx < TS * TK; idx += blockDim.x) {
-            int k, f;
-            if (!p.transB) { k = idx / TS; f = idx % TS; } else { f = idx / TK; k = idx % TK; }
-            const int gn = n0 + f, gk = k0 + k;
-            double v = 0.0;
-            if (gn < p.N && gk < p.K)
-                v = p.transB ? B[(int64_t)gn * p.ldb + gk] : B[(int64_t)gk * p.ldb + gn];
-            sB[k][f] = v;
-        }
-        __syncthreads();
+        const bool more = k0 + TK < p.K;
+        if (more) fetch_block(p, A, B, m0, n0, k0 + TK, r);
 #pragma unroll
         for (int kk = 0; kk < TK; kk += 4) {
             double a[2], bf[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                a[i] = sA[kk + t][wm + i * 8 + g];
-                bf[i] = sB[kk + t][wn + i * 8 + g];
+                a[i] = sA[cur][kk + t][wm + i * 8 + g];
+                bf[i] = sB[cur][kk + t][wn + i * 8 + g];
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
         }
+        if (more) store_block(p, r, sA[cur ^ 1], sB[cur ^ 1]);
         __syncthreads();
+        cur ^= 1;
     }
 
     double *D = p.D + (int64_t)b * p.sD;

@@ -206,15 +206,22 @@ class OO_energy:
     oao_coeff, nuc, nao, get_active_space_idx`` (+ ``run_rhf``/``hf.mo_coeff`` when
     ``oao_mo_coeff`` is None)."""
 
+    # bases up to this size are launch-bound: whole evaluations are replayed from CUDA graphs
+    GRAPH_MAX_NAO = 128
+
     def __init__(self, mol, ncas, nelecas, oao_mo_coeff=None, freeze_active=False, interface='torch',
-                 device=None, integral_path="class", eri_symmetry="auto"):
+                 device=None, integral_path="class", eri_symmetry="auto", cuda_graphs="auto"):
         """``integral_path``: ``"class"`` (default) transforms only the J/K integral classes that
         energy, gradient and Hessian read; ``"full"`` runs the complete four-index transform for
         every set of MO coefficients, as the reference does.  ``eri_symmetry``: ``"auto"`` lets the
         class path use the 8-fold symmetry of ``int2e_ao`` when the device check finds it (real-orbital
-        integrals always have it), ``"off"`` never assumes it."""
+        integrals always have it), ``"off"`` never assumes it.  ``cuda_graphs``: ``"auto"`` replays the batched
+        evaluations (``energy_gradient_hessian``, ``energies_from_kappas``) from a CUDA graph when the basis has
+        at most ``GRAPH_MAX_NAO`` orbitals, ``True`` / ``False`` force it."""
         assert integral_path in ("class", "full")
+        assert cuda_graphs in ("auto", True, False)
         self.integral_path = integral_path
+        self.cuda_graphs = (mol.nao <= self.GRAPH_MAX_NAO) if cuda_graphs == "auto" else bool(cuda_graphs)
         if interface != 'torch':
             raise ValueError("auto_oo_b200 implements the torch interface only (no JAX/XLA dispatch)")
         if oao_mo_coeff is None:
@@ -308,8 +315,9 @@ class OO_energy:
         returns ``(B,)`` on the device of ``kappas``.  Used by the speculative line search."""
         eng = self.engine
         kappas = _as_tensor(kappas).detach().reshape(-1, self.n_kappa)
-        E, _, _ = eng.evaluate(eng.to_padded(self.oao_mo_coeff, 2), eng.dev(one_rdm), eng.dev(two_rdm),
-                               kappa=eng.dev(kappas), want_hessian=False, path=self.integral_path)
+        run = eng.evaluate_graphed if self.cuda_graphs else eng.evaluate
+        E, _, _ = run(eng.to_padded(self.oao_mo_coeff, 2), eng.dev(one_rdm), eng.dev(two_rdm),
+                      kappa=eng.dev(kappas), want_hessian=False, path=self.integral_path)
         return E.to(kappas.device)
 
     # ------------------------------------------------------------------ Fock matrices / gradient
@@ -410,13 +418,26 @@ class OO_energy:
         kappa = _as_tensor(kappa).detach().reshape(-1, self.n_kappa)
         one, two = _as_tensor(one_rdm).detach(), _as_tensor(two_rdm).detach()
         on_host = kappa.device.type == "cpu"
+        Coao = eng.to_padded(self.oao_mo_coeff, 2)
+        if self.cuda_graphs:
+            # launch-bound sizes: one graph replay; host inputs go pinned -> static buffers, results come back
+            # from the graph's output buffers through pinned memory
+            if on_host:
+                kappa, one, two = (eng.stage_pinned(k, t.to(F64)) for k, t in
+                                   (("kappa", kappa), ("rdm1", one), ("rdm2", two)))
+            E, G, H = eng.evaluate_graphed(Coao, one, two, kappa=kappa, want_hessian=want_hessian,
+                                           path=self.integral_path, clone=not on_host)
+            if not on_host:
+                return E, G, H
+            out = (eng.stage_out("E", E), eng.stage_out("G", G), eng.stage_out("H", H) if want_hessian else None)
+            torch.cuda.current_stream(eng.device).synchronize()
+            return out
         if on_host:
             kd = eng.stage_in("kappa", kappa)
             d1 = eng.stage_in("rdm1", one)
             d2 = eng.stage_in("rdm2", two)
         else:
             kd, d1, d2 = kappa, one, two
-        Coao = eng.to_padded(self.oao_mo_coeff, 2)
         if not on_host:
             return eng.evaluate(Coao, d1, d2, kappa=kd, want_hessian=want_hessian, path=self.integral_path)
         # host results: the Hessian of evaluation b travels to pinned host memory on a copy stream

@@ -104,10 +104,16 @@ int oo_dgemm_small_f64(int transA, int transB, int M, int N, int K,
  * kappa[b][nk]; pair_l/pair_r[nk] = (row, col) of each non-redundant parameter
  * (row > col): K[l,r] = +kappa, K[r,l] = -kappa.  `squarings` >= ceil(log2(||K||_1/0.95))
  * (host-chosen; Pade-[7/7] of K/2^s, Newton-Schulz solve, s squarings).
+ * N <= oo_expm_device_squarings_max_n(): the whole chain is ONE launch out of shared memory, and
+ * `squarings` = -1 lets the kernel apply the same rule per matrix on the device (no host round trip).
  * U[b] is ld x ld.  ws: oo_workspace_bytes(OO_WS_ROTATION, N, ld, 0, batch).      */
 int oo_kappa_rotation_f64(const double *kappa, const int32_t *pair_l, const int32_t *pair_r,
                           int nk, int N, int ld, int batch, int squarings,
                           double *U, void *ws, size_t ws_bytes, void *stream);
+
+/* largest N for which `squarings` = -1 is accepted (0 when the fused kernel is disabled by
+ * the environment variable OO_OPT_EXPM_UNFUSED, kept for A/B tests)               */
+int oo_expm_device_squarings_max_n(void);
 
 /* expm(sign * A) of arbitrary (not nec. skew) ld x ld matrices with ||A||_1 <= 0.95 * 2^squarings */
 int oo_expm_f64(const double *A, double sign, int N, int ld, int batch, int squarings,

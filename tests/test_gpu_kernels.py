@@ -140,6 +140,66 @@ def test_expm_general_matrix(lib):
     assert (U.cpu()[:, :N, :N] - ref).abs().max().item() < 1e-12
 
 
+@pytest.mark.parametrize("N", [5, 8, 31, 40, 47, 56, 64, 65, 70, 130])
+def test_rotation_fused_and_multi_launch_routes(lib, N):
+    """expm(-K) for sizes on both sides of the shared-memory limit (64): explicit squaring count (both routes),
+    and the device-side per-matrix choice of the fused kernel, against torch.linalg.matrix_exp."""
+    from auto_oo_b200.engine import tril_pair_table
+    gen = torch.Generator().manual_seed(N)
+    ld = N + (N & 1)
+    nk = N * (N - 1) // 2
+    pl, pr = tril_pair_table(N, np.arange(nk))
+    B = 4
+    scale = torch.tensor([0.0, 0.02, 0.3, 2.5])[:, None] / np.sqrt(N)
+    kap = torch.randn(B, nk, dtype=F64, generator=gen) * scale
+    K = torch.zeros(B, N, N, dtype=F64)
+    K[:, pl.astype(np.int64), pr.astype(np.int64)] = kap
+    K = K - K.transpose(1, 2)
+    ref = torch.linalg.matrix_exp(-K)
+    s_host = max(0, int(np.ceil(np.log2(max(K.abs().sum(1).max().item(), 1e-300) / 0.95))))
+    kd, pld, prd = kap.cuda(), torch.as_tensor(pl).cuda(), torch.as_tensor(pr).cuda()
+    nbytes = lib.oo_workspace_bytes(1, N, ld, 0, B)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    modes = [s_host] + ([-1] if N <= lib.oo_expm_device_squarings_max_n() else [])
+    for s in modes:
+        U = torch.full((B, ld, ld), float("nan"), dtype=F64, device="cuda")
+        rc = lib.oo_kappa_rotation_f64(kd.data_ptr(), pld.data_ptr(), prd.data_ptr(), nk, N, ld, B, s, U.data_ptr(),
+                                       ws.data_ptr(), nbytes, _stream())
+        assert rc == 0
+        U = U.cpu()
+        assert (U[:, :N, :N] - ref).abs().max().item() < 5e-13, (N, s)
+        if ld > N:
+            assert U[:, N:, :].abs().max().item() == 0 and U[:, :, N:].abs().max().item() == 0
+    if N > lib.oo_expm_device_squarings_max_n():      # the multi-launch route needs the host's choice
+        assert lib.oo_kappa_rotation_f64(kd.data_ptr(), pld.data_ptr(), prd.data_ptr(), nk, N, ld, B, -1,
+                                         U.data_ptr(), ws.data_ptr(), nbytes, _stream()) == -2
+
+
+def test_graph_replay_equals_direct_evaluation():
+    """evaluate_graphed (one CUDA-graph launch per call) against evaluate, across changing inputs, batch sizes
+    and interleaved non-graph calls that share the workspaces."""
+    c = load_case("n28_cas66")
+    eng, p = engine_for(c)
+    Coao = eng.to_padded(c.oao_mo_coeff, 2)
+    d1, d2 = eng.dev(c.one_rdm), eng.dev(c.two_rdm)
+    gen = torch.Generator().manual_seed(4)
+    for trial, B in enumerate([1, 3, 1, 3, 8]):
+        kap = (torch.randn(B, p.n_kappa, dtype=F64, generator=gen) * 0.05).cuda()
+        Eg, Gg, Hg = eng.evaluate_graphed(Coao, d1 * (1 + 0.01 * trial), d2, kappa=kap)
+        if trial == 2:                                   # a non-graph call with a larger batch re-sizes workspaces
+            eng.evaluate(Coao, d1, d2, kappa=torch.zeros(16, p.n_kappa, dtype=F64, device="cuda"))
+        E, G, H = eng.evaluate(Coao, d1 * (1 + 0.01 * trial), d2, kappa=kap)
+        assert torch.equal(Eg, E) and torch.equal(Gg, G) and torch.equal(Hg, H)
+    assert len(eng._ws["graphs"]) == 3
+    Eg, Gg, Hg = eng.evaluate_graphed(Coao, d1, d2, kappa=None, want_hessian=False)
+    E, G, _ = eng.evaluate(Coao, d1, d2, want_hessian=False)
+    assert Hg is None and torch.equal(Eg, E) and torch.equal(Gg, G)
+    ref = c.ref
+    E, G, H = eng.evaluate_graphed(Coao, d1, d2, kappa=c.kappa[None].cuda())
+    assert abs(E.item() - float(ref["E"])) < TOL_E
+    assert np.abs(G[0].cpu().numpy() - ref["G"]).max() < TOL_GH and np.abs(H[0].cpu().numpy() - ref["H"]).max() < TOL_GH
+
+
 # ------------------------------------------------------------------ K2
 @pytest.mark.parametrize("name", SMALL_CASES)
 def test_integral_transforms_match_reference(name):

@@ -92,6 +92,32 @@ def main():
     t("hessian (At + GEMM + assemble)", lambda: eng.class_hessian(cls, F, one, two, out=H[None]),
       flop=2.0 * nI2 * ld2 * (2 * nI2 + 1))
     t("evaluate (E+G+H)", lambda: eng.evaluate(eng.to_padded(oo.oao_mo_coeff, 2), one, two, kappa=kap, H_out=H[None]))
+    Coao = eng.to_padded(oo.oao_mo_coeff, 2)
+    t("evaluate_graphed (E+G+H, one CUDA-graph launch)", lambda: eng.evaluate_graphed(Coao, one, two, kappa=kap,
+                                                                                       clone=False))
+    for B in (8, 64):
+        if nao > 128:
+            break
+        kb = random_kappa(oo.n_kappa, seed=4, device=dev, batch=B)
+        r = t(f"evaluate batch of {B} (direct)", lambda: eng.evaluate(Coao, one, two, kappa=kb))
+        t.rows[-1]["evals_per_s"] = B / t.rows[-1]["ms"] * 1e3
+        r = t(f"evaluate batch of {B} (graph)", lambda: eng.evaluate_graphed(Coao, one, two, kappa=kb, clone=False))
+        t.rows[-1]["evals_per_s"] = B / t.rows[-1]["ms"] * 1e3
+        del r
+    # the public API with host tensors (what NewtonStep / OO_pqc call), wall clock per call
+    import time
+    kh, oh, th = kap.cpu(), one.cpu(), two.cpu()
+    for graphs in (False, True):
+        oo.cuda_graphs = graphs
+        for _ in range(3):
+            oo.energy_gradient_hessian(kh, oh, th)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            oo.energy_gradient_hessian(kh, oh, th)
+        row = {"stage": f"OO_energy.energy_gradient_hessian host->host, cuda_graphs={graphs} (wall)",
+               "ms": (time.perf_counter() - t0) / 10 * 1e3}
+        t.rows.append(row)
+        print(row, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     tag = "" if eng.eri_is_symmetric() else "_general"
     with open(os.path.join(ROOT, "gpurun_out", f"stage_times_{wl}{tag}.json"), "w") as f:
