@@ -20,6 +20,8 @@
 
 namespace oo {
 
+int g_hessian_simple_assemble = 0;     // oo_set_option(OO_OPT_HESSIAN_SIMPLE_ASSEMBLE): 1 = per-thread kernel (A/B tests)
+
 int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
              int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
              int64_t strideC, cudaStream_t stream);
@@ -224,18 +226,26 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
             val += bz * nI2 * width;
         }
     }
+    // the column's (row, value) list goes to shared memory once: in the loop below every B load is then paired
+    // with two broadcast LDS instead of two more global loads through the same L1 pipe
+    extern __shared__ __align__(16) unsigned char spmm_smem[];
+    double *vl = reinterpret_cast<double *>(spmm_smem);
+    int *ix = reinterpret_cast<int *>(vl + width);
+    const int n = cnt[col];
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        ix[e] = idx[(int64_t)col * width + e];
+        vl[e] = val[(int64_t)col * width + e];
+    }
+    __syncthreads();
     const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2;
     if (c >= mat) return;
-    const int n = cnt[col];
-    const int *ix = idx + (int64_t)col * width;
-    const double *vl = val + (int64_t)col * width;
     double2 acc = make_double2(0.0, 0.0);
     int e = 0;
     for (; e + 4 <= n; e += 4) {
-        double2 b0 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c);
-        double2 b1 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 1] * mat + c);
-        double2 b2 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 2] * mat + c);
-        double2 b3 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 3] * mat + c);
+        double2 b0 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c));
+        double2 b1 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 1] * mat + c));
+        double2 b2 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 2] * mat + c));
+        double2 b3 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 3] * mat + c));
         const double v0 = vl[e], v1 = vl[e + 1], v2 = vl[e + 2], v3 = vl[e + 3];
         acc.x = fma(v0, b0.x, acc.x); acc.y = fma(v0, b0.y, acc.y);
         acc.x = fma(v1, b1.x, acc.x); acc.y = fma(v1, b1.y, acc.y);
@@ -243,7 +253,7 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
         acc.x = fma(v3, b3.x, acc.x); acc.y = fma(v3, b3.y, acc.y);
     }
     for (; e < n; ++e) {
-        const double2 b0 = *reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c);
+        const double2 b0 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c));
         const double v0 = vl[e];
         acc.x = fma(v0, b0.x, acc.x); acc.y = fma(v0, b0.y, acc.y);
     }
@@ -323,6 +333,131 @@ hess_assemble_kernel(TView tv, const double *__restrict__ F,
     H[(int64_t)j * nk + k] = v;
 }
 
+// ---- row-tiled assembly -----------------------------------------------------------------------
+// The kernel above reads T[(q s),(p r)] with consecutive threads on consecutive s: a different row of T per
+// thread, 32 cache lines per warp load.  Two of the four terms are contiguous in s (natural k order), the
+// other two in r.  With the pairs sorted by their row index (np.tril_indices order, what the engine passes)
+// a CTA takes one row j and RT consecutive orbital rows r, i.e. one contiguous k range, evaluates the
+// s-contiguous terms in k order, the r-contiguous terms in (s, r) order (warp = 32 consecutive r of one s:
+// two cache lines per load) into a shared-memory strip, and writes the strip out coalesced.
+// hess_pair_runs_kernel finds the k range of every orbital row (binary search) and verifies the structure
+// (rows non-decreasing, columns consecutive within a row); when it does not hold the same kernel falls
+// back to the per-thread form over k tiles -- decided on the device, no host round trip.
+constexpr int kAsmRows = 32;          // orbital rows per CTA
+constexpr int kAsmStrip = 5120;       // shared-memory strip (doubles)
+
+__global__ void hess_pair_runs_kernel(const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int N,
+                                      int *__restrict__ runs /* [N + 2]: start of row l; [N+1] = structure ok */) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int l = threadIdx.x; l <= N; l += blockDim.x) {      // lower_bound(pl, l)
+        int lo = 0, hi = nk;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (pl[mid] < l) lo = mid + 1; else hi = mid;
+        }
+        runs[l] = lo;
+    }
+    int mybad = 0;
+    for (int k = threadIdx.x + 1; k < nk; k += blockDim.x) {
+        if (pl[k] < pl[k - 1]) mybad = 1;
+        if (pl[k] == pl[k - 1] && pr[k] != pr[k - 1] + 1) mybad = 1;
+    }
+    for (int k = threadIdx.x; k < nk; k += blockDim.x)
+        if (pl[k] < 0 || pl[k] >= N || pr[k] < 0 || pr[k] >= N) mybad = 1;
+    if (mybad) bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) runs[N + 1] = bad ? 0 : 1;
+}
+
+__device__ __forceinline__ double hess_t(const TView &tv, int ld, int a, int c, int b, int d) {
+    // [a, c in I] T[(a c),(b d)]
+    if (a >= tv.nI || c >= tv.nI) return 0.0;
+    const int64_t off = (int64_t)b * ld + d;
+    if (tv.Taa && a >= tv.no && c >= tv.no)
+        return tv.Taa[((int64_t)(a - tv.no) * tv.na + (c - tv.no)) * ld * ld + off];
+    return tv.T[((int64_t)a * tv.nIs + c) * ld * ld + off];
+}
+
+__global__ void __launch_bounds__(256)
+hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t *__restrict__ pl,
+                          const int32_t *__restrict__ pr, const int *__restrict__ runs, int nk, int N, int ld,
+                          double *__restrict__ H) {
+    __shared__ double strip[kAsmStrip];
+    __shared__ int rstart[kAsmRows], rlen[kAsmRows], rs0[kAsmRows];
+    __shared__ int s_lo, s_hi;
+    const int j = blockIdx.y;
+    tv.T += blockIdx.z * tv.t_stride;
+    if (tv.Taa) tv.Taa += blockIdx.z * tv.taa_stride;
+    F += blockIdx.z * tv.f_stride;
+    H += blockIdx.z * tv.h_stride;
+    const int p = pl[j], q = pr[j];
+    double *Hj = H + (int64_t)j * nk;
+    const bool structured = runs[N + 1] != 0;
+    const int l0 = blockIdx.x * kAsmRows;
+    int kb = 0, ke = 0;
+    if (structured) {
+        kb = runs[l0];
+        ke = runs[min(l0 + kAsmRows, N)];
+        if (kb == ke) return;
+    }
+    if (!structured || ke - kb + kAsmRows > kAsmStrip) {
+        // per-thread form over k tiles (any pair list)
+        const int kbeg = structured ? kb : blockIdx.x * 256, kend = structured ? ke : nk;
+        const int step = structured ? 256 : gridDim.x * 256;
+        for (int k0 = kbeg; k0 < kend; k0 += step) {
+            const int k = k0 + threadIdx.x;
+            if (k >= kend) continue;
+            const int r = pl[k], s = pr[k];
+            Hj[k] = hess_x(tv, F, ld, p, q, r, s) - hess_x(tv, F, ld, p, q, s, r)
+                  - hess_x(tv, F, ld, q, p, r, s) + hess_x(tv, F, ld, q, p, s, r);
+        }
+        return;
+    }
+    if (threadIdx.x < kAsmRows) {
+        const int l = l0 + threadIdx.x;
+        const int a = l < N ? runs[l] : ke, b = l < N ? runs[l + 1] : ke;
+        rstart[threadIdx.x] = a - kb;
+        rlen[threadIdx.x] = b - a;
+        rs0[threadIdx.x] = b > a ? pr[a] : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int lo = N, hi = -1;
+        for (int i = 0; i < kAsmRows; ++i)
+            if (rlen[i] > 0) {
+                lo = min(lo, rs0[i]);
+                hi = max(hi, rs0[i] + rlen[i] - 1);
+            }
+        s_lo = lo;
+        s_hi = hi;
+    }
+    // pass A (k order): the two terms contiguous in s and the Fock terms
+    for (int i = threadIdx.x; i < ke - kb; i += blockDim.x) {
+        const int k = kb + i;
+        const int r = pl[k], s = pr[k];
+        double v = hess_t(tv, ld, p, r, q, s) - hess_t(tv, ld, q, r, p, s);
+        if (q == s) v -= F[(int64_t)p * ld + r] + F[(int64_t)r * ld + p];
+        if (q == r) v += F[(int64_t)p * ld + s] + F[(int64_t)s * ld + p];
+        if (p == s) v += F[(int64_t)q * ld + r] + F[(int64_t)r * ld + q];
+        if (p == r) v -= F[(int64_t)q * ld + s] + F[(int64_t)s * ld + q];
+        strip[i + (r - l0)] = v;                  // one pad slot per orbital row: conflict-free pass B
+    }
+    __syncthreads();
+    // pass B ((s, r) order, r fastest): the two terms contiguous in r
+    const int ns = s_hi - s_lo + 1;
+    for (int e = threadIdx.x; e < ns * kAsmRows; e += blockDim.x) {
+        const int ri = e % kAsmRows, s = s_lo + e / kAsmRows;
+        const int pos = s - rs0[ri];
+        if (pos < 0 || pos >= rlen[ri]) continue;
+        const int r = l0 + ri;
+        strip[rstart[ri] + ri + pos] += hess_t(tv, ld, q, s, p, r) - hess_t(tv, ld, p, s, q, r);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ke - kb; i += blockDim.x) Hj[kb + i] = strip[i + (pl[kb + i] - l0)];
+}
+
 
 // ---- API-parity helpers: dense full-space RDMs and the dense Y-matrix -----------------
 // (reference full_rdms oo_energy.py:342-379 and y_matrix :381-393 for an arbitrary dense
@@ -367,9 +502,28 @@ __global__ void y_permute_kernel(const double *__restrict__ T, int N, int ld, do
     }
 }
 
+size_t assemble_scratch_bytes(int ld) { return align_up((size_t)(ld + 2) * sizeof(int), 1024); }
+
+int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const int32_t *pr, int nk, int N, int ld,
+                    int batch, double *H, void *scratch, cudaStream_t stream) {
+    if (g_hessian_simple_assemble) {
+        dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk, (unsigned)batch);
+        hess_assemble_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, nk, ld, H);
+        OO_LAUNCH_CHECK();
+        return OO_OK;
+    }
+    int *runs = reinterpret_cast<int *>(scratch);
+    hess_pair_runs_kernel<<<1, 1024, 0, stream>>>(pl, pr, nk, N, runs);
+    OO_LAUNCH_CHECK();
+    dim3 grid((unsigned)ceil_div(N, kAsmRows), (unsigned)nk, (unsigned)batch);
+    hess_assemble_rows_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, runs, nk, N, ld, H);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
 struct HessLayout {
     int64_t lda, krows;
-    size_t off_b, off_t, total;
+    size_t off_b, off_t, off_runs, total;
 };
 
 HessLayout hess_layout(int ld, int nI) {
@@ -382,7 +536,8 @@ HessLayout hess_layout(int ld, int nI) {
     const size_t t_bytes = align_up((size_t)nI2 * ld * ld * sizeof(double), 1024);
     L.off_b = at_bytes;
     L.off_t = at_bytes + b_bytes;
-    L.total = at_bytes + b_bytes + t_bytes;
+    L.off_runs = at_bytes + b_bytes + t_bytes;
+    L.total = L.off_runs + assemble_scratch_bytes(ld);
     return L;
 }
 
@@ -424,13 +579,9 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     }
     int rc = dgemm_tn(At, B, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
     if (rc) return rc;
-    {
-        if (nk > 65535) return OO_ERR_UNSUPPORTED;
-        dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-        hess_assemble_kernel<<<grid, 256, 0, stream>>>(TView{T, nullptr, nI, nI, no, na, 0, 0, 0, 0}, F, pl, pr, nk, ld, H);
-        OO_LAUNCH_CHECK();
-    }
-    return OO_OK;
+    if (nk > 65535) return OO_ERR_UNSUPPORTED;
+    return launch_assemble(TView{T, nullptr, nI, nI, no, na, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1, H, w + L.off_runs,
+                           stream);
 }
 
 // Hessian from the class buffer of classes.cu: cls = [K rows; J rows; h' row] IS the B operand.
@@ -439,7 +590,7 @@ int g_hessian_dense = 0;     // oo_set_option(OO_OPT_HESSIAN_DENSE): 1 = one den
 struct ClassHessLayout {
     int width;                       // ELL width of the sparse part
     int64_t lda_c, krows_c;          // dense act-act block
-    size_t off_cnt, off_idx, off_val, off_flag, off_atc, off_bc, off_taa, off_t, total;
+    size_t off_cnt, off_idx, off_val, off_flag, off_atc, off_bc, off_taa, off_t, off_runs, total;
 };
 
 static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na, int batch) {
@@ -458,18 +609,19 @@ static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na, int ba
     L.off_bc = take((size_t)batch * L.krows_c * mat * sizeof(double));
     L.off_taa = take((size_t)batch * na2 * mat * sizeof(double));
     L.off_t = take((size_t)batch * nI2 * mat * sizeof(double));
+    L.off_runs = take(assemble_scratch_bytes(ld));
     L.total = off;
     return L;
 }
 
 size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch) {
     const HessLayout D = hess_layout(ld, nIp);
-    const size_t dense = D.off_b + (D.total - D.off_t);          // At + T (no gathered B); batch 1 only
+    const size_t dense = D.off_b + (D.total - D.off_t);          // At + T + pair runs (no gathered B); batch 1 only
     const size_t sparse = class_hess_layout(ld, nIp, no, na, batch).total;
     return dense > sparse ? dense : sparse;
 }
 
-static int class_hessian_dense(const double *cls, const double *F, const RdmView &rdm, int ld, int nIp,
+static int class_hessian_dense(const double *cls, const double *F, const RdmView &rdm, int N, int ld, int nIp,
                                const int32_t *pl, const int32_t *pr, int nk, double *H, void *ws,
                                cudaStream_t stream) {
     const HessLayout L = hess_layout(ld, nIp);
@@ -483,11 +635,8 @@ static int class_hessian_dense(const double *cls, const double *F, const RdmView
     OO_LAUNCH_CHECK();
     int rc = dgemm_tn(At, cls, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
     if (rc) return rc;
-    dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk);
-    hess_assemble_kernel<<<grid, 256, 0, stream>>>(
-        TView{T, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na, 0, 0, 0, 0}, F, pl, pr, nk, ld, H);
-    OO_LAUNCH_CHECK();
-    return OO_OK;
+    return launch_assemble(TView{T, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1,
+                           H, w + L.off_b + (L.off_runs - L.off_t), stream);
 }
 
 // batch evaluations: cls[b] (class buffers, contiguous), F[b] (ld^2), H[b] (nk^2); RDMs shared
@@ -508,7 +657,7 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     if (g_hessian_dense) {
         for (int b = 0; b < batch; ++b) {
             RdmView rb{d1 + b * sd1, d2 + b * sd2, no, na};
-            int rc = class_hessian_dense(cls + b * cls_stride, F + b * mat, rb, ld, nIp, pl, pr, nk,
+            int rc = class_hessian_dense(cls + b * cls_stride, F + b * mat, rb, N, ld, nIp, pl, pr, nk,
                                          H + (int64_t)b * nk * nk, ws, stream);
             if (rc) return rc;
         }
@@ -548,15 +697,14 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     // sparse remainder (accumulates into Taa for act-act columns)
     {
         dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256), (unsigned)batch);
-        hess_spmm_kernel<<<grid, 256, 0, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no, na,
+        const size_t smem = (size_t)L.width * (sizeof(double) + sizeof(int));
+        if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
+        hess_spmm_kernel<<<grid, 256, smem, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no, na,
                                                    nIp, mat, T, Taa);
         OO_LAUNCH_CHECK();
     }
-    dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk, (unsigned)batch);
-    hess_assemble_kernel<<<grid, 256, 0, stream>>>(
-        TView{T, Taa, no + na, nIp, no, na, nI2 * mat, na2 * mat, mat, (int64_t)nk * nk}, F, pl, pr, nk, ld, H);
-    OO_LAUNCH_CHECK();
-    return OO_OK;
+    return launch_assemble(TView{T, Taa, no + na, nIp, no, na, nI2 * mat, na2 * mat, mat, (int64_t)nk * nk}, F, pl, pr,
+                           nk, N, ld, batch, H, w + L.off_runs, stream);
 }
 
 int full_rdms(const double *d1, const double *d2, int no, int na, int N, double *one_full,

@@ -508,8 +508,10 @@ class OO_energy_geometries:
     ``kappa (G, n_kappa)`` and RDMs shared ``(na,na)/(na^4)`` or per geometry ``(G, ...)``."""
 
     def __init__(self, mols, ncas, nelecas, oao_mo_coeff, freeze_active=False, device=None,
-                 eri_symmetry="auto"):
+                 eri_symmetry="auto", cuda_graphs="auto"):
         mols = list(mols)
+        self.cuda_graphs = (mols[0].nao <= OO_energy.GRAPH_MAX_NAO) if cuda_graphs == "auto" else bool(cuda_graphs)
+        self._Coao_dev = self._Coao_src = None
         assert len(mols) > 0
         self.nao = mols[0].nao
         assert all(m.nao == self.nao for m in mols), "all geometries must share the basis size"
@@ -530,15 +532,31 @@ class OO_energy_geometries:
 
     def energy_gradient_hessian(self, kappa, one_rdm, two_rdm, want_hessian=True):
         """``(E (G,), gradient (G, n_kappa), Hessian (G, n_kappa, n_kappa))`` at
-        ``C_g expm(-K(kappa_g))`` for every geometry ``g``; results on the device of ``kappa``."""
+        ``C_g expm(-K(kappa_g))`` for every geometry ``g``; results on the device of ``kappa`` (host results
+        are views of reused pinned staging buffers, valid until the next call).  The whole pass is one
+        CUDA-graph launch when ``cuda_graphs`` is on."""
         eng = self.engine
         kappa = _as_tensor(kappa).detach().reshape(self.n_geometries, self.n_kappa)
-        Coao = eng.to_padded(self.oao_mo_coeff, 2, batch=self.n_geometries)
-        E, G, H = eng.evaluate(Coao, eng.dev(one_rdm), eng.dev(two_rdm), kappa=eng.dev(kappa),
-                               want_hessian=want_hessian, path="class")
-        if kappa.device.type == "cpu":
-            return E.cpu(), G.cpu(), (H.cpu() if want_hessian else None)
-        return E, G, H
+        one, two = _as_tensor(one_rdm).detach(), _as_tensor(two_rdm).detach()
+        on_host = kappa.device.type == "cpu"
+        src = (self.oao_mo_coeff, self.oao_mo_coeff._version)          # follows re-assignment and in-place writes
+        if self._Coao_dev is None or self._Coao_src[0] is not src[0] or self._Coao_src[1] != src[1]:
+            self._Coao_dev = eng.to_padded(self.oao_mo_coeff, 2, batch=self.n_geometries)
+            self._Coao_src = src
+        if on_host:
+            kappa, one, two = (eng.stage_pinned(k, t.to(F64)) for k, t in
+                               (("kappa", kappa), ("rdm1", one), ("rdm2", two)))
+        if self.cuda_graphs:
+            E, G, H = eng.evaluate_graphed(self._Coao_dev, one, two, kappa=kappa, want_hessian=want_hessian,
+                                           path="class", clone=not on_host)
+        else:
+            E, G, H = eng.evaluate(self._Coao_dev, eng.dev(one), eng.dev(two), kappa=eng.dev(kappa),
+                                   want_hessian=want_hessian, path="class")
+        if not on_host:
+            return E, G, H
+        out = (eng.stage_out("E", E), eng.stage_out("G", G), eng.stage_out("H", H) if want_hessian else None)
+        torch.cuda.current_stream(eng.device).synchronize()
+        return out
 
     def rotate(self, kappa):
         """``C_g <- C_g expm(-K(kappa_g))`` for every geometry (the re-basing step of the loop)."""
