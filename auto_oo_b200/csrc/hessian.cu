@@ -343,8 +343,8 @@ hess_assemble_kernel(TView tv, const double *__restrict__ F,
 // hess_pair_runs_kernel finds the k range of every orbital row (binary search) and verifies the structure
 // (rows non-decreasing, columns consecutive within a row); when it does not hold the same kernel falls
 // back to the per-thread form over k tiles -- decided on the device, no host round trip.
-constexpr int kAsmRows = 32;          // orbital rows per CTA
-constexpr int kAsmStrip = 5120;       // shared-memory strip (doubles)
+constexpr int kAsmRows = 32;                       // orbital rows per CTA
+constexpr int kAsmStrip = kAsmRows * (64 + 1);     // shared-memory strip (doubles): runs of up to 64 columns
 
 __global__ void hess_pair_runs_kernel(const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int N,
                                       int *__restrict__ runs /* [N + 2]: start of row l; [N+1] = structure ok */) {
@@ -376,24 +376,29 @@ __device__ __forceinline__ double hess_t(const TView &tv, int ld, int a, int c, 
     if (a >= tv.nI || c >= tv.nI) return 0.0;
     const int64_t off = (int64_t)b * ld + d;
     if (tv.Taa && a >= tv.no && c >= tv.no)
-        return tv.Taa[((int64_t)(a - tv.no) * tv.na + (c - tv.no)) * ld * ld + off];
-    return tv.T[((int64_t)a * tv.nIs + c) * ld * ld + off];
+        return __ldg(tv.Taa + ((int64_t)(a - tv.no) * tv.na + (c - tv.no)) * ld * ld + off);
+    return __ldg(tv.T + ((int64_t)a * tv.nIs + c) * ld * ld + off);
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ double fock_sym(const double *__restrict__ F, int ld, int a, int c) {
+    return __ldg(F + (int64_t)a * ld + c) + __ldg(F + (int64_t)c * ld + a);
+}
+
+constexpr int kAsmJ = 8;              // Hessian rows j per CTA (the row-tile bookkeeping is shared by all of them)
+
+__global__ void __launch_bounds__(256, 4)
 hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t *__restrict__ pl,
                           const int32_t *__restrict__ pr, const int *__restrict__ runs, int nk, int N, int ld,
                           double *__restrict__ H) {
     __shared__ double strip[kAsmStrip];
+    __shared__ unsigned char rowof[kAsmStrip];
     __shared__ int rstart[kAsmRows], rlen[kAsmRows], rs0[kAsmRows];
     __shared__ int s_lo, s_hi;
-    const int j = blockIdx.y;
     tv.T += blockIdx.z * tv.t_stride;
     if (tv.Taa) tv.Taa += blockIdx.z * tv.taa_stride;
     F += blockIdx.z * tv.f_stride;
     H += blockIdx.z * tv.h_stride;
-    const int p = pl[j], q = pr[j];
-    double *Hj = H + (int64_t)j * nk;
+    const int j0 = blockIdx.y * kAsmJ, j1 = min(j0 + kAsmJ, nk);
     const bool structured = runs[N + 1] != 0;
     const int l0 = blockIdx.x * kAsmRows;
     int kb = 0, ke = 0;
@@ -402,62 +407,69 @@ hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t 
         ke = runs[min(l0 + kAsmRows, N)];
         if (kb == ke) return;
     }
-    if (!structured || ke - kb + kAsmRows > kAsmStrip) {
-        // per-thread form over k tiles (any pair list)
+    // Rows r outside I kill the two s-contiguous terms ([p,r in I] and [q,r in I]); what is left is contiguous in
+    // r.  Tiles with a row inside I (a few short runs) and unstructured pair lists take the per-thread form.
+    if (!structured || l0 < tv.nI || ke - kb + kAsmRows > kAsmStrip) {
         const int kbeg = structured ? kb : blockIdx.x * 256, kend = structured ? ke : nk;
         const int step = structured ? 256 : gridDim.x * 256;
         for (int k0 = kbeg; k0 < kend; k0 += step) {
             const int k = k0 + threadIdx.x;
             if (k >= kend) continue;
             const int r = pl[k], s = pr[k];
-            Hj[k] = hess_x(tv, F, ld, p, q, r, s) - hess_x(tv, F, ld, p, q, s, r)
-                  - hess_x(tv, F, ld, q, p, r, s) + hess_x(tv, F, ld, q, p, s, r);
+            for (int j = j0; j < j1; ++j) {
+                const int p = pl[j], q = pr[j];
+                H[(int64_t)j * nk + k] = hess_x(tv, F, ld, p, q, r, s) - hess_x(tv, F, ld, p, q, s, r)
+                                       - hess_x(tv, F, ld, q, p, r, s) + hess_x(tv, F, ld, q, p, s, r);
+            }
         }
         return;
     }
     if (threadIdx.x < kAsmRows) {
         const int l = l0 + threadIdx.x;
         const int a = l < N ? runs[l] : ke, b = l < N ? runs[l + 1] : ke;
-        rstart[threadIdx.x] = a - kb;
+        rstart[threadIdx.x] = a - kb + threadIdx.x;        // one pad slot per orbital row: conflict-free strip writes
         rlen[threadIdx.x] = b - a;
-        rs0[threadIdx.x] = b > a ? pr[a] : 0;
+        const int first = b > a ? pr[a] : N, last = b > a ? first + (b - a) - 1 : -1;
+        rs0[threadIdx.x] = b > a ? first : 0;
+        int lo = first, hi = last;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (threadIdx.x == 0) {
+            s_lo = lo;
+            s_hi = hi;
+        }
     }
+    for (int i = threadIdx.x; i < ke - kb; i += blockDim.x) rowof[i] = (unsigned char)(pl[kb + i] - l0);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int lo = N, hi = -1;
-        for (int i = 0; i < kAsmRows; ++i)
-            if (rlen[i] > 0) {
-                lo = min(lo, rs0[i]);
-                hi = max(hi, rs0[i] + rlen[i] - 1);
-            }
-        s_lo = lo;
-        s_hi = hi;
-    }
-    // pass A (k order): the two terms contiguous in s and the Fock terms
-    for (int i = threadIdx.x; i < ke - kb; i += blockDim.x) {
-        const int k = kb + i;
-        const int r = pl[k], s = pr[k];
-        double v = hess_t(tv, ld, p, r, q, s) - hess_t(tv, ld, q, r, p, s);
-        if (q == s) v -= F[(int64_t)p * ld + r] + F[(int64_t)r * ld + p];
-        if (q == r) v += F[(int64_t)p * ld + s] + F[(int64_t)s * ld + p];
-        if (p == s) v += F[(int64_t)q * ld + r] + F[(int64_t)r * ld + q];
-        if (p == r) v -= F[(int64_t)q * ld + s] + F[(int64_t)s * ld + q];
-        strip[i + (r - l0)] = v;                  // one pad slot per orbital row: conflict-free pass B
-    }
-    __syncthreads();
-    // pass B ((s, r) order, r fastest): the two terms contiguous in r
+    // (s, r) order, r fastest: a warp reads 32 consecutive r of one row of T
     const int ns = s_hi - s_lo + 1;
-    for (int e = threadIdx.x; e < ns * kAsmRows; e += blockDim.x) {
-        const int ri = e % kAsmRows, s = s_lo + e / kAsmRows;
-        const int pos = s - rs0[ri];
-        if (pos < 0 || pos >= rlen[ri]) continue;
-        const int r = l0 + ri;
-        strip[rstart[ri] + ri + pos] += hess_t(tv, ld, q, s, p, r) - hess_t(tv, ld, p, s, q, r);
+    const int ri = threadIdx.x % kAsmRows, r = l0 + ri;
+    const int my_s0 = rs0[ri], my_len = rlen[ri], my_start = rstart[ri];
+    for (int j = j0; j < j1; ++j) {
+        const int p = pl[j], q = pr[j];
+        const bool p_in = p < tv.nI;
+#pragma unroll 2
+        for (int si = threadIdx.x / kAsmRows; si < ns; si += 256 / kAsmRows) {
+            const int s = s_lo + si;
+            const int pos = s - my_s0;
+            if (pos < 0 || pos >= my_len) continue;
+            double v = hess_t(tv, ld, q, s, p, r);
+            if (p_in) v -= hess_t(tv, ld, p, s, q, r);
+            if (q == s) v -= fock_sym(F, ld, p, r);
+            if (q == r) v += fock_sym(F, ld, p, s);
+            if (p == s) v += fock_sym(F, ld, q, r);
+            if (p == r) v -= fock_sym(F, ld, q, s);
+            strip[my_start + pos] = v;
+        }
+        __syncthreads();
+        double *Hj = H + (int64_t)j * nk + kb;
+        for (int i = threadIdx.x; i < ke - kb; i += blockDim.x) Hj[i] = strip[i + rowof[i]];
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < ke - kb; i += blockDim.x) Hj[kb + i] = strip[i + (pl[kb + i] - l0)];
 }
-
 
 // ---- API-parity helpers: dense full-space RDMs and the dense Y-matrix -----------------
 // (reference full_rdms oo_energy.py:342-379 and y_matrix :381-393 for an arbitrary dense
@@ -515,7 +527,7 @@ int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const i
     int *runs = reinterpret_cast<int *>(scratch);
     hess_pair_runs_kernel<<<1, 1024, 0, stream>>>(pl, pr, nk, N, runs);
     OO_LAUNCH_CHECK();
-    dim3 grid((unsigned)ceil_div(N, kAsmRows), (unsigned)nk, (unsigned)batch);
+    dim3 grid((unsigned)ceil_div(N, kAsmRows), (unsigned)ceil_div(nk, kAsmJ), (unsigned)batch);
     hess_assemble_rows_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, runs, nk, N, ld, H);
     OO_LAUNCH_CHECK();
     return OO_OK;
