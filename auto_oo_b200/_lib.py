@@ -66,11 +66,13 @@ _SIGNATURES = {
     "oo_class_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr,
                                     _ptr, _i32, _ptr, _ptr, _size, _ptr]),
     "oo_rdm_columns": (_i64, [_i32]),
-    "oo_rdm_excitations_f64": (_i32, [_ptr, _i32, _i32, _i32, _i64, _i64, _i32, _ptr, _ptr]),
+    "oo_rdm_excitations_f64": (_i32, [_ptr, _i32, _i32, _i32, _i64, _i64, _i32, _ptr, _ptr, _i64, _ptr]),
+    "oo_rdm_sector_flags_f64": (_i32, [_ptr, _i32, _i32, _i32, _ptr, _ptr]),
+    "oo_rdm_sector_mask": (_i32, [_ptr, _i32, _i32, _ptr, _ptr]),
     "oo_rdm_accumulate_f64": (_i32, [_ptr, _i32, _i64, _ptr, _ptr]),
     "oo_rdm_assemble_f64": (_i32, [_ptr, _i32, _ptr, _ptr, _ptr]),
     "oo_rdm_operator_matrix_f64": (_i32, [_ptr, _ptr, _i32, _ptr, _ptr]),
-    "oo_rdm_apply_gather_f64": (_i32, [_ptr, _ptr, _i32, _i32, _ptr, _ptr]),
+    "oo_rdm_apply_gather_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "oo_full_rdms_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "oo_y_matrix_f64": (_i32, [_ptr, _ptr, _i32, _i32, _ptr, _ptr, _size, _ptr]),
     "oo_pad_copy_f64": (_i32, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr]),

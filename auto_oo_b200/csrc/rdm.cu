@@ -52,9 +52,12 @@ __device__ __forceinline__ bool excite_source(uint32_t x, int bi, int bj, uint32
 // Phi[k][c] (transposed == 0, row length ncolp) or Phi[c][k] (transposed == 1, row length nrows)
 //   k = x - x0 (real parts) and nx + x - x0 (imaginary parts, complex input only)
 //   c < na^2: (E_rs v)[x], c = r*na + s;  c == na^2: v[x];  c > na^2: zero padding
+// xlist != null: rows are the COMPACT basis states x = xlist[x0 + xl] (x0 + xl >= nlist: zero row) -- the
+// particle-number sectors the state lives in (rdm_sector_* below); E_rs never leaves a sector.
 __global__ void __launch_bounds__(256) rdm_excite_kernel(const double *__restrict__ psi, int is_complex,
                                                          SpinMap sm, int64_t x0, int64_t nx, int ncolp,
-                                                         int transposed, double *__restrict__ Phi) {
+                                                         int transposed, double *__restrict__ Phi,
+                                                         const int32_t *__restrict__ xlist, int64_t nlist) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nx * ncolp) return;
     int64_t xl;
@@ -66,10 +69,16 @@ __global__ void __launch_bounds__(256) rdm_excite_kernel(const double *__restric
         xl = idx / ncolp;
         c = (int)(idx % ncolp);
     }
-    const uint32_t x = (uint32_t)(x0 + xl);
+    uint32_t x = (uint32_t)(x0 + xl);
+    bool live = true;
+    if (xlist) {
+        live = x0 + xl < nlist;
+        x = live ? (uint32_t)xlist[x0 + xl] : 0u;
+    }
     const int ncol = sm.na * sm.na;
     double re = 0.0, im = 0.0;
-    if (c < ncol) {
+    if (!live) {
+    } else if (c < ncol) {
         const int r = c / sm.na, s = c % sm.na;
 #pragma unroll
         for (int spin = 0; spin < 2; ++spin) {
@@ -147,32 +156,73 @@ __global__ void rdm_operator_matrix_kernel(const double *__restrict__ g1, const 
     M[idx] = v;
 }
 
-// w[x] = sum_pq sum_sigma sign * Wt[pq][xsrc]   (E_pq applied to column pq, summed)
+// w[x] = sum_pq sum_sigma sign * Wt[pq][xsrc]   (E_pq applied to column pq, summed).
+// Compact form (xlist/pos != null): k runs over the R compact basis states, x = xlist[k], and column xsrc of
+// Wt sits at pos[xsrc]; w (full length, zero-initialised by the caller) is written at x only.
 __global__ void __launch_bounds__(256) rdm_apply_gather_kernel(const double *__restrict__ Wre,
                                                                const double *__restrict__ Wim, SpinMap sm,
-                                                               int64_t D, double *__restrict__ w) {
-    const int64_t xi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (xi >= D) return;
-    const uint32_t x = (uint32_t)xi;
+                                                               int64_t R, int64_t ldW,
+                                                               const int32_t *__restrict__ xlist,
+                                                               const int32_t *__restrict__ pos,
+                                                               double *__restrict__ w) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= R) return;
+    const uint32_t x = xlist ? (uint32_t)xlist[k] : (uint32_t)k;
     double re = 0.0, im = 0.0;
     for (int p = 0; p < sm.na; ++p)
         for (int q = 0; q < sm.na; ++q) {
-            const int64_t row = (int64_t)(p * sm.na + q) * D;
+            const int64_t row = (int64_t)(p * sm.na + q) * ldW;
 #pragma unroll
             for (int spin = 0; spin < 2; ++spin) {
                 uint32_t xs;
                 double sg;
                 if (excite_source(x, sm.bit(p, spin), sm.bit(q, spin), xs, sg)) {
-                    re += sg * Wre[row + xs];
-                    if (Wim) im += sg * Wim[row + xs];
+                    const int64_t ks = pos ? (int64_t)pos[xs] : (int64_t)xs;
+                    re += sg * Wre[row + ks];
+                    if (Wim) im += sg * Wim[row + ks];
                 }
             }
         }
     if (Wim) {
-        reinterpret_cast<double2 *>(w)[xi] = make_double2(re, im);
+        reinterpret_cast<double2 *>(w)[x] = make_double2(re, im);
     } else {
-        w[xi] = re;
+        w[x] = re;
     }
+}
+
+// ---- particle-number sectors ---------------------------------------------------------------------
+// sector(x) = n_up(x) * (na + 1) + n_down(x).  Every E_rs conserves both counts, so Phi has non-zero rows only
+// on the sectors psi occupies: for the number-conserving ansaetze of the reference (one sector) that is
+// C(na, n_up) C(na, n_down) of the 4^na basis states (5 % at CAS(12,12)).
+struct SectorMasks {
+    uint32_t up, down;
+    int na;
+    __device__ __forceinline__ int id(uint32_t x) const { return __popc(x & up) * (na + 1) + __popc(x & down); }
+};
+
+__global__ void rdm_sector_flags_kernel(const double *__restrict__ psi, int is_complex, SectorMasks m, int64_t D,
+                                        int32_t *__restrict__ flags) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= D) return;
+    const bool nz = is_complex ? (psi[2 * x] != 0.0 || psi[2 * x + 1] != 0.0) : (psi[x] != 0.0);
+    if (nz) flags[m.id((uint32_t)x)] = 1;          // benign race: every writer stores 1
+}
+
+__global__ void rdm_sector_mask_kernel(const int32_t *__restrict__ flags, SectorMasks m, int64_t D,
+                                       int32_t *__restrict__ mask) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < D) mask[x] = flags[m.id((uint32_t)x)] ? 1 : 0;
+}
+
+SectorMasks sector_masks(int ncas, int up_then_down) {
+    SectorMasks m{0u, 0u, ncas};
+    const int nq = 2 * ncas;
+    for (int orb = 0; orb < ncas; ++orb)
+        for (int spin = 0; spin < 2; ++spin) {
+            const int q = up_then_down ? orb + spin * ncas : 2 * orb + spin;
+            (spin ? m.down : m.up) |= 1u << (nq - 1 - q);
+        }
+    return m;
 }
 
 inline int rdm_ncolp(int na) {
@@ -183,16 +233,16 @@ inline int rdm_ncolp(int na) {
 }  // namespace
 
 int rdm_excitations(const double *psi, int is_complex, int ncas, int up_then_down, int64_t x0, int64_t nx,
-                    int transposed, double *Phi, cudaStream_t stream) {
+                    int transposed, double *Phi, const int32_t *xlist, int64_t nlist, cudaStream_t stream) {
     OO_REQUIRE(psi && Phi && ncas > 0 && ncas <= 15 && x0 >= 0 && nx > 0);
-    OO_REQUIRE(x0 + nx <= (1ll << (2 * ncas)));
+    OO_REQUIRE(xlist ? (nlist >= 0 && nlist <= (1ll << (2 * ncas))) : (x0 + nx <= (1ll << (2 * ncas))));
     const SpinMap sm{2 * ncas, ncas, up_then_down ? 1 : 0};
     const int ncolp = rdm_ncolp(ncas);
     const int64_t total = nx * ncolp;
     const int64_t grid = ceil_div(total, 256);
     if (grid > 0x7fffffffll) return OO_ERR_UNSUPPORTED;
     rdm_excite_kernel<<<(unsigned)grid, 256, 0, stream>>>(psi, is_complex ? 1 : 0, sm, x0, nx, ncolp,
-                                                          transposed ? 1 : 0, Phi);
+                                                          transposed ? 1 : 0, Phi, xlist, nlist);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -204,8 +254,28 @@ extern "C" {
 int64_t oo_rdm_columns(int ncas) { return ncas > 0 ? oo::rdm_ncolp(ncas) : 0; }
 
 int oo_rdm_excitations_f64(const double *psi, int is_complex, int ncas, int up_then_down, int64_t x0, int64_t nx,
-                           int transposed, double *Phi, void *stream) {
-    return oo::rdm_excitations(psi, is_complex, ncas, up_then_down, x0, nx, transposed, Phi, (cudaStream_t)stream);
+                           int transposed, double *Phi, const int32_t *xlist, int64_t nlist, void *stream) {
+    return oo::rdm_excitations(psi, is_complex, ncas, up_then_down, x0, nx, transposed, Phi, xlist, nlist,
+                               (cudaStream_t)stream);
+}
+
+int oo_rdm_sector_flags_f64(const double *psi, int is_complex, int ncas, int up_then_down, int32_t *flags,
+                            void *stream) {
+    OO_REQUIRE(psi && flags && ncas > 0 && ncas <= 15);
+    const int64_t D = 1ll << (2 * ncas);
+    oo::rdm_sector_flags_kernel<<<(unsigned)oo::ceil_div(D, 256), 256, 0, (cudaStream_t)stream>>>(
+        psi, is_complex ? 1 : 0, oo::sector_masks(ncas, up_then_down), D, flags);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+int oo_rdm_sector_mask(const int32_t *flags, int ncas, int up_then_down, int32_t *mask, void *stream) {
+    OO_REQUIRE(flags && mask && ncas > 0 && ncas <= 15);
+    const int64_t D = 1ll << (2 * ncas);
+    oo::rdm_sector_mask_kernel<<<(unsigned)oo::ceil_div(D, 256), 256, 0, (cudaStream_t)stream>>>(
+        flags, oo::sector_masks(ncas, up_then_down), D, mask);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
 }
 
 int oo_rdm_accumulate_f64(const double *parts, int nparts, int64_t n, double *acc, void *stream) {
@@ -234,13 +304,15 @@ int oo_rdm_operator_matrix_f64(const double *g1, const double *g2, int ncas, dou
     return OO_OK;
 }
 
-int oo_rdm_apply_gather_f64(const double *Wt_re, const double *Wt_im, int ncas, int up_then_down, double *w,
-                            void *stream) {
-    OO_REQUIRE(Wt_re && w && ncas > 0 && ncas <= 15);
+int oo_rdm_apply_gather_f64(const double *Wt_re, const double *Wt_im, int ncas, int up_then_down, int64_t R,
+                            int64_t ldW, const int32_t *xlist, const int32_t *pos, double *w, void *stream) {
+    OO_REQUIRE(Wt_re && w && ncas > 0 && ncas <= 15 && R >= 0 && ldW >= R);
+    OO_REQUIRE((xlist == nullptr) == (pos == nullptr));
+    OO_REQUIRE(R <= (1ll << (2 * ncas)) && (xlist || R == (1ll << (2 * ncas))));
+    if (R == 0) return OO_OK;
     const oo::SpinMap sm{2 * ncas, ncas, up_then_down ? 1 : 0};
-    const int64_t D = 1ll << (2 * ncas);
-    oo::rdm_apply_gather_kernel<<<(unsigned)oo::ceil_div(D, 256), 256, 0, (cudaStream_t)stream>>>(Wt_re, Wt_im, sm,
-                                                                                                  D, w);
+    oo::rdm_apply_gather_kernel<<<(unsigned)oo::ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(
+        Wt_re, Wt_im, sm, R, ldW, xlist, pos, w);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }

@@ -270,12 +270,25 @@ int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma
  *  oo_rdm_apply_gather_f64     w[x] = sum_pq (E_pq Wt[pq])[x]   (Wt_im NULL for a real state).        */
 int64_t oo_rdm_columns(int ncas);
 int oo_rdm_excitations_f64(const double *psi, int is_complex, int ncas, int up_then_down,
-                           int64_t x0, int64_t nx, int transposed, double *Phi, void *stream);
+                           int64_t x0, int64_t nx, int transposed, double *Phi,
+                           const int32_t *xlist, int64_t nlist, void *stream);
 int oo_rdm_accumulate_f64(const double *parts, int nparts, int64_t n, double *acc, void *stream);
 int oo_rdm_assemble_f64(const double *C, int ncas, double *one_rdm, double *two_rdm, void *stream);
 int oo_rdm_operator_matrix_f64(const double *g1, const double *g2, int ncas, double *Mext, void *stream);
 int oo_rdm_apply_gather_f64(const double *Wt_re, const double *Wt_im, int ncas, int up_then_down,
+                            int64_t R, int64_t ldW, const int32_t *xlist, const int32_t *pos,
                             double *w, void *stream);
+/* Particle-number sectors (n_up, n_down) -> id n_up*(ncas+1)+n_down.  Every E_rs conserves both counts, so
+ * all of the above can run on the COMPACT list of basis states of the sectors psi occupies (one sector for the
+ * reference's number-conserving ansaetze: 5 % of the 4^ncas states at CAS(12,12)):
+ *  oo_rdm_sector_flags_f64  flags[id] = 1 where psi has a non-zero amplitude (flags zeroed by the caller),
+ *  oo_rdm_sector_mask       mask[x] = flags[id(x)]  (the caller turns it into xlist = nonzero(mask) and
+ *                           pos = exclusive scan);  xlist/nlist above: rows are x = xlist[x0 + k] (zero rows past
+ *                           nlist); apply_gather: R compact states, Wt row length ldW, column of x at pos[x],
+ *                           w full length and zero-initialised.  xlist = pos = NULL: all 4^ncas states.          */
+int oo_rdm_sector_flags_f64(const double *psi, int is_complex, int ncas, int up_then_down,
+                            int32_t *flags, void *stream);
+int oo_rdm_sector_mask(const int32_t *flags, int ncas, int up_then_down, int32_t *mask, void *stream);
 
 /* ---- API-parity helpers (not on the hot path) ------------------------------
  * Dense full-space RDMs exactly as full_rdms defines them (oo_energy.py:342-379):

@@ -150,6 +150,65 @@ def test_cuda_rdms_sum_rules_at_size(ncas, nelec):
     assert (two - two2).abs().max().item() < 1e-13
 
 
+def sector_state(ncas, seed, sectors, cplx, utd=False):
+    """random state supported on the given (n_up, n_down) particle-number sectors"""
+    rng = np.random.default_rng(seed)
+    D, nq = 4 ** ncas, 2 * ncas
+    up = [nq - 1 - (p if utd else 2 * p) for p in range(ncas)]
+    dn = [nq - 1 - (p + ncas if utd else 2 * p + 1) for p in range(ncas)]
+    x = np.arange(D)
+    nup = sum(((x >> b) & 1) for b in up)
+    ndn = sum(((x >> b) & 1) for b in dn)
+    keep = np.zeros(D, dtype=bool)
+    for a, b in sectors:
+        keep |= (nup == a) & (ndn == b)
+    psi = rng.standard_normal(D) + (1j * rng.standard_normal(D) if cplx else 0.0)
+    psi = np.where(keep, psi, 0.0)
+    return psi / np.linalg.norm(psi), int(keep.sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ncas,sectors,cplx,utd,chunk", [
+    (3, [(2, 1)], True, False, 4), (3, [(1, 1)], False, True, 1 << 18), (4, [(2, 2)], True, False, 16),
+    (4, [(2, 2), (1, 3)], False, False, 8), (3, [(0, 0)], False, False, 4), (5, [(3, 2)], True, True, 1 << 18)])
+def test_cuda_rdms_on_the_occupied_sectors_only(ncas, sectors, cplx, utd, chunk):
+    """Number-conserving states: every pass runs on the compact list of basis states of the occupied sectors
+    (found on the device) and gives the numbers of the full-space pass; values, the transition form with a
+    partner in other sectors, the operator application and first derivatives."""
+    from oracle import rdm_oracle as ro
+    from auto_oo_b200 import StatevectorRDM
+    psi, count = sector_state(ncas, 3, sectors, cplx, utd)
+    comp = StatevectorRDM(ncas, up_then_down=utd, chunk=chunk)
+    full = StatevectorRDM(ncas, up_then_down=utd, chunk=chunk, compact=False)
+    t = torch.as_tensor(psi).cuda().requires_grad_(True)
+    one, two = comp.get_rdms_from_state(t)
+    assert comp._k.last_rows == count and count < 4 ** ncas // 2
+    t2 = torch.as_tensor(psi).cuda().requires_grad_(True)
+    one_f, two_f = full.get_rdms_from_state(t2)
+    assert full._k.last_rows == 4 ** ncas
+    assert (one - one_f).abs().max().item() < 1e-13 and (two - two_f).abs().max().item() < 1e-13
+    if ncas <= 3:
+        r1, r2 = ro.rdms_from_state(psi, ncas, up_then_down=utd)
+        assert np.abs(one.detach().cpu().numpy() - r1).max() < 1e-13
+        assert np.abs(two.detach().cpu().numpy() - r2).max() < 1e-13
+    # first derivatives through the compact adjoint
+    rng = np.random.default_rng(8)
+    w1 = torch.as_tensor(rng.standard_normal((ncas,) * 2)).cuda()
+    w2 = torch.as_tensor(rng.standard_normal((ncas,) * 4)).cuda()
+    ((one * w1).sum() + (two * w2).sum()).backward()
+    ((one_f * w1).sum() + (two_f * w2).sum()).backward()
+    assert (t.grad - t2.grad).abs().max().item() < 1e-12
+    # transition form: the partner also lives in a sector the state does not occupy -> only the overlap counts
+    other, _ = sector_state(ncas, 4, sectors + [(min(ncas, sectors[0][0] + 1), sectors[0][1])], cplx, utd)
+    a1, a2 = comp.transition_rdms(torch.as_tensor(other).cuda(), torch.as_tensor(psi).cuda())
+    b1, b2 = full.transition_rdms(torch.as_tensor(other).cuda(), torch.as_tensor(psi).cuda())
+    assert comp._k.last_rows == count
+    assert (a1 - b1).abs().max().item() < 1e-13 and (a2 - b2).abs().max().item() < 1e-13
+    wa = comp.apply_operator(w1, w2, torch.as_tensor(psi).cuda())
+    wb = full.apply_operator(w1, w2, torch.as_tensor(psi).cuda())
+    assert (wa - wb).abs().max().item() < 1e-12
+
+
 def _dense_operators(ncas):
     from oracle import rdm_oracle as ro
     a, ad = ro.ladder_operators(2 * ncas)

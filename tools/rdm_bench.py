@@ -57,9 +57,28 @@ def main():
             t0 = time.perf_counter()
             ro.rdms_from_state(psi.cpu().numpy(), ncas)
             row["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+        # the physical case: a state of the half-filled (ncas/2 up, ncas/2 down) sector, which every
+        # number-conserving ansatz of the reference produces -- the passes run on that sector's basis states only
+        nq = 2 * ncas
+        x = torch.arange(D, device="cuda", dtype=torch.int64)
+        nup = sum(((x >> (nq - 1 - 2 * p)) & 1) for p in range(ncas))
+        ndn = sum(((x >> (nq - 2 - 2 * p)) & 1) for p in range(ncas))
+        keep = (nup == ncas // 2) & (ndn == ncas - ncas // 2)
+        ps = torch.where(keep, psi, torch.zeros_like(psi))
+        ps = ps / torch.linalg.vector_norm(ps)
+        row["sector_states"] = int(keep.sum().item())
+        row["sector_forward_ms"] = timed(lambda: rdm.get_rdms_from_state(ps))
+        assert rdm._k.last_rows == row["sector_states"]
+        p3 = ps.clone().requires_grad_(True)
+
+        def fbs():
+            one, two = rdm.get_rdms_from_state(p3)
+            (one.sum() + (two * two).sum()).backward()
+            p3.grad = None
+        row["sector_forward_backward_ms"] = timed(fbs)
         rows.append(row)
         print(row, flush=True)
-        del rdm, psi
+        del rdm, psi, ps, p3, x, nup, ndn, keep
         torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "rdm_bench.json"), "w") as f:
