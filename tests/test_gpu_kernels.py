@@ -67,10 +67,12 @@ def test_dgemm_tn_shared_operands(lib):
     assert (C.cpu() - ref).abs().max().item() < 1e-11
 
 
+@pytest.mark.parametrize("M,N,K,batch", [(45, 37, 29, 3), (46, 38, 30, 2), (114, 114, 114, 1), (256, 256, 256, 1),
+                                         (64, 34, 130, 2), (34, 34, 34, 5), (8, 8, 8, 1)])
 @pytest.mark.parametrize("tA,tB", [(0, 0), (1, 0), (0, 1), (1, 1)])
-def test_dgemm_small_epilogue(lib, tA, tB):
+def test_dgemm_small_epilogue(lib, tA, tB, M, N, K, batch):
+    """odd extents take the pipelined kernel, even ones (K <= 256) the one-shot panel kernel"""
     gen = torch.Generator(device="cuda").manual_seed(11)
-    M, N, K, batch = 45, 37, 29, 3
     A = torch.randn(batch, *((K, M) if tA else (M, K)), dtype=F64, device="cuda", generator=gen)
     B = torch.randn(batch, *((N, K) if tB else (K, N)), dtype=F64, device="cuda", generator=gen)
     E = torch.randn(batch, M, N, dtype=F64, device="cuda", generator=gen)
@@ -82,7 +84,7 @@ def test_dgemm_small_epilogue(lib, tA, tB):
     opA = A.transpose(1, 2) if tA else A
     opB = B.transpose(1, 2) if tB else B
     ref = 1.5 * torch.matmul(opA.cpu(), opB.cpu()) - 0.5 * E.cpu() + 2.0 * torch.eye(M, N, dtype=F64)
-    assert (D.cpu() - ref).abs().max().item() < 1e-12
+    assert (D.cpu() - ref).abs().max().item() < 1e-12 * max(1, K // 16)
 
 
 def test_pad_copy_roundtrip(lib):
