@@ -125,7 +125,8 @@ int oo_set_option(int key, int value) {
         return OO_OK;
     }
     if (key == OO_OPT_HESSIAN_SIMPLE_ASSEMBLE) {
-        oo::g_hessian_simple_assemble = value ? 1 : 0;
+        if (value < 0 || value > 2) return OO_ERR_INVALID_ARG;
+        oo::g_hessian_simple_assemble = value;
         return OO_OK;
     }
     return OO_ERR_INVALID_ARG;

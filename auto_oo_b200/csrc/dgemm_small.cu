@@ -285,7 +285,7 @@ int dgemm_small(int transA, int transB, int M, int N, int K, double alpha, const
         static bool configured = false;
         if (!configured) {
             OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)panel_smem_bytes(PK_MAX, 0, 1)));
+                                               (int)panel_smem_bytes(PK_MAX, 1, 0)));     // both panels k-major: the largest
             configured = true;
         }
         dgemm_panel_kernel<<<grid, PTHREADS, panel_smem_bytes(K, transA, transB), stream>>>(p);

@@ -20,7 +20,7 @@
 
 namespace oo {
 
-int g_hessian_simple_assemble = 0;     // oo_set_option(OO_OPT_HESSIAN_SIMPLE_ASSEMBLE): 1 = per-thread kernel (A/B tests)
+int g_hessian_simple_assemble = 0;     // oo_set_option(OO_OPT_HESSIAN_SIMPLE_ASSEMBLE): 0 auto, 1 per-thread kernel, 2 row-tiled kernel
 
 int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
              int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
@@ -410,16 +410,26 @@ hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t 
     // Rows r outside I kill the two s-contiguous terms ([p,r in I] and [q,r in I]); what is left is contiguous in
     // r.  Tiles with a row inside I (a few short runs) and unstructured pair lists take the per-thread form.
     if (!structured || l0 < tv.nI || ke - kb + kAsmRows > kAsmStrip) {
-        const int kbeg = structured ? kb : blockIdx.x * 256, kend = structured ? ke : nk;
-        const int step = structured ? 256 : gridDim.x * 256;
-        for (int k0 = kbeg; k0 < kend; k0 += step) {
-            const int k = k0 + threadIdx.x;
-            if (k >= kend) continue;
-            const int r = pl[k], s = pr[k];
-            for (int j = j0; j < j1; ++j) {
-                const int p = pl[j], q = pr[j];
+        // work items (j, k), k fastest: all 256 threads busy even when the tile holds a handful of pairs
+        const int nj = j1 - j0;
+        if (structured) {
+            const int cnt = ke - kb;
+            for (int idx = threadIdx.x; idx < cnt * nj; idx += blockDim.x) {
+                const int k = kb + idx % cnt, j = j0 + idx / cnt;
+                const int r = pl[k], s = pr[k], p = pl[j], q = pr[j];
                 H[(int64_t)j * nk + k] = hess_x(tv, F, ld, p, q, r, s) - hess_x(tv, F, ld, p, q, s, r)
                                        - hess_x(tv, F, ld, q, p, r, s) + hess_x(tv, F, ld, q, p, s, r);
+            }
+        } else {
+            for (int k0 = blockIdx.x * 256; k0 < nk; k0 += gridDim.x * 256) {
+                const int k = k0 + threadIdx.x;
+                if (k >= nk) continue;
+                const int r = pl[k], s = pr[k];
+                for (int j = j0; j < j1; ++j) {
+                    const int p = pl[j], q = pr[j];
+                    H[(int64_t)j * nk + k] = hess_x(tv, F, ld, p, q, r, s) - hess_x(tv, F, ld, p, q, s, r)
+                                           - hess_x(tv, F, ld, q, p, r, s) + hess_x(tv, F, ld, q, p, s, r);
+                }
             }
         }
         return;
@@ -518,7 +528,8 @@ size_t assemble_scratch_bytes(int ld) { return align_up((size_t)(ld + 2) * sizeo
 
 int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const int32_t *pr, int nk, int N, int ld,
                     int batch, double *H, void *scratch, cudaStream_t stream) {
-    if (g_hessian_simple_assemble) {
+    // small bases: a handful of CTAs either way, and the per-thread kernel needs no pair-structure pass
+    if (g_hessian_simple_assemble == 1 || (g_hessian_simple_assemble == 0 && N <= 64)) {
         dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk, (unsigned)batch);
         hess_assemble_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, nk, ld, H);
         OO_LAUNCH_CHECK();

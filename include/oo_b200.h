@@ -66,8 +66,9 @@ unsigned long long oo_launch_count(void);             /* kernels launched by thi
 enum {
     OO_OPT_HESSIAN_DENSE = 1,  /* 1: oo_class_hessian_f64 uses one dense GEMM over all of At instead of
                                   the dense act-act block + sparse remainder (same numbers)          */
-    OO_OPT_HESSIAN_SIMPLE_ASSEMBLE = 2   /* 1: one thread per Hessian element instead of the row-tiled,
-                                            shared-memory-transposed assembly (same numbers)          */
+    OO_OPT_HESSIAN_SIMPLE_ASSEMBLE = 2   /* Hessian assembly kernel: 0 = by size (one thread per element for N <= 64,
+                                            row-tiled / shared-memory-transposed above), 1 = always the former,
+                                            2 = always the latter (same numbers)                       */
 };
 int         oo_set_option(int key, int value);
 int         oo_device_info(int *sm_count, int *cc_major, int *cc_minor);

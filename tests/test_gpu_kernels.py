@@ -495,21 +495,23 @@ def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
     assert np.abs(Hd.cpu().numpy() - c.ref["H"]).max() < TOL_GH
     # assembly: row-tiled / shared-memory-transposed (default) against one thread per element; a pair list that
     # is not sorted by row (reversed) takes the per-thread form inside the tiled kernel
-    try:
-        assert lib.oo_set_option(2, 1) == 0
-        Hp = ints.hessian(F, d1, d2).clone()
-    finally:
-        lib.oo_set_option(2, 0)
-    assert (Hs - Hp).abs().max().item() < 1e-11
-    rev = torch.arange(eng.nk - 1, -1, -1, device=eng.device)
-    Hr = ints.hessian(F, d1, d2, pair_l=eng.pair_l[rev].contiguous(), pair_r=eng.pair_r[rev].contiguous())
-    assert (Hr - Hs[rev][:, rev]).abs().max().item() < 1e-11
-    # every (row, column) pair, the list OrbitalHessian.dense() passes: rows sorted, columns 0..N-1
     N = c.nao
+    rev = torch.arange(eng.nk - 1, -1, -1, device=eng.device)
     idx = torch.arange(N, device=eng.device, dtype=torch.int32)
-    Hall = ints.hessian(F, d1, d2, pair_l=idx.repeat_interleave(N).contiguous(), pair_r=idx.repeat(N).contiguous())
     flat = (eng.pair_l.long() * N + eng.pair_r.long())
-    assert (Hall[flat][:, flat] - Hs).abs().max().item() < 1e-11
+    for mode in (1, 2):                                   # 1: per-thread kernel, 2: row-tiled kernel (0: by size)
+        try:
+            assert lib.oo_set_option(2, mode) == 0
+            Hp = ints.hessian(F, d1, d2).clone()
+            Hr = ints.hessian(F, d1, d2, pair_l=eng.pair_l[rev].contiguous(), pair_r=eng.pair_r[rev].contiguous())
+            # every (row, column) pair, the list OrbitalHessian.dense() passes: rows sorted, columns 0..N-1
+            Hall = ints.hessian(F, d1, d2, pair_l=idx.repeat_interleave(N).contiguous(),
+                                pair_r=idx.repeat(N).contiguous())
+        finally:
+            lib.oo_set_option(2, 0)
+        assert (Hs - Hp).abs().max().item() < 1e-11
+        assert (Hr - Hs[rev][:, rev]).abs().max().item() < 1e-11
+        assert (Hall[flat][:, flat] - Hs).abs().max().item() < 1e-11
 
 
 @pytest.mark.parametrize("nao,nelec,ncas,nelecas", [(64, 64, 4, 4), (70, 100, 6, 6), (56, 36, 4, 4)])
