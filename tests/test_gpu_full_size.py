@@ -92,6 +92,13 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     assert (Gf - Gc).abs().max().item() < TOL_GH
     assert (Hf - Hc).abs().max().item() < TOL_GH
     assert (Hc[0] - Hc[0].T).abs().max().item() < TOL_GH
+    # Hessian assembly: the row-tiled kernel (taken at this size) against one thread per element
+    try:
+        assert eng.lib.oo_set_option(2, 1) == 0
+        _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.lib.oo_set_option(2, 0)
+    assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
     # general (no symmetry assumed) class route; the complete transform's N^4 workspace makes room first
     eng._eri_symmetric = False
     eng._ws.pop("i2e", None)
