@@ -275,9 +275,11 @@ def main():
         sampler.start()
     launches0 = lib.oo_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cls_events = []
     e0.record()
     for s in range(args.warmup, total_steps):
-        E, G, H = eng.evaluate(Coao, one, two, kappa=kappas[s], squarings=squarings, H_out=H_out)
+        E, G, H = eng.evaluate(Coao, one, two, kappa=kappas[s], squarings=squarings, H_out=H_out,
+                               transform_events=cls_events)
     e1.record()
     barrier()
     launches = lib.oo_launch_count() - launches0
@@ -335,6 +337,23 @@ def main():
         with open(prof) as f:
             roofline["traffic"] = json.load(f).get(args.workload)
 
+    # the headline arm's own transform (the GEMM launches of the J/K-class transform of every evaluation)
+    t_cls = sum(a.elapsed_time(b) for a, b in cls_events) * 1e-3
+    ld, nIp = eng.ld, eng.nIp
+    if eng.eri_is_symmetric():
+        ldp, npIp = int(lib.oo_pair_ld(ld)), int(lib.oo_pair_ld(nIp))
+        cls_flop = (2.0 * ld * ldp * nIp * ld + 2.0 * ldp * nIp * nIp * ld + 2.0 * ld * ld * nIp * nIp * ld
+                    + 8.0 * ld ** 3 * npIp)
+    else:
+        cls_flop = 2.0 * ld ** 4 * nIp + 12.0 * ld ** 3 * nIp * nIp
+    n_cls = B * args.steps
+    roofline_class = {"bound": "tensor", "kernel": "dgemm_tn_kernel x9 (J/K-class transform of the headline arm)",
+                      "achieved": cls_flop * n_cls / t_cls / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                      "frac": cls_flop * n_cls / t_cls / 1e12 / peak_tf, "flop_per_evaluation": cls_flop,
+                      "ms_per_evaluation": t_cls / n_cls * 1e3, "share_of_step": t_cls / t_local,
+                      "note": "algorithmic flop of the class transform (class index not padded to the 48-wide tile; "
+                              "includes its three HBM-bound pack/expand passes in the time)"}
+
     cpu = None
     if not args.no_cpu_baseline:
         r = cpu_oracle_sample(args.workload, CPU_SAMPLE_NAO)
@@ -358,6 +377,7 @@ def main():
                    "l2": "inputs larger than L2 (N^4 tensors of %.1f GB)" % (nao ** 4 * 8 / 1e9)
                    if nao ** 4 * 8 > 126e6 else "inputs fit L2; distinct kappa every evaluation"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "roofline_headline_arm": roofline_class,
         "cpu_baseline": cpu, "transform_tflops": 8.0 * nao ** 5 * n_transforms / t_transform / 1e12,
         "checksum": checksum,
     }
