@@ -20,7 +20,6 @@
 
 namespace oo {
 
-int g_hessian_spmm_ungrouped = 0;      // oo_set_option(OO_OPT_HESSIAN_SPMM_UNGROUPED): 1 = one column per CTA (A/B tests)
 int g_hessian_simple_assemble = 0;     // oo_set_option(OO_OPT_HESSIAN_SIMPLE_ASSEMBLE): 0 auto, 1 per-thread kernel, 2 row-tiled kernel
 
 int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
@@ -265,87 +264,6 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
         *o = t;
     } else {
         *reinterpret_cast<double2 *>(T + (int64_t)col * mat + c) = acc;
-    }
-}
-
-// Grouped form of the same product.  The non-zeros of At outside the act-act block follow the delta structure of
-// full_rdms: the 2 na columns (i t), (t i) of one occupied i draw on the SAME ~3 na rows of B (weighted by gamma),
-// and all na^2 act-act columns on the same 2 no diagonal rows.  One CTA therefore walks a whole group over its
-// 256-column tile, so those rows are fetched from L2 once and served from L1 for the rest of the group
-// (5.0e4 row fetches -> 1.6e4 at N = 256).  Same ELL lists, same per-column summation order as above.
-//   groups: [0, no): i;   [no, no + no^2): single occ-occ column (i j);   last: all act-act columns
-__global__ void __launch_bounds__(128)
-hess_spmm_grouped_kernel(const double *__restrict__ B, int64_t b_stride, const int *__restrict__ cnt,
-                         const int *__restrict__ idx, const double *__restrict__ val, int rdm_batched, int width,
-                         int no, int na, int nIs, int64_t mat, double *__restrict__ T, double *__restrict__ Taa) {
-    {
-        const int64_t bz = blockIdx.z, nI2 = (int64_t)nIs * nIs;
-        B += bz * b_stride;
-        T += bz * nI2 * mat;
-        Taa += bz * (int64_t)na * na * mat;
-        if (rdm_batched) {
-            cnt += bz * nI2;
-            idx += bz * nI2 * width;
-            val += bz * nI2 * width;
-        }
-    }
-    extern __shared__ __align__(16) unsigned char spmm_smem[];
-    double *vl = reinterpret_cast<double *>(spmm_smem);
-    int *ix = reinterpret_cast<int *>(vl + width);
-    const int gx = blockIdx.x;
-    int ncols, kind, gi = 0, gj = 0;
-    if (gx < no) {
-        kind = 0; gi = gx; ncols = 2 * na;
-    } else if (gx < no + no * no) {
-        kind = 1; gi = (gx - no) / no; gj = (gx - no) % no; ncols = 1;
-    } else {
-        kind = 2; ncols = na * na;
-    }
-    const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2;
-    for (int e0 = 0; e0 < ncols; ++e0) {
-        int p, r;
-        if (kind == 0) {
-            if (e0 < na) { p = gi; r = no + e0; } else { p = no + e0 - na; r = gi; }
-        } else if (kind == 1) {
-            p = gi; r = gj;
-        } else {
-            p = no + e0 / na; r = no + e0 % na;
-        }
-        const int col = p * nIs + r;
-        const int n = cnt[col];
-        __syncthreads();                                   // the previous column's list is no longer read
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            ix[e] = idx[(int64_t)col * width + e];
-            vl[e] = val[(int64_t)col * width + e];
-        }
-        __syncthreads();
-        if (c >= mat) continue;
-        double2 acc = make_double2(0.0, 0.0);
-        int e = 0;
-        for (; e + 4 <= n; e += 4) {
-            double2 b0 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c));
-            double2 b1 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 1] * mat + c));
-            double2 b2 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 2] * mat + c));
-            double2 b3 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e + 3] * mat + c));
-            const double v0 = vl[e], v1 = vl[e + 1], v2 = vl[e + 2], v3 = vl[e + 3];
-            acc.x = fma(v0, b0.x, acc.x); acc.y = fma(v0, b0.y, acc.y);
-            acc.x = fma(v1, b1.x, acc.x); acc.y = fma(v1, b1.y, acc.y);
-            acc.x = fma(v2, b2.x, acc.x); acc.y = fma(v2, b2.y, acc.y);
-            acc.x = fma(v3, b3.x, acc.x); acc.y = fma(v3, b3.y, acc.y);
-        }
-        for (; e < n; ++e) {
-            const double2 b0 = __ldg(reinterpret_cast<const double2 *>(B + (int64_t)ix[e] * mat + c));
-            const double v0 = vl[e];
-            acc.x = fma(v0, b0.x, acc.x); acc.y = fma(v0, b0.y, acc.y);
-        }
-        if (kind == 2) {
-            double2 *o = reinterpret_cast<double2 *>(Taa + ((int64_t)(p - no) * na + (r - no)) * mat + c);
-            double2 t = *o;
-            t.x += acc.x; t.y += acc.y;
-            *o = t;
-        } else {
-            *reinterpret_cast<double2 *>(T + (int64_t)col * mat + c) = acc;
-        }
     }
 }
 
@@ -801,17 +719,11 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     }
     // sparse remainder (accumulates into Taa for act-act columns)
     {
+        dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256), (unsigned)batch);
         const size_t smem = (size_t)L.width * (sizeof(double) + sizeof(int));
         if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
-        if (g_hessian_spmm_ungrouped) {
-            dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256), (unsigned)batch);
-            hess_spmm_kernel<<<grid, 256, smem, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no,
-                                                       na, nIp, mat, T, Taa);
-        } else {
-            dim3 grid((unsigned)(no + no * no + 1), (unsigned)ceil_div(mat / 2, 128), (unsigned)batch);
-            hess_spmm_grouped_kernel<<<grid, 128, smem, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched,
-                                                                  L.width, no, na, nIp, mat, T, Taa);
-        }
+        hess_spmm_kernel<<<grid, 256, smem, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no, na,
+                                                   nIp, mat, T, Taa);
         OO_LAUNCH_CHECK();
     }
     return launch_assemble(TView{T, Taa, no + na, nIp, no, na, nI2 * mat, na2 * mat, mat, (int64_t)nk * nk}, F, pl, pr,

@@ -99,12 +99,6 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     finally:
         eng.lib.oo_set_option(2, 0)
     assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
-    try:                                                  # sparse T-matrix part: one column per CTA against the grouped walk
-        assert eng.lib.oo_set_option(3, 1) == 0
-        _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
-    finally:
-        eng.lib.oo_set_option(3, 0)
-    assert torch.equal(Hf, Hc)
     # general (no symmetry assumed) class route; the complete transform's N^4 workspace makes room first
     eng._eri_symmetric = False
     eng._ws.pop("i2e", None)

@@ -495,12 +495,6 @@ def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
     assert np.abs(Hd.cpu().numpy() - c.ref["H"]).max() < TOL_GH
     # assembly: row-tiled / shared-memory-transposed (default) against one thread per element; a pair list that
     # is not sorted by row (reversed) takes the per-thread form inside the tiled kernel
-    try:                                                  # sparse remainder one column per CTA (default: grouped walk)
-        assert lib.oo_set_option(3, 1) == 0
-        Hu = ints.hessian(F, d1, d2).clone()
-    finally:
-        lib.oo_set_option(3, 0)
-    assert torch.equal(Hu, Hs)                            # same lists, same summation order
     N = c.nao
     rev = torch.arange(eng.nk - 1, -1, -1, device=eng.device)
     idx = torch.arange(N, device=eng.device, dtype=torch.int32)
