@@ -104,18 +104,77 @@ __global__ void hess_build_at_kernel(RdmView rdm, int nI, int swap_exch, int64_t
     }
 }
 
-// ---- sparse form of At (class path) ----------------------------------------------------------
+// ---- block structure of At (class path) -------------------------------------------------------
 // The full-space 2-RDM is a dense na^4 block plus Kronecker-delta core blocks (full_rdms,
-// oo_energy.py:356-379), so At is dense only for (p,r) act-act x (m,n) act-act (+ the one-body
-// row) and has O(na) entries per column elsewhere.  T = At^T B is therefore evaluated as
-//   T_aa[(v w), :]  = dense GEMM over the 2 na^2 + 1 act-act rows of B          (4 na^4 N^2 flop)
-//   T[(p r), :]    (+)= sum over the remaining non-zeros  val * B[k, :]          (L2-bound SpMM)
-// Both are generated from the same at_value() as the dense route, in increasing k (deterministic).
-__device__ __forceinline__ bool in_dense_block(int no, int nI, int p, int r, int m, int n) {
-    if (p < no || r < no) return false;
-    if (m < 0) return true;                               // one-body row
-    return m >= no && n >= no && m < nI && n < nI;
-}
+// oo_energy.py:356-379), so At = [dense blocks] + [O(1) entries per column]:
+//   C block  columns: the na^2 act-act pairs (t u) and the no occupied diagonal pairs (i i);
+//            rows:    exchange / Coulomb rows of the act-act pairs and of the occupied diagonal pairs, one-body row
+//            (Gamma_tuvw, and the delta_ij gamma / delta_ij delta_kl terms summed over a whole class)
+//            -> ONE TN-DGEMM  Tc = Atc^T Bc  on the tensor pipe                    (~4 (na^2+no)^2 N^2 flop)
+//   G block of every occupied i   columns: (i t) and (t i), t active;
+//            rows: exchange / Coulomb rows at the positions (i u) and (u i), u active (the gamma_tu delta_ij terms)
+//            -> hess_group_kernel: the 4 na rows are read once per column chunk, 2 na x 4 na coefficients in smem
+//   rest     (occ-occ pairs i != j: three entries per column) -> ELL SpMM (hess_spmm_kernel), which also adds
+//            whatever a column of the two blocks has outside its block (nothing for the reference's RDM layout).
+// Every coefficient comes from the same at_value() as the all-dense route; a row k is identified by its
+// position pair (a, b) = ((k mod nIs^2) / nIs, (k mod nIs^2) mod nIs), which makes the row sets independent of
+// the storage order of the exchange rows.
+struct Blocks {
+    int no, na, nIs;
+    __device__ __host__ int ncol_c() const { return na * na + no; }
+    __device__ __host__ int nrow_c() const { return 2 * (na * na + no) + 1; }
+    __device__ __host__ int ncol_g() const { return 2 * na; }
+    __device__ __host__ int nrow_g() const { return 4 * na; }
+    // column cc of the C block -> (p, r)
+    __device__ void col_c(int cc, int &p, int &r) const {
+        if (cc < na * na) { p = no + cc / na; r = no + cc % na; } else { p = r = cc - na * na; }
+    }
+    // row kc of the C block -> row of At / B
+    __device__ int64_t row_c(int kc) const {
+        const int nC = na * na + no;
+        const int64_t nI2 = (int64_t)nIs * nIs;
+        if (kc >= 2 * nC) return 2 * nI2;
+        const int j = kc % nC;
+        const int a = j < na * na ? no + j / na : j - na * na, b = j < na * na ? no + j % na : j - na * na;
+        return (kc >= nC ? nI2 : 0) + (int64_t)a * nIs + b;
+    }
+    // column e of the G block of occupied i -> (p, r);  row kg -> row of At / B
+    __device__ void col_g(int i, int e, int &p, int &r) const {
+        if (e < na) { p = i; r = no + e; } else { p = no + e - na; r = i; }
+    }
+    __device__ int64_t row_g(int i, int kg) const {
+        const int u = no + kg % na, part = kg / na;              // 0: exch (i u), 1: exch (u i), 2: coul (i u), 3: coul (u i)
+        const int a = (part & 1) ? u : i, b = (part & 1) ? i : u;
+        return (part >= 2 ? (int64_t)nIs * nIs : 0) + (int64_t)a * nIs + b;
+    }
+    // home of column (p, r): 1 = C block, 2 = G block, 0 = none (ELL only)
+    __device__ int home(int p, int r) const {
+        const int nI = no + na;
+        if (p >= nI || r >= nI) return 0;
+        const bool po = p < no, ro = r < no;
+        if (!po && !ro) return 1;
+        if (po && ro) return p == r ? 1 : 0;
+        return 2;
+    }
+    // is entry (row k, column (p r)) part of the column's dense block?
+    __device__ bool covered(int p, int r, int64_t k) const {
+        const int h = home(p, r);
+        if (h == 0) return false;
+        const int64_t nI2 = (int64_t)nIs * nIs;
+        const int nI = no + na;
+        if (k == 2 * nI2) return h == 1;
+        const int kk = (int)(k % nI2), a = kk / nIs, b = kk % nIs;
+        if (a >= nI || b >= nI) return false;
+        if (h == 1) return (a >= no && b >= no) || (a == b && a < no);
+        const int i = p < no ? p : r;
+        return (a == i && b >= no) || (b == i && a >= no);
+    }
+    // offset (in rows of ld^2 doubles) of column (p, r) inside its block's result buffer
+    __device__ int64_t slot_c(int p, int r) const { return p < no ? na * na + p : (p - no) * na + (r - no); }
+    __device__ int64_t slot_g(int p, int r) const {
+        return p < no ? (int64_t)p * 2 * na + (r - no) : (int64_t)r * 2 * na + na + (p - no);
+    }
+};
 
 // one warp per column (p r) of At: ELL list (k, val) of its non-zeros outside the dense block
 __global__ void __launch_bounds__(256)
@@ -141,7 +200,7 @@ hess_sparse_build_kernel(RdmView rdm0, int64_t sd1, int64_t sd2, int nIs, int sw
             if (k < krows) {
                 int m, n;
                 v = at_value(rdm, nIs, swap_exch, k, p, r, m, n);
-                if (in_dense_block(rdm.no, nI, p, r, m, n)) v = 0.0;
+                if (Blocks{rdm.no, rdm.na, nIs}.covered(p, r, k)) v = 0.0;
             }
             const unsigned mask = __ballot_sync(0xffffffffu, v != 0.0);
             if (v != 0.0) {
@@ -159,29 +218,21 @@ hess_sparse_build_kernel(RdmView rdm0, int64_t sd1, int64_t sd2, int nIs, int sw
     if (lane == 0) cnt[col] = base < width ? base : width;
 }
 
-// dense block operands: rows k' = [exchange act pairs | Coulomb act pairs | one-body]
-//   Atc[k', (v w)] and Bc[k', :] = the matching row of the class buffer
+// C block operands: Atc[kc, cc] and Bc[kc, :] = the matching row of the class buffer
 __global__ void hess_dense_at_kernel(RdmView rdm0, int64_t sd1, int64_t sd2, int nIs, int swap_exch, int64_t lda,
                                      double *__restrict__ Atc) {
     const RdmView rdm{rdm0.d1 + blockIdx.y * sd1, rdm0.d2 + blockIdx.y * sd2, rdm0.no, rdm0.na};
-    const int na = rdm.na, no = rdm.no, na2 = na * na;
-    const int64_t total = (int64_t)(2 * na2 + 1) * lda;
+    const Blocks bl{rdm.no, rdm.na, nIs};
+    const int64_t total = (int64_t)bl.nrow_c() * lda;
     Atc += (int64_t)blockIdx.y * total;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int kc = (int)(i / lda), col = (int)(i % lda);
+        const int kc = (int)(i / lda), cc = (int)(i % lda);
         double v = 0.0;
-        if (col < na2) {
-            const int p = no + col / na, r = no + col % na;
-            int64_t k;
-            if (kc < 2 * na2) {
-                const int a = no + (kc % na2) / na, b = no + (kc % na2) % na;   // the two act indices, row-major
-                k = (kc < na2 ? 0 : (int64_t)nIs * nIs) + (int64_t)a * nIs + b;
-            } else {
-                k = 2 * (int64_t)nIs * nIs;
-            }
-            int m, n;
-            v = at_value(rdm, nIs, swap_exch, k, p, r, m, n);
+        if (cc < bl.ncol_c()) {
+            int p, r, m, n;
+            bl.col_c(cc, p, r);
+            v = at_value(rdm, nIs, swap_exch, bl.row_c(kc), p, r, m, n);
         }
         Atc[i] = v;
     }
@@ -189,21 +240,59 @@ __global__ void hess_dense_at_kernel(RdmView rdm0, int64_t sd1, int64_t sd2, int
 
 __global__ void hess_dense_b_kernel(const double *__restrict__ cls, int64_t cls_stride, int no, int na, int nIs,
                                     int64_t mat, double *__restrict__ Bc) {
-    const int kc = blockIdx.y, na2 = na * na;
+    const Blocks bl{no, na, nIs};
+    const int kc = blockIdx.y;
     cls += (int64_t)blockIdx.z * cls_stride;
-    Bc += (int64_t)blockIdx.z * (2 * na2 + 1) * mat;
-    int64_t k;
-    if (kc < 2 * na2) {
-        const int a = no + (kc % na2) / na, b = no + (kc % na2) % na;
-        k = (kc < na2 ? 0 : (int64_t)nIs * nIs) + (int64_t)a * nIs + b;
-    } else {
-        k = 2 * (int64_t)nIs * nIs;
-    }
-    const double2 *src = reinterpret_cast<const double2 *>(cls + k * mat);
+    Bc += (int64_t)blockIdx.z * bl.nrow_c() * mat;
+    const double2 *src = reinterpret_cast<const double2 *>(cls + bl.row_c(kc) * mat);
     double2 *dst = reinterpret_cast<double2 *>(Bc + (int64_t)kc * mat);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mat / 2;
          i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = src[i];
+}
+
+// G blocks: Tg[i][e][c] = sum_kg coef[kg][e] B[row_g(i, kg)][c].  grid (no, column tiles of 256, batch), 128 threads,
+// two columns c per thread; the 2 na result columns are produced kGroupChunk at a time (accumulators in registers),
+// the 4 na B rows are re-read per chunk (L2), the coefficients sit in shared memory.
+constexpr int kGroupChunk = 8;
+
+__global__ void __launch_bounds__(128)
+hess_group_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, int64_t sd1, int64_t sd2,
+                  int rdm_batched, int nIs, int swap_exch, int64_t mat, double *__restrict__ Tg) {
+    extern __shared__ __align__(16) double coef[];                 // [4 na][2 na]
+    const int bz = blockIdx.z;
+    const RdmView rdm{rdm0.d1 + (rdm_batched ? bz * sd1 : 0), rdm0.d2 + (rdm_batched ? bz * sd2 : 0), rdm0.no,
+                      rdm0.na};
+    const Blocks bl{rdm.no, rdm.na, nIs};
+    const int i = blockIdx.x, nr = bl.nrow_g(), nc = bl.ncol_g();
+    for (int x = threadIdx.x; x < nr * nc; x += blockDim.x) {
+        int p, r, m, n;
+        bl.col_g(i, x % nc, p, r);
+        coef[x] = at_value(rdm, nIs, swap_exch, bl.row_g(i, x / nc), p, r, m, n);
+    }
+    __syncthreads();
+    const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2;
+    if (c >= mat) return;
+    B += bz * b_stride;
+    Tg += ((int64_t)bz * rdm.no + i) * nc * mat;
+    for (int e0 = 0; e0 < nc; e0 += kGroupChunk) {
+        double2 acc[kGroupChunk];
+#pragma unroll
+        for (int j = 0; j < kGroupChunk; ++j) acc[j] = make_double2(0.0, 0.0);
+        for (int kg = 0; kg < nr; ++kg) {
+            const double2 b = __ldg(reinterpret_cast<const double2 *>(B + bl.row_g(i, kg) * mat + c));
+            const double *cf = coef + kg * nc + e0;
+#pragma unroll
+            for (int j = 0; j < kGroupChunk; ++j) {
+                const double v = e0 + j < nc ? cf[j] : 0.0;
+                acc[j].x = fma(v, b.x, acc[j].x);
+                acc[j].y = fma(v, b.y, acc[j].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kGroupChunk; ++j)
+            if (e0 + j < nc) *reinterpret_cast<double2 *>(Tg + (int64_t)(e0 + j) * mat + c) = acc[j];
+    }
 }
 
 // T[(p r), c] (= or +=) sum_e val[e] * B[idx[e], c].   grid (columns (p r), column tiles of 512);
@@ -211,15 +300,19 @@ __global__ void hess_dense_b_kernel(const double *__restrict__ cls, int64_t cls_
 __global__ void __launch_bounds__(256)
 hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__restrict__ cnt,
                  const int *__restrict__ idx, const double *__restrict__ val, int rdm_batched, int width, int no,
-                 int na, int nIs, int64_t mat, double *__restrict__ T, double *__restrict__ Taa) {
+                 int na, int nIs, int64_t mat, double *__restrict__ T, double *__restrict__ Tc,
+                 double *__restrict__ Tg) {
     const int col = blockIdx.x;
     const int p = col / nIs, r = col % nIs, nI = no + na;
     if (p >= nI || r >= nI) return;
+    const Blocks bl{no, na, nIs};
+    const int home = bl.home(p, r);
     {
         const int64_t bz = blockIdx.z, nI2 = (int64_t)nIs * nIs;
         B += bz * b_stride;
         T += bz * nI2 * mat;
-        Taa += bz * (int64_t)na * na * mat;
+        Tc += bz * (int64_t)bl.ncol_c() * mat;
+        Tg += bz * (int64_t)no * bl.ncol_g() * mat;
         if (rdm_batched) {
             cnt += bz * nI2;
             idx += bz * nI2 * width;
@@ -232,6 +325,7 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
     double *vl = reinterpret_cast<double *>(spmm_smem);
     int *ix = reinterpret_cast<int *>(vl + width);
     const int n = cnt[col];
+    if (n == 0 && home != 0) return;                      // the column's dense block holds all of it
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         ix[e] = idx[(int64_t)col * width + e];
         vl[e] = val[(int64_t)col * width + e];
@@ -257,8 +351,8 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
         const double v0 = vl[e];
         acc.x = fma(v0, b0.x, acc.x); acc.y = fma(v0, b0.y, acc.y);
     }
-    if (p >= no && r >= no) {
-        double2 *o = reinterpret_cast<double2 *>(Taa + ((int64_t)(p - no) * na + (r - no)) * mat + c);
+    if (home != 0) {                                      // add to what the dense block produced
+        double2 *o = reinterpret_cast<double2 *>((home == 1 ? Tc + bl.slot_c(p, r) * mat : Tg + bl.slot_g(p, r) * mat) + c);
         double2 t = *o;
         t.x += acc.x; t.y += acc.y;
         *o = t;
@@ -295,9 +389,24 @@ __global__ void hess_gather_b_kernel(const double *__restrict__ h, const double 
 
 struct TView {
     const double *T;     // rows (a c) -> a * nIs + c
-    const double *Taa;   // optional: act-act rows (a - no) * na + (c - no); null = everything in T
+    const double *Taa;   // optional (class path): results of the C block (Blocks::slot_c); null = everything in T
+    const double *Tg;    // with Taa: results of the G blocks (Blocks::slot_g)
     int nI, nIs, no, na;
-    int64_t t_stride, taa_stride, f_stride, h_stride;   // per-evaluation strides (blockIdx.z)
+    int64_t t_stride, taa_stride, tg_stride, f_stride, h_stride;   // per-evaluation strides (blockIdx.z)
+    // row (a c) of T, a, c < nI  (ld2 = ld * ld)
+    __device__ __forceinline__ const double *row(int a, int c, int64_t ld2) const {
+        if (Taa) {
+            const Blocks bl{no, na, nIs};
+            const int h = bl.home(a, c);
+            if (h == 1) return Taa + bl.slot_c(a, c) * ld2;
+            if (h == 2) return Tg + bl.slot_g(a, c) * ld2;
+        }
+        return T + ((int64_t)a * nIs + c) * ld2;
+    }
+    __device__ __forceinline__ void at_batch(int b) {
+        T += b * t_stride;
+        if (Taa) { Taa += b * taa_stride; Tg += b * tg_stride; }
+    }
 };
 
 __device__ __forceinline__ double hess_x(const TView &tv, const double *__restrict__ F, int ld, int a, int b,
@@ -305,13 +414,7 @@ __device__ __forceinline__ double hess_x(const TView &tv, const double *__restri
     // X(a,b,c,d) = -(F_ac + F_ca) delta_bd + [a,c in I] T[(a c),(b d)]
     double v = 0.0;
     if (b == d) v = -(F[(int64_t)a * ld + c] + F[(int64_t)c * ld + a]);
-    if (a < tv.nI && c < tv.nI) {
-        const int64_t off = (int64_t)b * ld + d;
-        if (tv.Taa && a >= tv.no && c >= tv.no)
-            v += tv.Taa[((int64_t)(a - tv.no) * tv.na + (c - tv.no)) * ld * ld + off];
-        else
-            v += tv.T[((int64_t)a * tv.nIs + c) * ld * ld + off];
-    }
+    if (a < tv.nI && c < tv.nI) v += tv.row(a, c, (int64_t)ld * ld)[(int64_t)b * ld + d];
     return v;
 }
 
@@ -322,8 +425,7 @@ hess_assemble_kernel(TView tv, const double *__restrict__ F,
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (k >= nk) return;
-    tv.T += blockIdx.z * tv.t_stride;
-    if (tv.Taa) tv.Taa += blockIdx.z * tv.taa_stride;
+    tv.at_batch(blockIdx.z);
     F += blockIdx.z * tv.f_stride;
     H += blockIdx.z * tv.h_stride;
     const int p = pl[j], q = pr[j];
@@ -374,10 +476,7 @@ __global__ void hess_pair_runs_kernel(const int32_t *__restrict__ pl, const int3
 __device__ __forceinline__ double hess_t(const TView &tv, int ld, int a, int c, int b, int d) {
     // [a, c in I] T[(a c),(b d)]
     if (a >= tv.nI || c >= tv.nI) return 0.0;
-    const int64_t off = (int64_t)b * ld + d;
-    if (tv.Taa && a >= tv.no && c >= tv.no)
-        return __ldg(tv.Taa + ((int64_t)(a - tv.no) * tv.na + (c - tv.no)) * ld * ld + off);
-    return __ldg(tv.T + ((int64_t)a * tv.nIs + c) * ld * ld + off);
+    return __ldg(tv.row(a, c, (int64_t)ld * ld) + (int64_t)b * ld + d);
 }
 
 __device__ __forceinline__ double fock_sym(const double *__restrict__ F, int ld, int a, int c) {
@@ -394,8 +493,7 @@ hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t 
     __shared__ unsigned char rowof[kAsmStrip];
     __shared__ int rstart[kAsmRows], rlen[kAsmRows], rs0[kAsmRows];
     __shared__ int s_lo, s_hi;
-    tv.T += blockIdx.z * tv.t_stride;
-    if (tv.Taa) tv.Taa += blockIdx.z * tv.taa_stride;
+    tv.at_batch(blockIdx.z);
     F += blockIdx.z * tv.f_stride;
     H += blockIdx.z * tv.h_stride;
     const int j0 = blockIdx.y * kAsmJ, j1 = min(j0 + kAsmJ, nk);
@@ -603,7 +701,7 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     int rc = dgemm_tn(At, B, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
     if (rc) return rc;
     if (nk > 65535) return OO_ERR_UNSUPPORTED;
-    return launch_assemble(TView{T, nullptr, nI, nI, no, na, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1, H, w + L.off_runs,
+    return launch_assemble(TView{T, nullptr, nullptr, nI, nI, no, na, 0, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1, H, w + L.off_runs,
                            stream);
 }
 
@@ -612,16 +710,17 @@ int g_hessian_dense = 0;     // oo_set_option(OO_OPT_HESSIAN_DENSE): 1 = one den
 
 struct ClassHessLayout {
     int width;                       // ELL width of the sparse part
-    int64_t lda_c, krows_c;          // dense act-act block
-    size_t off_cnt, off_idx, off_val, off_flag, off_atc, off_bc, off_taa, off_t, off_runs, total;
+    int64_t lda_c, krows_c, ncol_c;  // C block
+    size_t off_cnt, off_idx, off_val, off_flag, off_atc, off_bc, off_taa, off_tg, off_t, off_runs, total;
 };
 
 static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na, int batch) {
     ClassHessLayout L;
     const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld, na2 = (int64_t)na * na;
     L.width = 2 * na * na + 2 * (no + na) + 8;
-    L.lda_c = (na2 + 1) & ~1ll;
-    L.krows_c = 2 * na2 + 1;
+    L.ncol_c = na2 + no;
+    L.lda_c = (L.ncol_c + 1) & ~1ll;
+    L.krows_c = 2 * L.ncol_c + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
     L.off_cnt = take((size_t)batch * nI2 * sizeof(int));
@@ -630,7 +729,8 @@ static ClassHessLayout class_hess_layout(int ld, int nIp, int no, int na, int ba
     L.off_flag = take(sizeof(int));
     L.off_atc = take((size_t)batch * L.krows_c * L.lda_c * sizeof(double));
     L.off_bc = take((size_t)batch * L.krows_c * mat * sizeof(double));
-    L.off_taa = take((size_t)batch * na2 * mat * sizeof(double));
+    L.off_taa = take((size_t)batch * L.ncol_c * mat * sizeof(double));
+    L.off_tg = take((size_t)batch * no * 2 * na * mat * sizeof(double) + 1024);
     L.off_t = take((size_t)batch * nI2 * mat * sizeof(double));
     L.off_runs = take(assemble_scratch_bytes(ld));
     L.total = off;
@@ -658,7 +758,7 @@ static int class_hessian_dense(const double *cls, const double *F, const RdmView
     OO_LAUNCH_CHECK();
     int rc = dgemm_tn(At, cls, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
     if (rc) return rc;
-    return launch_assemble(TView{T, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1,
+    return launch_assemble(TView{T, nullptr, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na, 0, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1,
                            H, w + L.off_b + (L.off_runs - L.off_t), stream);
 }
 
@@ -696,13 +796,14 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     double *Atc = reinterpret_cast<double *>(w + L.off_atc);
     double *Bc = reinterpret_cast<double *>(w + L.off_bc);
     double *Taa = reinterpret_cast<double *>(w + L.off_taa);
+    double *Tg = reinterpret_cast<double *>(w + L.off_tg);
     double *T = reinterpret_cast<double *>(w + L.off_t);
 
-    // sparse structure of At outside the act-act block (one table per set of RDMs)
+    // ELL lists of what lies outside the dense blocks (one table per set of RDMs)
     hess_sparse_build_kernel<<<dim3((unsigned)ceil_div(nI2, 8), (unsigned)nsets), 256, 0, stream>>>(
         rdm, sd1, sd2, nIp, 1, L.width, cnt, idx, val, flag);
     OO_LAUNCH_CHECK();
-    // dense act-act block: Taa[b] = Atc^T Bc[b]
+    // C block: Tc[b] = Atc^T Bc[b]
     {
         int64_t blocks = ceil_div(L.krows_c * L.lda_c, 256);
         hess_dense_at_kernel<<<dim3((unsigned)blocks, (unsigned)nsets), 256, 0, stream>>>(rdm, sd1, sd2, nIp, 1,
@@ -713,21 +814,30 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
         hess_dense_b_kernel<<<dim3((unsigned)bx, (unsigned)L.krows_c, (unsigned)batch), 256, 0, stream>>>(
             cls, cls_stride, no, na, nIp, mat, Bc);
         OO_LAUNCH_CHECK();
-        int rc = dgemm_tn(Atc, Bc, Taa, na2, mat, L.krows_c, L.lda_c, mat, mat, batch,
-                          rdm_batched ? L.krows_c * L.lda_c : 0, L.krows_c * mat, na2 * mat, stream);
+        int rc = dgemm_tn(Atc, Bc, Taa, L.ncol_c, mat, L.krows_c, L.lda_c, mat, mat, batch,
+                          rdm_batched ? L.krows_c * L.lda_c : 0, L.krows_c * mat, L.ncol_c * mat, stream);
         if (rc) return rc;
     }
-    // sparse remainder (accumulates into Taa for act-act columns)
+    // G blocks, one per occupied orbital
+    if (no > 0) {
+        const size_t smem = (size_t)4 * na * 2 * na * sizeof(double);
+        if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
+        dim3 grid((unsigned)no, (unsigned)ceil_div(mat / 2, 128), (unsigned)batch);
+        hess_group_kernel<<<grid, 128, smem, stream>>>(cls, cls_stride, rdm, sd1, sd2, rdm_batched, nIp, 1, mat, Tg);
+        OO_LAUNCH_CHECK();
+    }
+    // the rest (occ-occ pairs i != j), plus anything a block column has outside its block
     {
         dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256), (unsigned)batch);
         const size_t smem = (size_t)L.width * (sizeof(double) + sizeof(int));
         if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
         hess_spmm_kernel<<<grid, 256, smem, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no, na,
-                                                   nIp, mat, T, Taa);
+                                                   nIp, mat, T, Taa, Tg);
         OO_LAUNCH_CHECK();
     }
-    return launch_assemble(TView{T, Taa, no + na, nIp, no, na, nI2 * mat, na2 * mat, mat, (int64_t)nk * nk}, F, pl, pr,
-                           nk, N, ld, batch, H, w + L.off_runs, stream);
+    return launch_assemble(TView{T, Taa, Tg, no + na, nIp, no, na, nI2 * mat, L.ncol_c * mat,
+                                 (int64_t)no * 2 * na * mat, mat, (int64_t)nk * nk},
+                           F, pl, pr, nk, N, ld, batch, H, w + L.off_runs, stream);
 }
 
 int full_rdms(const double *d1, const double *d2, int no, int na, int N, double *one_full,
