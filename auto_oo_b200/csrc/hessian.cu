@@ -252,46 +252,52 @@ __global__ void hess_dense_b_kernel(const double *__restrict__ cls, int64_t cls_
 }
 
 // G blocks: Tg[i][e][c] = sum_kg coef[kg][e] B[row_g(i, kg)][c].  grid (no, column tiles of 256, batch), 128 threads,
-// two columns c per thread; the 2 na result columns are produced kGroupChunk at a time (accumulators in registers),
-// the 4 na B rows are re-read per chunk (L2), the coefficients sit in shared memory.
-constexpr int kGroupChunk = 8;
-
+// two columns c per thread; CH result columns at a time with the accumulators in registers (CH >= 2 na for the usual
+// active spaces: every B row is read exactly once), two B rows in flight per thread, coefficients and row offsets in
+// shared memory.
+template <int CH>
 __global__ void __launch_bounds__(128)
 hess_group_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, int64_t sd1, int64_t sd2,
                   int rdm_batched, int nIs, int swap_exch, int64_t mat, double *__restrict__ Tg) {
-    extern __shared__ __align__(16) double coef[];                 // [4 na][2 na]
+    extern __shared__ __align__(16) double coef[];                 // [4 na][2 na] then int64 row offsets [4 na]
     const int bz = blockIdx.z;
     const RdmView rdm{rdm0.d1 + (rdm_batched ? bz * sd1 : 0), rdm0.d2 + (rdm_batched ? bz * sd2 : 0), rdm0.no,
                       rdm0.na};
     const Blocks bl{rdm.no, rdm.na, nIs};
     const int i = blockIdx.x, nr = bl.nrow_g(), nc = bl.ncol_g();
+    int64_t *rowoff = reinterpret_cast<int64_t *>(coef + nr * nc);
     for (int x = threadIdx.x; x < nr * nc; x += blockDim.x) {
         int p, r, m, n;
         bl.col_g(i, x % nc, p, r);
         coef[x] = at_value(rdm, nIs, swap_exch, bl.row_g(i, x / nc), p, r, m, n);
     }
+    for (int x = threadIdx.x; x < nr; x += blockDim.x) rowoff[x] = bl.row_g(i, x) * mat;
     __syncthreads();
     const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2;
     if (c >= mat) return;
-    B += bz * b_stride;
-    Tg += ((int64_t)bz * rdm.no + i) * nc * mat;
-    for (int e0 = 0; e0 < nc; e0 += kGroupChunk) {
-        double2 acc[kGroupChunk];
+    B += bz * b_stride + c;
+    Tg += ((int64_t)bz * rdm.no + i) * nc * mat + c;
+    for (int e0 = 0; e0 < nc; e0 += CH) {
+        double2 acc[CH];
 #pragma unroll
-        for (int j = 0; j < kGroupChunk; ++j) acc[j] = make_double2(0.0, 0.0);
-        for (int kg = 0; kg < nr; ++kg) {
-            const double2 b = __ldg(reinterpret_cast<const double2 *>(B + bl.row_g(i, kg) * mat + c));
-            const double *cf = coef + kg * nc + e0;
+        for (int j = 0; j < CH; ++j) acc[j] = make_double2(0.0, 0.0);
+        for (int kg = 0; kg < nr; kg += 2) {                      // nr = 4 na is even
+            const double2 b0 = __ldg(reinterpret_cast<const double2 *>(B + rowoff[kg]));
+            const double2 b1 = __ldg(reinterpret_cast<const double2 *>(B + rowoff[kg + 1]));
+            const double *cf0 = coef + kg * nc + e0, *cf1 = cf0 + nc;
 #pragma unroll
-            for (int j = 0; j < kGroupChunk; ++j) {
-                const double v = e0 + j < nc ? cf[j] : 0.0;
-                acc[j].x = fma(v, b.x, acc[j].x);
-                acc[j].y = fma(v, b.y, acc[j].y);
+            for (int j = 0; j < CH; ++j) {
+                const bool in = e0 + j < nc;
+                const double v0 = in ? cf0[j] : 0.0, v1 = in ? cf1[j] : 0.0;
+                acc[j].x = fma(v0, b0.x, acc[j].x);
+                acc[j].y = fma(v0, b0.y, acc[j].y);
+                acc[j].x = fma(v1, b1.x, acc[j].x);
+                acc[j].y = fma(v1, b1.y, acc[j].y);
             }
         }
 #pragma unroll
-        for (int j = 0; j < kGroupChunk; ++j)
-            if (e0 + j < nc) *reinterpret_cast<double2 *>(Tg + (int64_t)(e0 + j) * mat + c) = acc[j];
+        for (int j = 0; j < CH; ++j)
+            if (e0 + j < nc) *reinterpret_cast<double2 *>(Tg + (int64_t)(e0 + j) * mat) = acc[j];
     }
 }
 
@@ -820,10 +826,15 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     }
     // G blocks, one per occupied orbital
     if (no > 0) {
-        const size_t smem = (size_t)4 * na * 2 * na * sizeof(double);
+        const size_t smem = (size_t)4 * na * (2 * na + 1) * sizeof(double);
         if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
         dim3 grid((unsigned)no, (unsigned)ceil_div(mat / 2, 128), (unsigned)batch);
-        hess_group_kernel<<<grid, 128, smem, stream>>>(cls, cls_stride, rdm, sd1, sd2, rdm_batched, nIp, 1, mat, Tg);
+#define OO_GROUP(CH) hess_group_kernel<CH><<<grid, 128, smem, stream>>>(cls, cls_stride, rdm, sd1, sd2, rdm_batched, \
+                                                                       nIp, 1, mat, Tg)
+        if (2 * na <= 8) OO_GROUP(8);
+        else if (2 * na <= 16) OO_GROUP(16);
+        else OO_GROUP(24);
+#undef OO_GROUP
         OO_LAUNCH_CHECK();
     }
     // the rest (occ-occ pairs i != j), plus anything a block column has outside its block
