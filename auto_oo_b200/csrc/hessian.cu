@@ -16,6 +16,8 @@
 // is ONE TN-DGEMM (dgemm_tn.cu: TMA + DMMA) of size nI^2 x ld^2 x (2 nI^2 + 1), and
 //   X(p,q,r,s) = -(F_pr + F_rp) d_qs + [p,r in I] T[(p r),(q s)]
 // is combined four ways directly into the (nk x nk) output.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace oo {
@@ -281,7 +283,7 @@ hess_group_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, 
         double2 acc[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) acc[j] = make_double2(0.0, 0.0);
-        for (int kg = 0; kg < nr; kg += 2) {                      // nr = 4 na is even
+        for (int kg = 0; kg < nr; kg += 2) {                      // nr = 4 na is even: two B rows in flight
             const double2 b0 = __ldg(reinterpret_cast<const double2 *>(B + rowoff[kg]));
             const double2 b1 = __ldg(reinterpret_cast<const double2 *>(B + rowoff[kg + 1]));
             const double *cf0 = coef + kg * nc + e0, *cf1 = cf0 + nc;
@@ -565,7 +567,7 @@ hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t 
     for (int j = j0; j < j1; ++j) {
         const int p = pl[j], q = pr[j];
         const bool p_in = p < tv.nI;
-#pragma unroll 2
+#pragma unroll 6
         for (int si = threadIdx.x / kAsmRows; si < ns; si += 256 / kAsmRows) {
             const int s = s_lo + si;
             const int pos = s - my_s0;
@@ -831,6 +833,7 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
         dim3 grid((unsigned)no, (unsigned)ceil_div(mat / 2, 128), (unsigned)batch);
 #define OO_GROUP(CH) hess_group_kernel<CH><<<grid, 128, smem, stream>>>(cls, cls_stride, rdm, sd1, sd2, rdm_batched, \
                                                                        nIp, 1, mat, Tg)
+        // (measured at N = 256, na = 12: 8 / 12 / 24 columns per pass all take 0.48-0.51 ms -- DRAM latency bound)
         if (2 * na <= 8) OO_GROUP(8);
         else if (2 * na <= 16) OO_GROUP(16);
         else OO_GROUP(24);
