@@ -675,6 +675,7 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ CUDA-graph replay of whole evaluations
     GRAPH_CACHE = 8
+    GRAPH_MAX_OUTPUT_BYTES = 256 << 20
 
     def evaluate_graphed(self, oao_mo_coeff, d1, d2, kappa=None, want_hessian=True, path="class", clone=True):
         """:meth:`evaluate` captured once per argument shape into a CUDA graph and replayed: one graph launch per
@@ -684,6 +685,11 @@ class HotPathEngine:
         copies (``clone=False``: the graph's own output buffers, overwritten by the next call).  For N above the fused-expm limit the squaring count is decided on the host (one synchronisation)
         and is part of the graph key."""
         Coao = oao_mo_coeff if oao_mo_coeff.dim() == 3 else oao_mo_coeff[None]
+        nb = max(Coao.shape[0], 1 if kappa is None else kappa.reshape(-1, self.nk).shape[0])
+        if want_hessian and nb * self.nk * self.nk * 8 > self.GRAPH_MAX_OUTPUT_BYTES:
+            # a graph pins its output buffers for its lifetime; work of this size is not launch-bound anyway
+            return self.evaluate(Coao, self.dev(d1), self.dev(d2), kappa=None if kappa is None else self.dev(kappa),
+                                 want_hessian=want_hessian, path=path)
         squarings = None
         if kappa is not None:
             kappa = kappa.reshape(-1, self.nk)
