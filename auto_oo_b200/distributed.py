@@ -44,6 +44,33 @@ F64 = torch.float64
 
 
 # --------------------------------------------------------------------------------------
+# process placement
+# --------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA node), so that
+    the pinned staging buffers it allocates next are first-touched on that node and its device<->host copies do
+    not cross the socket interconnect.  With one process per GPU, eight ranks otherwise share whatever node the
+    scheduler put them on (measured on 8 x B200: 87 GB/s aggregate D2H of the Hessians).  Best effort: returns the
+    CPU list, or None when NVML / the cgroup does not allow it."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:                                             # noqa: BLE001  (placement is an optimisation)
+        return None
+
+
+# --------------------------------------------------------------------------------------
 # independent evaluations
 # --------------------------------------------------------------------------------------
 def shard_range(n_items, world_size, rank):

@@ -210,7 +210,12 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
     if world > 1:
+        from auto_oo_b200.distributed import bind_to_gpu_numa_node
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
+        numa_cpus = bind_to_gpu_numa_node(phys)                # pinned staging buffers on the GPU's own node
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -368,6 +373,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "nao": nao, "cas": [nelecas, ncas], "n_kappa": nk,
                    "evals_per_step_per_gpu": B,
+                   "numa_bound_cpus": None if numa_cpus is None else len(numa_cpus),
                    "transform": ("symmetric J/K-class transform (packed AO pairs: N^4 nI + ~7 N^3 nI^2 flop), same E/G/H"
                                  if eng.eri_is_symmetric() else
                                  "general J/K-class transform (2N^4 nI + 12 N^3 nI^2 flop), same E/G/H"),
