@@ -212,6 +212,8 @@ def main():
     dev = torch.device("cuda", local)
     numa_cpus = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"               # the version banner goes to stdout, next to the JSON line
         from auto_oo_b200.distributed import bind_to_gpu_numa_node
         visible = os.environ.get("CUDA_VISIBLE_DEVICES")
         phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
