@@ -24,14 +24,14 @@ extern int g_hessian_dense;
 extern int g_hessian_simple_assemble;
 
 int sm_count() {
-    static int cached = 0;
-    if (cached > 0) return cached;
+    static int cached[64] = {};                         // per device
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return 148;
+    if (cached[dev] > 0) return cached[dev];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
         return 148;
-    cached = n;
-    return cached;
+    cached[dev] = n;
+    return n;
 }
 
 // cuTensorMapEncodeTiled is a driver-API symbol; fetch it through the runtime so the

@@ -41,6 +41,18 @@ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
+// Function attributes (opt-in dynamic shared memory) are per DEVICE: `once_per_device(mask)` is true the first time
+// it is called with the calling thread's current device for a given call-site mask (devices 0..63; a process that
+// drives several GPUs configures each of them).  Benign race: two threads may both configure the same device.
+inline bool once_per_device(unsigned long long &mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    const unsigned long long bit = 1ull << dev;
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 // ---- FP64 tensor-core MMA (DMMA.8x8x4) --------------------------------------
 // Fragment ownership for lane = 4*g + t (g = 0..7, t = 0..3):
 //   a = A[g][t]   (row-major 8x4),  b = B[t][g]  (col-major 4x8),

@@ -282,11 +282,10 @@ int dgemm_small(int transA, int transB, int M, int N, int K, double alpha, const
     p.eye_n = eye_n < 0 ? (M < N ? M : N) : eye_n;
     dim3 grid((unsigned)ceil_div(N, TS), (unsigned)ceil_div(M, TS), (unsigned)batch);
     if (panel_eligible(p)) {
-        static bool configured = false;
-        if (!configured) {
+        static unsigned long long configured = 0;
+        if (once_per_device(configured)) {
             OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)panel_smem_bytes(PK_MAX, 1, 0)));     // both panels k-major: the largest
-            configured = true;
         }
         dgemm_panel_kernel<<<grid, PTHREADS, panel_smem_bytes(K, transA, transB), stream>>>(p);
         OO_LAUNCH_CHECK();

@@ -304,8 +304,8 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     args.b_batched = b_batched;
     args.zero = 0;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (once_per_device(attr_set)) {
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 0>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
@@ -315,7 +315,6 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());

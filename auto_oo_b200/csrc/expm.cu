@@ -292,12 +292,11 @@ bool expm_fused_enabled() {
 
 template <int GR, int GC>
 int launch_expm_fused(const FusedExpmArgs &p, int batch, cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured = 0;
     const size_t smem = fused_smem_bytes(p.n8);
-    if (!configured) {
+    if (once_per_device(configured)) {
         OO_CUDA_CHECK(cudaFuncSetAttribute(expm_fused_kernel<GR, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)fused_smem_bytes(kFusedMaxN8)));
-        configured = true;
     }
     expm_fused_kernel<GR, GC><<<batch, kFusedThreads, smem, stream>>>(p);
     OO_LAUNCH_CHECK();

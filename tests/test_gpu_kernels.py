@@ -514,6 +514,34 @@ def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
         assert (Hall[flat][:, flat] - Hs).abs().max().item() < 1e-11
 
 
+@pytest.mark.parametrize("nao,nelec,ncas,nelecas,freeze", [
+    (5, 4, 1, 2, False), (5, 4, 1, 2, True), (6, 2, 2, 2, False), (9, 10, 3, 2, False), (12, 6, 5, 4, True),
+    (3, 2, 3, 2, False), (4, 8, 1, 2, False), (66, 20, 3, 2, False)])
+def test_unusual_orbital_spaces_against_the_oracle(nao, nelec, ncas, nelecas, freeze):
+    """one active orbital, no core, no virtuals, every orbital active, odd sizes, N just above the fused-expm
+    limit: E, gradient and Hessian of the class path and of the complete transform against the CPU oracle"""
+    from auto_oo_b200.engine import HotPathEngine
+    from auto_oo_b200.synthetic import SyntheticMol, random_rdms, random_kappa
+    from oracle import oo_oracle as orc
+    mol = SyntheticMol(nao, nelec, seed=nao + ncas)
+    occ, act, virt = mol.get_active_space_idx(ncas, nelecas)
+    pidx = orc.non_redundant_indices(occ, act, virt, freeze)
+    if len(pidx) == 0:
+        pytest.skip("no non-redundant rotation")
+    prob = orc.OracleProblem(mol.int1e_ao, mol.int2e_ao, mol.oao_coeff, mol.random_oao_mo_coeff, mol.nuc, nelec, ncas,
+                             nelecas, freeze)
+    one, two = random_rdms(ncas, nelecas, seed=3)
+    kap = random_kappa(len(pidx), seed=3, scale=0.2)
+    Eo, Go, Ho = prob.evaluate(one, two, kap, ispace=nao > 13)
+    eng = HotPathEngine(mol.int1e_ao, mol.int2e_ao, mol.oao_coeff, mol.nuc, nao, len(occ), ncas, pidx)
+    Coao = eng.to_padded(mol.random_oao_mo_coeff, 2)
+    for path in ("class", "full"):
+        E, G, H = eng.evaluate(Coao, one, two, kappa=kap[None], path=path)
+        assert abs(E.item() - float(Eo)) < TOL_E, path
+        assert (G[0].cpu() - Go).abs().max().item() < TOL_GH, path
+        assert (H[0].cpu() - Ho).abs().max().item() < TOL_GH, path
+
+
 @pytest.mark.parametrize("nao,nelec,ncas,nelecas", [(64, 64, 4, 4), (70, 100, 6, 6), (56, 36, 4, 4)])
 def test_class_transform_with_wide_class_index(nao, nelec, ncas, nelecas):
     """Class index nIp in (16, 64]: exercises the 32/48/64-wide GEMM tiles and the dual-store epilogue
