@@ -34,6 +34,10 @@ int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C
                          int64_t strideA, int64_t strideB, int64_t strideC, int64_t strideC2,
                          cudaStream_t stream);
 
+int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
+                        int64_t nrows2, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
+                        int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream);
+
 namespace {
 
 // dst[c][r] = src[r][c]  (rows x cols doubles), 32x32 tiles through padded shared memory
@@ -296,6 +300,8 @@ int pack_eri_pairs(const double *g, double *gpk, int ld, cudaStream_t stream) {
     return OO_OK;
 }
 
+int g_class_unfused_pack = 0;    // oo_set_option(OO_OPT_CLASS_UNFUSED_PACK): 1 = separate pack_class_pairs pass (A/B tests)
+
 size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch) {
     const size_t ld2 = (size_t)ld * ld, ldp = (size_t)pair_ld(ld), npIp = (size_t)pair_ld(nIp);
     const size_t t1 = (size_t)ld * ldp * nIp, t1t = ld2 * ld * nIp;
@@ -331,17 +337,28 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp, batch,
                                    strideG, strideC, sT1, sT1t, stream)))
         return rc;
-    const dim3 pgrid((unsigned)ld2, (unsigned)batch);
-    // ---- J
-    Q(T1, sT1, X, sX, ldp * nIp, nIp);                                   // X[pq,m,n]
-    pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 1, sX, sXp);   // Xf[p,q,mn]
-    OO_LAUNCH_CHECK();
+    // ---- J: quarter 2 writes the class pairs m >= n straight into Xf[p,q,mn] (both orders of the AO pair)
+    if (g_class_unfused_pack) {
+        const dim3 pgrid((unsigned)ld2, (unsigned)batch);
+        Q(T1, sT1, X, sX, ldp * nIp, nIp);                               // X[pq,m,n]
+        pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 1, sX, sXp);
+        OO_LAUNCH_CHECK();
+    } else if ((rc = dgemm_tn_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * nIp, nIp, batch, sT1, strideC,
+                                         sXp, stream))) {
+        return rc;
+    }
     Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X'[q,mn,a]
     Q(P1, sXp, Jp, sXp, npIp * ld, ld);                                  // Jp[mn,a,b]
-    // ---- K
-    Q(T1t, sT1t, X, sX, ld2 * nIp, nIp);                                 // X2[p,s,m,n]
-    pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 0, sX, sXp);   // X2p[p,s,mn]
-    OO_LAUNCH_CHECK();
+    // ---- K: X2[p,s,m,n] = sum_q T1t[q,(p s m)] C[q,n], kept as X2p[p,s,mn]
+    if (g_class_unfused_pack) {
+        const dim3 pgrid((unsigned)ld2, (unsigned)batch);
+        Q(T1t, sT1t, X, sX, ld2 * nIp, nIp);
+        pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 0, sX, sXp);
+        OO_LAUNCH_CHECK();
+    } else if ((rc = dgemm_tn_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * nIp, nIp, batch, sT1t, strideC,
+                                         sXp, stream))) {
+        return rc;
+    }
     Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X3[s,mn,a]
     Q(P1, sXp, Kp, sXp, npIp * ld, ld);                                  // Kp[mn,a,b]
 #undef Q

@@ -45,6 +45,9 @@ struct TnArgs {
     // (classes.cu: T1[s,p,q,m] and T1t[q,p,s,m] from the same accumulators, no separate swap pass)
     // or (mode 2, symmetric class transform) rows (a, pq) with pq = p(p+1)/2 + q a packed lower-triangular
     // pair of d1 orbitals (d2 = padded pair count): C2 receives the value at rows (q p a) AND (p q a)
+    // or (modes 3 / 4, class-pair packing; C itself is NOT written) rows (r2, m) with m < d0 a class index and
+    // columns n: only n <= m is kept, at C2[r2'][m(m+1)/2 + n] with row length d2 -- r2' = r2 (mode 4), or
+    // both (p q) and (q p) of the packed pair r2 = p(p+1)/2 + q of d1 orbitals (mode 3)
     double *C2;
     int d0, d1, d2;
     int64_t M, N;
@@ -61,7 +64,8 @@ struct TnArgs {
     uint32_t zero;
 };
 
-// DUAL: 0 = plain store, 1 = second store with rows (a b c) -> (c b a), 2 = packed-pair unpack (see TnArgs)
+// DUAL: 0 = plain store, 1 = second store with rows (a b c) -> (c b a), 2 = packed-pair unpack,
+// 3 / 4 = class-pair packing instead of the plain store (see TnArgs)
 template <class Cfg, int DUAL>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -240,6 +244,36 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             crow3 = base2 + (((int64_t)p * args.d1 + q) * args.d0 + a) * args.ldc;
                         }
                     }
+                    if (DUAL >= 3) {
+                        const int m = (int)(row % args.d0);
+                        const int64_t r2 = row / args.d0;
+                        double *base2 = args.C2 + (int64_t)b * args.strideC2 + (int64_t)m * (m + 1) / 2;
+                        if (DUAL == 4) {
+                            crow2 = base2 + r2 * args.d2;
+                        } else {
+                            int p = (int)((sqrt(8.0 * (double)r2 + 1.0) - 1.0) * 0.5);
+                            while ((int64_t)(p + 1) * (p + 2) / 2 <= r2) ++p;
+                            while ((int64_t)p * (p + 1) / 2 > r2) --p;
+                            const int q = (int)(r2 - (int64_t)p * (p + 1) / 2);
+                            if (p < args.d1) {
+                                crow2 = base2 + ((int64_t)p * args.d1 + q) * args.d2;
+                                crow3 = base2 + ((int64_t)q * args.d1 + p) * args.d2;
+                            }
+                        }
+                        if (crow2) {
+#pragma unroll
+                            for (int ni = 0; ni < Cfg::NT; ++ni)
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    const int col = n0 + wn * Cfg::WTN + ni * 8 + 2 * t + c;
+                                    if (col <= m && col < args.N) {
+                                        crow2[col] = acc[mi][ni][c];
+                                        if (DUAL == 3) crow3[col] = acc[mi][ni][c];
+                                    }
+                                }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int ni = 0; ni < Cfg::NT; ++ni) {
                         const int64_t col = (int64_t)n0 + wn * Cfg::WTN + ni * 8 + 2 * t;
@@ -265,7 +299,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
 struct TnDual {
     double *C2 = nullptr;
-    int mode = 0;               // 1 = swap02, 2 = packed-pair unpack
+    int mode = 0;               // 1 = swap02, 2 = packed-pair unpack, 3 / 4 = class-pair packing (tri / plain rows)
     int d0 = 0, d1 = 0, d2 = 0;
     int64_t strideC2 = 0;
 };
@@ -315,10 +349,20 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 3>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 4>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    if (dual.C2 && dual.mode == 2)
+    if (dual.C2 && dual.mode == 4)
+        dgemm_tn_kernel<Cfg, 4><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    else if (dual.C2 && dual.mode == 3)
+        dgemm_tn_kernel<Cfg, 3><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    else if (dual.C2 && dual.mode == 2)
         dgemm_tn_kernel<Cfg, 2><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     else if (dual.C2)
         dgemm_tn_kernel<Cfg, 1><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
@@ -396,6 +440,26 @@ int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C
     dual.strideC2 = strideC2;
     return dgemm_tn_impl(At, B, C, (int64_t)d0 * dP, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC,
                          stream, dual);
+}
+
+// Rows (r2, m), m < nclass, columns n < N (= nclass): only the class pairs n <= m are stored, packed, at
+// P[r2'][m(m+1)/2 + n] (row length npair_ld); nothing else is written.  tri_rows: r2 = p(p+1)/2 + q is a packed
+// pair of `dorb` orbitals (nrows2 >= dorb(dorb+1)/2 rows, padding skipped) and both P[(p q)] and P[(q p)] are
+// written; otherwise r2' = r2.  This is the quarter-2 GEMM of the symmetric class transform with
+// pack_class_pairs fused into its epilogue.
+int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
+                        int64_t nrows2, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
+                        int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream) {
+    OO_REQUIRE(P && nclass > 0 && dorb > 0 && nrows2 > 0 && npair_ld >= (int64_t)nclass * (nclass + 1) / 2);
+    TnDual dual;
+    dual.C2 = P;
+    dual.mode = tri_rows ? 3 : 4;
+    dual.d0 = nclass;
+    dual.d1 = dorb;
+    dual.d2 = (int)npair_ld;
+    dual.strideC2 = strideP;
+    const int64_t ldc = nclass + (nclass & 1);
+    return dgemm_tn_impl(At, B, P, nrows2 * nclass, nclass, K, lda, ldb, ldc, batch, strideA, strideB, 0, stream, dual);
 }
 
 }  // namespace oo

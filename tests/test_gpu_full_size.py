@@ -99,6 +99,13 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     finally:
         eng.lib.oo_set_option(2, 0)
     assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
+    # class-pair packing: fused into the quarter-2 GEMM epilogues (default) against the separate pass
+    try:
+        assert eng.lib.oo_set_option(3, 1) == 0
+        Eu, Gu, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.lib.oo_set_option(3, 0)
+    assert torch.equal(Eu, Ec) and torch.equal(Gu, Gc) and torch.equal(Hf, Hc)
     # general (no symmetry assumed) class route; the complete transform's N^4 workspace makes room first
     eng._eri_symmetric = False
     eng._ws.pop("i2e", None)

@@ -333,6 +333,13 @@ def test_class_transform_equals_slices_of_full_transform(name, sym):
     assert (cls[-1][:N, :N] - h).abs().max().item() < 1e-12
     if eng.ld > N:                                       # zero padding survives
         assert cls[:, N:, :].abs().max().item() == 0.0 and cls[:, :, N:].abs().max().item() == 0.0
+    if sym == "auto":                                    # class-pair packing fused into the quarter-2 epilogue vs a separate pass
+        try:
+            assert eng.lib.oo_set_option(3, 1) == 0
+            cls_u = eng.class_integrals(Cp)[0].cpu()
+        finally:
+            eng.lib.oo_set_option(3, 0)
+        assert torch.equal(cls_u, cls)
 
 
 def test_eri_symmetry_defect_and_pair_packing(lib):
