@@ -343,7 +343,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         Q(T1, sT1, X, sX, ldp * nIp, nIp);                               // X[pq,m,n]
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 1, sX, sXp);
         OO_LAUNCH_CHECK();
-    } else if ((rc = dgemm_tn_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * nIp, nIp, batch, sT1, strideC,
+    } else if ((rc = dgemm_tn_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * nIp, ld, batch, sT1, strideC,
                                          sXp, stream))) {
         return rc;
     }
@@ -355,7 +355,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         Q(T1t, sT1t, X, sX, ld2 * nIp, nIp);
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 0, sX, sXp);
         OO_LAUNCH_CHECK();
-    } else if ((rc = dgemm_tn_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * nIp, nIp, batch, sT1t, strideC,
+    } else if ((rc = dgemm_tn_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * nIp, ld, batch, sT1t, strideC,
                                          sXp, stream))) {
         return rc;
     }
