@@ -38,6 +38,10 @@ int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_ro
                         int64_t nrows2, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
                         int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream);
 
+int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int transpose_mirror, int nclass, int dorb,
+                          int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int64_t ld_out, int batch,
+                          int64_t strideA, int64_t strideB, int64_t strideOut, cudaStream_t stream);
+
 namespace {
 
 // dst[c][r] = src[r][c]  (rows x cols doubles), 32x32 tiles through padded shared memory
@@ -328,6 +332,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     double *P1 = P0 + (int64_t)batch * sXp;
     double *Jp = P1 + (int64_t)batch * sXp;
     double *Kp = Jp + (int64_t)batch * sXp;
+    double *Kout = cls, *Jout = cls + nI2 * ld2;
     int rc;
 #define Q(in, sIn, out, sOut, M, Ncols)                                                                  \
     if ((rc = dgemm_tn((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), batch, (sIn), strideC, (sOut), \
@@ -348,7 +353,12 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         return rc;
     }
     Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X'[q,mn,a]
-    Q(P1, sXp, Jp, sXp, npIp * ld, ld);                                  // Jp[mn,a,b]
+    if (g_class_unfused_pack) {
+        Q(P1, sXp, Jp, sXp, npIp * ld, ld);                              // Jp[mn,a,b]
+    } else if ((rc = dgemm_tn_class_expand(P1, C, Jout, 0, nIp, ld, npIp, ld, npIp * ld, ld, ld, batch, sXp,
+                                           strideC, sCls, stream))) {    // J[m,n,a,b] = J[n,m,a,b]
+        return rc;
+    }
     // ---- K: X2[p,s,m,n] = sum_q T1t[q,(p s m)] C[q,n], kept as X2p[p,s,mn]
     if (g_class_unfused_pack) {
         const dim3 pgrid((unsigned)ld2, (unsigned)batch);
@@ -360,7 +370,14 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         return rc;
     }
     Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X3[s,mn,a]
-    Q(P1, sXp, Kp, sXp, npIp * ld, ld);                                  // Kp[mn,a,b]
+    if (g_class_unfused_pack) {
+        Q(P1, sXp, Kp, sXp, npIp * ld, ld);                              // Kp[mn,a,b]
+    } else {
+        if ((rc = dgemm_tn_class_expand(P1, C, Kout, 1, nIp, ld, npIp, ld, npIp * ld, ld, ld, batch, sXp, strideC,
+                                        sCls, stream)))                  // K[m,n,a,b], K[n,m,b,a]
+            return rc;
+        return OO_OK;
+    }
 #undef Q
     const unsigned t = (unsigned)ceil_div(ld, 32);
     expand_class_kernel<<<dim3(t, t, (unsigned)(npI * batch)), 256, 0, stream>>>(Jp, Kp, cls, ld, nIp, (int)npI,

@@ -48,6 +48,9 @@ struct TnArgs {
     // or (modes 3 / 4, class-pair packing; C itself is NOT written) rows (r2, m) with m < d0 a class index and
     // columns n: only n <= m is kept, at C2[r2'][m(m+1)/2 + n] with row length d2 -- r2' = r2 (mode 4), or
     // both (p q) and (q p) of the packed pair r2 = p(p+1)/2 + q of d1 orbitals (mode 3)
+    // or (mode 5, class-pair expansion; C itself is NOT written) rows (mn, a), mn = m(m+1)/2 + n a packed class
+    // pair of d0 indices, a < d1, columns b < N = d1: C2[(m n), a, b] always and, for m != n, C2[(n m), a, b]
+    // (d2 == 0) or the transposed C2[(n m), b, a] (d2 != 0)
     double *C2;
     int d0, d1, d2;
     int64_t M, N;
@@ -65,7 +68,7 @@ struct TnArgs {
 };
 
 // DUAL: 0 = plain store, 1 = second store with rows (a b c) -> (c b a), 2 = packed-pair unpack,
-// 3 / 4 = class-pair packing instead of the plain store (see TnArgs)
+// 3 / 4 = class-pair packing, 5 = class-pair expansion instead of the plain store (see TnArgs)
 template <class Cfg, int DUAL>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -244,6 +247,35 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             crow3 = base2 + (((int64_t)p * args.d1 + q) * args.d0 + a) * args.ldc;
                         }
                     }
+                    if (DUAL == 5) {
+                        const int a = (int)(row % args.d1);
+                        const int mn = (int)(row / args.d1);
+                        int m = (int)((sqrt(8.0 * mn + 1.0) - 1.0) * 0.5);
+                        while ((m + 1) * (m + 2) / 2 <= mn) ++m;
+                        while (m * (m + 1) / 2 > mn) --m;
+                        const int n = mn - m * (m + 1) / 2;
+                        if (m >= args.d0) continue;                          // padding of the pair index
+                        double *base2 = args.C2 + (int64_t)b * args.strideC2;
+                        const int64_t plane = (int64_t)args.d1 * args.ldc;
+                        crow2 = base2 + ((int64_t)m * args.d0 + n) * plane + (int64_t)a * args.ldc;
+                        double *mirror = base2 + ((int64_t)n * args.d0 + m) * plane;
+                        const bool second = m != n, transposed = args.d2 != 0;
+#pragma unroll
+                        for (int ni = 0; ni < Cfg::NT; ++ni) {
+                            const int col = n0 + wn * Cfg::WTN + ni * 8 + 2 * t;
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                if (col + c >= args.N) continue;
+                                const double v = acc[mi][ni][c];
+                                crow2[col + c] = v;
+                                if (second) {
+                                    if (transposed) mirror[(int64_t)(col + c) * args.ldc + a] = v;
+                                    else mirror[(int64_t)a * args.ldc + col + c] = v;
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     if (DUAL >= 3) {
                         const int m = (int)(row % args.d0);
                         const int64_t r2 = row / args.d0;
@@ -299,7 +331,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
 struct TnDual {
     double *C2 = nullptr;
-    int mode = 0;               // 1 = swap02, 2 = packed-pair unpack, 3 / 4 = class-pair packing (tri / plain rows)
+    int mode = 0;               // 1 = swap02, 2 = packed-pair unpack, 3 / 4 = class-pair packing (tri / plain rows), 5 = class-pair expansion
     int d0 = 0, d1 = 0, d2 = 0;
     int64_t strideC2 = 0;
 };
@@ -355,10 +387,15 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 4>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 5>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    if (dual.C2 && dual.mode == 4)
+    if (dual.C2 && dual.mode == 5)
+        dgemm_tn_kernel<Cfg, 5><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    else if (dual.C2 && dual.mode == 4)
         dgemm_tn_kernel<Cfg, 4><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     else if (dual.C2 && dual.mode == 3)
         dgemm_tn_kernel<Cfg, 3><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
@@ -460,6 +497,25 @@ int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_ro
     dual.strideC2 = strideP;
     const int64_t ldc = nclass + (nclass & 1);
     return dgemm_tn_impl(At, B, P, nrows2 * nclass, nclass, K, lda, ldb, ldc, batch, strideA, strideB, 0, stream, dual);
+}
+
+// Rows (mn, a): mn < npair_ld a packed class pair (m >= n) of `nclass` indices, a < dorb; columns b < dorb.
+// Out[(m n), a, b] is written for every pair and, for m != n, Out[(n m), a, b] (transpose_mirror == 0: the
+// Coulomb class, J[n,m] = J[m,n]) or Out[(n m), b, a] (the exchange class, K[n,m] = K[m,n]^T); planes of
+// dorb x ld_out doubles.  The last quarter of the symmetric class transform with expand_class fused into it.
+int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int transpose_mirror, int nclass, int dorb,
+                          int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int64_t ld_out, int batch,
+                          int64_t strideA, int64_t strideB, int64_t strideOut, cudaStream_t stream) {
+    OO_REQUIRE(Out && nclass > 0 && dorb > 0 && npair_ld >= (int64_t)nclass * (nclass + 1) / 2 && ld_out >= dorb);
+    TnDual dual;
+    dual.C2 = Out;
+    dual.mode = 5;
+    dual.d0 = nclass;
+    dual.d1 = dorb;
+    dual.d2 = transpose_mirror ? 1 : 0;
+    dual.strideC2 = strideOut;
+    return dgemm_tn_impl(At, B, Out, npair_ld * dorb, dorb, K, lda, ldb, ld_out, batch, strideA, strideB, 0, stream,
+                         dual);
 }
 
 }  // namespace oo
