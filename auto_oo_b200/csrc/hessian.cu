@@ -506,16 +506,21 @@ hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t 
     H += blockIdx.z * tv.h_stride;
     const int j0 = blockIdx.y * kAsmJ, j1 = min(j0 + kAsmJ, nk);
     const bool structured = runs[N + 1] != 0;
-    const int l0 = blockIdx.x * kAsmRows;
+    // row tiles: tile 0 = the orbital rows inside I (short runs, all four terms: per-thread form), tile t >= 1 =
+    // kAsmRows rows outside I
+    const int rows_in = min(tv.nI, N);
+    const int l0 = blockIdx.x == 0 ? 0 : rows_in + ((int)blockIdx.x - 1) * kAsmRows;
+    const int l1 = blockIdx.x == 0 ? rows_in : min(l0 + kAsmRows, N);
     int kb = 0, ke = 0;
     if (structured) {
+        if (l0 >= N) return;
         kb = runs[l0];
-        ke = runs[min(l0 + kAsmRows, N)];
+        ke = runs[l1];
         if (kb == ke) return;
     }
     // Rows r outside I kill the two s-contiguous terms ([p,r in I] and [q,r in I]); what is left is contiguous in
     // r.  Tiles with a row inside I (a few short runs) and unstructured pair lists take the per-thread form.
-    if (!structured || l0 < tv.nI || ke - kb + kAsmRows > kAsmStrip) {
+    if (!structured || blockIdx.x == 0 || ke - kb + kAsmRows > kAsmStrip) {
         // work items (j, k), k fastest: all 256 threads busy even when the tile holds a handful of pairs
         const int nj = j1 - j0;
         if (structured) {
@@ -644,7 +649,8 @@ int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const i
     int *runs = reinterpret_cast<int *>(scratch);
     hess_pair_runs_kernel<<<1, 1024, 0, stream>>>(pl, pr, nk, N, runs);
     OO_LAUNCH_CHECK();
-    dim3 grid((unsigned)ceil_div(N, kAsmRows), (unsigned)ceil_div(nk, kAsmJ), (unsigned)batch);
+    const int rows_out = N > tv.nI ? N - tv.nI : 0;
+    dim3 grid((unsigned)(1 + ceil_div(rows_out, kAsmRows)), (unsigned)ceil_div(nk, kAsmJ), (unsigned)batch);
     hess_assemble_rows_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, runs, nk, N, ld, H);
     OO_LAUNCH_CHECK();
     return OO_OK;
