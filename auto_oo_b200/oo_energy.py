@@ -481,8 +481,10 @@ class OO_energy:
         one = _as_tensor(one_rdm)
         for n in range(max_iterations):
             kappa = torch.zeros(self.n_kappa, dtype=F64, device=one.device)
-            gradient = self.kappa_matrix_to_vector(self.analytic_gradient(one_rdm, two_rdm))
-            hessian = self.full_hessian_to_matrix(self.analytic_hessian(one_rdm, two_rdm))
+            # gradient and Hessian at the current orbitals from ONE fused evaluation (one transform, one graph
+            # replay for small bases) instead of the reference's analytic_gradient + analytic_hessian calls
+            _, G, H = self.energy_gradient_hessian(kappa[None], one_rdm, two_rdm)
+            gradient, hessian = G[0].clone(), H[0].clone()
             kappa, lowest_eigenvalue = opt.damped_newton_step(objective_fn, (kappa,), gradient, hessian)
             self.oao_mo_coeff = self.get_transformed_mo(self.oao_mo_coeff, kappa)
             energy = self.energy_from_mo_coeff(self.mo_coeff, one_rdm, two_rdm).item()

@@ -48,13 +48,13 @@ class NewtonStep:
         if lowest_eigenvalue < self.lambda_min and self.aug:
             if self.verbose:
                 print("augmenting hessian...")
-            shift = self.mu + self.rho * abs(lowest_eigenvalue)
-            eye = torch.eye(hessian.shape[0], dtype=hessian.dtype, device=hessian.device)
-            evals, evecs = torch.linalg.eigh(hessian + shift * eye)
+            # H + shift I has the eigenvectors of H and its eigenvalues moved by shift: the reference's second
+            # eigh (newton_raphson.py:117-121) is not needed
+            evals = evals + (self.mu + self.rho * abs(lowest_eigenvalue))
             if self.verbose:
                 print("Lowest eigenvalue of augmented hessian:", evals[0].item())
-        hessian_inv = evecs @ torch.diag(1 / evals) @ evecs.T
-        return -(hessian_inv @ gradient), lowest_eigenvalue
+        # -(V diag(1/w) V^T) g without forming the inverse
+        return -(evecs @ ((evecs.T @ gradient) / evals)), lowest_eigenvalue
 
     def backtracking(self, objective_fn, parameters, dp, gradient):
         """Reference ``:131-192``."""
