@@ -23,6 +23,7 @@ size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch);
 extern int g_hessian_dense;
 extern int g_hessian_simple_assemble;
 extern int g_class_unfused_pack;
+extern int g_hessian_group_unstreamed;
 
 int sm_count() {
     static int cached[64] = {};                         // per device
@@ -123,6 +124,10 @@ unsigned long long oo_launch_count(void) { return oo::g_launch_count; }
 int oo_set_option(int key, int value) {
     if (key == OO_OPT_HESSIAN_DENSE) {
         oo::g_hessian_dense = value ? 1 : 0;
+        return OO_OK;
+    }
+    if (key == OO_OPT_HESSIAN_GROUP_UNSTREAMED) {
+        oo::g_hessian_group_unstreamed = value ? 1 : 0;
         return OO_OK;
     }
     if (key == OO_OPT_CLASS_UNFUSED_PACK) {

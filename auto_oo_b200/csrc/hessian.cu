@@ -22,6 +22,7 @@
 
 namespace oo {
 
+int g_hessian_group_unstreamed = 0;    // oo_set_option(OO_OPT_HESSIAN_GROUP_UNSTREAMED): 1 = register-only G-block kernel (A/B tests)
 int g_hessian_simple_assemble = 0;     // oo_set_option(OO_OPT_HESSIAN_SIMPLE_ASSEMBLE): 0 auto, 1 per-thread kernel, 2 row-tiled kernel
 
 int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
@@ -300,6 +301,108 @@ hess_group_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, 
 #pragma unroll
         for (int j = 0; j < CH; ++j)
             if (e0 + j < nc) *reinterpret_cast<double2 *>(Tg + (int64_t)(e0 + j) * mat) = acc[j];
+    }
+}
+
+// Streamed form of the same product for large ld^2: the kernel above keeps only two 16-byte loads per thread in
+// flight and ends up DRAM-latency bound (2.4 TB/s at N = 256).  Here a CTA owns a contiguous range of
+// (occupied i, column tile) work items; for each item ONE thread issues a bulk asynchronous copy
+// (cp.async.bulk, completion on an mbarrier) per B row -- 4 na row segments of 2 KB into a shared-memory stage,
+// two stages, so ~100-200 KB are in flight per SM while the 128 threads run the 4 na x 2 na FMAs of the previous
+// tile out of shared memory.  Same coefficients, same summation order over kg as hess_group_kernel.
+constexpr int kGrpTile = 256;                       // columns per tile: one double2 per thread
+constexpr int kGrpStages = 2;
+
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+size_t group_stream_smem_bytes(int na) {
+    return (size_t)kGrpStages * 4 * na * kGrpTile * sizeof(double) + (size_t)4 * na * 2 * na * sizeof(double) +
+           kGrpStages * sizeof(uint64_t) + 16;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(128, 1)
+hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, int64_t sd1, int64_t sd2,
+                         int rdm_batched, int nIs, int swap_exch, int64_t mat, double *__restrict__ Tg,
+                         int tiles_per_i, int items_per_cta) {
+    extern __shared__ __align__(128) unsigned char gs_smem[];
+    const int bz = blockIdx.y;
+    const RdmView rdm{rdm0.d1 + (rdm_batched ? bz * sd1 : 0), rdm0.d2 + (rdm_batched ? bz * sd2 : 0), rdm0.no,
+                      rdm0.na};
+    const Blocks bl{rdm.no, rdm.na, nIs};
+    const int nr = bl.nrow_g(), nc = bl.ncol_g();
+    double *stage_buf = reinterpret_cast<double *>(gs_smem);
+    double *coef = stage_buf + (size_t)kGrpStages * nr * kGrpTile;
+    uint64_t *full = reinterpret_cast<uint64_t *>(coef + nr * nc);
+    const int total = rdm.no * tiles_per_i;
+    const int w0 = blockIdx.x * items_per_cta, w1 = min(w0 + items_per_cta, total);
+    if (w0 >= w1) return;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGrpStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    B += bz * b_stride;
+    Tg += (int64_t)bz * rdm.no * nc * mat;
+
+    auto issue = [&](int w, int s) {                       // thread 0: all row segments of work item w into stage s
+        const int i = w / tiles_per_i;
+        const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile;
+        const uint32_t seg = (uint32_t)((mat - c0 < kGrpTile ? mat - c0 : kGrpTile) * sizeof(double));
+        mbar_arrive_expect_tx(&full[s], seg * nr);
+        double *dst = stage_buf + (size_t)s * nr * kGrpTile;
+        for (int kg = 0; kg < nr; ++kg) bulk_load(dst + kg * kGrpTile, B + bl.row_g(i, kg) * mat + c0, seg, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < kGrpStages && w0 + k < w1; ++k) issue(w0 + k, k);
+
+    int cur_i = -1;
+    for (int w = w0; w < w1; ++w) {
+        const int k = w - w0, s = k % kGrpStages;
+        const int i = w / tiles_per_i;
+        if (i != cur_i) {                                  // (at most twice per CTA) coefficients of occupied i
+            __syncthreads();
+            for (int x = threadIdx.x; x < nr * nc; x += blockDim.x) {
+                int p, r, m, n;
+                bl.col_g(i, x % nc, p, r);
+                coef[x] = at_value(rdm, nIs, swap_exch, bl.row_g(i, x / nc), p, r, m, n);
+            }
+            __syncthreads();
+            cur_i = i;
+        }
+        mbar_wait(&full[s], (uint32_t)(k / kGrpStages) & 1u);
+        const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile;
+        const int64_t c = c0 + 2 * threadIdx.x;
+        const double *st = stage_buf + (size_t)s * nr * kGrpTile + 2 * threadIdx.x;
+        double *out = Tg + (int64_t)i * nc * mat + c;
+        if (c < mat) {
+            for (int e0 = 0; e0 < nc; e0 += CH) {
+                double2 acc[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) acc[j] = make_double2(0.0, 0.0);
+#pragma unroll 2
+                for (int kg = 0; kg < nr; ++kg) {
+                    const double2 b = *reinterpret_cast<const double2 *>(st + kg * kGrpTile);
+                    const double *cf = coef + kg * nc + e0;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        const double v = e0 + j < nc ? cf[j] : 0.0;
+                        acc[j].x = fma(v, b.x, acc[j].x);
+                        acc[j].y = fma(v, b.y, acc[j].y);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    if (e0 + j < nc) *reinterpret_cast<double2 *>(out + (int64_t)(e0 + j) * mat) = acc[j];
+            }
+        }
+        __syncthreads();                                   // every thread is done with stage s
+        if (threadIdx.x == 0 && w + kGrpStages < w1) issue(w + kGrpStages, s);
     }
 }
 
@@ -836,6 +939,29 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     if (no > 0) {
         const size_t smem = (size_t)4 * na * (2 * na + 1) * sizeof(double);
         if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
+        const size_t smem_stream = group_stream_smem_bytes(na);
+        if (!g_hessian_group_unstreamed && mat >= 16 * kGrpTile && smem_stream <= 220 * 1024 && batch <= 65535) {
+            // large ld^2: bulk-async streamed kernel, one CTA per SM, contiguous ranges of (i, tile) work items
+            const int tiles_per_i = (int)ceil_div(mat, kGrpTile);
+            const int total = no * tiles_per_i;
+            const int ctas = total < sm_count() ? total : sm_count();
+            const int items = (int)ceil_div(total, ctas);
+            dim3 sgrid((unsigned)ceil_div(total, items), (unsigned)batch);
+#define OO_GROUP_STREAM(CH)                                                                                        \
+    do {                                                                                                           \
+        static unsigned long long cfgd = 0;                                                                        \
+        if (once_per_device(cfgd))                                                                                 \
+            OO_CUDA_CHECK(cudaFuncSetAttribute(hess_group_stream_kernel<CH>,                                       \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
+        hess_group_stream_kernel<CH><<<sgrid, 128, smem_stream, stream>>>(cls, cls_stride, rdm, sd1, sd2,          \
+                                                                         rdm_batched, nIp, 1, mat, Tg,             \
+                                                                         tiles_per_i, items);                     \
+    } while (0)
+            if (2 * na <= 8) OO_GROUP_STREAM(8);
+            else if (2 * na <= 16) OO_GROUP_STREAM(16);
+            else OO_GROUP_STREAM(24);
+#undef OO_GROUP_STREAM
+        } else {
         dim3 grid((unsigned)no, (unsigned)ceil_div(mat / 2, 128), (unsigned)batch);
 #define OO_GROUP(CH) hess_group_kernel<CH><<<grid, 128, smem, stream>>>(cls, cls_stride, rdm, sd1, sd2, rdm_batched, \
                                                                        nIp, 1, mat, Tg)
@@ -844,6 +970,7 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
         else if (2 * na <= 16) OO_GROUP(16);
         else OO_GROUP(24);
 #undef OO_GROUP
+        }
         OO_LAUNCH_CHECK();
     }
     // the rest (occ-occ pairs i != j), plus anything a block column has outside its block

@@ -99,6 +99,13 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     finally:
         eng.lib.oo_set_option(2, 0)
     assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
+    # G blocks of the Hessian T-matrix: bulk-async streamed kernel (taken at this size) against per-thread loads
+    try:
+        assert eng.lib.oo_set_option(4, 1) == 0
+        _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.lib.oo_set_option(4, 0)
+    assert torch.equal(Hf, Hc)
     # class-pair packing: fused into the quarter-2 GEMM epilogues (default) against the separate pass
     try:
         assert eng.lib.oo_set_option(3, 1) == 0
