@@ -304,13 +304,19 @@ hess_group_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, 
     }
 }
 
-// Streamed form of the same product for large ld^2: the kernel above keeps only two 16-byte loads per thread in
-// flight and ends up DRAM-latency bound (2.4 TB/s at N = 256).  Here a CTA owns a contiguous range of
-// (occupied i, column tile) work items; for each item ONE thread issues a bulk asynchronous copy
-// (cp.async.bulk, completion on an mbarrier) per B row -- 4 na row segments of 2 KB into a shared-memory stage,
-// two stages, so ~100-200 KB are in flight per SM while the 128 threads run the 4 na x 2 na FMAs of the previous
-// tile out of shared memory.  Same coefficients, same summation order over kg as hess_group_kernel.
-constexpr int kGrpTile = 256;                       // columns per tile: one double2 per thread
+// Streamed tensor-core form of the same product for large ld^2.  The kernel above issues one shared-memory
+// coefficient load per two FMAs and ends up issue-bound at 2.4 TB/s (N = 256), however many loads are in flight.
+// A G block is a small GEMM, Tg_i[e, c] = sum_kg coef[kg, e] B[row(kg), c] with K = 4 na, so:
+//   * a CTA owns a contiguous range of (occupied i, 256-column tile) work items; per item ONE thread issues a
+//     bulk asynchronous copy (cp.async.bulk, completion on an mbarrier) per B row into a shared-memory stage
+//     (4 na segments of 2 KB, two stages => 100-200 KB in flight per SM);
+//   * four warps run FP64 DMMA.8x8x4 on the stage: M = 64 columns c per warp, N = 2 na result rows, K = 4 na;
+//     stage rows are 260 doubles apart and coefficient rows NCP + 4 (both = 4 mod 8): conflict-free fragments;
+//   * the accumulators go straight to Tg (64-byte runs).
+// Same coefficients (at_value) as hess_group_kernel; the summation order inside a DMMA differs, so the two agree
+// to round-off, not bit for bit.
+constexpr int kGrpTile = 256;                       // columns per tile
+constexpr int kGrpRow = kGrpTile + 4;               // stage row stride (doubles)
 constexpr int kGrpStages = 2;
 
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
@@ -321,11 +327,12 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint
 }
 
 size_t group_stream_smem_bytes(int na) {
-    return (size_t)kGrpStages * 4 * na * kGrpTile * sizeof(double) + (size_t)4 * na * 2 * na * sizeof(double) +
+    const int ncp = (2 * na + 7) / 8 * 8;
+    return (size_t)kGrpStages * 4 * na * kGrpRow * sizeof(double) + (size_t)4 * na * (ncp + 4) * sizeof(double) +
            kGrpStages * sizeof(uint64_t) + 16;
 }
 
-template <int CH>
+template <int NT>                                   // result rows padded to 8 NT >= 2 na
 __global__ void __launch_bounds__(128, 1)
 hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, int64_t sd1, int64_t sd2,
                          int rdm_batched, int nIs, int swap_exch, int64_t mat, double *__restrict__ Tg,
@@ -336,9 +343,10 @@ hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView
                       rdm0.na};
     const Blocks bl{rdm.no, rdm.na, nIs};
     const int nr = bl.nrow_g(), nc = bl.ncol_g();
+    constexpr int CS = 8 * NT + 4;                  // coefficient row stride
     double *stage_buf = reinterpret_cast<double *>(gs_smem);
-    double *coef = stage_buf + (size_t)kGrpStages * nr * kGrpTile;
-    uint64_t *full = reinterpret_cast<uint64_t *>(coef + nr * nc);
+    double *coef = stage_buf + (size_t)kGrpStages * nr * kGrpRow;
+    uint64_t *full = reinterpret_cast<uint64_t *>(coef + nr * CS);
     const int total = rdm.no * tiles_per_i;
     const int w0 = blockIdx.x * items_per_cta, w1 = min(w0 + items_per_cta, total);
     if (w0 >= w1) return;
@@ -355,51 +363,64 @@ hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView
         const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile;
         const uint32_t seg = (uint32_t)((mat - c0 < kGrpTile ? mat - c0 : kGrpTile) * sizeof(double));
         mbar_arrive_expect_tx(&full[s], seg * nr);
-        double *dst = stage_buf + (size_t)s * nr * kGrpTile;
-        for (int kg = 0; kg < nr; ++kg) bulk_load(dst + kg * kGrpTile, B + bl.row_g(i, kg) * mat + c0, seg, &full[s]);
+        double *dst = stage_buf + (size_t)s * nr * kGrpRow;
+        for (int kg = 0; kg < nr; ++kg) bulk_load(dst + kg * kGrpRow, B + bl.row_g(i, kg) * mat + c0, seg, &full[s]);
     };
     if (threadIdx.x == 0)
         for (int k = 0; k < kGrpStages && w0 + k < w1; ++k) issue(w0 + k, k);
 
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     int cur_i = -1;
     for (int w = w0; w < w1; ++w) {
         const int k = w - w0, s = k % kGrpStages;
         const int i = w / tiles_per_i;
         if (i != cur_i) {                                  // (at most twice per CTA) coefficients of occupied i
             __syncthreads();
-            for (int x = threadIdx.x; x < nr * nc; x += blockDim.x) {
-                int p, r, m, n;
-                bl.col_g(i, x % nc, p, r);
-                coef[x] = at_value(rdm, nIs, swap_exch, bl.row_g(i, x / nc), p, r, m, n);
+            for (int x = threadIdx.x; x < nr * 8 * NT; x += blockDim.x) {
+                const int kg = x / (8 * NT), e = x % (8 * NT);
+                double v = 0.0;
+                if (e < nc) {
+                    int p, r, m, n;
+                    bl.col_g(i, e, p, r);
+                    v = at_value(rdm, nIs, swap_exch, bl.row_g(i, kg), p, r, m, n);
+                }
+                coef[kg * CS + e] = v;
             }
             __syncthreads();
             cur_i = i;
         }
         mbar_wait(&full[s], (uint32_t)(k / kGrpStages) & 1u);
-        const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile;
-        const int64_t c = c0 + 2 * threadIdx.x;
-        const double *st = stage_buf + (size_t)s * nr * kGrpTile + 2 * threadIdx.x;
-        double *out = Tg + (int64_t)i * nc * mat + c;
-        if (c < mat) {
-            for (int e0 = 0; e0 < nc; e0 += CH) {
-                double2 acc[CH];
+        const double *st = stage_buf + (size_t)s * nr * kGrpRow + 64 * warp + g;
+        double acc[8][NT][2];
 #pragma unroll
-                for (int j = 0; j < CH; ++j) acc[j] = make_double2(0.0, 0.0);
-#pragma unroll 2
-                for (int kg = 0; kg < nr; ++kg) {
-                    const double2 b = *reinterpret_cast<const double2 *>(st + kg * kGrpTile);
-                    const double *cf = coef + kg * nc + e0;
+        for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) {
-                        const double v = e0 + j < nc ? cf[j] : 0.0;
-                        acc[j].x = fma(v, b.x, acc[j].x);
-                        acc[j].y = fma(v, b.y, acc[j].y);
-                    }
+            for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int k0 = 0; k0 < nr; k0 += 4) {               // nr = 4 na
+            double a[8], bf[NT];
+            const double *srow = st + (k0 + t) * kGrpRow;
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt) a[mt] = srow[8 * mt];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bf[nt] = coef[(k0 + t) * CS + 8 * nt + g];
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf[nt]);
+        }
+        const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile + 64 * warp + g;
+        double *out = Tg + (int64_t)i * nc * mat;
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+            const int64_t c = c0 + 8 * mt;
+            if (c >= mat) continue;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int e = 8 * nt + 2 * t + cc;
+                    if (e < nc) out[(int64_t)e * mat + c] = acc[mt][nt][cc];
                 }
-#pragma unroll
-                for (int j = 0; j < CH; ++j)
-                    if (e0 + j < nc) *reinterpret_cast<double2 *>(out + (int64_t)(e0 + j) * mat) = acc[j];
-            }
         }
         __syncthreads();                                   // every thread is done with stage s
         if (threadIdx.x == 0 && w + kGrpStages < w1) issue(w + kGrpStages, s);
@@ -940,7 +961,8 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
         const size_t smem = (size_t)4 * na * (2 * na + 1) * sizeof(double);
         if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
         const size_t smem_stream = group_stream_smem_bytes(na);
-        if (!g_hessian_group_unstreamed && mat >= 16 * kGrpTile && smem_stream <= 220 * 1024 && batch <= 65535) {
+        if (!g_hessian_group_unstreamed && mat >= 16 * kGrpTile && 2 * na <= 24 && smem_stream <= 220 * 1024 &&
+            batch <= 65535) {
             // large ld^2: bulk-async streamed kernel, one CTA per SM, contiguous ranges of (i, tile) work items
             const int tiles_per_i = (int)ceil_div(mat, kGrpTile);
             const int total = no * tiles_per_i;
@@ -957,9 +979,9 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
                                                                          rdm_batched, nIp, 1, mat, Tg,             \
                                                                          tiles_per_i, items);                     \
     } while (0)
-            if (2 * na <= 8) OO_GROUP_STREAM(8);
-            else if (2 * na <= 16) OO_GROUP_STREAM(16);
-            else OO_GROUP_STREAM(24);
+            if (2 * na <= 8) OO_GROUP_STREAM(1);
+            else if (2 * na <= 16) OO_GROUP_STREAM(2);
+            else OO_GROUP_STREAM(3);
 #undef OO_GROUP_STREAM
         } else {
         dim3 grid((unsigned)no, (unsigned)ceil_div(mat / 2, 128), (unsigned)batch);

@@ -105,7 +105,7 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
         _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
         eng.lib.oo_set_option(4, 0)
-    assert torch.equal(Hf, Hc)
+    assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())     # DMMA vs FMA summation order
     # class-pair packing: fused into the quarter-2 GEMM epilogues (default) against the separate pass
     try:
         assert eng.lib.oo_set_option(3, 1) == 0
