@@ -310,7 +310,7 @@ hess_group_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, 
 //   * a CTA owns a contiguous range of (occupied i, 256-column tile) work items; per item ONE thread issues a
 //     bulk asynchronous copy (cp.async.bulk, completion on an mbarrier) per B row into a shared-memory stage
 //     (4 na segments of 2 KB, two stages => 100-200 KB in flight per SM);
-//   * four warps run FP64 DMMA.8x8x4 on the stage: M = 64 columns c per warp, N = 2 na result rows, K = 4 na;
+//   * eight warps run FP64 DMMA.8x8x4 on the stage: M = 32 columns c per warp, N = 2 na result rows, K = 4 na;
 //     stage rows are 260 doubles apart and coefficient rows NCP + 4 (both = 4 mod 8): conflict-free fragments;
 //   * the accumulators go straight to Tg (64-byte runs).
 // Same coefficients (at_value) as hess_group_kernel; the summation order inside a DMMA differs, so the two agree
@@ -332,8 +332,11 @@ size_t group_stream_smem_bytes(int na) {
            kGrpStages * sizeof(uint64_t) + 16;
 }
 
+constexpr int kGrpWarps = 8;                        // 32 columns (4 DMMA row tiles) per warp
+constexpr int kGrpMT = kGrpTile / kGrpWarps / 8;
+
 template <int NT>                                   // result rows padded to 8 NT >= 2 na
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(32 * kGrpWarps, 1)
 hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView rdm0, int64_t sd1, int64_t sd2,
                          int rdm_batched, int nIs, int swap_exch, int64_t mat, double *__restrict__ Tg,
                          int tiles_per_i, int items_per_cta) {
@@ -358,18 +361,20 @@ hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView
     B += bz * b_stride;
     Tg += (int64_t)bz * rdm.no * nc * mat;
 
-    auto issue = [&](int w, int s) {                       // thread 0: all row segments of work item w into stage s
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    auto issue = [&](int w, int s) {                       // warp 0: all row segments of work item w into stage s
         const int i = w / tiles_per_i;
         const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile;
         const uint32_t seg = (uint32_t)((mat - c0 < kGrpTile ? mat - c0 : kGrpTile) * sizeof(double));
-        mbar_arrive_expect_tx(&full[s], seg * nr);
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], seg * nr);
+        __syncwarp();
         double *dst = stage_buf + (size_t)s * nr * kGrpRow;
-        for (int kg = 0; kg < nr; ++kg) bulk_load(dst + kg * kGrpRow, B + bl.row_g(i, kg) * mat + c0, seg, &full[s]);
+        for (int kg = lane; kg < nr; kg += 32)             // one or two bulk copies per lane
+            bulk_load(dst + kg * kGrpRow, B + bl.row_g(i, kg) * mat + c0, seg, &full[s]);
     };
-    if (threadIdx.x == 0)
+    if (warp == 0)
         for (int k = 0; k < kGrpStages && w0 + k < w1; ++k) issue(w0 + k, k);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     int cur_i = -1;
     for (int w = w0; w < w1; ++w) {
         const int k = w - w0, s = k % kGrpStages;
@@ -390,28 +395,29 @@ hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView
             cur_i = i;
         }
         mbar_wait(&full[s], (uint32_t)(k / kGrpStages) & 1u);
-        const double *st = stage_buf + (size_t)s * nr * kGrpRow + 64 * warp + g;
-        double acc[8][NT][2];
+        const double *st = stage_buf + (size_t)s * nr * kGrpRow + 8 * kGrpMT * warp + g;
+        double acc[kGrpMT][NT][2];
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt)
+        for (int mt = 0; mt < kGrpMT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll 2
         for (int k0 = 0; k0 < nr; k0 += 4) {               // nr = 4 na
-            double a[8], bf[NT];
+            double a[kGrpMT], bf[NT];
             const double *srow = st + (k0 + t) * kGrpRow;
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt) a[mt] = srow[8 * mt];
+            for (int mt = 0; mt < kGrpMT; ++mt) a[mt] = srow[8 * mt];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) bf[nt] = coef[(k0 + t) * CS + 8 * nt + g];
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt)
+            for (int mt = 0; mt < kGrpMT; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf[nt]);
         }
-        const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile + 64 * warp + g;
+        const int64_t c0 = (int64_t)(w % tiles_per_i) * kGrpTile + 8 * kGrpMT * warp + g;
         double *out = Tg + (int64_t)i * nc * mat;
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
+        for (int mt = 0; mt < kGrpMT; ++mt) {
             const int64_t c = c0 + 8 * mt;
             if (c >= mat) continue;
 #pragma unroll
@@ -423,7 +429,7 @@ hess_group_stream_kernel(const double *__restrict__ B, int64_t b_stride, RdmView
                 }
         }
         __syncthreads();                                   // every thread is done with stage s
-        if (threadIdx.x == 0 && w + kGrpStages < w1) issue(w + kGrpStages, s);
+        if (warp == 0 && w + kGrpStages < w1) issue(w + kGrpStages, s);
     }
 }
 
@@ -975,7 +981,7 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
         if (once_per_device(cfgd))                                                                                 \
             OO_CUDA_CHECK(cudaFuncSetAttribute(hess_group_stream_kernel<CH>,                                       \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
-        hess_group_stream_kernel<CH><<<sgrid, 128, smem_stream, stream>>>(cls, cls_stride, rdm, sd1, sd2,          \
+        hess_group_stream_kernel<CH><<<sgrid, 32 * kGrpWarps, smem_stream, stream>>>(cls, cls_stride, rdm, sd1, sd2,          \
                                                                          rdm_batched, nIp, 1, mat, Tg,             \
                                                                          tiles_per_i, items);                     \
     } while (0)
