@@ -24,6 +24,7 @@ extern int g_hessian_dense;
 extern int g_hessian_simple_assemble;
 extern int g_class_unfused_pack;
 extern int g_hessian_group_unstreamed;
+extern int g_hessian_assemble_unstreamed;
 
 int sm_count() {
     static int cached[64] = {};                         // per device
@@ -124,6 +125,10 @@ unsigned long long oo_launch_count(void) { return oo::g_launch_count; }
 int oo_set_option(int key, int value) {
     if (key == OO_OPT_HESSIAN_DENSE) {
         oo::g_hessian_dense = value ? 1 : 0;
+        return OO_OK;
+    }
+    if (key == OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED) {
+        oo::g_hessian_assemble_unstreamed = value ? 1 : 0;
         return OO_OK;
     }
     if (key == OO_OPT_HESSIAN_GROUP_UNSTREAMED) {

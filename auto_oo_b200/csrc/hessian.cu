@@ -22,6 +22,7 @@
 
 namespace oo {
 
+int g_hessian_assemble_unstreamed = 0; // oo_set_option(OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED): 1 = no bulk-async assembly kernel
 int g_hessian_group_unstreamed = 0;    // oo_set_option(OO_OPT_HESSIAN_GROUP_UNSTREAMED): 1 = register-only G-block kernel (A/B tests)
 int g_hessian_simple_assemble = 0;     // oo_set_option(OO_OPT_HESSIAN_SIMPLE_ASSEMBLE): 0 auto, 1 per-thread kernel, 2 row-tiled kernel
 
@@ -586,10 +587,13 @@ hess_assemble_kernel(TView tv, const double *__restrict__ F,
 constexpr int kAsmRows = 32;                       // orbital rows per CTA
 constexpr int kAsmStrip = kAsmRows * (64 + 1);     // shared-memory strip (doubles): runs of up to 64 columns
 
+// runs[l] = first k of orbital row l (l <= N); runs[N+1] = 1 when the pair list is row-sorted with consecutive
+// columns inside a row; runs[N+2] = S > 0 when, in addition, every row l >= rows_in (rows_in = nI rounded up to
+// even) holds exactly the columns 0 .. S-1 with S <= min(nI, 64): the layout the streamed assembly needs.
 __global__ void hess_pair_runs_kernel(const int32_t *__restrict__ pl, const int32_t *__restrict__ pr, int nk, int N,
-                                      int *__restrict__ runs /* [N + 2]: start of row l; [N+1] = structure ok */) {
-    __shared__ int bad;
-    if (threadIdx.x == 0) bad = 0;
+                                      int nI, int *__restrict__ runs) {
+    __shared__ int bad, nonuniform;
+    if (threadIdx.x == 0) bad = nonuniform = 0;
     __syncthreads();
     for (int l = threadIdx.x; l <= N; l += blockDim.x) {      // lower_bound(pl, l)
         int lo = 0, hi = nk;
@@ -608,7 +612,16 @@ __global__ void hess_pair_runs_kernel(const int32_t *__restrict__ pl, const int3
         if (pl[k] < 0 || pl[k] >= N || pr[k] < 0 || pr[k] >= N) mybad = 1;
     if (mybad) bad = 1;
     __syncthreads();
-    if (threadIdx.x == 0) runs[N + 1] = bad ? 0 : 1;
+    const int rows_in = min((nI + 1) & ~1, N);
+    const int S = rows_in < N ? runs[rows_in + 1] - runs[rows_in] : 0;
+    if (!bad)
+        for (int l = rows_in + threadIdx.x; l < N; l += blockDim.x)
+            if (runs[l + 1] - runs[l] != S || S <= 0 || pr[runs[l]] != 0) nonuniform = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        runs[N + 1] = bad ? 0 : 1;
+        runs[N + 2] = (!bad && !nonuniform && S > 0 && S <= nI && S <= 64) ? S : 0;
+    }
 }
 
 __device__ __forceinline__ double hess_t(const TView &tv, int ld, int a, int c, int b, int d) {
@@ -626,7 +639,7 @@ constexpr int kAsmJ = 8;              // Hessian rows j per CTA (the row-tile bo
 __global__ void __launch_bounds__(256, 4)
 hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t *__restrict__ pl,
                           const int32_t *__restrict__ pr, const int *__restrict__ runs, int nk, int N, int ld,
-                          double *__restrict__ H) {
+                          double *__restrict__ H, int stream_partner) {
     __shared__ double strip[kAsmStrip];
     __shared__ unsigned char rowof[kAsmStrip];
     __shared__ int rstart[kAsmRows], rlen[kAsmRows], rs0[kAsmRows];
@@ -638,7 +651,8 @@ hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t 
     const bool structured = runs[N + 1] != 0;
     // row tiles: tile 0 = the orbital rows inside I (short runs, all four terms: per-thread form), tile t >= 1 =
     // kAsmRows rows outside I
-    const int rows_in = min(tv.nI, N);
+    const int rows_in = min((tv.nI + 1) & ~1, N);
+    if (blockIdx.x > 0 && stream_partner && runs[N + 2] > 0) return;      // hess_assemble_stream_kernel has these tiles
     const int l0 = blockIdx.x == 0 ? 0 : rows_in + ((int)blockIdx.x - 1) * kAsmRows;
     const int l1 = blockIdx.x == 0 ? rows_in : min(l0 + kAsmRows, N);
     int kb = 0, ke = 0;
@@ -722,6 +736,76 @@ hess_assemble_rows_kernel(TView tv, const double *__restrict__ F, const int32_t 
     }
 }
 
+// Streamed assembly of the rows outside I (the bulk: (N - nI) / N of the orbital rows).  For a Hessian row
+// j = (p, q) and 32 orbital rows r, the surviving term T[(q s),(p r)] is, for each column s, one 256-byte piece of
+// a row of T: warp jj issues those S pieces of "its" j as bulk asynchronous copies (cp.async.bulk -> shared memory,
+// one mbarrier per j), so all 8 x S pieces of the CTA (90 KB at N = 256) are in flight at once instead of one
+// 8-byte load per thread; the pieces are then transposed through a padded strip and written out coalesced.
+// Needs the uniform pair layout hess_pair_runs_kernel certifies (runs[N+2] = S); otherwise this kernel returns at
+// once and hess_assemble_rows_kernel does the tiles.
+__global__ void __launch_bounds__(256)
+hess_assemble_stream_kernel(TView tv, const double *__restrict__ F, const int32_t *__restrict__ pl,
+                            const int32_t *__restrict__ pr, const int *__restrict__ runs, int nk, int N, int ld,
+                            double *__restrict__ H) {
+    extern __shared__ __align__(128) unsigned char as_smem[];
+    const int S = runs[N + 2];
+    if (S == 0) return;
+    const int rows_in = min((tv.nI + 1) & ~1, N);
+    const int l0 = rows_in + (int)blockIdx.x * kAsmRows;
+    if (l0 >= N) return;
+    const int nrows = min(kAsmRows, N - l0);
+    const uint32_t seg = (uint32_t)(min(kAsmRows, ld - l0) * sizeof(double));     // even count: 16-byte multiple
+    const int kb = runs[l0];
+    double *stage = reinterpret_cast<double *>(as_smem);                          // [kAsmJ][S][kAsmRows]
+    double *strip = stage + (size_t)kAsmJ * S * kAsmRows;                         // [kAsmRows][S + 1]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(strip + kAsmRows * (S + 1) + ((kAsmRows * (S + 1)) & 1));
+    tv.at_batch(blockIdx.z);
+    F += blockIdx.z * tv.f_stride;
+    H += blockIdx.z * tv.h_stride;
+    const int j0 = blockIdx.y * kAsmJ, j1 = min(j0 + kAsmJ, nk);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ld2 = (int64_t)ld * ld;
+    if (threadIdx.x == 0) {
+        for (int jj = 0; jj < kAsmJ; ++jj) mbar_init(&bar[jj], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    {                                                     // warp jj fetches the pieces of Hessian row j0 + jj
+        const int j = j0 + warp;
+        if (j < j1) {
+            const int p = pl[j], q = pr[j];
+            if (q < tv.nI) {
+                if (lane == 0) mbar_arrive_expect_tx(&bar[warp], seg * S);
+                __syncwarp();
+                for (int sx = lane; sx < S; sx += 32)
+                    bulk_load(stage + ((size_t)warp * S + sx) * kAsmRows, tv.row(q, sx, ld2) + (int64_t)p * ld + l0, seg,
+                              &bar[warp]);
+            }
+        }
+    }
+    for (int jj = 0; jj < j1 - j0; ++jj) {
+        const int j = j0 + jj;
+        const int p = pl[j], q = pr[j];
+        const bool q_in = q < tv.nI, p_in = p < tv.nI;
+        if (q_in) mbar_wait(&bar[jj], 0);
+        const int r = l0 + lane;
+        if (lane < nrows) {
+            for (int sx = warp; sx < S; sx += 8) {
+                double v = q_in ? stage[((size_t)jj * S + sx) * kAsmRows + lane] : 0.0;
+                if (p_in) v -= __ldg(tv.row(p, sx, ld2) + (int64_t)q * ld + r);
+                if (q == sx) v -= fock_sym(F, ld, p, r);
+                if (p == sx) v += fock_sym(F, ld, q, r);
+                if (p == r) v -= fock_sym(F, ld, q, sx);
+                strip[lane * (S + 1) + sx] = v;
+            }
+        }
+        __syncthreads();
+        double *Hj = H + (int64_t)j * nk + kb;
+        for (int i = threadIdx.x; i < nrows * S; i += blockDim.x) Hj[i] = strip[(i / S) * (S + 1) + i % S];
+        __syncthreads();
+    }
+}
+
 // ---- API-parity helpers: dense full-space RDMs and the dense Y-matrix -----------------
 // (reference full_rdms oo_energy.py:342-379 and y_matrix :381-393 for an arbitrary dense
 // two_full; the Hessian path above never materialises either)
@@ -765,7 +849,7 @@ __global__ void y_permute_kernel(const double *__restrict__ T, int N, int ld, do
     }
 }
 
-size_t assemble_scratch_bytes(int ld) { return align_up((size_t)(ld + 2) * sizeof(int), 1024); }
+size_t assemble_scratch_bytes(int ld) { return align_up((size_t)(ld + 3) * sizeof(int), 1024); }
 
 int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const int32_t *pr, int nk, int N, int ld,
                     int batch, double *H, void *scratch, cudaStream_t stream) {
@@ -777,12 +861,26 @@ int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const i
         return OO_OK;
     }
     int *runs = reinterpret_cast<int *>(scratch);
-    hess_pair_runs_kernel<<<1, 1024, 0, stream>>>(pl, pr, nk, N, runs);
+    hess_pair_runs_kernel<<<1, 1024, 0, stream>>>(pl, pr, nk, N, tv.nI, runs);
     OO_LAUNCH_CHECK();
-    const int rows_out = N > tv.nI ? N - tv.nI : 0;
+    const int rows_in = (tv.nI + 1) & ~1;
+    const int rows_out = N > rows_in ? N - rows_in : 0;
+    const int smax = tv.nI < 64 ? tv.nI : 64;
+    const size_t smem = ((size_t)kAsmJ * smax * kAsmRows + (size_t)kAsmRows * (smax + 1) + 2 + kAsmJ) * sizeof(double);
+    const int streamed = !g_hessian_assemble_unstreamed && rows_out > 0 &&
+                         smem <= 110 * 1024;
     dim3 grid((unsigned)(1 + ceil_div(rows_out, kAsmRows)), (unsigned)ceil_div(nk, kAsmJ), (unsigned)batch);
-    hess_assemble_rows_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, runs, nk, N, ld, H);
+    hess_assemble_rows_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, runs, nk, N, ld, H, streamed);
     OO_LAUNCH_CHECK();
+    if (streamed) {
+        static unsigned long long cfgd = 0;
+        if (once_per_device(cfgd))
+            OO_CUDA_CHECK(cudaFuncSetAttribute(hess_assemble_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               110 * 1024));
+        dim3 sgrid((unsigned)ceil_div(rows_out, kAsmRows), (unsigned)ceil_div(nk, kAsmJ), (unsigned)batch);
+        hess_assemble_stream_kernel<<<sgrid, 256, smem, stream>>>(tv, F, pl, pr, runs, nk, N, ld, H);
+        OO_LAUNCH_CHECK();
+    }
     return OO_OK;
 }
 

@@ -99,6 +99,13 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     finally:
         eng.lib.oo_set_option(2, 0)
     assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
+    # assembly of the rows outside occ+act: bulk-async streamed kernel (default) against the load-per-thread kernel
+    try:
+        assert eng.lib.oo_set_option(5, 1) == 0
+        _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.lib.oo_set_option(5, 0)
+    assert torch.equal(Hf, Hc)
     # G blocks of the Hessian T-matrix: bulk-async streamed kernel (taken at this size) against per-thread loads
     try:
         assert eng.lib.oo_set_option(4, 1) == 0
