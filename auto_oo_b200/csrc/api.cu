@@ -23,7 +23,6 @@ size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch);
 extern int g_hessian_dense;
 extern int g_hessian_simple_assemble;
 extern int g_class_unfused_pack;
-extern int g_tn_one_cta_per_sm;
 extern int g_hessian_group_unstreamed;
 extern int g_hessian_assemble_unstreamed;
 
@@ -134,10 +133,6 @@ int oo_set_option(int key, int value) {
     }
     if (key == OO_OPT_HESSIAN_GROUP_UNSTREAMED) {
         oo::g_hessian_group_unstreamed = value ? 1 : 0;
-        return OO_OK;
-    }
-    if (key == OO_OPT_TN_ONE_CTA_PER_SM) {
-        oo::g_tn_one_cta_per_sm = value ? 1 : 0;
         return OO_OK;
     }
     if (key == OO_OPT_CLASS_UNFUSED_PACK) {

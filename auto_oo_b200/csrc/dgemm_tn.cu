@@ -23,15 +23,9 @@ namespace oo {
 template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_>
 struct TnCfg {
     static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_;
-    static constexpr int NCW = WGM * WGN;            // consumer warps: two warpgroups, or one (two CTAs per SM)
+    static constexpr int NCW = WGM * WGN;            // consumer warps (two warpgroups)
     static constexpr int THREADS = (NCW + 4) * 32;   // + one producer warpgroup (its first warp issues TMA)
-    static_assert(NCW == 8 || NCW == 4, "register re-allocation assumes 1 or 2 consumer warpgroups + 1 producer warpgroup");
-    // NCW == 8: one CTA per SM (384 threads, 168 registers at launch -> 40 producer / 232 consumer).
-    // NCW == 4: TWO CTAs per SM (256 threads, 128 at launch -> 40 / 216: 2 * 128 * (40 + 216) = 65536): the two
-    // CTAs work on different tiles and drift apart, so one's epilogue overlaps the other's DMMA main loop.
-    static constexpr int CTAS_PER_SM = NCW == 8 ? 1 : 2;
-    static constexpr int REG_PRODUCER = 40;
-    static constexpr int REG_CONSUMER = NCW == 8 ? 232 : 216;
+    static_assert(NCW == 8, "register re-allocation below assumes 2 consumer warpgroups + 1 producer warpgroup");
     static constexpr int WTM = BM / WGM, WTN = BN / WGN;
     static constexpr int MT = WTM / 8, NT = WTN / 8;
     static constexpr int CHUNK_BYTES = BK * 128;     // one TMA box: [BK][16 doubles]
@@ -76,7 +70,7 @@ struct TnArgs {
 // DUAL: 0 = plain store, 1 = second store with rows (a b c) -> (c b a), 2 = packed-pair unpack,
 // 3 / 4 = class-pair packing, 5 = class-pair expansion instead of the plain store (see TnArgs)
 template <class Cfg, int DUAL>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM)
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const TnArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -108,7 +102,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // two consumer warpgroups grow to 232, which holds the 128 accumulator registers of the 64x32 /
     // 32x48 warp tiles plus fragments and addressing without spilling.
     if (warp >= Cfg::NCW) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REG_PRODUCER));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ===================== TMA producer =====================
         if (warp == Cfg::NCW && lane == 0) {
             int stage = 0;
@@ -140,7 +134,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REG_CONSUMER));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ===================== DMMA consumers =====================
         const int g = lane >> 2, t = lane & 3;
         const int wm = warp / Cfg::WGN, wn = warp % Cfg::WGN;
@@ -398,8 +392,7 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
                                            Cfg::SMEM_BYTES));
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
-    const int64_t resident = (int64_t)Cfg::CTAS_PER_SM * sm_count();
-    const int grid = (int)(total < resident ? total : resident);
+    const int grid = (int)(total < sm_count() ? total : sm_count());
     if (dual.C2 && dual.mode == 5)
         dgemm_tn_kernel<Cfg, 5><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     else if (dual.C2 && dual.mode == 4)
@@ -422,11 +415,6 @@ using TnMid = TnCfg<256, 64, 16, 4, 2, 4>;     // N in (48, 64]
 using TnMid48 = TnCfg<256, 48, 16, 8, 1, 4>;   // N in (32, 48] : warp tile 32x48 (class index nIp = 44 at N=256)
 using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (16, 32] : warp tile 32x32
 using TnSlim = TnCfg<256, 16, 16, 8, 1, 4>;    // N <= 16 : warp tile 32x16
-// two-CTAs-per-SM variants (same warp tiles, half the CTA tile)
-using TnWide2 = TnCfg<64, 128, 16, 1, 4, 4>;   // warp tile 64x32
-using TnMid48x2 = TnCfg<128, 48, 16, 4, 1, 4>; // warp tile 32x48
-
-int g_tn_one_cta_per_sm = 0;    // oo_set_option(OO_OPT_TN_ONE_CTA_PER_SM): 1 = the single-CTA configurations only (A/B tests)
 
 static int dgemm_tn_impl(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
                          int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
@@ -438,16 +426,12 @@ static int dgemm_tn_impl(const double *At, const double *B, double *C, int64_t M
     OO_REQUIRE((strideA % 2) == 0 && (strideB % 2) == 0 && (strideC % 2) == 0);
     OO_REQUIRE(((uintptr_t)At % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0);
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
-    // large problems: two smaller CTAs per SM (epilogue / main-loop overlap); small ones keep the big tile
-    const bool two = !g_tn_one_cta_per_sm && M * batch >= (int64_t)4 * 148 * 256;
     if (N > 64)
-        return two ? launch_tn<TnWide2>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual)
-                   : launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
+        return launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 48)
         return launch_tn<TnMid>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 32)
-        return two ? launch_tn<TnMid48x2>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual)
-                   : launch_tn<TnMid48>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
+        return launch_tn<TnMid48>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 16)
         return launch_tn<TnNarrow>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     return launch_tn<TnSlim>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);

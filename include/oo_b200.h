@@ -66,8 +66,6 @@ unsigned long long oo_launch_count(void);             /* kernels launched by thi
 enum {
     OO_OPT_HESSIAN_DENSE = 1,  /* 1: oo_class_hessian_f64 uses one dense GEMM over all of At instead of
                                   the dense act-act block + sparse remainder (same numbers)          */
-    OO_OPT_TN_ONE_CTA_PER_SM = 6,        /* 1: TN-DGEMM always with one 384-thread CTA per SM instead of two 256-thread
-                                            CTAs (half tiles) on large problems (same numbers)                */
     OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED = 5, /* 1: Hessian assembly without the bulk-async streamed kernel for the
                                                rows outside occ+act (same numbers)                            */
     OO_OPT_HESSIAN_GROUP_UNSTREAMED = 4, /* 1: G blocks of the Hessian T-matrix with per-thread loads instead of the
