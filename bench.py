@@ -218,7 +218,18 @@ def main():
         visible = os.environ.get("CUDA_VISIBLE_DEVICES")
         phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
         numa_cpus = bind_to_gpu_numa_node(phys)                # pinned staging buffers on the GPU's own node
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to fd 1 when the communicator is created: keep stdout for the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.load()
 
     nao, nelec, ncas, nelecas = CONFIG_SHAPES[args.workload]
