@@ -413,7 +413,10 @@ class OO_energy:
         ``kappa_matrix_to_vector(analytic_gradient(mo_coeff=C'))`` and
         ``full_hessian_to_matrix(analytic_hessian(mo_coeff=C'))`` fused so that one four-index
         transform serves all three.  Host tensors in (staged through pinned memory), host tensors
-        out: ``(B,)``, ``(B, n_kappa)``, ``(B, n_kappa, n_kappa)``; CUDA tensors in -> CUDA out."""
+        out: ``(B,)``, ``(B, n_kappa)``, ``(B, n_kappa, n_kappa)``; CUDA tensors in -> CUDA out.
+        The host results are views of reused pinned staging buffers (a 765 MB Hessian per evaluation at
+        N=256 is not copied a second time): they stay valid until the next call of this method -- clone what
+        must outlive it."""
         eng = self.engine
         kappa = _as_tensor(kappa).detach().reshape(-1, self.n_kappa)
         one, two = _as_tensor(one_rdm).detach(), _as_tensor(two_rdm).detach()

@@ -80,3 +80,14 @@ def test_slab_transform_single_process():
     for mode in ("reduce_scatter", "all_to_all"):
         st = SlabTransform(n, mode=mode, gemm=torch_gemm_tn)
         assert (st(st.take_slab(g), *Cs) - ref).abs().max().item() < 1e-11
+
+
+def test_numa_binding_is_best_effort():
+    """bind_to_gpu_numa_node never raises: without NVML / a GPU it reports None and leaves the affinity alone."""
+    import os
+    from auto_oo_b200.distributed import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_numa_node(0)
+    after = os.sched_getaffinity(0)
+    assert cpus is None and after == before or set(cpus) == after
+    os.sched_setaffinity(0, before)

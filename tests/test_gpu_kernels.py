@@ -196,6 +196,16 @@ def test_graph_replay_equals_direct_evaluation():
     Eg, Gg, Hg = eng.evaluate_graphed(Coao, d1, d2, kappa=None, want_hessian=False)
     E, G, _ = eng.evaluate(Coao, d1, d2, want_hessian=False)
     assert Hg is None and torch.equal(Eg, E) and torch.equal(Gg, G)
+    # outputs too large to pin inside a graph: the call falls back to the direct path
+    eng.GRAPH_MAX_OUTPUT_BYTES = 1
+    try:
+        n_graphs = len(eng._ws["graphs"])
+        kap = (torch.randn(2, p.n_kappa, dtype=F64, generator=gen) * 0.05).cuda()
+        Ef, Gf, Hf = eng.evaluate_graphed(Coao, d1, d2, kappa=kap)
+        E, G, H = eng.evaluate(Coao, d1, d2, kappa=kap)
+        assert torch.equal(Ef, E) and torch.equal(Hf, H) and len(eng._ws["graphs"]) == n_graphs
+    finally:
+        del eng.GRAPH_MAX_OUTPUT_BYTES
     ref = c.ref
     E, G, H = eng.evaluate_graphed(Coao, d1, d2, kappa=c.kappa[None].cuda())
     assert abs(E.item() - float(ref["E"])) < TOL_E
