@@ -920,45 +920,74 @@ HessLayout hess_layout(int ld, int nI) {
 
 }  // namespace
 
-size_t hessian_ws_bytes(int ld, int nI) { return hess_layout(ld, nI).total; }
+int class_hessian(const double *cls, const double *F, const double *d1, int64_t sd1, const double *d2,
+                  int64_t sd2, int no, int na, int N, int ld, int nIp, int batch, const int32_t *pl,
+                  const int32_t *pr, int nk, double *H, void *ws, size_t ws_bytes, cudaStream_t stream);
+size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch);
 
+namespace {
+// class-layout B operand from the complete tensor: rows [K(n,m) | J(m,n) | h], m, n < nIp (zero rows beyond nI)
+//   K[n,m,a,b] = g'[a,m,n,b],  J[m,n,a,b] = g'[a,b,m,n]   (the layout classes.cu produces)
+__global__ void hess_gather_class_kernel(const double *__restrict__ h, const double *__restrict__ g, int nI, int nIp,
+                                         int ld, double *__restrict__ B) {
+    const int64_t nI2 = (int64_t)nIp * nIp, mat = (int64_t)ld * ld;
+    const int64_t total = (2 * nI2 + 1) * mat;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t k = i / mat, c = i % mat;
+        const int a = (int)(c / ld), b = (int)(c % ld);
+        double v = 0.0;
+        if (k < nI2) {
+            const int n = (int)(k / nIp), m = (int)(k % nIp);
+            if (m < nI && n < nI) v = g[(((int64_t)a * ld + m) * ld + n) * ld + b];
+        } else if (k < 2 * nI2) {
+            const int kk = (int)(k - nI2), m = kk / nIp, n = kk % nIp;
+            if (m < nI && n < nI) v = g[(((int64_t)a * ld + b) * ld + m) * ld + n];
+        } else {
+            v = h[c];
+        }
+        B[i] = v;
+    }
+}
+
+size_t full_hessian_b_bytes(int ld, int nIp) {
+    return align_up((size_t)(2 * (size_t)nIp * nIp + 1) * ld * ld * sizeof(double), 1024);
+}
+}  // namespace
+
+// workspace of oo_hessian_f64: the gathered class-layout operand + the class Hessian's own workspace (largest over
+// the occ / act splits of nI, which this query does not know)
+size_t hessian_ws_bytes(int ld, int nI) {
+    const int nIp = nI + (nI & 1);
+    size_t worst = 0;
+    for (int na = 1; na <= nI; ++na) {
+        const size_t w = class_hessian_ws_bytes(ld, nIp, nI - na, na, 1);
+        worst = w > worst ? w : worst;
+    }
+    return full_hessian_b_bytes(ld, nIp) + worst;
+}
+
+// Hessian from the COMPLETE transformed tensor g' (oo_hessian_f64): the J / K classes are gathered out of g' into the
+// class layout (one HBM-bound pass) and the block-structured class Hessian below does the rest -- the same kernels
+// for both integral representations.
 int hessian(const double *h, const double *g, const double *F, const double *d1, const double *d2,
             int no, int na, int N, int ld, const int32_t *pl, const int32_t *pr, int nk, double *H,
             void *ws, size_t ws_bytes, cudaStream_t stream) {
     OO_REQUIRE(h && g && F && d1 && d2 && H && ws && pl && pr);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0);
-    const int nI = no + na;
-    const HessLayout L = hess_layout(ld, nI);
-    if (ws_bytes < L.total) return OO_ERR_WORKSPACE;
-    if (nk > 65535 * 1) {
-        // grid.y carries j
-        if (nk > 2147483647 / 1) return OO_ERR_UNSUPPORTED;
-    }
-    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
-    double *At = reinterpret_cast<double *>(w);
-    double *B = reinterpret_cast<double *>(w + L.off_b);
-    double *T = reinterpret_cast<double *>(w + L.off_t);
-    const int64_t nI2 = (int64_t)nI * nI;
-    const int64_t mat = (int64_t)ld * ld;
-
-    RdmView rdm{d1, d2, no, na};
-    {
-        int64_t blocks = ceil_div(L.krows * L.lda, 256);
-        if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-        hess_build_at_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rdm, nI, 0, L.lda, At);
-        OO_LAUNCH_CHECK();
-    }
-    {
-        int64_t blocks = ceil_div(L.krows * mat, 256);
-        if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
-        hess_gather_b_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h, g, nI, ld, B);
-        OO_LAUNCH_CHECK();
-    }
-    int rc = dgemm_tn(At, B, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
-    if (rc) return rc;
+    const int nI = no + na, nIp = nI + (nI & 1);
+    const size_t b_bytes = full_hessian_b_bytes(ld, nIp);
+    const size_t c_bytes = class_hessian_ws_bytes(ld, nIp, no, na, 1);
+    if (ws_bytes < b_bytes + c_bytes) return OO_ERR_WORKSPACE;
     if (nk > 65535) return OO_ERR_UNSUPPORTED;
-    return launch_assemble(TView{T, nullptr, nullptr, nI, nI, no, na, 0, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1, H, w + L.off_runs,
-                           stream);
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    double *B = reinterpret_cast<double *>(w);
+    const int64_t mat = (int64_t)ld * ld;
+    int64_t blocks = ceil_div((2 * (int64_t)nIp * nIp + 1) * mat, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    hess_gather_class_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h, g, nI, nIp, ld, B);
+    OO_LAUNCH_CHECK();
+    return class_hessian(B, F, d1, 0, d2, 0, no, na, N, ld, nIp, 1, pl, pr, nk, H, w + b_bytes, c_bytes, stream);
 }
 
 // Hessian from the class buffer of classes.cu: cls = [K rows; J rows; h' row] IS the B operand.
