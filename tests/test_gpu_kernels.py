@@ -212,6 +212,35 @@ def test_graph_replay_equals_direct_evaluation():
     assert np.abs(G[0].cpu().numpy() - ref["G"]).max() < TOL_GH and np.abs(H[0].cpu().numpy() - ref["H"]).max() < TOL_GH
 
 
+@pytest.mark.parametrize("name", ["n11_cas43", "n34_cas44", "n43_cas34"])
+def test_hessian_output_guards_stay_untouched(name, lib):
+    """(compute-sanitizer is not available on the GPU pool.)  The Hessian is written into the middle of a larger
+    buffer whose guard zones hold a bit pattern; every assembly kernel (per-thread, row-tiled, bulk-async
+    streamed) must leave the guards alone and fill every element in between."""
+    c = load_case(name)
+    eng, p = engine_for(c)
+    Coao = eng.to_padded(c.oao_mo_coeff, 2)
+    d1, d2 = eng.dev(c.one_rdm), eng.dev(c.two_rdm)
+    nk, B, pad = eng.nk, 2, 4096
+    kap = torch.stack([c.kappa, 0.5 * c.kappa]).cuda()
+    sentinel = float.fromhex("-0x1.deadbeef00000p+700")
+    ref = None
+    for mode in (1, 2):
+        big = torch.full((B * nk * nk + 2 * pad,), sentinel, dtype=F64, device="cuda")
+        H = big[pad:pad + B * nk * nk].view(B, nk, nk)
+        try:
+            assert lib.oo_set_option(2, mode) == 0
+            eng.evaluate(Coao, d1, d2, kappa=kap, H_out=H)
+        finally:
+            lib.oo_set_option(2, 0)
+        torch.cuda.synchronize()
+        assert bool((big[:pad] == sentinel).all()) and bool((big[-pad:] == sentinel).all())
+        assert not bool((H == sentinel).any())
+        ref = H.clone() if ref is None else ref
+        assert (H - ref).abs().max().item() < 1e-11
+    assert np.abs(ref[0].cpu().numpy() - c.ref["H"]).max() < TOL_GH
+
+
 # ------------------------------------------------------------------ K2
 @pytest.mark.parametrize("name", SMALL_CASES)
 def test_integral_transforms_match_reference(name):
