@@ -187,12 +187,13 @@ def test_graph_replay_equals_direct_evaluation():
     gen = torch.Generator().manual_seed(4)
     for trial, B in enumerate([1, 3, 1, 3, 8]):
         kap = (torch.randn(B, p.n_kappa, dtype=F64, generator=gen) * 0.05).cuda()
-        Eg, Gg, Hg = eng.evaluate_graphed(Coao, d1 * (1 + 0.01 * trial), d2, kappa=kap)
+        Eg, Gg, Hg = eng.evaluate_graphed(Coao, d1 * (1 + 0.01 * trial), d2, kappa=kap)   # first sight of B: direct
         if trial == 2:                                   # a non-graph call with a larger batch re-sizes workspaces
             eng.evaluate(Coao, d1, d2, kappa=torch.zeros(16, p.n_kappa, dtype=F64, device="cuda"))
         E, G, H = eng.evaluate(Coao, d1 * (1 + 0.01 * trial), d2, kappa=kap)
         assert torch.equal(Eg, E) and torch.equal(Gg, G) and torch.equal(Hg, H)
-    assert len(eng._ws["graphs"]) == 3
+    assert len(eng._ws["graphs"]) == 2 and len(eng._ws["graph_seen"]) == 3        # B = 1, 3 captured; B = 8 seen once
+    eng.evaluate_graphed(Coao, d1, d2, kappa=None, want_hessian=False)
     Eg, Gg, Hg = eng.evaluate_graphed(Coao, d1, d2, kappa=None, want_hessian=False)
     E, G, _ = eng.evaluate(Coao, d1, d2, want_hessian=False)
     assert Hg is None and torch.equal(Eg, E) and torch.equal(Gg, G)
