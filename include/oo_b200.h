@@ -62,19 +62,19 @@ const char *oo_error_string(int code);
 int         oo_last_cuda_error(void);                 /* cudaError_t of the last OO_ERR_CUDA */
 unsigned long long oo_launch_count(void);             /* kernels launched by this library so far */
 
-/* process-wide switches (A/B timing and tests) */
+/* process-wide switches (A/B timing and tests); every setting gives the same numbers to round-off */
 enum {
-    OO_OPT_HESSIAN_DENSE = 1,  /* 1: oo_class_hessian_f64 uses one dense GEMM over all of At instead of
-                                  the dense act-act block + sparse remainder (same numbers)          */
-    OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED = 5, /* 1: Hessian assembly without the bulk-async streamed kernel for the
-                                               rows outside occ+act (same numbers)                            */
-    OO_OPT_HESSIAN_GROUP_UNSTREAMED = 4, /* 1: G blocks of the Hessian T-matrix with per-thread loads instead of the
-                                            bulk-async (cp.async.bulk + mbarrier) streamed kernel (same numbers) */
-    OO_OPT_CLASS_UNFUSED_PACK = 3,       /* 1: symmetric class transform packs the class pairs m >= n in a separate
-                                            pass instead of in the epilogue of the quarter-2 GEMMs (same numbers) */
-    OO_OPT_HESSIAN_SIMPLE_ASSEMBLE = 2   /* Hessian assembly kernel: 0 = by size (one thread per element for N <= 64,
-                                            row-tiled / shared-memory-transposed above), 1 = always the former,
-                                            2 = always the latter (same numbers)                       */
+    OO_OPT_HESSIAN_DENSE = 1,               /* 1: oo_class_hessian_f64 runs ONE dense GEMM over all of At instead of
+                                               the block form (C-block GEMM + G blocks + ELL remainder)          */
+    OO_OPT_HESSIAN_SIMPLE_ASSEMBLE = 2,     /* Hessian assembly: 0 = by size (one thread per element for N <= 64,
+                                               row-tiled + bulk-async streamed above), 1 = always the former,
+                                               2 = always the latter                                             */
+    OO_OPT_CLASS_UNFUSED_PACK = 3,          /* 1: symmetric class transform with separate pack / expand passes
+                                               instead of the fused epilogues of its quarter-2 / last-quarter GEMMs */
+    OO_OPT_HESSIAN_GROUP_UNSTREAMED = 4,    /* 1: G blocks of the Hessian T-matrix with per-thread loads instead of
+                                               the cp.async.bulk + mbarrier streamed DMMA kernel                  */
+    OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED = 5  /* 1: Hessian assembly without the bulk-async streamed kernel for the
+                                               rows outside occ+act                                              */
 };
 int         oo_set_option(int key, int value);
 int         oo_device_info(int *sm_count, int *cc_major, int *cc_minor);
