@@ -111,6 +111,67 @@ fock_core_active_kernel(const double *__restrict__ h, int64_t h_stride, const GV
     }
 }
 
+// Class-buffer form of the same two matrices: every J / K row of the class buffer is an (m, n) plane, so a thread
+// owns two consecutive (m, n) elements and streams down the 2 no + 2 na^2 rows it needs (coalesced 16-byte loads,
+// four rows in flight) instead of one strided 8-byte load per lane:
+//   F^I = h + sum_i (2 J[(i i)] - K[(i i)]),   F^A = sum_vw gamma_vw (J[(v w)] - K[(v w)] / 2)
+__global__ void __launch_bounds__(256)
+fock_core_active_class_kernel(const double *__restrict__ h, int64_t h_stride, const ClassView gv,
+                              const double *__restrict__ d1, int64_t sd1, int no, int na, int N, int ld,
+                              double *__restrict__ FI, double *__restrict__ FA) {
+    extern __shared__ double s_d1[];   // gamma (na*na)
+    const int b = blockIdx.y;
+    const double *d1b = d1 + (int64_t)b * sd1;
+    for (int e = threadIdx.x; e < na * na; e += blockDim.x) s_d1[e] = d1b[e];
+    __syncthreads();
+    const int64_t mat = (int64_t)ld * ld;
+    const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (e0 >= mat) return;
+    const ClassView gb = gv.at(b);
+    const int nIp = gb.nIp;
+    const double *J = gb.J + e0, *K = gb.K + e0;
+    double2 fi = *reinterpret_cast<const double2 *>(h + (int64_t)b * h_stride + e0);
+    double2 fa = make_double2(0.0, 0.0);
+    for (int i = 0; i < no; ++i) {
+        const int64_t row = ((int64_t)i * nIp + i) * mat;
+        const double2 j = __ldg(reinterpret_cast<const double2 *>(J + row));
+        const double2 k = __ldg(reinterpret_cast<const double2 *>(K + row));
+        fi.x += 2.0 * j.x - k.x;
+        fi.y += 2.0 * j.y - k.y;
+    }
+#pragma unroll 2
+    for (int e = 0; e < na * na; ++e) {
+        const int64_t row = ((int64_t)(no + e / na) * nIp + (no + e % na)) * mat;
+        const double2 j = __ldg(reinterpret_cast<const double2 *>(J + row));
+        const double2 k = __ldg(reinterpret_cast<const double2 *>(K + row));
+        const double gm = s_d1[e];
+        fa.x += gm * (j.x - 0.5 * k.x);
+        fa.y += gm * (j.y - 0.5 * k.y);
+    }
+    // rows / columns beyond N are zero padding
+    const int m = (int)(e0 / ld), n = (int)(e0 % ld);
+    if (m >= N) fi = fa = make_double2(0.0, 0.0);
+    if (n >= N) fi.x = fa.x = 0.0;
+    if (n + 1 >= N) fi.y = fa.y = 0.0;
+    *reinterpret_cast<double2 *>(FI + (int64_t)b * mat + e0) = fi;
+    if (FA) *reinterpret_cast<double2 *>(FA + (int64_t)b * mat + e0) = fa;
+}
+
+template <class GV>
+static void launch_fock_core_active(const double *h, int64_t h_stride, const GV &gv, const double *d1, int64_t sd1,
+                                    int no, int na, int N, int ld, int batch, double *FI, double *FA, size_t sm1,
+                                    cudaStream_t stream) {
+    dim3 grid((unsigned)ceil_div((int64_t)ld * ld, 8), (unsigned)batch);
+    fock_core_active_kernel<GV><<<grid, 256, sm1, stream>>>(h, h_stride, gv, d1, sd1, no, na, N, ld, FI, FA);
+}
+
+static void launch_fock_core_active(const double *h, int64_t h_stride, const ClassView &gv, const double *d1,
+                                    int64_t sd1, int no, int na, int N, int ld, int batch, double *FI, double *FA,
+                                    size_t sm1, cudaStream_t stream) {
+    dim3 grid((unsigned)ceil_div((int64_t)ld * ld / 2, 256), (unsigned)batch);
+    fock_core_active_class_kernel<<<grid, 256, sm1, stream>>>(h, h_stride, gv, d1, sd1, no, na, N, ld, FI, FA);
+}
+
 // ---------------------------------------------------------------- generalized Fock
 // grid (ld, batch): block n computes column n of F (rows = first index).
 //   F[i,n] = 2 (FI[n,i] + FA[n,i])                       i in occ
@@ -293,11 +354,8 @@ static int fock_gradient_t(const double *h, int64_t h_stride, const GV &gv, cons
     const size_t sm1 = (size_t)na * na * sizeof(double);
     const size_t sm3 = (size_t)na * na * na * sizeof(double);
     if (sm1 > 48 * 1024 || sm3 > 48 * 1024) return OO_ERR_UNSUPPORTED;   // na <= 18
-    {
-        dim3 grid((unsigned)ceil_div((int64_t)ld * ld, 8), (unsigned)batch);
-        fock_core_active_kernel<GV><<<grid, 256, sm1, stream>>>(h, h_stride, gv, d1, sd1, no, na, N, ld, FI, FA);
-        OO_LAUNCH_CHECK();
-    }
+    launch_fock_core_active(h, h_stride, gv, d1, sd1, no, na, N, ld, batch, FI, FA, sm1, stream);
+    OO_LAUNCH_CHECK();
     {
         dim3 grid((unsigned)ld, (unsigned)batch);
         fock_general_kernel<GV><<<grid, 256, sm3, stream>>>(gv, FI, FA, d1, sd1, d2, sd2, no, na, N, ld, F);
