@@ -115,38 +115,57 @@ fock_core_active_kernel(const double *__restrict__ h, int64_t h_stride, const GV
 // owns two consecutive (m, n) elements and streams down the 2 no + 2 na^2 rows it needs (coalesced 16-byte loads,
 // four rows in flight) instead of one strided 8-byte load per lane:
 //   F^I = h + sum_i (2 J[(i i)] - K[(i i)]),   F^A = sum_vw gamma_vw (J[(v w)] - K[(v w)] / 2)
+constexpr int kFockCols = 64;      // element pairs per CTA; 256 / kFockCols row groups share the row loop
+
 __global__ void __launch_bounds__(256)
 fock_core_active_class_kernel(const double *__restrict__ h, int64_t h_stride, const ClassView gv,
                               const double *__restrict__ d1, int64_t sd1, int no, int na, int N, int ld,
                               double *__restrict__ FI, double *__restrict__ FA) {
-    extern __shared__ double s_d1[];   // gamma (na*na)
+    extern __shared__ double s_d1[];   // gamma (na*na), then the partial sums of the row groups
+    constexpr int kGroups = 256 / kFockCols;
+    double2 *red = reinterpret_cast<double2 *>(s_d1 + ((na * na + 1) & ~1));      // [2][kGroups][kFockCols]
     const int b = blockIdx.y;
     const double *d1b = d1 + (int64_t)b * sd1;
     for (int e = threadIdx.x; e < na * na; e += blockDim.x) s_d1[e] = d1b[e];
     __syncthreads();
     const int64_t mat = (int64_t)ld * ld;
-    const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    if (e0 >= mat) return;
+    const int tx = threadIdx.x % kFockCols, ty = threadIdx.x / kFockCols;
+    const int64_t e0 = ((int64_t)blockIdx.x * kFockCols + tx) * 2;
+    const bool live = e0 < mat;
     const ClassView gb = gv.at(b);
     const int nIp = gb.nIp;
     const double *J = gb.J + e0, *K = gb.K + e0;
-    double2 fi = *reinterpret_cast<const double2 *>(h + (int64_t)b * h_stride + e0);
-    double2 fa = make_double2(0.0, 0.0);
-    for (int i = 0; i < no; ++i) {
-        const int64_t row = ((int64_t)i * nIp + i) * mat;
-        const double2 j = __ldg(reinterpret_cast<const double2 *>(J + row));
-        const double2 k = __ldg(reinterpret_cast<const double2 *>(K + row));
-        fi.x += 2.0 * j.x - k.x;
-        fi.y += 2.0 * j.y - k.y;
-    }
+    double2 fi = make_double2(0.0, 0.0), fa = make_double2(0.0, 0.0);
+    if (live) {
 #pragma unroll 2
-    for (int e = 0; e < na * na; ++e) {
-        const int64_t row = ((int64_t)(no + e / na) * nIp + (no + e % na)) * mat;
-        const double2 j = __ldg(reinterpret_cast<const double2 *>(J + row));
-        const double2 k = __ldg(reinterpret_cast<const double2 *>(K + row));
-        const double gm = s_d1[e];
-        fa.x += gm * (j.x - 0.5 * k.x);
-        fa.y += gm * (j.y - 0.5 * k.y);
+        for (int r = ty; r < no + na * na; r += kGroups) {       // fixed assignment of rows to groups: deterministic
+            const bool core = r < no;
+            const int e = r - no;
+            const int a = core ? r : no + e / na, c = core ? r : no + e % na;
+            const int64_t row = ((int64_t)a * nIp + c) * mat;
+            const double2 j = __ldg(reinterpret_cast<const double2 *>(J + row));
+            const double2 k = __ldg(reinterpret_cast<const double2 *>(K + row));
+            if (core) {
+                fi.x += 2.0 * j.x - k.x;
+                fi.y += 2.0 * j.y - k.y;
+            } else {
+                const double gm = s_d1[e];
+                fa.x += gm * (j.x - 0.5 * k.x);
+                fa.y += gm * (j.y - 0.5 * k.y);
+            }
+        }
+    }
+    red[ty * kFockCols + tx] = fi;
+    red[(kGroups + ty) * kFockCols + tx] = fa;
+    __syncthreads();
+    if (ty != 0 || !live) return;
+    fi = *reinterpret_cast<const double2 *>(h + (int64_t)b * h_stride + e0);
+    fa = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const double2 pi = red[g * kFockCols + tx], pa = red[(kGroups + g) * kFockCols + tx];
+        fi.x += pi.x; fi.y += pi.y;
+        fa.x += pa.x; fa.y += pa.y;
     }
     // rows / columns beyond N are zero padding
     const int m = (int)(e0 / ld), n = (int)(e0 % ld);
@@ -168,8 +187,10 @@ static void launch_fock_core_active(const double *h, int64_t h_stride, const GV 
 static void launch_fock_core_active(const double *h, int64_t h_stride, const ClassView &gv, const double *d1,
                                     int64_t sd1, int no, int na, int N, int ld, int batch, double *FI, double *FA,
                                     size_t sm1, cudaStream_t stream) {
-    dim3 grid((unsigned)ceil_div((int64_t)ld * ld / 2, 256), (unsigned)batch);
-    fock_core_active_class_kernel<<<grid, 256, sm1, stream>>>(h, h_stride, gv, d1, sd1, no, na, N, ld, FI, FA);
+    dim3 grid((unsigned)ceil_div((int64_t)ld * ld / 2, kFockCols), (unsigned)batch);
+    const size_t smem = (size_t)((na * na + 1) & ~1) * sizeof(double) + 2 * 256 * sizeof(double2);
+    fock_core_active_class_kernel<<<grid, 256, smem, stream>>>(h, h_stride, gv, d1, sd1, no, na, N, ld, FI, FA);
+    (void)sm1;
 }
 
 // ---------------------------------------------------------------- generalized Fock
