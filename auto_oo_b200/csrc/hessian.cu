@@ -202,9 +202,8 @@ hess_sparse_build_kernel(RdmView rdm0, int64_t sd1, int64_t sd2, int nIs, int sw
             const int64_t k = k0 + lane;
             double v = 0.0;
             if (k < krows) {
-                int m, n;
-                v = at_value(rdm, nIs, swap_exch, k, p, r, m, n);
-                if (Blocks{rdm.no, rdm.na, nIs}.covered(p, r, k)) v = 0.0;
+                int m, n;                                  // (block entries are not even evaluated: no Gamma loads here)
+                if (!Blocks{rdm.no, rdm.na, nIs}.covered(p, r, k)) v = at_value(rdm, nIs, swap_exch, k, p, r, m, n);
             }
             const unsigned mask = __ballot_sync(0xffffffffu, v != 0.0);
             if (v != 0.0) {
