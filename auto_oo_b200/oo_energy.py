@@ -422,12 +422,14 @@ class OO_energy:
         one, two = _as_tensor(one_rdm).detach(), _as_tensor(two_rdm).detach()
         on_host = kappa.device.type == "cpu"
         Coao = eng.to_padded(self.oao_mo_coeff, 2)
+        if on_host and kappa.shape[0] == 1 and not bool(kappa.any()):
+            kappa = None                                   # expm(0) = 1: the rotation stage is skipped altogether
         if self.cuda_graphs:
             # launch-bound sizes: one graph replay; host inputs go pinned -> static buffers, results come back
             # from the graph's output buffers through pinned memory
             if on_host:
-                kappa, one, two = (eng.stage_pinned(k, t.to(F64)) for k, t in
-                                   (("kappa", kappa), ("rdm1", one), ("rdm2", two)))
+                one, two = eng.stage_pinned("rdm1", one.to(F64)), eng.stage_pinned("rdm2", two.to(F64))
+                kappa = None if kappa is None else eng.stage_pinned("kappa", kappa.to(F64))
             E, G, H = eng.evaluate_graphed(Coao, one, two, kappa=kappa, want_hessian=want_hessian,
                                            path=self.integral_path, clone=not on_host)
             if not on_host:
@@ -436,7 +438,7 @@ class OO_energy:
             torch.cuda.current_stream(eng.device).synchronize()
             return out
         if on_host:
-            kd = eng.stage_in("kappa", kappa)
+            kd = None if kappa is None else eng.stage_in("kappa", kappa)
             d1 = eng.stage_in("rdm1", one)
             d2 = eng.stage_in("rdm2", two)
         else:
@@ -445,7 +447,7 @@ class OO_energy:
             return eng.evaluate(Coao, d1, d2, kappa=kd, want_hessian=want_hessian, path=self.integral_path)
         # host results: the Hessian of evaluation b travels to pinned host memory on a copy stream
         # while evaluation b+1 computes
-        B, nk = kd.shape[0], self.n_kappa
+        B, nk = 1 if kd is None else kd.shape[0], self.n_kappa
         H_dev = eng.workspace_tensor("H_batch", (B, nk, nk)) if want_hessian else None
         H_host = eng.pinned("H", (B, nk, nk)) if want_hessian else None
         main = torch.cuda.current_stream(eng.device)
