@@ -5,6 +5,12 @@
     save_problem("ch2nh.npz", mol, oao_mo_coeff=C, theta=theta)      # where PySCF exists
     mol, extras = load_problem("ch2nh.npz")                          # anywhere
     oo = OO_energy(mol, ncas, nelecas, oao_mo_coeff=extras["oao_mo_coeff"])
+
+Real-orbital two-electron integrals are 8-fold symmetric; ``save_problem`` then stores only the
+``P(P+1)/2`` unique elements (``P = N(N+1)/2``, PySCF's ``s8`` order: lower triangle of the pair-by-pair
+matrix of lower-triangular pairs), an eighth of the dense tensor, and ``load_problem`` expands them.
+``save_trajectory`` / ``load_trajectory`` checkpoint the orbitals (and circuit parameters, energies) of an
+optimisation or of the geometries of a Berry-phase loop.
 """
 from __future__ import annotations
 
@@ -40,13 +46,58 @@ class ArrayMol:
         return occ_idx, act_idx, virt_idx
 
 
-def save_problem(path, mol, nelectron=None, **extras):
-    """Write ``mol``'s integrals (and any extra arrays: ``oao_mo_coeff``, ``theta``, RDMs, ...)."""
+def pack_eri_s8(g):
+    """Unique elements of an 8-fold symmetric ``(N,N,N,N)`` tensor: ``out[tri(PQ, RS)]`` with ``PQ = tri(p, q)``,
+    ``p >= q``, ``PQ >= RS`` (``tri(a, b) = a(a+1)/2 + b``).  Raises if ``g`` is not 8-fold symmetric."""
+    g = np.asarray(g, dtype=np.float64)
+    n = g.shape[0]
+    scale = max(np.abs(g).max(), 1e-300)
+    if (np.abs(g - g.transpose(1, 0, 2, 3)).max() > 1e-12 * scale
+            or np.abs(g - g.transpose(2, 3, 0, 1)).max() > 1e-12 * scale):
+        raise ValueError("two-electron integrals are not 8-fold symmetric")
+    p, q = np.tril_indices(n)
+    pairs = g[p, q][:, p, q]                                 # (P, P) pair-by-pair matrix
+    a, b = np.tril_indices(len(p))
+    return np.ascontiguousarray(pairs[a, b])
+
+
+def unpack_eri_s8(packed, nao):
+    """Inverse of :func:`pack_eri_s8`: the dense ``(N,N,N,N)`` tensor."""
+    p, q = np.tril_indices(nao)
+    P = len(p)
+    a, b = np.tril_indices(P)
+    if packed.shape != (len(a),):
+        raise ValueError("packed integrals do not match a basis of size %d" % nao)
+    pairs = np.empty((P, P))
+    pairs[a, b] = packed
+    pairs[b, a] = packed
+    half = np.empty((P, nao, nao))
+    half[:, p, q] = pairs
+    half[:, q, p] = pairs
+    g = np.empty((nao, nao, nao, nao))
+    g[p, q] = half
+    g[q, p] = half
+    return g
+
+
+def save_problem(path, mol, nelectron=None, eri_packing="auto", **extras):
+    """Write ``mol``'s integrals (and any extra arrays: ``oao_mo_coeff``, ``theta``, RDMs, ...).
+    ``eri_packing``: ``"s8"`` stores the unique elements of the 8-fold symmetric ERI tensor (error if it is not
+    symmetric), ``"dense"`` the full tensor, ``"auto"`` packs when the symmetry holds."""
     ne = nelectron if nelectron is not None else getattr(mol, "nelectron", None)
     if ne is None:
         raise ValueError("nelectron is required (mol has no .nelectron)")
+    if eri_packing not in ("auto", "s8", "dense"):
+        raise ValueError("eri_packing must be 'auto', 's8' or 'dense'")
+    eri = np.asarray(mol.int2e_ao)
+    if eri_packing != "dense":
+        try:
+            eri = pack_eri_s8(eri)
+        except ValueError:
+            if eri_packing == "s8":
+                raise
     data = dict(format_version=np.asarray(FORMAT_VERSION), int1e_ao=np.asarray(mol.int1e_ao),
-                int2e_ao=np.asarray(mol.int2e_ao), overlap=np.asarray(mol.overlap),
+                int2e_ao=eri, overlap=np.asarray(mol.overlap),
                 oao_coeff=np.asarray(mol.oao_coeff), nuc=np.asarray(float(mol.nuc)), nelectron=np.asarray(int(ne)))
     for k, v in extras.items():
         if k in data:
@@ -63,7 +114,38 @@ def load_problem(path):
             raise ValueError(f"{path}: missing fields {missing}")
         if int(d["format_version"]) != FORMAT_VERSION:
             raise ValueError(f"{path}: unsupported format version {int(d['format_version'])}")
-        mol = ArrayMol(d["int1e_ao"], d["int2e_ao"], d["overlap"], d["oao_coeff"], float(d["nuc"]),
+        eri = d["int2e_ao"]
+        if eri.ndim == 1:                                    # s8-packed
+            eri = unpack_eri_s8(eri, d["int1e_ao"].shape[0])
+        mol = ArrayMol(d["int1e_ao"], eri, d["overlap"], d["oao_coeff"], float(d["nuc"]),
                        int(d["nelectron"]))
         extras = {k: d[k] for k in d.files if k not in _REQUIRED and k != "format_version"}
     return mol, extras
+
+
+def save_trajectory(path, oao_mo_coeff, theta=None, energies=None, **meta):
+    """Checkpoint of an optimisation / a loop over geometries: ``oao_mo_coeff`` is a sequence of ``(N, N)``
+    matrices (one per iteration or geometry, e.g. the fourth return value of ``OO_pqc.full_optimization``),
+    ``theta`` the matching circuit parameters, ``energies`` the energy list; ``meta``: any further arrays."""
+    tonp = lambda v: np.asarray(v.detach().cpu() if hasattr(v, "detach") else v)
+    data = dict(format_version=np.asarray(FORMAT_VERSION), oao_mo_coeff=np.stack([tonp(c) for c in oao_mo_coeff]))
+    if theta is not None:
+        data["theta"] = np.stack([tonp(t).reshape(-1) for t in theta])
+        if data["theta"].shape[0] != data["oao_mo_coeff"].shape[0]:
+            raise ValueError("theta and oao_mo_coeff trajectories differ in length")
+    if energies is not None:
+        data["energies"] = np.asarray([float(e) for e in energies])
+    for k, v in meta.items():
+        if k in data:
+            raise ValueError(f"extra array name {k!r} collides with a trajectory field")
+        data[k] = tonp(v)
+    np.savez_compressed(path, **data)
+
+
+def load_trajectory(path):
+    """Returns a dict with ``oao_mo_coeff (T, N, N)`` and whatever else :func:`save_trajectory` stored."""
+    with np.load(path) as d:
+        if "oao_mo_coeff" not in d.files or int(d["format_version"]) != FORMAT_VERSION:
+            raise ValueError(f"{path}: not a trajectory file of format version {FORMAT_VERSION}")
+        return {k: d[k] for k in d.files if k != "format_version"}
+

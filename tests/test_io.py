@@ -2,7 +2,8 @@
 import numpy as np
 import pytest
 
-from auto_oo_b200.io import ArrayMol, load_problem, save_problem
+from auto_oo_b200.io import (ArrayMol, load_problem, load_trajectory, pack_eri_s8, save_problem, save_trajectory,
+                             unpack_eri_s8)
 from auto_oo_b200.synthetic import SyntheticMol
 
 
@@ -31,3 +32,52 @@ def test_errors(tmp_path):
     np.savez(tmp_path / "bad.npz", int1e_ao=np.eye(2))
     with pytest.raises(ValueError):
         load_problem(tmp_path / "bad.npz")
+
+
+def test_s8_packing_roundtrip_and_size(tmp_path):
+    mol = SyntheticMol(9, 10, seed=3)
+    g = np.asarray(mol.int2e_ao)
+    packed = pack_eri_s8(g)
+    P = 9 * 10 // 2
+    assert packed.shape == (P * (P + 1) // 2,)
+    assert np.array_equal(unpack_eri_s8(packed, 9), g)
+    save_problem(tmp_path / "s8.npz", mol)
+    save_problem(tmp_path / "dense.npz", mol, eri_packing="dense")
+    with np.load(tmp_path / "s8.npz") as d:
+        assert d["int2e_ao"].ndim == 1
+    for name in ("s8.npz", "dense.npz"):
+        m2, _ = load_problem(tmp_path / name)
+        assert np.array_equal(m2.int2e_ao, g)
+    bad = g.copy()
+    bad[0, 1, 2, 3] += 1.0                                   # breaks the symmetry
+    with pytest.raises(ValueError):
+        pack_eri_s8(bad)
+
+    class Asym:
+        int1e_ao, int2e_ao, overlap, oao_coeff, nuc, nelectron = mol.int1e_ao, bad, mol.overlap, mol.oao_coeff, 0.0, 10
+    save_problem(tmp_path / "auto.npz", Asym())              # auto: falls back to the dense tensor
+    m3, _ = load_problem(tmp_path / "auto.npz")
+    assert np.array_equal(m3.int2e_ao, bad)
+    with pytest.raises(ValueError):
+        save_problem(tmp_path / "x.npz", Asym(), eri_packing="s8")
+
+
+def test_trajectory_checkpoint(tmp_path):
+    import torch
+    Cs = [torch.eye(4, dtype=torch.float64) * (i + 1) for i in range(3)]
+    thetas = [torch.full((2, 1), 0.1 * i, dtype=torch.float64) for i in range(3)]
+    save_trajectory(tmp_path / "t.npz", Cs, theta=thetas, energies=[-1.0, -1.5, -1.6], geometry=np.arange(3.0))
+    t = load_trajectory(tmp_path / "t.npz")
+    assert t["oao_mo_coeff"].shape == (3, 4, 4) and t["theta"].shape == (3, 2)
+    assert np.allclose(t["energies"], [-1.0, -1.5, -1.6]) and np.array_equal(t["geometry"], np.arange(3.0))
+    assert np.array_equal(t["oao_mo_coeff"][2], 3 * np.eye(4))
+    with pytest.raises(ValueError):
+        save_trajectory(tmp_path / "bad.npz", Cs, theta=thetas[:2])
+    with pytest.raises(ValueError):
+        load_trajectory(tmp_path / "missing.npz") if (tmp_path / "missing.npz").exists() else load_problem_as_trajectory(tmp_path)
+
+
+def load_problem_as_trajectory(tmp_path):
+    mol = SyntheticMol(4, 4, seed=0)
+    save_problem(tmp_path / "p.npz", mol)
+    return load_trajectory(tmp_path / "p.npz")
