@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 F64 = torch.float64
 METRIC = "oo_energy_gradient_hessian_evals_per_sec"
 UNIT = "evals/s"
-CPU_SAMPLE_NAO = 96          # the CPU oracle runs the same CAS at this basis size (N=256 cannot run on a host);
+CPU_SAMPLE_NAO = int(os.environ.get("OO_BENCH_CPU_SAMPLE_NAO", "96"))   # the CPU oracle runs the same CAS at this basis size (N=256 cannot run on a host);
                              # one E+G+H sample at N=96 is 10-15 s of work on 8-16 cores
 
 
@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
     from auto_oo_b200.synthetic import CONFIG_SHAPES
     nao, nelec, ncas, nelecas = CONFIG_SHAPES[args.workload]
     # keep the whole run to a few minutes whatever --steps / --warmup the driver passes
-    nao_s = CPU_SAMPLE_NAO if args.steps + args.warmup <= 8 else 80 if args.steps + args.warmup <= 24 else 64
+    nao_s = CPU_SAMPLE_NAO if args.steps + args.warmup <= 8 else min(CPU_SAMPLE_NAO, 80 if args.steps + args.warmup <= 24 else 64)
     for _ in range(max(1, args.warmup)):
         cpu_oracle_sample(args.workload, nao_s)
     wall, res = 0.0, None
