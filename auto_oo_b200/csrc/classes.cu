@@ -128,8 +128,10 @@ int class_transform(const double *gp, int64_t strideG, const double *C, int64_t 
 //       Q1   T1[s,pq,m] = sum_r gpk[r,(s pq)] C[r,m]              N^4 nI flop (half of the general Q1)
 //     its epilogue also writes the unpacked, pair-first copy T1t[q,p,s,m] = T1t[p,q,s,m] for K;
 //   * J[m,n,a,b] = J[n,m,a,b] and K[n,m,a,b] = K[m,n,b,a]: only class pairs m >= n go through
-//     the last two quarters (packed pair index mn), and one HBM-bound pass expands them into
-//     the class buffer.
+//     the last two quarters (packed pair index mn).  The "pack" and "expand" steps below are epilogue modes of
+//     the GEMMs next to them (dgemm_tn_class_pack / dgemm_tn_class_expand: the quarter-2 GEMM stores only n <= m,
+//     packed; the last-quarter GEMM stores (m n) and its mirror (n m), transposed for K); the separate kernels
+//     remain behind OO_OPT_CLASS_UNFUSED_PACK for A/B tests.
 //       J:  Q2   X[pq,m,n]    = sum_s T1[s,(pq m)] C[s,n]
 //           pack Xf[p,q,mn]   = X[tri(p,q),m,n]                     (pair index unpacked, class pair packed)
 //           Q3   X'[q,mn,a]   = sum_p Xf[p,(q mn)] C[p,a]

@@ -13,9 +13,13 @@
 //     At[(m n),      (p r)] = 2 (Gf_pmrn + Gf_pmnr)     B[(m n),      (q s)] = g_qmns
 //     At[nI^2+(m n), (p r)] = 2  Gf_prmn                B[nI^2+(m n), (q s)] = g_qsmn
 //     At[2 nI^2,     (p r)] = 2  gf_pr                  B[2 nI^2,     (q s)] = h_qs
-// is ONE TN-DGEMM (dgemm_tn.cu: TMA + DMMA) of size nI^2 x ld^2 x (2 nI^2 + 1), and
+// is a product of size nI^2 x ld^2 x (2 nI^2 + 1), and
 //   X(p,q,r,s) = -(F_pr + F_rp) d_qs + [p,r in I] T[(p r),(q s)]
 // is combined four ways directly into the (nk x nk) output.
+// B is the class buffer of classes.cu (or is gathered into that layout from the complete g').  At is not dense:
+// it splits into the C block (one TN-DGEMM), one G block per occupied orbital (bulk-async streamed DMMA kernel)
+// and an ELL remainder -- see "block structure of At" below; OO_OPT_HESSIAN_DENSE keeps the single dense GEMM
+// over all of At for A/B tests.  The assembly is row-tiled and, for the rows outside I, streamed with bulk copies.
 #include <stdlib.h>
 
 #include "common.cuh"
