@@ -45,13 +45,17 @@ class SyntheticMol:
     shape, rank ``2N``) so ``g`` is 8-fold symmetric and positive;
     ``S = I + 0.1 sym(randn)/sqrt(N)``, ``oao_coeff = S^{-1/2}``; ``nuc = 9``.
     Tensors are float64 on ``device``; numpy views are exposed for CPU.
+    ``rng_device``: where the random numbers are drawn (default: ``device``).  ``rng_device="cpu"`` with a
+    CUDA ``device`` gives the same ``h, S, B, C_oao`` as the all-CPU object of the same seed (the golden
+    fixtures are produced on the CPU); only the product ``B B^T`` is then formed on the device.
     """
 
-    def __init__(self, nao, nelec, seed=0, device="cpu", eri_rank=None, build_eri=True):
+    def __init__(self, nao, nelec, seed=0, device="cpu", eri_rank=None, build_eri=True, rng_device=None):
         self.nao = int(nao)
         self.nelectron = int(nelec)
         self.seed = int(seed)
-        dev = torch.device(device)
+        out_dev = torch.device(device)
+        dev = out_dev if rng_device is None else torch.device(rng_device)
         gen = torch.Generator(device=dev).manual_seed(20240 + self.seed)
         N = self.nao
         R = int(eri_rank) if eri_rank else 2 * N
@@ -64,18 +68,18 @@ class SyntheticMol:
         X = ((v * w.pow(-0.5)) @ v.T).to(dev)
         B = torch.randn(N, N, R, **kw)
         B = 0.5 * (B + B.transpose(0, 1)) / _math.sqrt(R)
-        self._B = B
-        self._int1e = h
-        self._overlap = S
-        self._oao = X
+        c = torch.randn(N, N, **kw)                  # drawn here so the stream does not depend on build_eri
+        self._B = B.to(out_dev)
+        self._int1e = h.to(out_dev)
+        self._overlap = S.to(out_dev)
+        self._oao = X.to(out_dev)
         self.nuc = 9.0
         self._int2e = None
         if build_eri:
             self._int2e = self.build_eri()
-        c = torch.randn(N, N, **kw)
         q, r = torch.linalg.qr(c.cpu())
         q = q * torch.sign(torch.diagonal(r))[None, :]
-        self._oao_mo = q.to(dev)
+        self._oao_mo = q.to(out_dev)
 
     def build_eri(self, out=None):
         """g[p,q,r,s] = 0.3 * sum_P B[p,q,P] B[r,s,P]; chunked so N=256 builds on device."""

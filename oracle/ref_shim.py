@@ -1,5 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- import the VERBATIM reference hot path from
-``/root/reference`` (this container only; the path does not exist on the GPU box).
+``/root/reference`` (this container) or, where that path does not exist (the GPU box), from the
+unmodified install under ``baseline/_ref`` (``pip install --no-deps --target baseline/_ref /root/reference``,
+git-ignored, shipped with the snapshot).
 
 The reference needs ``pennylane`` (for ``pennylane.math``), ``pyscf`` and
 ``openfermion`` at import time; none is installed.  This module registers
@@ -23,7 +25,13 @@ import numpy as np
 import torch
 
 REF_ROOT = os.environ.get("AUTO_OO_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the unmodified reference as installed by ``pip install --no-deps --target baseline/_ref /root/reference``
+# (git-ignored; it travels to the GPU box with the snapshot, /root/reference does not)
+_INSTALLED = os.path.join(_REPO, "baseline", "_ref", "auto_oo")
 _SRC = os.path.join(REF_ROOT, "src", "auto_oo")
+if not os.path.isfile(os.path.join(_SRC, "oo_energy.py")) and os.path.isfile(os.path.join(_INSTALLED, "oo_energy.py")):
+    _SRC = _INSTALLED
 
 
 def reference_available() -> bool:
@@ -167,7 +175,7 @@ def load_reference():
     if _loaded is not None:
         return _loaded
     if not reference_available():
-        raise RuntimeError(f"reference sources not found under {REF_ROOT}")
+        raise RuntimeError(f"reference sources not found under {REF_ROOT} or {_INSTALLED}")
 
     saved = {k: sys.modules.get(k) for k in
              ("pennylane", "pennylane.math", "pyscf", "openfermion",
@@ -216,6 +224,47 @@ def load_reference():
         if saved[k] is not None:
             sys.modules[k] = saved[k]
     return ns
+
+
+_drivers = {}
+
+
+def load_reference_oo_pqc(oo_energy_module=None):
+    """The VERBATIM ``oo_pqc.py`` of the reference (``OO_pqc`` with ``full_optimization``, ``full_gradient``,
+    ``full_hessian`` ...; oo_pqc.py:30-207) executed with ``auto_oo.oo_energy`` bound to ``oo_energy_module``:
+    ``None`` -> the verbatim reference module (an all-reference CPU run); ``auto_oo_b200.oo_energy`` -> the
+    reference's own driver class derived from the CUDA ``OO_energy`` ("the drivers run unchanged").
+    ``auto_oo.utils.newton_raphson`` is the verbatim module in both cases; ``auto_oo.pqc`` (PennyLane circuits,
+    out of scope) is a stub that only provides the ``Parameterized_circuit`` name used in an annotation."""
+    ref = load_reference()
+    key = "reference" if oo_energy_module is None else oo_energy_module.__name__
+    if key in _drivers:
+        return _drivers[key]
+    target = ref.oo_energy if oo_energy_module is None else oo_energy_module
+    names = ("pennylane", "pennylane.math", "auto_oo.oo_energy", "auto_oo.pqc")
+    saved = {k: sys.modules.get(k) for k in names}
+    pl = types.ModuleType("pennylane")
+    pl.math = ref.math
+    pl.__path__ = []
+    pqc_stub = types.ModuleType("auto_oo.pqc")
+    pqc_stub.Parameterized_circuit = type("Parameterized_circuit", (), {})
+    sys.modules.update({"pennylane": pl, "pennylane.math": ref.math, "auto_oo.oo_energy": target,
+                        "auto_oo.pqc": pqc_stub})
+    try:
+        modname = "auto_oo.oo_pqc__" + key.replace(".", "_")
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(_SRC, "oo_pqc.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        for k in names:
+            if saved[k] is not None:
+                sys.modules[k] = saved[k]
+            else:
+                sys.modules.pop(k, None)
+        sys.modules["auto_oo.oo_energy"] = ref.oo_energy
+    _drivers[key] = mod
+    return mod
 
 
 class FakeMol:

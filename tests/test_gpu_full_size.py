@@ -1,7 +1,12 @@
 """GPU: the BASELINE.json configurations at their FULL sizes (cfg 4: 114 AOs CAS(6,6); cfg 5: 256 AOs
-CAS(12,12); cfg 2: 64 geometries of 34 AOs CAS(4,4)).  The CPU oracle needs minutes (cfg 4) or cannot
-run at all (cfg 5: a dozen N^4 tensors), so parity is checked here through properties that do not depend
-on the size:
+CAS(12,12); cfg 2: 64 geometries of 34 AOs CAS(4,4)).
+
+Parity with the reference: ``tests/golden/n114_cas66.npz`` holds E, the packed gradient and a digest of the
+Hessian (diagonal, products with 8 probe vectors, 20 000 sampled elements, Frobenius norm) computed by the
+VERBATIM reference on the seeded inputs this module regenerates; ``n256_cas1212.npz`` the same from
+``oracle/class_oracle.py`` (the reference cannot run at N = 256; that oracle is pinned on the verbatim
+reference up to N = 114) -- ``oracle/make_golden_large.py``.  Both integral routes are compared with them at
+1e-10 Ha / 1e-8 per element.  On top of that, properties that do not depend on the size:
 
 * the rotation by the identity returns the AO integrals bit for bit;
 * an orthogonal rotation preserves the Frobenius norm and the two pair traces of the ERI tensor,
@@ -16,31 +21,42 @@ on the size:
 
 Tolerances: energy 1e-10 Ha, gradient / Hessian elements 1e-8 (BASELINE.json north_star), scaled only
 where a finite-difference truncation error enters (stated at the assertion)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from helpers import TOL_E, TOL_GH
+from helpers import GOLDEN, TOL_E, TOL_GH
 
 pytestmark = pytest.mark.gpu
 F64 = torch.float64
 
 FULL = ["c6h6_ccpvdz_cas66", "synthetic_n256_cas1212"]
+GOLDEN_OF = {"c6h6_ccpvdz_cas66": "n114_cas66", "synthetic_n256_cas1212": "n256_cas1212"}
+SEED = 11                      # oracle/make_golden_large.py draws its inputs from the same seed, on the CPU
 
 
 class Problem:
     def __init__(self, workload):
         from auto_oo_b200 import OO_energy
         from auto_oo_b200.synthetic import CONFIG_SHAPES, SyntheticMol, random_rdms, random_kappa
+        self.workload = workload
         self.dev = dev = torch.device("cuda", 0)
         self.nao, self.nelec, self.ncas, self.nelecas = CONFIG_SHAPES[workload]
-        self.mol = SyntheticMol(self.nao, self.nelec, seed=11, device=dev)
+        # random numbers drawn on the CPU (as the golden generator does), B B^T formed on the device
+        self.mol = SyntheticMol(self.nao, self.nelec, seed=SEED, device=dev, rng_device="cpu")
+        m = self.mol
+        self.input_checksum = np.array([float(m._int1e.sum()), float(m._B.sum()), float(m._oao.sum()),
+                                        float(m._oao_mo.sum()), float((m._B ** 2).sum())])
+        self.g_sum = float(m._int2e.sum())
         self.oo = OO_energy(self.mol, self.ncas, self.nelecas, oao_mo_coeff=self.mol.random_oao_mo_coeff,
                             device=dev)
         self.mol._B = None
         self.eng = self.oo.engine
-        self.one, self.two = random_rdms(self.ncas, self.nelecas, seed=11, device=dev)
-        self.kappa = random_kappa(self.oo.n_kappa, seed=11, device=dev, batch=2)
+        one, two = random_rdms(self.ncas, self.nelecas, seed=SEED)
+        self.one, self.two = one.to(dev), two.to(dev)
+        self.kappa = random_kappa(self.oo.n_kappa, seed=SEED, batch=2).to(dev)
         self.Coao = self.eng.to_padded(self.oo.oao_mo_coeff, 2)
 
 
@@ -51,6 +67,44 @@ def prob(request):
     p.eng.release_workspaces()
     del p
     torch.cuda.empty_cache()
+
+
+def _compare_with_golden(d, E, G, H, what):
+    """E (1,), G (1, nk), H (nk, nk) device tensors against the fixture's reference values."""
+    assert abs(E[0].item() - float(d["E"])) < TOL_E, what
+    assert np.abs(G[0].cpu().numpy() - d["G"]).max() < TOL_GH, what
+    assert np.abs(H.diagonal().cpu().numpy() - d["H_diag"]).max() < TOL_GH, what
+    si = torch.as_tensor(d["H_sample_i"], device=H.device)
+    sj = torch.as_tensor(d["H_sample_j"], device=H.device)
+    assert np.abs(H[si, sj].cpu().numpy() - d["H_samples"]).max() < TOL_GH, what
+    V = torch.as_tensor(d["H_probes"], device=H.device)                       # unit 2-norm probes
+    assert np.abs((V @ H.T).cpu().numpy() - d["H_times_probes"]).max() < TOL_GH, what
+    assert abs(torch.linalg.matrix_norm(H).item() - float(d["H_fro"])) < TOL_GH * max(1.0, float(d["H_fro"])), what
+
+
+def test_energy_gradient_hessian_match_the_reference_golden(prob):
+    """cfg 4 against the verbatim reference, cfg 5 against the class-path oracle, both integral routes
+    (oo_energy.py:199-202, :404-424)."""
+    d = np.load(os.path.join(GOLDEN, GOLDEN_OF[prob.workload] + ".npz"))
+    assert np.allclose(prob.input_checksum, d["checksum"], rtol=1e-12, atol=0), \
+        "seeded inputs no longer reproduce the fixture's inputs"
+    assert abs(prob.g_sum - float(d["g_sum"])) <= 1e-10 * abs(float(d["g_sum"]))
+    assert np.array_equal(prob.kappa[0].cpu().numpy(), d["kappa"])
+    eng, nk = prob.eng, prob.oo.n_kappa
+    H = torch.empty(1, nk, nk, dtype=F64, device=prob.dev)
+    for path in ("class", "full"):
+        E, G, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=H, path=path)
+        _compare_with_golden(d, E, G, H[0], path)
+    del H
+    # the active-space Hamiltonian of the same rotation through the public API (active_space.py:147-174)
+    U = eng.rotation(prob.kappa[:1])
+    Cp = eng.from_padded(eng.mo_coeff(prob.Coao, U), 2)[0]
+    c0, c1, c2 = prob.oo.get_active_integrals(Cp)
+    assert abs(c0.item() - float(d["c0"])) < TOL_E
+    assert np.abs(c1.cpu().numpy() - d["c1"]).max() < TOL_E and np.abs(c2.cpu().numpy() - d["c2"]).max() < TOL_E
+    # and the host-tensor face of the fused call
+    Eh, Gh, Hh = prob.oo.energy_gradient_hessian(prob.kappa[:1].cpu(), prob.one.cpu(), prob.two.cpu())
+    _compare_with_golden(d, Eh, Gh, Hh[0], "host face")
 
 
 def test_identity_is_exact_and_orthogonal_rotation_preserves_invariants(prob):

@@ -132,3 +132,31 @@ def test_hessian_sparse_row_bound(no, na):
                 nnz -= int(a1[p, r][no:, no:].sum()) + int(a2[p, r][no:, no:].sum()) + int(d1[p, r] != 0)
             worst = max(worst, nnz)
     assert worst <= 2 * na * na + 2 * ni + 8, worst
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_class_oracle_matches_reference_outputs(name):
+    """oracle/class_oracle.py (the form that scales to N = 256) against the verbatim-reference fixtures."""
+    from oracle.class_oracle import ClassProblem
+    c = load_case(name)
+    p = ClassProblem(c.int1e_ao, c.int2e_ao, c.oao_coeff, c.oao_mo_coeff, c.nuc, c.nelec, c.ncas, c.nelecas,
+                     c.freeze)
+    r = c.ref
+    ev = p.at(c.kappa)
+    c0, c1, c2 = ev.hamiltonian()
+    assert abs(float(c0) - float(r["c0"])) < TOL_E
+    assert np.abs(c1.numpy() - r["c1"]).max() < 1e-11 and np.abs(c2.numpy() - r["c2"]).max() < 1e-11
+    assert abs(ev.energy(c.one_rdm, c.two_rdm).item() - float(r["E"])) < 1e-12 * max(1.0, abs(float(r["E"])))
+    assert np.abs(ev.gradient(c.one_rdm, c.two_rdm).numpy() - r["G"]).max() < 1e-12
+    assert np.abs(ev.hessian(c.one_rdm, c.two_rdm).numpy() - r["H"]).max() < 1e-12
+
+
+def test_full_size_fixtures_are_pinned():
+    """n114: verbatim reference, with both oracles' differences at that size recorded by the generator;
+    n256: the class oracle (oracle/make_golden_large.py)."""
+    d = np.load(os.path.join(GOLDEN, "n114_cas66.npz"))
+    assert str(d["source"]) == "verbatim reference"
+    assert d["class_oracle_vs_reference"].max() < 1e-12 and d["oo_oracle_vs_reference"].max() < 1e-12
+    assert d["G"].shape == (2283,) and d["H_diag"].shape == (2283,) and float(d["H_asym"]) < 1e-10
+    d = np.load(os.path.join(GOLDEN, "n256_cas1212.npz"))
+    assert d["G"].shape == (9778,) and d["H_times_probes"].shape == (8, 9778) and float(d["H_asym"]) < 1e-10
