@@ -17,9 +17,14 @@ _i64 = C.c_int64
 _f64 = C.c_double
 _ptr = C.c_void_p
 _size = C.c_size_t
+_u32 = C.c_uint
 
 OO_WS_ROTATION, OO_WS_INT2E, OO_WS_HESSIAN, OO_WS_INT1E, OO_WS_YMATRIX = 1, 2, 3, 4, 5
 OO_WS_CLASS_TRANSFORM, OO_WS_CLASS_BUFFER, OO_WS_CLASS_HESSIAN, OO_WS_CLASS_TRANSFORM_SYM = 6, 7, 8, 9
+# per-call variant switches (include/oo_b200.h)
+OO_FLAG_HESSIAN_DENSE, OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT, OO_FLAG_HESSIAN_ASSEMBLE_TILED = 1, 2, 4
+OO_FLAG_CLASS_UNFUSED_PACK, OO_FLAG_HESSIAN_GROUP_UNSTREAMED, OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 8, 16, 32
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/oo_b200.h one to one
 _SIGNATURES = {
@@ -27,7 +32,6 @@ _SIGNATURES = {
     "oo_error_string": (C.c_char_p, [_i32]),
     "oo_last_cuda_error": (_i32, []),
     "oo_launch_count": (C.c_ulonglong, []),
-    "oo_set_option": (_i32, [_i32, _i32]),
     "oo_device_info": (_i32, [C.POINTER(_i32)] * 3),
     "oo_workspace_bytes": (_size, [_i32, _i32, _i32, _i32, _i32]),
     "oo_dgemm_tn_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
@@ -51,20 +55,21 @@ _SIGNATURES = {
                                     _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "oo_fock_gradient_vjp_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "oo_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32,
-                              _ptr, _ptr, _size, _ptr]),
+                              _ptr, _ptr, _size, _u32, _ptr]),
     "oo_transpose_f64": (_i32, [_ptr, _ptr, _i64, _i64, _ptr]),
     "oo_class_transform_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
     "oo_eri_symmetry_defect_f64": (_i32, [_ptr, _i32, _ptr, _ptr]),
     "oo_pair_ld": (_i64, [_i32]),
     "oo_pack_eri_pairs_f64": (_i32, [_ptr, _ptr, _i32, _ptr]),
-    "oo_class_transform_sym_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _ptr]),
+    "oo_class_transform_sym_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _u32,
+                                          _ptr]),
     "oo_class_active_hamiltonian_f64": (_i32, [_ptr, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr, _ptr,
                                                _ptr, _ptr]),
     "oo_class_fock_gradient_f64": (_i32, [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                                           _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "oo_class_fock_gradient_vjp_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "oo_class_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr,
-                                    _ptr, _i32, _ptr, _ptr, _size, _ptr]),
+                                    _ptr, _i32, _ptr, _ptr, _size, _u32, _ptr]),
     "oo_rdm_columns": (_i64, [_i32]),
     "oo_rdm_excitations_f64": (_i32, [_ptr, _i32, _i32, _i32, _i64, _i64, _i32, _ptr, _ptr, _i64, _ptr]),
     "oo_rdm_sector_flags_f64": (_i32, [_ptr, _i32, _i32, _i32, _ptr, _ptr]),
@@ -96,16 +101,16 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build_library()          # raises if nvcc is unavailable
+    # build_library() returns at once when the stamp next to the .so matches the digest of the sources in the
+    # tree; an edited csrc/*.cu therefore never runs against a stale binary (raises if nvcc is unavailable)
+    path = _build.build_library()
     lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)                # AttributeError = symbol missing: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.oo_abi_version() != 1:
-        raise OOError(f"ABI mismatch: library {lib.oo_abi_version()} != binding 1")
+    if lib.oo_abi_version() != ABI_VERSION:
+        raise OOError(f"ABI mismatch: library {lib.oo_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -45,6 +45,8 @@ def build_library(force=False, verbose=False):
     """Compile every .cu for sm_100a and link the shared library.  Returns its path."""
     os.makedirs(OUT_DIR, exist_ok=True)
     stamp = os.path.join(OUT_DIR, "build.sha256")
+    if not force and os.path.exists(LIB_PATH) and not os.path.isdir(CSRC):
+        return LIB_PATH                       # binary-only deployment: nothing to compare the library with
     digest = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
         with open(stamp) as f:

@@ -20,11 +20,6 @@ size_t class_transform_ws_bytes(int ld, int nIp, int batch);
 size_t class_buffer_bytes(int ld, int nIp);
 size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch);
 size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch);
-extern int g_hessian_dense;
-extern int g_hessian_simple_assemble;
-extern int g_class_unfused_pack;
-extern int g_hessian_group_unstreamed;
-extern int g_hessian_assemble_unstreamed;
 
 int sm_count() {
     static int cached[64] = {};                         // per device
@@ -121,31 +116,6 @@ const char *oo_error_string(int code) {
 int oo_last_cuda_error(void) { return oo::g_last_cuda_error; }
 
 unsigned long long oo_launch_count(void) { return oo::g_launch_count; }
-
-int oo_set_option(int key, int value) {
-    if (key == OO_OPT_HESSIAN_DENSE) {
-        oo::g_hessian_dense = value ? 1 : 0;
-        return OO_OK;
-    }
-    if (key == OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED) {
-        oo::g_hessian_assemble_unstreamed = value ? 1 : 0;
-        return OO_OK;
-    }
-    if (key == OO_OPT_HESSIAN_GROUP_UNSTREAMED) {
-        oo::g_hessian_group_unstreamed = value ? 1 : 0;
-        return OO_OK;
-    }
-    if (key == OO_OPT_CLASS_UNFUSED_PACK) {
-        oo::g_class_unfused_pack = value ? 1 : 0;
-        return OO_OK;
-    }
-    if (key == OO_OPT_HESSIAN_SIMPLE_ASSEMBLE) {
-        if (value < 0 || value > 2) return OO_ERR_INVALID_ARG;
-        oo::g_hessian_simple_assemble = value;
-        return OO_OK;
-    }
-    return OO_ERR_INVALID_ARG;
-}
 
 int oo_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     int dev = 0;

@@ -131,7 +131,7 @@ int class_transform(const double *gp, int64_t strideG, const double *C, int64_t 
 //     the last two quarters (packed pair index mn).  The "pack" and "expand" steps below are epilogue modes of
 //     the GEMMs next to them (dgemm_tn_class_pack / dgemm_tn_class_expand: the quarter-2 GEMM stores only n <= m,
 //     packed; the last-quarter GEMM stores (m n) and its mirror (n m), transposed for K); the separate kernels
-//     remain behind OO_OPT_CLASS_UNFUSED_PACK for A/B tests.
+//     remain behind OO_FLAG_CLASS_UNFUSED_PACK for A/B tests.
 //       J:  Q2   X[pq,m,n]    = sum_s T1[s,(pq m)] C[s,n]
 //           pack Xf[p,q,mn]   = X[tri(p,q),m,n]                     (pair index unpacked, class pair packed)
 //           Q3   X'[q,mn,a]   = sum_p Xf[p,(q mn)] C[p,a]
@@ -306,8 +306,6 @@ int pack_eri_pairs(const double *g, double *gpk, int ld, cudaStream_t stream) {
     return OO_OK;
 }
 
-int g_class_unfused_pack = 0;    // oo_set_option(OO_OPT_CLASS_UNFUSED_PACK): 1 = separate pack_class_pairs pass (A/B tests)
-
 size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch) {
     const size_t ld2 = (size_t)ld * ld, ldp = (size_t)pair_ld(ld), npIp = (size_t)pair_ld(nIp);
     const size_t t1 = (size_t)ld * ldp * nIp, t1t = ld2 * ld * nIp;
@@ -317,7 +315,9 @@ size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch) {
 }
 
 int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int64_t strideC, int N, int ld,
-                        int nIp, int batch, double *cls, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                        int nIp, int batch, double *cls, void *ws, size_t ws_bytes, unsigned flags,
+                        cudaStream_t stream) {
+    const bool g_class_unfused_pack = (flags & OO_FLAG_CLASS_UNFUSED_PACK) != 0;   // separate pack / expand passes
     OO_REQUIRE(gpk && C && cls && ws);
     OO_REQUIRE(N > 0 && ld >= N && (ld % 2) == 0 && nIp > 0 && (nIp % 2) == 0 && nIp <= ld && batch > 0);
     if (ws_bytes < class_transform_sym_ws_bytes(ld, nIp, batch)) return OO_ERR_WORKSPACE;
@@ -408,8 +408,8 @@ int oo_pack_eri_pairs_f64(const double *g_ao, double *g_packed, int ld, void *st
 
 int oo_class_transform_sym_f64(const double *g_packed, int64_t strideG, const double *C, int64_t strideC, int N,
                                int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
-                               void *stream) {
-    return oo::class_transform_sym(g_packed, strideG, C, strideC, N, ld, nIp, batch, cls, ws, ws_bytes,
+                               unsigned flags, void *stream) {
+    return oo::class_transform_sym(g_packed, strideG, C, strideC, N, ld, nIp, batch, cls, ws, ws_bytes, flags,
                                    (cudaStream_t)stream);
 }
 

@@ -18,7 +18,7 @@
 // is combined four ways directly into the (nk x nk) output.
 // B is the class buffer of classes.cu (or is gathered into that layout from the complete g').  At is not dense:
 // it splits into the C block (one TN-DGEMM), one G block per occupied orbital (bulk-async streamed DMMA kernel)
-// and an ELL remainder -- see "block structure of At" below; OO_OPT_HESSIAN_DENSE keeps the single dense GEMM
+// and an ELL remainder -- see "block structure of At" below; OO_FLAG_HESSIAN_DENSE keeps the single dense GEMM
 // over all of At for A/B tests.  The assembly is row-tiled and, for the rows outside I, streamed with bulk copies.
 #include <stdlib.h>
 
@@ -26,9 +26,6 @@
 
 namespace oo {
 
-int g_hessian_assemble_unstreamed = 0; // oo_set_option(OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED): 1 = no bulk-async assembly kernel
-int g_hessian_group_unstreamed = 0;    // oo_set_option(OO_OPT_HESSIAN_GROUP_UNSTREAMED): 1 = register-only G-block kernel (A/B tests)
-int g_hessian_simple_assemble = 0;     // oo_set_option(OO_OPT_HESSIAN_SIMPLE_ASSEMBLE): 0 auto, 1 per-thread kernel, 2 row-tiled kernel
 
 int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
              int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
@@ -869,9 +866,12 @@ __global__ void y_permute_kernel(const double *__restrict__ T, int N, int ld, do
 size_t assemble_scratch_bytes(int ld) { return align_up((size_t)(ld + 3) * sizeof(int), 1024); }
 
 int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const int32_t *pr, int nk, int N, int ld,
-                    int batch, double *H, void *scratch, cudaStream_t stream) {
+                    int batch, double *H, void *scratch, unsigned flags, cudaStream_t stream) {
+    const bool per_element = (flags & OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT) != 0;
+    const bool tiled = (flags & OO_FLAG_HESSIAN_ASSEMBLE_TILED) != 0;
+    const bool g_hessian_assemble_unstreamed = (flags & OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED) != 0;
     // small bases: a handful of CTAs either way, and the per-thread kernel needs no pair-structure pass
-    if (g_hessian_simple_assemble == 1 || (g_hessian_simple_assemble == 0 && N <= 64)) {
+    if (per_element || (!tiled && N <= 64)) {
         dim3 grid((unsigned)ceil_div(nk, 256), (unsigned)nk, (unsigned)batch);
         hess_assemble_kernel<<<grid, 256, 0, stream>>>(tv, F, pl, pr, nk, ld, H);
         OO_LAUNCH_CHECK();
@@ -925,7 +925,8 @@ HessLayout hess_layout(int ld, int nI) {
 
 int class_hessian(const double *cls, const double *F, const double *d1, int64_t sd1, const double *d2,
                   int64_t sd2, int no, int na, int N, int ld, int nIp, int batch, const int32_t *pl,
-                  const int32_t *pr, int nk, double *H, void *ws, size_t ws_bytes, cudaStream_t stream);
+                  const int32_t *pr, int nk, double *H, void *ws, size_t ws_bytes, unsigned flags,
+                  cudaStream_t stream);
 size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch);
 
 namespace {
@@ -975,7 +976,7 @@ size_t hessian_ws_bytes(int ld, int nI) {
 // for both integral representations.
 int hessian(const double *h, const double *g, const double *F, const double *d1, const double *d2,
             int no, int na, int N, int ld, const int32_t *pl, const int32_t *pr, int nk, double *H,
-            void *ws, size_t ws_bytes, cudaStream_t stream) {
+            void *ws, size_t ws_bytes, unsigned flags, cudaStream_t stream) {
     OO_REQUIRE(h && g && F && d1 && d2 && H && ws && pl && pr);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0);
     const int nI = no + na, nIp = nI + (nI & 1);
@@ -990,12 +991,11 @@ int hessian(const double *h, const double *g, const double *F, const double *d1,
     if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
     hess_gather_class_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h, g, nI, nIp, ld, B);
     OO_LAUNCH_CHECK();
-    return class_hessian(B, F, d1, 0, d2, 0, no, na, N, ld, nIp, 1, pl, pr, nk, H, w + b_bytes, c_bytes, stream);
+    return class_hessian(B, F, d1, 0, d2, 0, no, na, N, ld, nIp, 1, pl, pr, nk, H, w + b_bytes, c_bytes, flags,
+                         stream);
 }
 
 // Hessian from the class buffer of classes.cu: cls = [K rows; J rows; h' row] IS the B operand.
-int g_hessian_dense = 0;     // oo_set_option(OO_OPT_HESSIAN_DENSE): 1 = one dense GEMM over all of At
-
 struct ClassHessLayout {
     int width;                       // ELL width of the sparse part
     int64_t lda_c, krows_c, ncol_c;  // C block
@@ -1034,7 +1034,7 @@ size_t class_hessian_ws_bytes(int ld, int nIp, int no, int na, int batch) {
 
 static int class_hessian_dense(const double *cls, const double *F, const RdmView &rdm, int N, int ld, int nIp,
                                const int32_t *pl, const int32_t *pr, int nk, double *H, void *ws,
-                               cudaStream_t stream) {
+                               unsigned flags, cudaStream_t stream) {
     const HessLayout L = hess_layout(ld, nIp);
     uint8_t *w = reinterpret_cast<uint8_t *>(ws);
     double *At = reinterpret_cast<double *>(w);
@@ -1047,16 +1047,19 @@ static int class_hessian_dense(const double *cls, const double *F, const RdmView
     int rc = dgemm_tn(At, cls, T, nI2, mat, L.krows, L.lda, mat, mat, 1, 0, 0, 0, stream);
     if (rc) return rc;
     return launch_assemble(TView{T, nullptr, nullptr, rdm.no + rdm.na, nIp, rdm.no, rdm.na, 0, 0, 0, 0, 0}, F, pl, pr, nk, N, ld, 1,
-                           H, w + L.off_b + (L.off_runs - L.off_t), stream);
+                           H, w + L.off_b + (L.off_runs - L.off_t), flags, stream);
 }
 
 // batch evaluations: cls[b] (class buffers, contiguous), F[b] (ld^2), H[b] (nk^2); RDMs shared
 // (stride 0) or per evaluation.
 int class_hessian(const double *cls, const double *F, const double *d1, int64_t sd1, const double *d2,
                   int64_t sd2, int no, int na, int N, int ld, int nIp, int batch, const int32_t *pl,
-                  const int32_t *pr, int nk, double *H, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                  const int32_t *pr, int nk, double *H, void *ws, size_t ws_bytes, unsigned flags,
+                  cudaStream_t stream) {
     OO_REQUIRE(cls && F && d1 && d2 && H && ws && pl && pr);
     OO_REQUIRE(no >= 0 && na > 0 && no + na <= N && ld >= N && (ld % 2) == 0 && nk > 0 && batch > 0);
+    const bool g_hessian_dense = (flags & OO_FLAG_HESSIAN_DENSE) != 0;
+    const bool g_hessian_group_unstreamed = (flags & OO_FLAG_HESSIAN_GROUP_UNSTREAMED) != 0;
     OO_REQUIRE(nIp >= no + na && (nIp % 2) == 0 && nIp <= ld);
     const int rdm_batched = (batch > 1 && (sd1 != 0 || sd2 != 0)) ? 1 : 0;
     const int nsets = rdm_batched ? batch : 1;
@@ -1069,7 +1072,7 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
         for (int b = 0; b < batch; ++b) {
             RdmView rb{d1 + b * sd1, d2 + b * sd2, no, na};
             int rc = class_hessian_dense(cls + b * cls_stride, F + b * mat, rb, N, ld, nIp, pl, pr, nk,
-                                         H + (int64_t)b * nk * nk, ws, stream);
+                                         H + (int64_t)b * nk * nk, ws, flags, stream);
             if (rc) return rc;
         }
         return OO_OK;
@@ -1156,7 +1159,7 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     }
     return launch_assemble(TView{T, Taa, Tg, no + na, nIp, no, na, nI2 * mat, L.ncol_c * mat,
                                  (int64_t)no * 2 * na * mat, mat, (int64_t)nk * nk},
-                           F, pl, pr, nk, N, ld, batch, H, w + L.off_runs, stream);
+                           F, pl, pr, nk, N, ld, batch, H, w + L.off_runs, flags, stream);
 }
 
 int full_rdms(const double *d1, const double *d2, int no, int na, int N, double *one_full,
@@ -1207,8 +1210,8 @@ int y_matrix(const double *g, const double *two_full, int N, int ld, double *Y, 
 extern "C" int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
                               const double *gamma, const double *Gamma, int no, int na, int N, int ld,
                               const int32_t *pair_l, const int32_t *pair_r, int nk, double *H, void *ws,
-                              size_t ws_bytes, void *stream) {
-    return oo::hessian(h_mo, g_mo, F, gamma, Gamma, no, na, N, ld, pair_l, pair_r, nk, H, ws, ws_bytes,
+                              size_t ws_bytes, unsigned flags, void *stream) {
+    return oo::hessian(h_mo, g_mo, F, gamma, Gamma, no, na, N, ld, pair_l, pair_r, nk, H, ws, ws_bytes, flags,
                        (cudaStream_t)stream);
 }
 
@@ -1226,7 +1229,7 @@ extern "C" int oo_class_hessian_f64(const double *cls, const double *F, const do
                                     int64_t stride_rdm1, const double *Gamma, int64_t stride_rdm2, int no,
                                     int na, int N, int ld, int nIp, int batch, const int32_t *pair_l,
                                     const int32_t *pair_r, int nk, double *H, void *ws, size_t ws_bytes,
-                                    void *stream) {
+                                    unsigned flags, void *stream) {
     return oo::class_hessian(cls, F, gamma, stride_rdm1, Gamma, stride_rdm2, no, na, N, ld, nIp, batch, pair_l,
-                             pair_r, nk, H, ws, ws_bytes, (cudaStream_t)stream);
+                             pair_r, nk, H, ws, ws_bytes, flags, (cudaStream_t)stream);
 }

@@ -12,8 +12,9 @@
 
    * ``mode="reduce_scatter"`` (the decomposition named in BASELINE.json): rank ``r`` holds the slab
      ``g[p in P_r, :, :, :]`` of the LEADING AO index.  Quarter 1 gives partial sums over ``p in P_r``
-     for every destination block of the new index ``i``; chunk ``d`` (``i in I_d``) is summed onto rank
-     ``d`` (NCCL ``reduce_scatter``: N^4 doubles leave every rank).  Quarters 2-4 are local.
+     for every destination block of the new index ``i``; block ``d`` (``i in I_d``) is summed onto rank
+     ``d`` by NCCL ``reduce_scatter_tensor`` calls over row chunks, each overlapped with the GEMMs of the next
+     chunk (N^4 doubles leave every rank).  Quarters 2-4 are local.
    * ``mode="all_to_all"``: rank ``r`` holds ``g[:, :, (r s) in RS_r]`` (a slab of the TRAILING pair).
      Quarters 1-2 need no communication (the contracted indices p, q are complete on every rank);
      one ``all_to_all`` re-shards ``[(rs)_loc, i, j] -> [(rs), i_loc, j]`` (N^4/G doubles leave every
@@ -149,6 +150,11 @@ class SlabTransform:
         else:
             assert self.n % self.world == 0, "reduce_scatter mode needs world_size | n"
         self.blk = self.n // self.world                 # |I_d| for every destination
+        if gemm is None:
+            # oo_dgemm_tn_f64 needs even leading dimensions (16-byte TMA strides); the per-destination operands
+            # C0[:, I_d] and the exchanged chunks have leading dimension n / world
+            assert self.n % 2 == 0 and self.blk % 2 == 0, \
+                f"the CUDA TN-GEMM needs n and n / world_size even (n={self.n}, world={self.world}): pad n"
 
     # ---- which part of g_ao each rank holds
     def in_range(self):
@@ -195,32 +201,48 @@ class SlabTransform:
             cur = out.reshape(self.n, -1)                 # next leading index is the slowest of `out`
         return cur.reshape(self.blk, self.n, self.n, self.n)
 
+    RS_CHUNKS = 8            # the reduce-scatter of quarter 1 is issued in this many row chunks (overlap with compute)
+
     def _quarter1_reduce_scatter(self, g_slab, C0):
+        """Partial sums over this rank's p-slab for EVERY destination block of i, reduce-scattered over the ranks
+        in row chunks: chunk c+1 is computed while the NCCL ``reduce_scatter`` of chunk c is on the wire."""
         n, W, blk = self.n, self.world, self.blk
         lo, hi = self.in_range()
-        At = g_slab.reshape(hi - lo, n * n * n)                      # [p_loc, (q r s)]
-        mine = torch.empty(n * n * n, blk, dtype=F64, device=g_slab.device)
+        rows = n * n * n
+        At = g_slab.reshape(hi - lo, rows)                           # [p_loc, (q r s)]
+        mine = torch.empty(rows, blk, dtype=F64, device=g_slab.device)
         if W == 1:
             self.gemm(At, C0, mine)
             return mine.reshape(n, n * n * blk)
-        bufs = [torch.empty_like(mine) for _ in range(2)]
+        Cd = [C0[lo:hi, d * blk:(d + 1) * blk].contiguous() for d in range(W)]     # [p_loc, i in I_d]
+        step = -(-rows // self.RS_CHUNKS)
+        step += step & 1                                             # even row offsets keep 16-byte alignment
+        bufs = [torch.empty(W * step * blk, dtype=F64, device=g_slab.device) for _ in range(2)]
         pending = []
-        for d in range(W):
-            buf = bufs[d % 2]
+        for c, r0 in enumerate(range(0, rows, step)):
+            r1 = min(rows, r0 + step)
             if len(pending) >= 2:                                    # the buffer we are about to reuse
                 pending.pop(0).wait()
-            Cd = C0[lo:hi, d * blk:(d + 1) * blk].contiguous()       # [p_loc, i in I_d]
-            self.gemm(At, Cd, buf)
-            # sum of chunk d over all ranks lands on rank d: a reduce-scatter issued chunk by chunk
-            # so that chunk d+1 is computed while chunk d is on the wire
-            pending.append(dist.reduce(buf, dst=self._global_rank(d), op=dist.ReduceOp.SUM,
-                                       group=self.group, async_op=True))
-            if d == self.rank:
-                keep = buf
-                bufs[d % 2] = torch.empty_like(mine)                 # do not overwrite the result chunk
+            part = bufs[c % 2][: W * (r1 - r0) * blk].view(W, r1 - r0, blk)
+            for d in range(W):
+                self.gemm(At[:, r0:r1], Cd[d], part[d])
+            pending.append(self._reduce_scatter_async(mine[r0:r1], part))
         for w in pending:
             w.wait()
-        return keep.reshape(n, n * n * blk)                          # [q, (r s i_loc)]
+        return mine.reshape(n, n * n * blk)                          # [q, (r s i_loc)]
+
+    def _reduce_scatter_async(self, out, parts):
+        """``out = sum over ranks of parts[my rank]`` (parts: [W, ...] contiguous); returns an object with
+        ``wait()``.  NCCL: ``reduce_scatter_tensor``; gloo (CPU tests) has no reduce-scatter: all-reduce + slice."""
+        if dist.get_backend(self.group) == "gloo":
+            work = dist.all_reduce(parts, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+            class _Then:
+                def wait(_self):
+                    work.wait()
+                    out.copy_(parts[self.rank])
+            return _Then()
+        return dist.reduce_scatter_tensor(out, parts, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _quarters12_all_to_all(self, g_slab, C0, C1):
         n, W, blk = self.n, self.world, self.blk

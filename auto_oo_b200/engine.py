@@ -9,6 +9,7 @@ device memory, streams and index tables; every arithmetic step is a kernel of
 from __future__ import annotations
 
 import math as _math
+import weakref
 
 import numpy as np
 import torch
@@ -33,6 +34,59 @@ def tril_pair_table(nao, params_idx):
     return rows[pidx].astype(np.int32), cols[pidx].astype(np.int32)
 
 
+class _DeviceLib:
+    """The ctypes library with every call made under the engine's CUDA device: kernels launch on the
+    CURRENT device, so an engine built with ``device="cuda:1"`` must not depend on what the caller's current
+    device happens to be."""
+
+    def __init__(self, lib, index):
+        self._lib, self._index = lib, int(index)
+
+    def __getattr__(self, name):
+        fn, idx = getattr(self._lib, name), self._index
+
+        def call(*args):
+            if torch.cuda.current_device() == idx:
+                return fn(*args)
+            with torch.cuda.device(idx):
+                return fn(*args)
+
+        call.__name__ = name
+        setattr(self, name, call)                         # bound once per entry point
+        return call
+
+
+class _Hold:
+    """Token of a lazy consumer (an ``OrbitalHessian``, the autograd context of a gradient) of a set of
+    transformed integrals: while one is alive the engine does not recycle that buffer for the next transform."""
+    __slots__ = ("__weakref__",)
+
+
+class _IntegralsKey:
+    """What a cached set of transformed integrals was computed from: a tag ("mo": the matrix IS the MO
+    coefficients, "oao": OAO->MO coefficients to be multiplied by S^-1/2, "C": a padded device matrix), the source
+    tensor (kept alive, so its identity + version counter is a valid sync-free hit test) with a private copy of its
+    values, and optionally a rotation vector.  Host tensors are compared on the host; only a DEVICE tensor that is
+    not the very object seen last costs a device comparison (one synchronisation)."""
+
+    def __init__(self, tag, src, kappa=None):
+        self.tag, self.src, self.version = tag, src, src._version
+        self.value = src.detach().clone()
+        self.kappa = None if kappa is None else kappa.detach().clone()
+
+    def matches(self, tag, src, kappa=None):
+        if tag != self.tag or (kappa is None) != (self.kappa is None):
+            return False
+        if kappa is not None and not (kappa.shape == self.kappa.shape and kappa.device == self.kappa.device
+                                      and torch.equal(kappa, self.kappa)):
+            return False
+        if src is self.src and src._version == self.version:
+            return True
+        if src.shape != self.value.shape or src.device != self.value.device or src.dtype != self.value.dtype:
+            return False
+        return bool(torch.equal(src.detach(), self.value))
+
+
 class MOIntegrals:
     """Transformed integrals of ONE set of MO coefficients on the device, in either representation:
     ``kind="full"`` -- (h', g') with the complete ld^4 tensor of the four-index transform, or
@@ -41,6 +95,19 @@ class MOIntegrals:
 
     def __init__(self, eng, kind, h=None, g=None, cls=None):
         self.eng, self.kind, self.h, self.g, self.cls = eng, kind, h, g, cls
+        self._holds = weakref.WeakSet()
+
+    def hold(self):
+        """A token for a consumer that will read these integrals LATER (``OrbitalHessian.matrix``, a gradient's
+        ``backward``): as long as the token lives, the engine allocates a new buffer for the next transform
+        instead of overwriting this one, so interleaved calls stay as safe as with the reference's dense values."""
+        tok = _Hold()
+        self._holds.add(tok)
+        return tok
+
+    @property
+    def held(self):
+        return len(self._holds) > 0
 
     def active_hamiltonian(self):
         if self.kind == "class":
@@ -91,8 +158,11 @@ class HotPathEngine:
         batch then uses geometry ``b`` (class path only)."""
         if not torch.cuda.is_available():
             raise _lib.OOError("auto_oo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-        self.lib = _lib.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _DeviceLib(_lib.load(), self.device.index)
+        self.flags = 0                                 # OO_FLAG_* variant switches passed with every call (A/B tests)
         self.N = int(nao)
         self.ld = pad_even(self.N)
         self.no, self.na = int(no), int(na)
@@ -116,10 +186,7 @@ class HotPathEngine:
         self._eri_symmetric = None if eri_symmetry == "auto" else False
         self.eri_defect = None
         self._ws = {}
-        self._cache_key = None
-        self._cache_val = None
-        self._ccache_key = None
-        self._ccache_val = None
+        self._icache = {}                              # kind -> (_IntegralsKey | None, MOIntegrals)
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -218,7 +285,7 @@ class HotPathEngine:
 
     def release_workspaces(self):
         self._ws.clear()
-        self._cache_key = self._cache_val = None
+        self._icache.clear()
 
     # ------------------------------------------------------------------ K1
     def squarings_for(self, kappa):
@@ -306,29 +373,47 @@ class HotPathEngine:
                                                     _p(out), _p(ws), nbytes, self.stream), "int2e_transform")
         return out
 
-    def integrals(self, C, kind="class"):
-        """:class:`MOIntegrals` for one padded C (ld, ld), cached by the value of C."""
+    # ------------------------------------------------------------------ cache of transformed integrals
+    def _recycle(self, kind):
+        """The big buffer of the last transform of this kind (class buffer / g') for reuse, or None when there is
+        none or a lazy consumer still holds it (:meth:`MOIntegrals.hold`): the cache entry is dropped either way."""
+        ent = self._icache.pop(kind, None)
+        if ent is None or ent[1].held:
+            return None
+        return ent[1].cls if kind == "class" else ent[1].g
+
+    def _park(self, kind, buf):
+        """Keep a scratch buffer of :meth:`evaluate` for the next transform (no key: never a cache hit)."""
+        if buf is not None and buf.shape[0] == 1:
+            self._icache[kind] = (None, MOIntegrals(self, kind, cls=buf) if kind == "class"
+                                  else MOIntegrals(self, kind, g=buf))
+
+    def integrals_for(self, kind, tag, src, make_C, kappa=None):
+        """:class:`MOIntegrals` of kind "class" / "full", cached under (tag, src[, kappa]) -- see
+        :class:`_IntegralsKey`; ``make_C()`` supplies the padded (ld, ld) MO coefficients on a miss."""
+        ent = self._icache.get(kind)
+        if ent is not None and ent[0] is not None and ent[0].matches(tag, src, kappa):
+            return ent[1]
+        C = make_C().reshape(1, self.ld, self.ld)
+        buf = self._recycle(kind)
         if kind == "class":
-            cls = self.class_integrals_cached(C)
-            return MOIntegrals(self, "class", cls=cls)
-        h, g = self.mo_integrals(C)
-        return MOIntegrals(self, "full", h=h, g=g)
+            ints = MOIntegrals(self, "class", cls=self.class_integrals(C, out=buf))
+        else:
+            ints = MOIntegrals(self, "full", h=self.int1e_transform(C), g=self.int2e_transform(C, out=buf))
+        self._icache[kind] = (_IntegralsKey(tag, src, kappa), ints)
+        return ints
+
+    def integrals(self, C, kind="class"):
+        """:class:`MOIntegrals` for one padded device matrix C (ld, ld), cached by identity / value of C."""
+        return self.integrals_for(kind, "C", C, lambda: C)
 
     def mo_integrals(self, C):
-        """(h', g') for padded C (B, ld, ld); the last single-matrix result is cached by value."""
+        """(h', g') for padded C (ld, ld) or (B, ld, ld); a single matrix goes through the cache."""
         C = C if C.dim() == 3 else C[None]
-        if C.shape[0] == 1 and self._cache_key is not None and torch.equal(self._cache_key, C):
-            return self._cache_val
-        if C.shape[0] == 1 and self._cache_val is not None:
-            out = self._cache_val[1]                      # reuse the N^4 buffer
-            self._cache_key = self._cache_val = None
-        else:
-            out = None
-        h = self.int1e_transform(C)
-        g = self.int2e_transform(C, out=out)
         if C.shape[0] == 1:
-            self._cache_key, self._cache_val = C.clone(), (h, g)
-        return h, g
+            ints = self.integrals(C[0], kind="full")
+            return ints.h, ints.g
+        return self.int1e_transform(C), self.int2e_transform(C)
 
     # ------------------------------------------------------------------ class (partial-transform) path
     def pair_transposed_eri(self):
@@ -386,7 +471,7 @@ class HotPathEngine:
         else:
             self.pair_transposed_eri()
         self.g_ao = None
-        self._cache_key = self._cache_val = None
+        self._icache.pop("full", None)
         self._ws.pop("i2e", None)
 
     def class_rows(self):
@@ -405,7 +490,7 @@ class HotPathEngine:
             gp, sg = self._geo(self.packed_eri(), geo_lo, geo_lo + B)
             self._check(self.lib.oo_class_transform_sym_f64(_p(gp), sg, _p(C), ld * ld if B > 1 else 0,
                                                             self.N, ld, nIp, B, _p(cls), _p(ws), nbytes,
-                                                            self.stream), "class_transform_sym")
+                                                            self.flags, self.stream), "class_transform_sym")
         else:
             nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, B)
             ws = self.workspace("cls", nbytes)
@@ -421,17 +506,6 @@ class HotPathEngine:
                                                         _p(ws1), nb1, self.stream), "int1e_transform")
         else:                                                # batched: dense scratch, then a strided device copy
             cls[:, rows - 1].copy_(self.int1e_transform(C, geo=(geo_lo, None)))
-        return cls
-
-    def class_integrals_cached(self, C):
-        """As class_integrals for ONE C, but the last result is cached by the value of C."""
-        C = C.reshape(1, self.ld, self.ld)
-        if self._ccache_key is not None and torch.equal(self._ccache_key, C):
-            return self._ccache_val
-        buf = self._ccache_val
-        self._ccache_key = self._ccache_val = None
-        cls = self.class_integrals(C, out=buf)
-        self._ccache_key, self._ccache_val = C.clone(), cls
         return cls
 
     def class_active_hamiltonian(self, cls, geo_lo=0):
@@ -483,7 +557,7 @@ class HotPathEngine:
         ws = self.workspace("chess", nbytes)
         self._check(self.lib.oo_class_hessian_f64(_p(cls), _p(F), _p(d1), s1, _p(d2), s2, self.no, self.na, self.N,
                                                   self.ld, self.nIp, B, _p(pl), _p(pr), nk, _p(H), _p(ws), nbytes,
-                                                  self.stream), "class_hessian")
+                                                  self.flags, self.stream), "class_hessian")
         return H
 
     def class_chunk(self, B):
@@ -558,7 +632,7 @@ class HotPathEngine:
         ws = self.workspace("hess", nbytes)
         self._check(self.lib.oo_hessian_f64(_p(h), _p(g), _p(F), _p(d1), _p(d2), self.no, self.na, self.N,
                                             self.ld, _p(pl), _p(pr), nk, _p(H), _p(ws),
-                                            nbytes, self.stream), "hessian")
+                                            nbytes, self.flags, self.stream), "hessian")
         return H
 
     def full_rdms(self, d1, d2):
@@ -623,8 +697,7 @@ class HotPathEngine:
         assert path == "class" or self.n_geom == 0, "geometry batches use the class path"
         if path == "class":
             chunk = self.class_chunk(B)
-            cbuf = self._ccache_val
-            self._ccache_key = self._ccache_val = None
+            cbuf = self._recycle("class")
             for lo in range(0, B, chunk):
                 hi = min(B, lo + chunk)
                 if transform_events is not None:
@@ -645,13 +718,10 @@ class HotPathEngine:
                 if on_result is not None:
                     for b in range(lo, hi):
                         on_result(b)
-            self._ccache_val = cbuf if cbuf.shape[0] == 1 else None     # keep a single-evaluation buffer for reuse
+            self._park("class", cbuf)                        # a single-evaluation buffer is kept for reuse
             return E, G, H
         hs = self.int1e_transform(C)
-        gbuf = None
-        if self._cache_val is not None:
-            gbuf = self._cache_val[1]
-            self._cache_key = self._cache_val = None
+        gbuf = self._recycle("full")
         for b in range(B):
             if transform_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -671,6 +741,7 @@ class HotPathEngine:
                 self.hessian(h1[0], gbuf[0], F[0], d1b, d2b, out=H[b])
             if on_result is not None:
                 on_result(b)
+        self._park("full", gbuf)
         return E, G, H
 
     # ------------------------------------------------------------------ CUDA-graph replay of whole evaluations
@@ -714,7 +785,6 @@ class HotPathEngine:
             if dst is not None:
                 dst.copy_(src, non_blocking=True)
         graph.replay()
-        self._ccache_key = None                               # the replay rewrote the cached class buffer
         E, G, H = out
         if not clone:
             return E, G, H
@@ -730,6 +800,9 @@ class HotPathEngine:
                                     squarings=squarings, path=path)
         self.eri_is_symmetric()                               # host-synchronising one-off decisions happen here,
         cur = torch.cuda.current_stream(self.device)          # not inside the capture
+        # the graph gets a class / g' buffer of its own: it rewrites that buffer at every replay, so it must never
+        # be one that the eager cache hands out to a lazy consumer (OrbitalHessian, a gradient's backward)
+        eager = {k: self._icache.pop(k) for k in list(self._icache)}
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
@@ -742,5 +815,7 @@ class HotPathEngine:
             out = run()
         # the graph has the addresses of every workspace it touched baked in: keep those tensors alive even if
         # a later, larger call replaces them in the workspace table
-        keep = [v for v in self._ws.values() if torch.is_tensor(v)] + [self._ccache_val, self.g_packed, self.g_pairT]
+        keep = ([v for v in self._ws.values() if torch.is_tensor(v)] + [self.g_packed, self.g_pairT]
+                + [ent[1] for ent in self._icache.values()])
+        self._icache = eager
         return graph, static, out, keep

@@ -163,6 +163,7 @@ class _GradientFn(torch.autograd.Function):
     def forward(ctx, one_rdm, two_rdm, eng, ints):
         FI, FA, F, G, _ = ints.fock_gradient(eng.dev(one_rdm), eng.dev(two_rdm), want_vector=False)
         ctx.eng, ctx.ints, ctx.FI = eng, ints, FI
+        ctx.hold = ints.hold()                       # backward reads the integrals: keep their buffer from reuse
         ctx.dev1, ctx.dev2 = one_rdm.device, two_rdm.device
         return eng.from_padded(G, 2)[0].to(one_rdm.device)
 
@@ -180,6 +181,7 @@ class OrbitalHessian:
 
     def __init__(self, eng, ints, F, one_rdm, two_rdm, like):
         self._eng, self._ints, self._F = eng, ints, F
+        self._hold = ints.hold()                     # matrix() / dense() read the integrals later
         self._d1, self._d2 = eng.dev(one_rdm), eng.dev(two_rdm)
         self._like = like
         self.shape = (eng.N,) * 4
@@ -285,10 +287,20 @@ class OO_energy:
         return _like(eng.from_padded(out[None], 2)[0], mo_coeff)
 
     # ------------------------------------------------------------------ energy
-    def _mo_integrals(self, mo_coeff):
-        """Transformed integrals at ``mo_coeff`` (class representation, cached by value)."""
+    def _mo_integrals(self, mo_coeff=None, kappa=None):
+        """Transformed integrals at ``mo_coeff`` (default: the current ``self.mo_coeff``, optionally rotated by
+        ``kappa``), cached under what they were computed from: the same tensor object with an unchanged version
+        counter, or equal values (compared on the host for host tensors), is a hit without a device round trip."""
         eng = self.engine
-        return eng.integrals(eng.to_padded(_as_tensor(mo_coeff).detach(), 2), kind=self.integral_path)
+        if mo_coeff is None:
+            src = self.oao_mo_coeff
+            if kappa is None:
+                make = lambda: eng.mo_coeff(eng.to_padded(src, 2))[0]
+            else:
+                make = lambda: eng.mo_coeff(eng.to_padded(src, 2), eng.rotation(kappa.reshape(1, -1)))[0]
+            return eng.integrals_for(self.integral_path, "oao", src, make, kappa=kappa)
+        src = _as_tensor(mo_coeff)
+        return eng.integrals_for(self.integral_path, "mo", src, lambda: eng.to_padded(src.detach(), 2))
 
     def get_active_integrals(self, mo_coeff):
         """``(c0, c1, c2)`` of the active-space Hamiltonian in chemist notation
@@ -304,11 +316,8 @@ class OO_energy:
 
     def energy_from_kappa(self, kappa, one_rdm, two_rdm):
         """Energy at ``C' = C expm(-K(kappa))`` (reference ``oo_energy.py:199-202``)."""
-        eng = self.engine
-        U = eng.rotation(_as_tensor(kappa).detach().reshape(1, -1))
-        C = eng.mo_coeff(eng.to_padded(self.oao_mo_coeff, 2), U)
-        c0, c1, c2 = eng.integrals(C[0], kind=self.integral_path).active_hamiltonian()
-        return _EnergyFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), eng, c0, c1, c2)
+        c0, c1, c2 = self._mo_integrals(kappa=_as_tensor(kappa).detach()).active_hamiltonian()
+        return _EnergyFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, c0, c1, c2)
 
     def energies_from_kappas(self, kappas, one_rdm, two_rdm):
         """``energy_from_kappa`` for a batch ``kappas (B, n_kappa)`` in one pass (batched launches);
@@ -362,7 +371,7 @@ class OO_energy:
 
     def analytic_gradient(self, one_rdm, two_rdm, mo_coeff=None):
         """Reference ``oo_energy.py:404-413``; differentiable in the RDMs."""
-        ints = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
+        ints = self._mo_integrals(mo_coeff)
         return _GradientFn.apply(_as_tensor(one_rdm), _as_tensor(two_rdm), self.engine, ints)
 
     # ------------------------------------------------------------------ Hessian
@@ -387,8 +396,7 @@ class OO_energy:
 
     def analytic_hessian(self, one_rdm, two_rdm, mo_coeff=None):
         """Reference ``oo_energy.py:415-424``; returns an :class:`OrbitalHessian`."""
-        ints = self._mo_integrals(self.mo_coeff if mo_coeff is None else mo_coeff)
-        return self._hessian(ints, one_rdm, two_rdm, _as_tensor(one_rdm))
+        return self._hessian(self._mo_integrals(mo_coeff), one_rdm, two_rdm, _as_tensor(one_rdm))
 
     def _hessian(self, ints, one_rdm, two_rdm, like):
         eng = self.engine

@@ -102,9 +102,11 @@ class NewtonStep:
         assert wolfe(1., gradient, dp, alpha=self.alpha) < 0
         slope = torch.dot(gradient, dp).item()
         t, num, accepted, new_energy = 1., 0, None, None
-        while accepted is None and num <= self.lmax:
+        while accepted is None and num < self.lmax:
             ts = []
-            while len(ts) < self.speculate and num + len(ts) <= self.lmax:
+            # the sequential search (reference :165-176) gives up when the (lmax+1)-th halving fails, i.e. it can
+            # accept at most beta^lmax: no more than lmax candidates in total
+            while len(ts) < self.speculate and num + len(ts) < self.lmax:
                 t = self.beta * t
                 ts.append(t)
             if not ts:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define OO_ABI_VERSION 1
+#define OO_ABI_VERSION 2
 
 enum {
     OO_OK = 0,
@@ -62,21 +62,22 @@ const char *oo_error_string(int code);
 int         oo_last_cuda_error(void);                 /* cudaError_t of the last OO_ERR_CUDA */
 unsigned long long oo_launch_count(void);             /* kernels launched by this library so far */
 
-/* process-wide switches (A/B timing and tests); every setting gives the same numbers to round-off */
+/* per-call variant switches (A/B timing and tests), OR-ed into the `flags` argument of the entry points that
+ * have more than one implementation; every setting gives the same numbers to round-off.  There is no
+ * process-wide mutable state: two threads driving different streams can use different flags.             */
 enum {
-    OO_OPT_HESSIAN_DENSE = 1,               /* 1: oo_class_hessian_f64 runs ONE dense GEMM over all of At instead of
-                                               the block form (C-block GEMM + G blocks + ELL remainder)          */
-    OO_OPT_HESSIAN_SIMPLE_ASSEMBLE = 2,     /* Hessian assembly: 0 = by size (one thread per element for N <= 64,
-                                               row-tiled + bulk-async streamed above), 1 = always the former,
-                                               2 = always the latter                                             */
-    OO_OPT_CLASS_UNFUSED_PACK = 3,          /* 1: symmetric class transform with separate pack / expand passes
-                                               instead of the fused epilogues of its quarter-2 / last-quarter GEMMs */
-    OO_OPT_HESSIAN_GROUP_UNSTREAMED = 4,    /* 1: G blocks of the Hessian T-matrix with per-thread loads instead of
-                                               the cp.async.bulk + mbarrier streamed DMMA kernel                  */
-    OO_OPT_HESSIAN_ASSEMBLE_UNSTREAMED = 5  /* 1: Hessian assembly without the bulk-async streamed kernel for the
-                                               rows outside occ+act                                              */
+    OO_FLAG_HESSIAN_DENSE = 1,                 /* oo_class_hessian_f64 / oo_hessian_f64: ONE dense GEMM over all of At
+                                                  instead of the block form (C-block GEMM + G blocks + ELL remainder) */
+    OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT = 2,  /* Hessian assembly: always one thread per element (default: that form
+                                                  for N <= 64, row-tiled + bulk-async streamed above)                 */
+    OO_FLAG_HESSIAN_ASSEMBLE_TILED = 4,        /* Hessian assembly: always the row-tiled form                         */
+    OO_FLAG_CLASS_UNFUSED_PACK = 8,            /* oo_class_transform_sym_f64: separate pack / expand passes instead of
+                                                  the fused epilogues of its quarter-2 / last-quarter GEMMs           */
+    OO_FLAG_HESSIAN_GROUP_UNSTREAMED = 16,     /* G blocks of the Hessian T-matrix with per-thread loads instead of the
+                                                  cp.async.bulk + mbarrier streamed DMMA kernel                       */
+    OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 32   /* Hessian assembly without the bulk-async streamed kernel for the rows
+                                                  outside occ+act                                                     */
 };
-int         oo_set_option(int key, int value);
 int         oo_device_info(int *sm_count, int *cc_major, int *cc_minor);
 size_t      oo_workspace_bytes(int which, int N, int ld, int nI, int batch);
 
@@ -205,7 +206,7 @@ int oo_hessian_f64(const double *h_mo, const double *g_mo, const double *F,
                    const double *gamma, const double *Gamma,
                    int no, int na, int N, int ld,
                    const int32_t *pair_l, const int32_t *pair_r, int nk,
-                   double *H, void *ws, size_t ws_bytes, void *stream);
+                   double *H, void *ws, size_t ws_bytes, unsigned flags, void *stream);
 
 /* ---- partial ("class") transform path -------------------------------------------
  * Energy, gradient and the I-space Hessian read g' only through two classes with two
@@ -240,7 +241,7 @@ int64_t oo_pair_ld(int ld);
 int     oo_pack_eri_pairs_f64(const double *g_ao, double *g_packed, int ld, void *stream);
 int     oo_class_transform_sym_f64(const double *g_packed, int64_t strideG, const double *C, int64_t strideC,
                                    int N, int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
-                                   void *stream);
+                                   unsigned flags, void *stream);
 int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp,
                                     int batch, double e_nuc, const double *e_nuc_batch, double *c0,
                                     double *c1, double *c2, void *stream);
@@ -255,7 +256,7 @@ int oo_class_fock_gradient_vjp_f64(const double *cls, const double *FI, const do
 int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma, int64_t stride_rdm1,
                          const double *Gamma, int64_t stride_rdm2, int no, int na, int N, int ld,
                          int nIp, int batch, const int32_t *pair_l, const int32_t *pair_r, int nk,
-                         double *H, void *ws, size_t ws_bytes, void *stream);
+                         double *H, void *ws, size_t ws_bytes, unsigned flags, void *stream);
                          /* batched: cls[b], F[b] (ld^2), H[b] (nk^2) contiguous per evaluation */
 
 /* ---- RDMs from a state vector (the producer of the hot path's gamma, Gamma) -----

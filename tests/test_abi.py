@@ -22,7 +22,7 @@ def test_library_builds_and_loads():
     path = build.build_library()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.oo_abi_version() == 1
+    assert lib.oo_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -251,3 +251,61 @@ def test_geometry_batch_matches_one_object_per_geometry():
     batch.rotate(kap)
     E2, _, _ = batch.energy_gradient_hessian(torch.zeros_like(kap), one, two, want_hessian=False)
     assert (E2 - E).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("path", ["class", "full"])
+def test_lazy_hessian_and_gradient_survive_interleaved_evaluations(path):
+    """The reference returns dense values, so ``H = analytic_hessian(...)``, other evaluations, then
+    ``full_hessian_to_matrix(H)`` -- or a ``backward()`` through ``analytic_gradient`` after other calls -- is safe
+    there.  Here both are lazy consumers of a device buffer: the engine must not recycle that buffer under them."""
+    c = load_case("n13_bigkappa")
+    r = c.ref
+    oo = make_oo(c, integral_path=path)
+    Cp = torch.as_tensor(r["mo_coeff_rot"])
+    one = c.one_rdm.clone().requires_grad_(True)
+    two = c.two_rdm.clone().requires_grad_(True)
+    H = oo.analytic_hessian(c.one_rdm, c.two_rdm, mo_coeff=Cp)            # lazy handle
+    Gm = oo.analytic_gradient(one, two, mo_coeff=Cp)                      # backward comes later
+    w = torch.as_tensor(np.random.default_rng(0).standard_normal(Gm.shape))
+    # other orbitals in between, through every entry point that transforms integrals
+    k2 = 0.3 * c.kappa
+    oo.energy_from_kappa(k2, c.one_rdm, c.two_rdm)
+    oo.energies_from_kappas(torch.stack([k2, 2 * k2]), c.one_rdm, c.two_rdm)
+    for _ in range(3):                                                    # third call replays a captured graph
+        oo.energy_gradient_hessian(torch.stack([k2, -k2]), c.one_rdm, c.two_rdm)
+    oo.analytic_gradient(c.one_rdm, c.two_rdm)
+    oo.get_active_integrals(oo.mo_coeff)
+    assert np.abs(oo.full_hessian_to_matrix(H).numpy() - r["H"]).max() < TOL_GH
+    (Gm * w).sum().backward()
+    # adjoint through the oracle's gradient matrix
+    from oracle import oo_oracle as orc
+    p = c.oracle()
+    o1 = c.one_rdm.clone().requires_grad_(True)
+    o2 = c.two_rdm.clone().requires_grad_(True)
+    h, g = p.mo_integrals(c.kappa)
+    (orc.gradient_matrix(h, g, o1, o2, p.occ_idx, p.act_idx) * w).sum().backward()
+    assert (one.grad - o1.grad).abs().max().item() < TOL_GH and (two.grad - o2.grad).abs().max().item() < TOL_GH
+
+
+def test_cache_follows_orbital_updates_without_value_comparisons_on_the_device():
+    """Same tensor object + version counter -> hit; in-place write or re-assignment of ``oao_mo_coeff`` -> miss."""
+    c = load_case("n13_cas22")
+    oo = make_oo(c)
+    eng = oo.engine
+    n0 = eng.lib.oo_launch_count()
+    E0 = oo.energy_from_mo_coeff(oo.mo_coeff, c.one_rdm, c.two_rdm).item()
+    oo.analytic_gradient(c.one_rdm, c.two_rdm)
+    n1 = eng.lib.oo_launch_count()
+    oo.analytic_gradient(c.one_rdm, c.two_rdm)                            # same orbitals: no transform
+    oo.analytic_hessian(c.one_rdm, c.two_rdm)
+    n2 = eng.lib.oo_launch_count()
+    assert n2 - n1 < (n1 - n0) / 2
+    U = oo.kappa_to_mo_coeff(c.kappa)
+    oo.oao_mo_coeff = oo.oao_mo_coeff @ U                                 # re-assignment (oo_pqc.py:191)
+    E1 = oo.energy_from_mo_coeff(oo.mo_coeff, c.one_rdm, c.two_rdm).item()
+    assert abs(E1 - float(c.ref["E"])) < TOL_E and abs(E1 - E0) > 1e-6
+    G1 = oo.kappa_matrix_to_vector(oo.analytic_gradient(c.one_rdm, c.two_rdm))
+    assert np.abs(G1.numpy() - c.ref["G"]).max() < TOL_GH
+    oo.oao_mo_coeff.copy_(torch.as_tensor(c.oao_mo_coeff))                # in-place write: version counter moves
+    G0 = oo.kappa_matrix_to_vector(oo.analytic_gradient(c.one_rdm, c.two_rdm))
+    assert np.abs(G0.numpy() - c.ref["G0"]).max() < TOL_GH

@@ -27,6 +27,7 @@ import numpy as np
 import pytest
 import torch
 
+from auto_oo_b200 import _lib
 from helpers import GOLDEN, TOL_E, TOL_GH
 
 pytestmark = pytest.mark.gpu
@@ -111,7 +112,6 @@ def test_identity_is_exact_and_orthogonal_rotation_preserves_invariants(prob):
     eng, N, ld = prob.eng, prob.nao, prob.eng.ld
     # three N^4 buffers are live below (103 GB at N = 256): drop what the class path built in earlier tests
     eng.release_workspaces()
-    eng._ccache_key = eng._ccache_val = None
     eng.g_packed = eng.g_pairT = None
     torch.cuda.empty_cache()
     g = eng.g_ao
@@ -153,37 +153,37 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     assert (Hc[0] - Hc[0].T).abs().max().item() < TOL_GH
     # Hessian assembly: the row-tiled kernel (taken at this size) against one thread per element
     try:
-        assert eng.lib.oo_set_option(2, 1) == 0
+        eng.flags = _lib.OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT
         _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
-        eng.lib.oo_set_option(2, 0)
+        eng.flags = 0
     assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
     # assembly of the rows outside occ+act: bulk-async streamed kernel (default) against the load-per-thread kernel
     try:
-        assert eng.lib.oo_set_option(5, 1) == 0
+        eng.flags = _lib.OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED
         _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
-        eng.lib.oo_set_option(5, 0)
+        eng.flags = 0
     assert torch.equal(Hf, Hc)
     # G blocks of the Hessian T-matrix: bulk-async streamed kernel (taken at this size) against per-thread loads
     try:
-        assert eng.lib.oo_set_option(4, 1) == 0
+        eng.flags = _lib.OO_FLAG_HESSIAN_GROUP_UNSTREAMED
         _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
-        eng.lib.oo_set_option(4, 0)
+        eng.flags = 0
     assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())     # DMMA vs FMA summation order
     # class-pair packing: fused into the quarter-2 GEMM epilogues (default) against the separate pass
     try:
-        assert eng.lib.oo_set_option(3, 1) == 0
+        eng.flags = _lib.OO_FLAG_CLASS_UNFUSED_PACK
         Eu, Gu, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
-        eng.lib.oo_set_option(3, 0)
+        eng.flags = 0
     assert torch.equal(Eu, Ec) and torch.equal(Gu, Gc) and torch.equal(Hf, Hc)
     # general (no symmetry assumed) class route; the complete transform's N^4 workspace makes room first
     eng._eri_symmetric = False
     eng._ws.pop("i2e", None)
     eng._ws.pop("cls", None)
-    eng._ccache_key = eng._ccache_val = None
+    eng._icache.clear()
     try:
         Hg = Hf
         Eg, Gg, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hg, path="class")
@@ -191,7 +191,7 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
         eng._eri_symmetric = True
         eng.g_pairT = None
         eng._ws.pop("cls", None)
-        eng._ccache_key = eng._ccache_val = None
+        eng._icache.clear()
         torch.cuda.empty_cache()
     assert (Eg - Ec).abs().max().item() < TOL_E
     assert (Gg - Gc).abs().max().item() < TOL_GH

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from auto_oo_b200 import _lib
 from helpers import ALL_CASES, SMALL_CASES, GOLDEN, TOL_E, TOL_GH, load_case
 
 pytestmark = pytest.mark.gpu
@@ -230,10 +231,10 @@ def test_hessian_output_guards_stay_untouched(name, lib):
         big = torch.full((B * nk * nk + 2 * pad,), sentinel, dtype=F64, device="cuda")
         H = big[pad:pad + B * nk * nk].view(B, nk, nk)
         try:
-            assert lib.oo_set_option(2, mode) == 0
+            eng.flags = 2 * mode                      # OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT / _TILED
             eng.evaluate(Coao, d1, d2, kappa=kap, H_out=H)
         finally:
-            lib.oo_set_option(2, 0)
+            eng.flags = 0
         torch.cuda.synchronize()
         assert bool((big[:pad] == sentinel).all()) and bool((big[-pad:] == sentinel).all())
         assert not bool((H == sentinel).any())
@@ -375,10 +376,10 @@ def test_class_transform_equals_slices_of_full_transform(name, sym):
         assert cls[:, N:, :].abs().max().item() == 0.0 and cls[:, :, N:].abs().max().item() == 0.0
     if sym == "auto":                                    # class-pair packing fused into the quarter-2 epilogue vs a separate pass
         try:
-            assert eng.lib.oo_set_option(3, 1) == 0
+            eng.flags = _lib.OO_FLAG_CLASS_UNFUSED_PACK
             cls_u = eng.class_integrals(Cp)[0].cpu()
         finally:
-            eng.lib.oo_set_option(3, 0)
+            eng.flags = 0
         assert torch.equal(cls_u, cls)
 
 
@@ -525,7 +526,7 @@ def test_slab_transform_world1_on_cuda_gemm(mode):
 @pytest.mark.parametrize("name", ["n7_cas44", "n7_cas44_frozen", "n8_nocore", "n11_cas43", "n28_cas66", "n34_cas44"])
 def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
     """oo_class_hessian_f64: dense act-act block + sparse remainder (default) against the single
-    dense GEMM over all of At (OO_OPT_HESSIAN_DENSE), and both against the verbatim reference."""
+    dense GEMM over all of At (OO_FLAG_HESSIAN_DENSE), and both against the verbatim reference."""
     c = load_case(name)
     eng, p = engine_for(c)
     ints = eng.integrals(eng.to_padded(c.ref["mo_coeff_rot"], 2), kind="class")
@@ -533,10 +534,10 @@ def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
     F = ints.fock_gradient(d1, d2, want_matrix=False, want_vector=False)[2]
     Hs = ints.hessian(F, d1, d2).clone()
     try:
-        assert lib.oo_set_option(1, 1) == 0
+        eng.flags = _lib.OO_FLAG_HESSIAN_DENSE
         Hd = ints.hessian(F, d1, d2).clone()
     finally:
-        lib.oo_set_option(1, 0)
+        eng.flags = 0
     assert (Hs - Hd).abs().max().item() < 1e-11
     assert np.abs(Hs.cpu().numpy() - c.ref["H"]).max() < TOL_GH
     assert np.abs(Hd.cpu().numpy() - c.ref["H"]).max() < TOL_GH
@@ -548,14 +549,14 @@ def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
     flat = (eng.pair_l.long() * N + eng.pair_r.long())
     for mode in (1, 2):                                   # 1: per-thread kernel, 2: row-tiled kernel (0: by size)
         try:
-            assert lib.oo_set_option(2, mode) == 0
+            eng.flags = 2 * mode                      # OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT / _TILED
             Hp = ints.hessian(F, d1, d2).clone()
             Hr = ints.hessian(F, d1, d2, pair_l=eng.pair_l[rev].contiguous(), pair_r=eng.pair_r[rev].contiguous())
             # every (row, column) pair, the list OrbitalHessian.dense() passes: rows sorted, columns 0..N-1
             Hall = ints.hessian(F, d1, d2, pair_l=idx.repeat_interleave(N).contiguous(),
                                 pair_r=idx.repeat(N).contiguous())
         finally:
-            lib.oo_set_option(2, 0)
+            eng.flags = 0
         assert (Hs - Hp).abs().max().item() < 1e-11
         assert (Hr - Hs[rev][:, rev]).abs().max().item() < 1e-11
         assert (Hall[flat][:, flat] - Hs).abs().max().item() < 1e-11

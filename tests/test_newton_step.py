@@ -4,6 +4,7 @@ made by oracle/make_golden.py) and the reference's own synthetic objectives
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from auto_oo_b200.utils.newton_raphson import NewtonStep, split_list_shapes
@@ -106,3 +107,20 @@ def test_speculative_line_search_equals_sequential():
         assert torch.equal(x_seq, x_spec)
     assert calls and max(calls) <= 4
     assert x_seq.abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("lmax,accepted", [(3, 0.0), (4, 2.0 ** -4)])
+def test_speculative_line_search_gives_up_where_the_sequential_one_does(lmax, accepted):
+    """f = x^2 from x = 1 along dp = -16: the first step length that decreases f is beta^4.  With lmax = 3 the
+    sequential search (reference newton_raphson.py:165-176) evaluates beta^4 but reports failure (t = 0); the
+    batched search must not accept it either."""
+    def f(x):
+        return torch.sum(x ** 2)
+
+    f.batched = lambda plist: torch.stack([f(p[0]) for p in plist])
+    x = torch.tensor([1.0], dtype=torch.float64)
+    g = torch.tensor([2.0], dtype=torch.float64)
+    dp = torch.tensor([-16.0], dtype=torch.float64)
+    for spec in (0, 2, 4, 8):
+        newx, _ = NewtonStep(verbose=0, lmax=lmax, speculate=spec).backtracking(f, (x,), dp, g)
+        assert torch.equal(newx, x + accepted * dp), (spec, newx)
