@@ -70,6 +70,8 @@ _SIGNATURES = {
     "oo_class_fock_gradient_vjp_f64": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "oo_class_hessian_f64": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr,
                                     _ptr, _i32, _ptr, _ptr, _size, _u32, _ptr]),
+    "oo_pack_lower_f64": (_i32, [_ptr, _i32, _i32, _ptr, _ptr]),
+    "oo_copy_f64": (_i32, [_ptr, _ptr, _i64, _ptr]),
     "oo_rdm_columns": (_i64, [_i32]),
     "oo_rdm_excitations_f64": (_i32, [_ptr, _i32, _i32, _i32, _i64, _i64, _i32, _ptr, _ptr, _i64, _ptr]),
     "oo_rdm_sector_flags_f64": (_i32, [_ptr, _i32, _i32, _i32, _ptr, _ptr]),

@@ -340,12 +340,18 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     if ((rc = dgemm_tn((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), batch, (sIn), strideC, (sOut), \
                        stream)))                                                                         \
     return rc
+    // OO_FLAG_CLASS_STAGE(k): run only the selected GEMM stages (k = 0: quarter 1; 1-3: Coulomb class; 4-6: exchange
+    // class) on the intermediates a complete call left in the workspace -- per-kernel timing from the caller's side
+    const unsigned stage_mask = (flags >> 16) & 0x7fu;
+    auto run = [&](int k) { return stage_mask == 0 || ((stage_mask >> k) & 1u); };
+    if (stage_mask && g_class_unfused_pack) return OO_ERR_INVALID_ARG;
     // Q1: rows (s, pq); the epilogue also writes T1t[q,p,s,m] and T1t[p,q,s,m]
-    if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp, batch,
-                                   strideG, strideC, sT1, sT1t, stream)))
+    if (run(0) && (rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp,
+                                             batch, strideG, strideC, sT1, sT1t, stream)))
         return rc;
     // ---- J: quarter 2 writes the class pairs m >= n straight into Xf[p,q,mn] (both orders of the AO pair)
-    if (g_class_unfused_pack) {
+    if (!run(1)) {
+    } else if (g_class_unfused_pack) {
         const dim3 pgrid((unsigned)ld2, (unsigned)batch);
         Q(T1, sT1, X, sX, ldp * nIp, nIp);                               // X[pq,m,n]
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 1, sX, sXp);
@@ -354,15 +360,17 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
                                          sXp, stream))) {
         return rc;
     }
-    Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X'[q,mn,a]
-    if (g_class_unfused_pack) {
+    if (run(2)) Q(P0, sXp, P1, sXp, ld * npIp, ld);                      // X'[q,mn,a]
+    if (!run(3)) {
+    } else if (g_class_unfused_pack) {
         Q(P1, sXp, Jp, sXp, npIp * ld, ld);                              // Jp[mn,a,b]
     } else if ((rc = dgemm_tn_class_expand(P1, C, Jout, 0, nIp, ld, npIp, ld, npIp * ld, ld, ld, batch, sXp,
                                            strideC, sCls, stream))) {    // J[m,n,a,b] = J[n,m,a,b]
         return rc;
     }
     // ---- K: X2[p,s,m,n] = sum_q T1t[q,(p s m)] C[q,n], kept as X2p[p,s,mn]
-    if (g_class_unfused_pack) {
+    if (!run(4)) {
+    } else if (g_class_unfused_pack) {
         const dim3 pgrid((unsigned)ld2, (unsigned)batch);
         Q(T1t, sT1t, X, sX, ld2 * nIp, nIp);
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 0, sX, sXp);
@@ -371,7 +379,8 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
                                          sXp, stream))) {
         return rc;
     }
-    Q(P0, sXp, P1, sXp, ld * npIp, ld);                                  // X3[s,mn,a]
+    if (run(5)) Q(P0, sXp, P1, sXp, ld * npIp, ld);                      // X3[s,mn,a]
+    if (!run(6)) return OO_OK;
     if (g_class_unfused_pack) {
         Q(P1, sXp, Kp, sXp, npIp * ld, ld);                              // Kp[mn,a,b]
     } else {

@@ -1162,6 +1162,54 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
                            F, pl, pr, nk, N, ld, batch, H, w + L.off_runs, flags, stream);
 }
 
+namespace {
+// P[b][i(i+1)/2 + j] = H[b][i][j], j <= i: the lower triangle of the symmetric Hessian, rows back to back
+// (np.tril_indices(n) order).  Four rows per CTA; reads and writes are contiguous runs of i+1 doubles.
+__global__ void __launch_bounds__(256) pack_lower_kernel(const double *__restrict__ H, int n, int64_t npk,
+                                                         double *__restrict__ P) {
+    const double *Hb = H + (int64_t)blockIdx.y * n * n;
+    double *Pb = P + (int64_t)blockIdx.y * npk;
+    const int i0 = blockIdx.x * 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + r;
+        if (i >= n) return;
+        const double *src = Hb + (int64_t)i * n;
+        double *dst = Pb + (int64_t)i * (i + 1) / 2;
+        for (int j = threadIdx.x; j <= i; j += 256) dst[j] = src[j];
+    }
+}
+}  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) copy_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+}  // namespace
+
+// dst[i] = src[i] by a kernel: src may be PINNED HOST memory (read over PCIe through the unified address space).
+// Small inputs (kappa, RDMs) enter the device this way so that no DMA-engine copy of the compute stream can queue
+// behind the multi-millisecond device->host copy of a Hessian that a copy stream has in flight.
+int copy_f64(const double *src, double *dst, int64_t n, cudaStream_t stream) {
+    OO_REQUIRE(src && dst && n >= 0);
+    if (n == 0) return OO_OK;
+    int64_t blocks = ceil_div(n, 256);
+    if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+    copy_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, n);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+int pack_lower(const double *H, int n, int batch, double *P, cudaStream_t stream) {
+    OO_REQUIRE(H && P && n > 0 && batch > 0);
+    if (batch > 65535) return OO_ERR_UNSUPPORTED;
+    pack_lower_kernel<<<dim3((unsigned)ceil_div(n, 4), (unsigned)batch), 256, 0, stream>>>(
+        H, n, (int64_t)n * (n + 1) / 2, P);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
 int full_rdms(const double *d1, const double *d2, int no, int na, int N, double *one_full,
               double *two_full, cudaStream_t stream) {
     OO_REQUIRE(d1 && d2 && one_full && two_full);
@@ -1213,6 +1261,14 @@ extern "C" int oo_hessian_f64(const double *h_mo, const double *g_mo, const doub
                               size_t ws_bytes, unsigned flags, void *stream) {
     return oo::hessian(h_mo, g_mo, F, gamma, Gamma, no, na, N, ld, pair_l, pair_r, nk, H, ws, ws_bytes, flags,
                        (cudaStream_t)stream);
+}
+
+extern "C" int oo_copy_f64(const double *src, double *dst, int64_t n, void *stream) {
+    return oo::copy_f64(src, dst, n, (cudaStream_t)stream);
+}
+
+extern "C" int oo_pack_lower_f64(const double *H, int n, int batch, double *packed, void *stream) {
+    return oo::pack_lower(H, n, batch, packed, (cudaStream_t)stream);
 }
 
 extern "C" int oo_full_rdms_f64(const double *gamma, const double *Gamma, int no, int na, int N,

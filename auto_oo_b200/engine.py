@@ -174,6 +174,7 @@ class HotPathEngine:
         self.nk = len(pl)
         self.pair_l = torch.as_tensor(pl, device=self.device)
         self.pair_r = torch.as_tensor(pr, device=self.device)
+        self._pair_host = (torch.as_tensor(pl).long(), torch.as_tensor(pr).long())   # for host-side decisions
         with torch.cuda.device(self.device):
             self.h_ao = None if int1e_ao is None else self.to_padded(int1e_ao, 2, batch=G)
             self.X = None if oao_coeff is None else self.to_padded(oao_coeff, 2, batch=G)
@@ -274,6 +275,43 @@ class HotPathEngine:
         buf.copy_(dev_tensor, non_blocking=True)
         return buf
 
+    def pack_lower(self, H, out=None):
+        """Lower triangles (np.tril_indices order) of symmetric device matrices ``H (B, n, n)`` -> ``(B, n(n+1)/2)``."""
+        H = H if H.dim() == 3 else H[None]
+        B, n = H.shape[0], H.shape[1]
+        P = out if out is not None else torch.empty(B, n * (n + 1) // 2, dtype=F64, device=self.device)
+        if n > 0 and B > 0:
+            self._check(self.lib.oo_pack_lower_f64(_p(H), n, B, _p(P), self.stream), "pack_lower")
+        return P
+
+    def upload_pinned(self, pinned):
+        """Device copy of a PINNED host tensor made by a kernel that reads the host memory directly (no DMA-engine
+        copy on the compute stream -- see ``oo_copy_f64``)."""
+        out = torch.empty(tuple(pinned.shape), dtype=F64, device=self.device)
+        self._check(self.lib.oo_copy_f64(pinned.data_ptr(), _p(out), pinned.numel(), self.stream), "copy")
+        return out
+
+    def resident_oao(self, oao_mo_coeff):
+        """Padded device copy of ``OO_energy.oao_mo_coeff``, re-uploaded only when the tensor object or its version
+        counter changes (callers re-assign it or write into it: oo_pqc.py:191, Berry cell 22)."""
+        ent = self._ws.get("oao_dev")
+        if ent is None or ent[0] is not oao_mo_coeff or ent[1] != oao_mo_coeff._version:
+            ent = (oao_mo_coeff, oao_mo_coeff._version, self.to_padded(oao_mo_coeff, 2))
+            self._ws["oao_dev"] = ent
+        return ent[2]
+
+    def result_slot(self, slot, shapes):
+        """One of the two alternating sets of host-result staging buffers of ``energy_gradient_hessian``:
+        pinned tensors of the given shapes (dict name -> shape) plus a completion event, rebuilt when a shape
+        changes.  Two sets let the device->host copies of one call overlap the computation of the next."""
+        ent = self._ws.get(("slot", slot))
+        if ent is None or ent["shapes"] != shapes:
+            self._ws[("slot", slot)] = None
+            ent = {"shapes": dict(shapes), "done": None,
+                   "host": {k: torch.empty(tuple(v), dtype=F64, pin_memory=True) for k, v in shapes.items()}}
+            self._ws[("slot", slot)] = ent
+        return ent
+
     def workspace_tensor(self, key, shape):
         """Reused float64 device buffer of the given shape."""
         buf = self._ws.get(("t", key))
@@ -295,7 +333,7 @@ class HotPathEngine:
             return 0
         if k.device.type == "cpu":
             colsum = torch.zeros(k.shape[0], self.N, dtype=F64)
-            pl, pr = self.pair_l.cpu().long(), self.pair_r.cpu().long()
+            pl, pr = self._pair_host
         else:
             colsum = torch.zeros(k.shape[0], self.N, dtype=F64, device=k.device)
             pl, pr = self.pair_l.long(), self.pair_r.long()
@@ -666,7 +704,7 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ whole evaluations
     def evaluate(self, oao_mo_coeff, d1, d2, kappa=None, want_hessian=True, squarings=None,
-                 H_out=None, transform_events=None, path="class", on_result=None):
+                 H_out=None, stage_events=None, path="class", on_result=None):
         """E (B,), packed gradient (B, nk) and Hessian (B, nk, nk) at C' = X C_oao expm(-K(kappa_b)).
 
         ``oao_mo_coeff``: padded (ld, ld) or (B, ld, ld) device tensor; ``kappa``: (B, nk) or None.
@@ -675,15 +713,25 @@ class HotPathEngine:
         J/K integral classes E, G and H read (partial transform); ``path="full"`` the complete
         four-index transform.  Evaluations are processed
         one at a time through the N^4 stages (one g' buffer + one workspace in HBM).
-        ``transform_events``: optional list that receives a (start, end) CUDA-event pair around
-        every 4-index transform (four TN-DGEMM launches) for the roofline figure.
+        ``stage_events``: optional dict that receives, per stage name ("rotation", "transform", "energy",
+        "fock_gradient", "hessian"), a list of (start, end) CUDA-event pairs recorded on the launching stream
+        around the kernels of that stage (bench.py's roofline figures).
         ``on_result(b)`` is called after the kernels of evaluation ``b`` are enqueued (used to start
         the device->host copy of its Hessian while evaluation ``b+1`` computes)."""
+        def staged(name, fn):
+            if stage_events is None:
+                return fn()
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            out = fn()
+            ev[1].record()
+            stage_events.setdefault(name, []).append(ev)
+            return out
+
         Coao = oao_mo_coeff if oao_mo_coeff.dim() == 3 else oao_mo_coeff[None]
         if kappa is not None:
             kappa = self.dev(kappa).reshape(-1, self.nk)
-            U = self.rotation(kappa, squarings)
-            C = self.mo_coeff(Coao, U)
+            C = staged("rotation", lambda: self.mo_coeff(Coao, self.rotation(kappa, squarings)))
         else:
             C = self.mo_coeff(Coao)
         B = C.shape[0]
@@ -700,21 +748,19 @@ class HotPathEngine:
             cbuf = self._recycle("class")
             for lo in range(0, B, chunk):
                 hi = min(B, lo + chunk)
-                if transform_events is not None:
-                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                    ev[0].record()
-                cbuf = self.class_integrals(C[lo:hi], out=cbuf, geo_lo=lo)
-                if transform_events is not None:
-                    ev[1].record()
-                    transform_events.append(ev)
+                cbuf = staged("transform", lambda: self.class_integrals(C[lo:hi], out=cbuf, geo_lo=lo))
                 d1b = d1[lo:hi] if d1.dim() == 3 else d1
                 d2b = d2[lo:hi] if d2.dim() == 5 else d2
-                c0, c1, c2 = self.class_active_hamiltonian(cbuf, geo_lo=lo)
-                E[lo:hi] = self.energy(c0, c1, c2, d1b, d2b)
-                FI, FA, F, _, gv = self.class_fock_gradient(cbuf, d1b, d2b, want_matrix=False)
+
+                def energy():
+                    c0, c1, c2 = self.class_active_hamiltonian(cbuf, geo_lo=lo)
+                    E[lo:hi] = self.energy(c0, c1, c2, d1b, d2b)
+                staged("energy", energy)
+                FI, FA, F, _, gv = staged("fock_gradient",
+                                          lambda: self.class_fock_gradient(cbuf, d1b, d2b, want_matrix=False))
                 G[lo:hi] = gv
                 if want_hessian:
-                    self.class_hessian(cbuf, F, d1b, d2b, out=H[lo:hi])
+                    staged("hessian", lambda: self.class_hessian(cbuf, F, d1b, d2b, out=H[lo:hi]))
                 if on_result is not None:
                     for b in range(lo, hi):
                         on_result(b)
@@ -723,13 +769,7 @@ class HotPathEngine:
         hs = self.int1e_transform(C)
         gbuf = self._recycle("full")
         for b in range(B):
-            if transform_events is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            gbuf = self.int2e_transform(C[b:b + 1], out=gbuf)
-            if transform_events is not None:
-                ev[1].record()
-                transform_events.append(ev)
+            gbuf = staged("transform", lambda: self.int2e_transform(C[b:b + 1], out=gbuf))
             h1 = hs[b:b + 1]
             d1b = d1[b] if d1.dim() == 3 else d1
             d2b = d2[b] if d2.dim() == 5 else d2

@@ -31,7 +31,8 @@ from .engine import HotPathEngine, F64
 from .utils.newton_raphson import NewtonStep
 
 __all__ = [
-    "OO_energy", "OO_energy_geometries", "OrbitalHessian", "general_4index_transform", "uniform_4index_transform",
+    "OO_energy", "OO_energy_geometries", "OrbitalHessian", "PendingEvaluation", "unpack_hessian",
+    "general_4index_transform", "uniform_4index_transform",
     "int1e_transform", "int2e_transform", "mo_ao_to_mo_oao", "vector_to_skew_symmetric",
     "skew_symmetric_to_vector", "non_redundant_indices",
 ]
@@ -173,6 +174,42 @@ class _GradientFn(torch.autograd.Function):
         eng = ctx.eng
         g1, g2 = ctx.ints.fock_gradient_vjp(ctx.FI, eng.to_padded(gbar, 2))
         return g1.to(ctx.dev1), g2.to(ctx.dev2), None, None
+
+
+class PendingEvaluation:
+    """Results of :meth:`OO_energy.energy_gradient_hessian` that may still be on their way to the host."""
+
+    def __init__(self, results, event, copy):
+        self._results, self._event, self._copy = results, event, copy
+
+    def wait(self):
+        """``(E, gradient, Hessian)`` once every device->host copy of the call has completed."""
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        if self._copy:
+            self._results = tuple(None if t is None else t.clone() for t in self._results)
+            self._copy = False
+        return self._results
+
+
+def unpack_hessian(packed):
+    """``(..., n (n+1)/2)`` lower triangle in ``np.tril_indices`` order (``hessian_format="packed"``) ->
+    symmetric ``(..., n, n)``, in the array type of the input."""
+    m = packed.shape[-1]
+    n = (int(np.sqrt(8 * m + 1)) - 1) // 2
+    assert n * (n + 1) // 2 == m
+    rows, cols = np.tril_indices(n)
+    if torch.is_tensor(packed):
+        r = torch.as_tensor(rows, device=packed.device)
+        c = torch.as_tensor(cols, device=packed.device)
+        out = packed.new_empty(packed.shape[:-1] + (n, n))
+    else:
+        r, c = rows, cols
+        out = np.empty(packed.shape[:-1] + (n, n), dtype=packed.dtype)
+    out[..., r, c] = packed
+    out[..., c, r] = packed
+    return out
 
 
 class OrbitalHessian:
@@ -415,66 +452,132 @@ class OO_energy:
         return part[self.params_idx, :][:, self.params_idx]
 
     # ------------------------------------------------------------------ batched evaluation
-    def energy_gradient_hessian(self, kappa, one_rdm, two_rdm, want_hessian=True):
+    def energy_gradient_hessian(self, kappa, one_rdm, two_rdm, want_hessian=True, hessian_format="dense",
+                                pinned_results=False, wait=True):
         """``E``, packed gradient and Hessian matrix at ``C expm(-K(kappa_b))`` for a batch of
         rotations ``kappa (B, n_kappa)`` -- the three reference calls ``energy_from_kappa``,
         ``kappa_matrix_to_vector(analytic_gradient(mo_coeff=C'))`` and
         ``full_hessian_to_matrix(analytic_hessian(mo_coeff=C'))`` fused so that one four-index
-        transform serves all three.  Host tensors in (staged through pinned memory), host tensors
-        out: ``(B,)``, ``(B, n_kappa)``, ``(B, n_kappa, n_kappa)``; CUDA tensors in -> CUDA out.
-        The host results are views of reused pinned staging buffers (a 765 MB Hessian per evaluation at
-        N=256 is not copied a second time): they stay valid until the next call of this method -- clone what
-        must outlive it."""
+        transform serves all three.  CUDA tensors in -> fresh CUDA tensors out.  Host tensors in (staged through
+        pinned memory) -> host tensors out: ``(B,)``, ``(B, n_kappa)`` and the Hessians, which travel to the host
+        on a copy stream while the next evaluation computes.
+
+        ``hessian_format``: ``"dense"`` -> ``(B, n_kappa, n_kappa)``; ``"packed"`` -> ``(B, n_kappa (n_kappa+1)/2)``,
+        the lower triangle of the symmetric matrix in ``np.tril_indices`` order (:func:`unpack_hessian` restores
+        the matrix) -- half the device->host bytes, which is what bounds the end-to-end rate at N = 256.
+        ``pinned_results=False`` (default): the host results are fresh tensors owned by the caller, as in the
+        reference.  ``True``: they are views of the engine's pinned staging buffers -- no second copy of a 765 MB
+        Hessian -- of which there are two sets used in turn: results stay valid until the call after next.
+        ``wait=False`` returns a :class:`PendingEvaluation` at once; its ``wait()`` gives the results.  With at most
+        two calls in flight the copies of one call overlap the computation of the next."""
+        assert hessian_format in ("dense", "packed")
         eng = self.engine
         kappa = _as_tensor(kappa).detach().reshape(-1, self.n_kappa)
         one, two = _as_tensor(one_rdm).detach(), _as_tensor(two_rdm).detach()
         on_host = kappa.device.type == "cpu"
-        Coao = eng.to_padded(self.oao_mo_coeff, 2)
-        if on_host and kappa.shape[0] == 1 and not bool(kappa.any()):
+        packed = hessian_format == "packed" and want_hessian
+        Coao = eng.resident_oao(self.oao_mo_coeff)
+        B, nk = kappa.shape[0], self.n_kappa
+        if on_host and B == 1 and not bool(kappa.any()):
             kappa = None                                   # expm(0) = 1: the rotation stage is skipped altogether
-        if self.cuda_graphs:
-            # launch-bound sizes: one graph replay; host inputs go pinned -> static buffers, results come back
-            # from the graph's output buffers through pinned memory
-            if on_host:
-                one, two = eng.stage_pinned("rdm1", one.to(F64)), eng.stage_pinned("rdm2", two.to(F64))
-                kappa = None if kappa is None else eng.stage_pinned("kappa", kappa.to(F64))
-            E, G, H = eng.evaluate_graphed(Coao, one, two, kappa=kappa, want_hessian=want_hessian,
-                                           path=self.integral_path, clone=not on_host)
-            if not on_host:
-                return E, G, H
-            out = (eng.stage_out("E", E), eng.stage_out("G", G), eng.stage_out("H", H) if want_hessian else None)
-            torch.cuda.current_stream(eng.device).synchronize()
-            return out
-        if on_host:
-            kd = None if kappa is None else eng.stage_in("kappa", kappa)
-            d1 = eng.stage_in("rdm1", one)
-            d2 = eng.stage_in("rdm2", two)
-        else:
-            kd, d1, d2 = kappa, one, two
         if not on_host:
-            return eng.evaluate(Coao, d1, d2, kappa=kd, want_hessian=want_hessian, path=self.integral_path)
-        # host results: the Hessian of evaluation b travels to pinned host memory on a copy stream
-        # while evaluation b+1 computes
-        B, nk = 1 if kd is None else kd.shape[0], self.n_kappa
-        H_dev = eng.workspace_tensor("H_batch", (B, nk, nk)) if want_hessian else None
-        H_host = eng.pinned("H", (B, nk, nk)) if want_hessian else None
-        main = torch.cuda.current_stream(eng.device)
-        side = eng.copy_stream()
+            run = eng.evaluate_graphed if self.cuda_graphs else eng.evaluate
+            E, G, H = run(Coao, one, two, kappa=kappa, want_hessian=want_hessian, path=self.integral_path)
+            out = (E, G, eng.pack_lower(H) if packed else H)
+            return out if wait else PendingEvaluation(out, None, False)
 
-        def ship(b):
+        # ---- host face: alternate between two sets of pinned staging buffers
+        self._result_slot = slot = (getattr(self, "_result_slot", -1) + 1) % 2
+        shapes = {"E": (B,), "G": (B, nk), "kappa": (B, nk), "rdm1": tuple(one.shape), "rdm2": tuple(two.shape)}
+        if want_hessian:
+            shapes["H"] = (B, nk * (nk + 1) // 2) if packed else (B, nk, nk)
+        ent = eng.result_slot(slot, shapes)
+        if ent["done"] is not None:
+            ent["done"].synchronize()                      # the call before last has landed (normally long ago)
+        host = ent["host"]
+        main = torch.cuda.current_stream(eng.device)
+        # inputs: pinned staging, read by a kernel (a DMA copy on the compute stream would queue behind the
+        # device->host copy of the previous call's last Hessian)
+        host["rdm1"].copy_(one)
+        host["rdm2"].copy_(two)
+        d1, d2 = eng.upload_pinned(host["rdm1"]), eng.upload_pinned(host["rdm2"])
+        kd = squarings = None
+        if kappa is not None:
+            host["kappa"].copy_(kappa)
+            kd = eng.upload_pinned(host["kappa"])
+            if self.nao > eng.lib.oo_expm_device_squarings_max_n():
+                # decided from the HOST copy: the device variant ends in a scalar device->host copy, which would
+                # wait behind the previous call's Hessian on the copy engine
+                squarings = eng.squarings_for(kappa)
+        done = torch.cuda.Event()
+        if self.cuda_graphs:
+            # launch-bound sizes: one graph replay, results straight from the graph's output buffers
+            E, G, H = eng.evaluate_graphed(Coao, d1, d2, kappa=kd, want_hessian=want_hessian,
+                                           path=self.integral_path, clone=False)
+            host["E"].copy_(E, non_blocking=True)
+            host["G"].copy_(G, non_blocking=True)
             if want_hessian:
+                host["H"].copy_(eng.pack_lower(H) if packed else H, non_blocking=True)
+            done.record(main)
+        else:
+            # the Hessian of evaluation b goes to pinned host memory on a copy stream while evaluation b+1 computes
+            side = eng.copy_stream()
+            H_dev = eng.workspace_tensor("H_batch", (B, nk, nk)) if want_hessian else None
+            Hp_dev = eng.workspace_tensor(("H_packed", slot), (B, nk * (nk + 1) // 2)) if packed else None
+            if want_hessian and not packed:
+                main.wait_stream(side)                     # dense copies of the previous call read H_dev itself
+
+            def ship(b):
+                if not want_hessian:
+                    return
+                src = H_dev[b]
+                if packed:
+                    eng.pack_lower(H_dev[b:b + 1], out=Hp_dev[b:b + 1])
+                    src = Hp_dev[b]
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
                 with torch.cuda.stream(side):
-                    H_host[b].copy_(H_dev[b], non_blocking=True)
+                    host["H"][b].copy_(src, non_blocking=True)
 
-        E, G, _ = eng.evaluate(Coao, d1, d2, kappa=kd, want_hessian=want_hessian, path=self.integral_path,
-                               H_out=H_dev, on_result=ship)
-        out = (eng.stage_out("E", E), eng.stage_out("G", G), H_host)
-        main.synchronize()
-        side.synchronize()
-        return out
+            E, G, _ = eng.evaluate(Coao, d1, d2, kappa=kd, want_hessian=want_hessian, squarings=squarings,
+                                   path=self.integral_path, H_out=H_dev, on_result=ship)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):                  # every device->host copy of the call is on the copy stream
+                host["E"].copy_(E, non_blocking=True)
+                host["G"].copy_(G, non_blocking=True)
+            E.record_stream(side)
+            G.record_stream(side)
+            done.record(side)
+        ent["done"] = done
+        pending = PendingEvaluation((host["E"], host["G"], host["H"] if want_hessian else None), done,
+                                    copy=not pinned_results)
+        return pending.wait() if wait else pending
+
+    def energy_gradient_newton_direction(self, kappa, one_rdm, two_rdm, **newton_kwargs):
+        """Device-resident Newton mode of :meth:`energy_gradient_hessian`: for every rotation of the batch the
+        Hessian is built AND consumed in HBM -- ``NewtonStep.newton_step`` (one ``eigh`` on the device, the
+        augmented-Hessian shift of ``utils/newton_raphson.py:78-129``) -- and only ``E (B,)``, the gradient
+        ``(B, n_kappa)``, the Newton direction ``(B, n_kappa)`` and the lowest Hessian eigenvalue ``(B,)`` come
+        back (on the device of ``kappa``).  ``newton_kwargs`` go to :class:`NewtonStep` (``mu, rho, lambda_min, aug``)."""
+        eng = self.engine
+        kappa = _as_tensor(kappa).detach().reshape(-1, self.n_kappa)
+        dev_in = kappa.device
+        opt = NewtonStep(verbose=0, **newton_kwargs)
+        Coao = eng.to_padded(self.oao_mo_coeff, 2)
+        d1, d2, kd = eng.dev(_as_tensor(one_rdm).detach()), eng.dev(_as_tensor(two_rdm).detach()), eng.dev(kappa)
+        B = kd.shape[0]
+        dk = torch.empty(B, self.n_kappa, dtype=F64, device=eng.device)
+        lam = torch.empty(B, dtype=F64)
+        Es, Gs = [], []
+        H = eng.workspace_tensor("H_newton", (1, self.n_kappa, self.n_kappa))
+        for b in range(B):                                   # one Hessian resident at a time
+            E, G, _ = eng.evaluate(Coao, d1[b:b + 1] if d1.dim() == 3 else d1, d2[b:b + 1] if d2.dim() == 5 else d2,
+                                   kappa=kd[b:b + 1], H_out=H, path=self.integral_path)
+            dk[b], lam[b] = opt.newton_step(G[0], H[0])
+            Es.append(E)
+            Gs.append(G)
+        return (torch.cat(Es).to(dev_in), torch.cat(Gs).to(dev_in), dk.to(dev_in), lam.to(dev_in))
 
     # ------------------------------------------------------------------ driver
     def orbital_optimization(self, one_rdm, two_rdm, conv_tol=1e-8, max_iterations=100, verbose=0,
@@ -497,7 +600,7 @@ class OO_energy:
             # gradient and Hessian at the current orbitals from ONE fused evaluation (one transform, one graph
             # replay for small bases) instead of the reference's analytic_gradient + analytic_hessian calls
             _, G, H = self.energy_gradient_hessian(kappa[None], one_rdm, two_rdm)
-            gradient, hessian = G[0].clone(), H[0].clone()
+            gradient, hessian = G[0], H[0]
             kappa, lowest_eigenvalue = opt.damped_newton_step(objective_fn, (kappa,), gradient, hessian)
             self.oao_mo_coeff = self.get_transformed_mo(self.oao_mo_coeff, kappa)
             energy = self.energy_from_mo_coeff(self.mo_coeff, one_rdm, two_rdm).item()
@@ -545,11 +648,11 @@ class OO_energy_geometries:
         self.oao_mo_coeff = C if C.dim() == 3 else C[None].repeat(G, 1, 1)
         assert self.oao_mo_coeff.shape[0] == G
 
-    def energy_gradient_hessian(self, kappa, one_rdm, two_rdm, want_hessian=True):
+    def energy_gradient_hessian(self, kappa, one_rdm, two_rdm, want_hessian=True, pinned_results=False):
         """``(E (G,), gradient (G, n_kappa), Hessian (G, n_kappa, n_kappa))`` at
-        ``C_g expm(-K(kappa_g))`` for every geometry ``g``; results on the device of ``kappa`` (host results
-        are views of reused pinned staging buffers, valid until the next call).  The whole pass is one
-        CUDA-graph launch when ``cuda_graphs`` is on."""
+        ``C_g expm(-K(kappa_g))`` for every geometry ``g``; results on the device of ``kappa``.  Host results are
+        fresh tensors; with ``pinned_results=True`` they are views of the reused pinned staging buffers instead
+        (valid until the next call).  The whole pass is one CUDA-graph launch when ``cuda_graphs`` is on."""
         eng = self.engine
         kappa = _as_tensor(kappa).detach().reshape(self.n_geometries, self.n_kappa)
         one, two = _as_tensor(one_rdm).detach(), _as_tensor(two_rdm).detach()
@@ -571,7 +674,7 @@ class OO_energy_geometries:
             return E, G, H
         out = (eng.stage_out("E", E), eng.stage_out("G", G), eng.stage_out("H", H) if want_hessian else None)
         torch.cuda.current_stream(eng.device).synchronize()
-        return out
+        return out if pinned_results else tuple(None if t is None else t.clone() for t in out)
 
     def rotate(self, kappa):
         """``C_g <- C_g expm(-K(kappa_g))`` for every geometry (the re-basing step of the loop)."""

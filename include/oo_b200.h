@@ -78,6 +78,10 @@ enum {
     OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 32   /* Hessian assembly without the bulk-async streamed kernel for the rows
                                                   outside occ+act                                                     */
 };
+/* oo_class_transform_sym_f64 only: run just the selected GEMM stages (k = 0: quarter 1 over packed pairs; 1, 2, 3:
+ * quarters 2-4 of the Coulomb class; 4, 5, 6: of the exchange class) on the intermediates a complete call left in
+ * the workspace.  Lets a caller time one kernel with events on both sides (bench.py); no stage bit = all stages. */
+#define OO_FLAG_CLASS_STAGE(k) (1u << (16 + (k)))
 int         oo_device_info(int *sm_count, int *cc_major, int *cc_minor);
 size_t      oo_workspace_bytes(int which, int N, int ld, int nI, int batch);
 
@@ -258,6 +262,16 @@ int oo_class_hessian_f64(const double *cls, const double *F, const double *gamma
                          int nIp, int batch, const int32_t *pair_l, const int32_t *pair_r, int nk,
                          double *H, void *ws, size_t ws_bytes, unsigned flags, void *stream);
                          /* batched: cls[b], F[b] (ld^2), H[b] (nk^2) contiguous per evaluation */
+
+/* Lower triangle (diagonal included) of `batch` symmetric n x n matrices, rows back to back in np.tril_indices(n)
+ * order: packed[b][i(i+1)/2 + j] = H[b][i][j], j <= i.  The orbital Hessian of full_hessian_to_matrix
+ * (oo_energy.py:395-402) is symmetric; shipping the triangle halves the device->host bytes per evaluation.   */
+int oo_pack_lower_f64(const double *H, int n, int batch, double *packed, void *stream);
+
+/* dst[i] = src[i], i < n, by a kernel.  `src` may be pinned host memory (cudaHostAlloc; read over PCIe through the
+ * unified address space): the small per-call inputs of an evaluation (kappa, gamma, Gamma) reach the device
+ * without a DMA-engine copy, which would otherwise queue behind the device->host copy of the previous Hessian. */
+int oo_copy_f64(const double *src, double *dst, int64_t n, void *stream);
 
 /* ---- RDMs from a state vector (the producer of the hot path's gamma, Gamma) -----
  * replaces Parameterized_circuit.get_rdms_from_state (pqc.py:192-218) with the operators of

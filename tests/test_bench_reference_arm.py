@@ -1,4 +1,4 @@
-"""CPU: the reference arm of bench.py (``--impl reference``: the reference's algorithm on the host cores) prints one
+"""CPU: the reference arm of bench.py (``--impl reference``: the verbatim reference on the host cores) prints one
 JSON line with the keys the driver reads; under torchrun only rank 0 works and prints."""
 import json
 import os
@@ -24,7 +24,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "oo_energy_gradient_hessian_evals_per_sec"
     assert d["unit"] == "evals/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["config"]["workload"] == "synthetic_n256_cas1212"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and "verbatim reference" in cb["sample"]
+    assert cb["extrapolated"] is True and cb["sample_nao"] == 20 and cb["scale"] > 1 and cb["steps_measured"] == 1
+    assert abs(cb["value"] - d["value"]) <= 1e-12 * d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -309,3 +309,56 @@ def test_cache_follows_orbital_updates_without_value_comparisons_on_the_device()
     oo.oao_mo_coeff.copy_(torch.as_tensor(c.oao_mo_coeff))                # in-place write: version counter moves
     G0 = oo.kappa_matrix_to_vector(oo.analytic_gradient(c.one_rdm, c.two_rdm))
     assert np.abs(G0.numpy() - c.ref["G0"]).max() < TOL_GH
+
+
+@pytest.mark.parametrize("name,graphs", [("n13_cas22", True), ("n13_cas22", False), ("n28_cas66", False)])
+def test_packed_hessian_pinned_results_and_pending_calls(name, graphs):
+    """hessian_format="packed" is the lower triangle of the dense result; default results are fresh tensors,
+    pinned_results=True are staging views that survive one further call; wait=False pipelines two calls."""
+    from auto_oo_b200 import unpack_hessian, PendingEvaluation
+    c = load_case(name)
+    oo = make_oo(c, cuda_graphs=graphs)
+    nk = oo.n_kappa
+    kaps = [torch.stack([c.kappa * s, -c.kappa * s]) for s in (1.0, 0.5, 0.25, 0.125)]
+    dense = [oo.energy_gradient_hessian(k, c.one_rdm, c.two_rdm) for k in kaps]
+    assert np.abs(dense[0][2][0].numpy() - c.ref["H"]).max() < TOL_GH and abs(dense[0][0][0].item() - float(c.ref["E"])) < TOL_E
+    assert not dense[0][2].is_pinned() and dense[0][2].data_ptr() != dense[1][2].data_ptr()
+    rows, cols = np.tril_indices(nk)
+    for k, (E, G, H) in zip(kaps, dense):
+        Ep, Gp, Hp = oo.energy_gradient_hessian(k, c.one_rdm, c.two_rdm, hessian_format="packed")
+        assert Hp.shape == (2, nk * (nk + 1) // 2)
+        assert torch.equal(Ep, E) and torch.equal(Gp, G) and torch.equal(Hp, H[:, rows, cols])
+        assert (unpack_hessian(Hp) - H).abs().max().item() < 1e-9          # H is symmetric to round-off
+        assert np.array_equal(unpack_hessian(Hp.numpy()), unpack_hessian(Hp).numpy())
+    # device tensors in -> device tensors out, same numbers
+    Ed, Gd, Hd = oo.energy_gradient_hessian(kaps[0].cuda(), c.one_rdm.cuda(), c.two_rdm.cuda(), hessian_format="packed")
+    assert Hd.is_cuda and torch.equal(Hd.cpu(), dense[0][2][:, rows, cols])
+    # pinned staging views: a result survives exactly one further call
+    a = oo.energy_gradient_hessian(kaps[0], c.one_rdm, c.two_rdm, pinned_results=True)
+    assert a[2].is_pinned()
+    b = oo.energy_gradient_hessian(kaps[1], c.one_rdm, c.two_rdm, pinned_results=True)
+    assert torch.equal(a[2], dense[0][2]) and torch.equal(b[2], dense[1][2]) and a[2].data_ptr() != b[2].data_ptr()
+    # two calls in flight
+    p0 = oo.energy_gradient_hessian(kaps[2], c.one_rdm, c.two_rdm, hessian_format="packed", pinned_results=True, wait=False)
+    p1 = oo.energy_gradient_hessian(kaps[3], c.one_rdm, c.two_rdm, hessian_format="packed", pinned_results=True, wait=False)
+    assert isinstance(p0, PendingEvaluation)
+    r0, r1 = p0.wait(), p1.wait()
+    assert torch.equal(r0[0], dense[2][0]) and torch.equal(r0[2], dense[2][2][:, rows, cols])
+    assert torch.equal(r1[1], dense[3][1]) and torch.equal(r1[2], dense[3][2][:, rows, cols])
+    E0, G0, H0 = oo.energy_gradient_hessian(torch.zeros(1, nk, dtype=F64), c.one_rdm, c.two_rdm, want_hessian=False)
+    assert H0 is None and np.abs(G0[0].numpy() - c.ref["G0"]).max() < TOL_GH
+
+
+def test_newton_direction_mode_equals_host_newton_step():
+    """E, G, the Newton direction and the lowest eigenvalue with the Hessian kept on the device == the reference's
+    ``NewtonStep.newton_step`` (newton_raphson.py:78-129) applied to the host gradient and Hessian."""
+    from auto_oo_b200 import NewtonStep
+    c = load_case("n28_cas66")
+    oo = make_oo(c)
+    kap = torch.stack([c.kappa, torch.zeros_like(c.kappa)])
+    E, G, dk, lam = oo.energy_gradient_newton_direction(kap, c.one_rdm, c.two_rdm)
+    Eh, Gh, Hh = oo.energy_gradient_hessian(kap, c.one_rdm, c.two_rdm)
+    assert E.device.type == "cpu" and torch.equal(E, Eh) and torch.equal(G, Gh)
+    for b in range(2):
+        dp, l0 = NewtonStep(verbose=0).newton_step(Gh[b], Hh[b])
+        assert abs(l0 - lam[b].item()) < 1e-8 and (dp - dk[b]).abs().max().item() < 1e-7 * max(1.0, dp.abs().max().item())
