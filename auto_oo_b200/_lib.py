@@ -24,6 +24,7 @@ OO_WS_CLASS_TRANSFORM, OO_WS_CLASS_BUFFER, OO_WS_CLASS_HESSIAN, OO_WS_CLASS_TRAN
 # per-call variant switches (include/oo_b200.h)
 OO_FLAG_HESSIAN_DENSE, OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT, OO_FLAG_HESSIAN_ASSEMBLE_TILED = 1, 2, 4
 OO_FLAG_CLASS_UNFUSED_PACK, OO_FLAG_HESSIAN_GROUP_UNSTREAMED, OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 8, 16, 32
+OO_FLAG_CLASS_Q2_RECTANGULAR, OO_FLAG_CLASS_ERI_8FOLD = 64, 128
 ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/oo_b200.h one to one
@@ -61,6 +62,7 @@ _SIGNATURES = {
     "oo_eri_symmetry_defect_f64": (_i32, [_ptr, _i32, _ptr, _ptr]),
     "oo_pair_ld": (_i64, [_i32]),
     "oo_pack_eri_pairs_f64": (_i32, [_ptr, _ptr, _i32, _ptr]),
+    "oo_pack_eri_8fold_f64": (_i32, [_ptr, _ptr, _i32, _ptr]),
     "oo_class_transform_sym_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _u32,
                                           _ptr]),
     "oo_class_active_hamiltonian_f64": (_i32, [_ptr, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr, _ptr,

@@ -70,6 +70,25 @@ int encode_tmap_3d_f64(CUtensorMap *map, const void *base, uint64_t dim0, uint64
     return OO_OK;
 }
 
+int encode_tmap_4d_f64(CUtensorMap *map, const void *base, const uint64_t dims_in[4], const uint64_t strides_elems[3],
+                       const uint32_t box_in[4]) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return OO_ERR_NO_DEVICE;
+    cuuint64_t dims[4] = {dims_in[0], dims_in[1], dims_in[2], dims_in[3]};
+    cuuint64_t strides[3] = {strides_elems[0] * sizeof(double), strides_elems[1] * sizeof(double),
+                             strides_elems[2] * sizeof(double)};
+    cuuint32_t box[4] = {box_in[0], box_in[1], box_in[2], box_in[3]};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = (int)r;
+        return OO_ERR_CUDA;
+    }
+    return OO_OK;
+}
+
 // K2b.  Each quarter is  Out[(q r s), i] = sum_p In[p, (q r s)] C[p, i]: the contracted
 // (leading) index leaves at the front and its image arrives at the back, so after four
 // quarters [p,q,r,s] -> [q,r,s,i] -> [r,s,i,j] -> [s,i,j,k] -> [i,j,k,l].

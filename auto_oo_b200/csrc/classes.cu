@@ -38,6 +38,14 @@ int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_ro
                         int64_t nrows2, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
                         int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream);
 
+int dgemm_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2, int dorb, int dP, int64_t N,
+                        int64_t K, int64_t ldb, int64_t ldc, int batch, int64_t strideA8, int64_t strideB,
+                        int64_t strideC, int64_t strideC2, cudaStream_t stream);
+bool dgemm_tn_tri_supported(int nclass);
+int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
+                            int64_t ngroups, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
+                            int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream);
+
 int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int transpose_mirror, int nclass, int dorb,
                           int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int64_t ld_out, int batch,
                           int64_t strideA, int64_t strideB, int64_t strideOut, cudaStream_t stream);
@@ -216,6 +224,26 @@ __global__ void __launch_bounds__(256) pack_pairs_kernel(const double *__restric
     }
 }
 
+// g8[RS][PQ] = g[r, s, p, q] for r >= s, p >= q (both pairs packed: the 8-fold symmetry class representatives);
+// PQ in [npair, ldp) zero.  One CTA per RS row.
+__global__ void __launch_bounds__(256) pack_8fold_kernel(const double *__restrict__ g, double *__restrict__ g8,
+                                                         int ld, int64_t ldp) {
+    int r, s;
+    tri_decode((int)blockIdx.x, r, s);
+    const double *src = g + ((int64_t)r * ld + s) * (int64_t)ld * ld;
+    double *dst = g8 + (int64_t)blockIdx.x * ldp;
+    const int npair = (int)tri_count(ld);
+    for (int pq = threadIdx.x; pq < ldp; pq += blockDim.x) {
+        double v = 0.0;
+        if (pq < npair) {
+            int p, q;
+            tri_decode(pq, p, q);
+            v = src[(int64_t)p * ld + q];
+        }
+        dst[pq] = v;
+    }
+}
+
 // dst[b][row][mn] = src[b][srow][m*nIp + n], m >= n, mn = m(m+1)/2 + n (zero for mn >= npI);
 // srow = row (identity) or, with tri_rows, row = (p,q) of ld x ld and srow = tri(max,min).
 __global__ void __launch_bounds__(128) pack_class_pairs_kernel(const double *__restrict__ src,
@@ -306,6 +334,15 @@ int pack_eri_pairs(const double *g, double *gpk, int ld, cudaStream_t stream) {
     return OO_OK;
 }
 
+int pack_eri_8fold(const double *g, double *g8, int ld, cudaStream_t stream) {
+    OO_REQUIRE(g && g8 && ld > 0 && (ld % 2) == 0);
+    const int64_t rows = tri_count(ld);
+    if (rows > 0x7fffffffll) return OO_ERR_UNSUPPORTED;
+    pack_8fold_kernel<<<(unsigned)rows, 256, 0, stream>>>(g, g8, ld, pair_ld(ld));
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
 size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch) {
     const size_t ld2 = (size_t)ld * ld, ldp = (size_t)pair_ld(ld), npIp = (size_t)pair_ld(nIp);
     const size_t t1 = (size_t)ld * ldp * nIp, t1t = ld2 * ld * nIp;
@@ -342,13 +379,23 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     return rc
     // OO_FLAG_CLASS_STAGE(k): run only the selected GEMM stages (k = 0: quarter 1; 1-3: Coulomb class; 4-6: exchange
     // class) on the intermediates a complete call left in the workspace -- per-kernel timing from the caller's side
+    // quarter 2 on the triangular kernel (dgemm_tri.cu: only the class pairs n <= m are computed) unless the
+    // class count is outside its range or the caller asks for the rectangular GEMM + packing epilogue
+    const bool tri_q2 = dgemm_tn_tri_supported(nIp) && !(flags & OO_FLAG_CLASS_Q2_RECTANGULAR);
     const unsigned stage_mask = (flags >> 16) & 0x7fu;
     auto run = [&](int k) { return stage_mask == 0 || ((stage_mask >> k) & 1u); };
     if (stage_mask && g_class_unfused_pack) return OO_ERR_INVALID_ARG;
     // Q1: rows (s, pq); the epilogue also writes T1t[q,p,s,m] and T1t[p,q,s,m]
-    if (run(0) && (rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp,
-                                             batch, strideG, strideC, sT1, sT1t, stream)))
+    if (!run(0)) {
+    } else if (flags & OO_FLAG_CLASS_ERI_8FOLD) {
+        // gpk is the 8-fold packed tensor g8[RS][PQ]: the quarter-1 producer gathers its k-rows from it
+        if ((rc = dgemm_tn_q1_packed8(gpk, C, T1, T1t, ld, (int)ldp, nIp, ld, ld, nIp, batch, strideG, strideC, sT1,
+                                      sT1t, stream)))
+            return rc;
+    } else if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp,
+                                          batch, strideG, strideC, sT1, sT1t, stream))) {
         return rc;
+    }
     // ---- J: quarter 2 writes the class pairs m >= n straight into Xf[p,q,mn] (both orders of the AO pair)
     if (!run(1)) {
     } else if (g_class_unfused_pack) {
@@ -356,6 +403,10 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         Q(T1, sT1, X, sX, ldp * nIp, nIp);                               // X[pq,m,n]
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 1, sX, sXp);
         OO_LAUNCH_CHECK();
+    } else if (tri_q2) {
+        if ((rc = dgemm_tn_tri_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * nIp, ld, batch, sT1, strideC, sXp,
+                                          stream)))
+            return rc;
     } else if ((rc = dgemm_tn_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * nIp, ld, batch, sT1, strideC,
                                          sXp, stream))) {
         return rc;
@@ -375,6 +426,10 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         Q(T1t, sT1t, X, sX, ld2 * nIp, nIp);
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 0, sX, sXp);
         OO_LAUNCH_CHECK();
+    } else if (tri_q2) {
+        if ((rc = dgemm_tn_tri_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * nIp, ld, batch, sT1t, strideC,
+                                          sXp, stream)))
+            return rc;
     } else if ((rc = dgemm_tn_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * nIp, ld, batch, sT1t, strideC,
                                          sXp, stream))) {
         return rc;
@@ -410,6 +465,10 @@ int oo_eri_symmetry_defect_f64(const double *g_ao, int ld, double *defect3, void
 }
 
 int64_t oo_pair_ld(int ld) { return ld > 0 ? oo::pair_ld(ld) : 0; }
+
+int oo_pack_eri_8fold_f64(const double *g_ao, double *g_packed8, int ld, void *stream) {
+    return oo::pack_eri_8fold(g_ao, g_packed8, ld, (cudaStream_t)stream);
+}
 
 int oo_pack_eri_pairs_f64(const double *g_ao, double *g_packed, int ld, void *stream) {
     return oo::pack_eri_pairs(g_ao, g_packed, ld, (cudaStream_t)stream);

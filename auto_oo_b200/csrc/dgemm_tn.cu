@@ -33,6 +33,13 @@ struct TnCfg {
     static constexpr int B_BYTES = (BN / 16) * CHUNK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
+    // "linear A" stages (AMODE 1 below): BK rows of BM doubles, each fetched by ONE bulk copy from an arbitrary
+    // global address, row pitch BM*8 + 16 bytes.  The pitch is 4 banks mod 32, which makes the fragment loads
+    // (lane (g,t): k = 2t + j, row 8 mi + g) conflict free without any swizzle.
+    static constexpr int LIN_PITCH = BM * 8 + 16;
+    static constexpr int LIN_A_BYTES = (BK * LIN_PITCH + 1023) / 1024 * 1024;      // B chunks stay 1024-aligned
+    static constexpr int LIN_STAGE_BYTES = LIN_A_BYTES + B_BYTES;
+    static constexpr int LIN_SMEM_BYTES = STAGES * LIN_STAGE_BYTES + 2 * STAGES * 8 + 1024;
     static_assert(WTM % 16 == 0 && WTN % 16 == 0, "warp tile must cover whole 16-wide chunks");
     static_assert(BK % 8 == 0, "BK must be a multiple of 8");
     static_assert((BK / 4) % 2 == 0, "the substep double buffer assumes an even number of substeps per k-block");
@@ -58,6 +65,12 @@ struct TnArgs {
     int kblocks;
     int tiles_m, tiles_n, batch;
     int a_batched, b_batched;
+    // AMODE 1 (quarter 1 over 8-fold packed AO integrals): A8[RS][PQ] with RS = r(r+1)/2 + s (r >= s) and PQ a packed
+    // pair (row length d2); the tile (s, PQ-range) takes its k-row r from row RS(max(r,s), min(r,s)).  Rows of the
+    // product are (s, PQ) as in mode 2 (d0 = number of s, d2 = padded pair count); K = number of r.
+    const double *A8;
+    int64_t strideA8;
+    int K;
     // Always 0, but opaque to the compiler: ANDed with bits of every fragment a consumer loaded from
     // a stage and added to the address of that stage's "empty" arrive.  The arrive thus has a true
     // register dependency on the LDS results, so it cannot be issued while a shared-memory load of
@@ -67,16 +80,25 @@ struct TnArgs {
     uint32_t zero;
 };
 
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // DUAL: 0 = plain store, 1 = second store with rows (a b c) -> (c b a), 2 = packed-pair unpack,
 // 3 / 4 = class-pair packing, 5 = class-pair expansion instead of the plain store (see TnArgs)
-template <class Cfg, int DUAL>
+// AMODE: 0 = A through the tensor map (K-major matrix), 1 = A rows gathered from the 8-fold packed AO integrals
+template <class Cfg, int DUAL, int AMODE = 0>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const TnArgs args) {
+    constexpr int STAGE_BYTES = AMODE ? Cfg::LIN_STAGE_BYTES : Cfg::STAGE_BYTES;
+    constexpr int A_BYTES = AMODE ? Cfg::LIN_A_BYTES : Cfg::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + Cfg::STAGES;
 
     const int warp = threadIdx.x >> 5;
@@ -89,13 +111,20 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             mbar_init(&empty_bar[s], Cfg::NCW);
         }
         fence_barrier_init();
-        tma_prefetch_desc(&mapA);
+        if (!AMODE) tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
     }
     __syncthreads();
 
     const int tiles_per_batch = args.tiles_m * args.tiles_n;
     const int64_t total_tiles = (int64_t)tiles_per_batch * args.batch;
+    // AMODE 1 walks the m-tiles as (PQ-tile outer, s inner): the CTAs that run together share one PQ panel of
+    // A8, and every row RS(r, s) of that panel is needed twice -- by tile s at step r and by tile r at step s --
+    // so the second use is served from L2 (the 8-fold packed tensor is read from HBM about once).
+    auto lin_tile = [&](int mt, int &s, int &pq0) {
+        s = mt % args.d0;
+        pq0 = (mt / args.d0) * Cfg::BM;
+    };
 
     // Register re-allocation (setmaxnreg): the CTA starts with 168 registers per thread (384 threads,
     // three warps per SM sub-partition); the producer warpgroup gives most of its share back and the
@@ -104,7 +133,48 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp >= Cfg::NCW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ===================== TMA producer =====================
-        if (warp == Cfg::NCW && lane == 0) {
+        if (AMODE && warp == Cfg::NCW) {
+            // linear-A producer: the whole warp takes part, lane k issues the bulk copy of k-row k
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = (int)(tile / tiles_per_batch);
+                const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
+                int s, pq0;
+                lin_tile(rem / args.tiles_n, s, pq0);
+                const int n0 = (rem % args.tiles_n) * Cfg::BN;
+                const int bb = args.b_batched ? b : 0;
+                const int rows = (args.d2 - pq0) < Cfg::BM ? (args.d2 - pq0) : Cfg::BM;   // even: d2 and BM are
+                const uint32_t row_bytes = (uint32_t)rows * 8u;
+                const double *Ab = args.A8 + (int64_t)b * args.strideA8 + pq0;
+                for (int kb = 0; kb < args.kblocks; ++kb) {
+                    if (lane == 0) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::BK * row_bytes + Cfg::B_BYTES);
+                    }
+                    __syncwarp();
+                    const uint32_t sA = smem_base + stage * STAGE_BYTES;
+                    const int k0 = kb * Cfg::BK;
+                    if (lane < Cfg::BK) {
+                        int r = k0 + lane;
+                        r = r < args.K ? r : args.K - 1;         // rows past K meet zero rows of B (TMA fill)
+                        const int hi = r > s ? r : s, lo = r > s ? s : r;
+                        const double *src = Ab + ((int64_t)hi * (hi + 1) / 2 + lo) * args.d2;
+                        bulk_load_1d(sA + lane * Cfg::LIN_PITCH, src, row_bytes, &full_bar[stage]);
+                    }
+                    if (lane == 0) {
+                        uint8_t *sB = smem + stage * STAGE_BYTES + A_BYTES;
+#pragma unroll
+                        for (int c = 0; c < Cfg::BN / 16; ++c)
+                            tma_load_3d(sB + c * Cfg::CHUNK_BYTES, &mapB, &full_bar[stage], n0 + 16 * c, k0, bb);
+                    }
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        } else if (warp == Cfg::NCW && lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -148,8 +218,9 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const uint32_t krow = 2 * t + j;
                 x[h][j] = krow * 128u + ((((uint32_t)(h * 8 + g)) * 8u) ^ (krow << 4));
             }
-        const uint32_t a_warp_off = (uint32_t)(wm * Cfg::WTM / 16) * Cfg::CHUNK_BYTES;
-        const uint32_t b_warp_off = Cfg::A_BYTES + (uint32_t)(wn * Cfg::WTN / 16) * Cfg::CHUNK_BYTES;
+        const uint32_t a_warp_off = AMODE ? (uint32_t)(wm * Cfg::WTM + g) * 8u + (uint32_t)(2 * t) * Cfg::LIN_PITCH
+                                          : (uint32_t)(wm * Cfg::WTM / 16) * Cfg::CHUNK_BYTES;
+        const uint32_t b_warp_off = A_BYTES + (uint32_t)(wn * Cfg::WTN / 16) * Cfg::CHUNK_BYTES;
 
         // registers are the scarce resource here (3 warps share one SM sub-partition's file: 168 per
         // thread): one running k-block counter carries both the ring slot and its phase, and the
@@ -171,12 +242,13 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             double a[2][Cfg::MT], bf[2][Cfg::NT];
             uint32_t loaded = 0, loaded_next = 0;       // XOR of the high words read from the current / next stage
             auto load_frags = [&](int buf, uint32_t st, int sub, uint32_t &lx) {
-                const uint32_t sbase = smem_base + st * Cfg::STAGE_BYTES;
+                const uint32_t sbase = smem_base + st * STAGE_BYTES;
                 const uint32_t abase = sbase + a_warp_off, bbase = sbase + b_warp_off;
                 const int kk = sub >> 1, j = sub & 1;
 #pragma unroll
                 for (int mi = 0; mi < Cfg::MT; ++mi)
-                    a[buf][mi] = lds_f64(abase + (mi >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[mi & 1][j]);
+                    a[buf][mi] = AMODE ? lds_f64(abase + (kk * 8 + j) * Cfg::LIN_PITCH + mi * 64)
+                                       : lds_f64(abase + (mi >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[mi & 1][j]);
 #pragma unroll
                 for (int ni = 0; ni < Cfg::NT; ++ni)
                     bf[buf][ni] = lds_f64(bbase + (ni >> 1) * Cfg::CHUNK_BYTES + kk * 1024 + x[ni & 1][j]);
@@ -219,13 +291,19 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             // epilogue: registers -> global (16-byte stores, rows of 64 B per MMA tile)
             const int b = (int)(tile / (uint32_t)tiles_per_batch);
             const int rem = (int)(tile - (uint32_t)b * (uint32_t)tiles_per_batch);
-            const int m0 = (rem / args.tiles_n) * Cfg::BM;
+            int64_t m0 = (int64_t)(rem / args.tiles_n) * Cfg::BM, m_end = args.M;
+            if (AMODE) {                                   // rows (s, PQ) of one s: global row s * d2 + PQ
+                int s, pq0;
+                lin_tile(rem / args.tiles_n, s, pq0);
+                m0 = (int64_t)s * args.d2 + pq0;
+                m_end = (int64_t)(s + 1) * args.d2;
+            }
             const int n0 = (rem % args.tiles_n) * Cfg::BN;
             double *Cb = args.C + (int64_t)b * args.strideC;
 #pragma unroll
             for (int mi = 0; mi < Cfg::MT; ++mi) {
-                const int64_t row = (int64_t)m0 + wm * Cfg::WTM + mi * 8 + g;
-                if (row < args.M) {
+                const int64_t row = m0 + wm * Cfg::WTM + mi * 8 + g;
+                if (row < m_end) {
                     double *crow = Cb + row * args.ldc;
                     double *crow2 = nullptr, *crow3 = nullptr;
                     if (DUAL == 1) {
@@ -369,6 +447,9 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     args.a_batched = a_batched;
     args.b_batched = b_batched;
     args.zero = 0;
+    args.A8 = nullptr;
+    args.strideA8 = 0;
+    args.K = (int)K;
 
     static unsigned long long attr_set = 0;
     if (once_per_device(attr_set)) {
@@ -405,6 +486,50 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
         dgemm_tn_kernel<Cfg, 1><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     else
         dgemm_tn_kernel<Cfg, 0><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
+    OO_LAUNCH_CHECK();
+    return OO_OK;
+}
+
+// Quarter 1 of the symmetric class transform straight from the 8-fold packed AO integrals (AMODE 1):
+//   T1[(s, PQ), m] = sum_r A8[RS(r, s)][PQ] C[r, m],   RS(r, s) = tri(max, min),
+// stored as C[(s PQ), m] and, pair unpacked, at C2 rows (q p s) and (p q s) (the mode-2 epilogue).
+template <class Cfg>
+static int launch_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2, int S, int dorb, int dP,
+                                int64_t N, int64_t K, int64_t ldb, int64_t ldc, int batch, int64_t strideA8,
+                                int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream) {
+    CUtensorMap mapB;
+    const int b_batched = (batch > 1 && strideB != 0);
+    int rc = encode_tmap_3d_f64(&mapB, B, (uint64_t)N, (uint64_t)K, b_batched ? batch : 1, (uint64_t)ldb,
+                                b_batched ? (uint64_t)strideB : (uint64_t)ldb * K, 16, Cfg::BK);
+    if (rc) return rc;
+    TnArgs args;
+    args.C = C;
+    args.C2 = C2;
+    args.d0 = S;
+    args.d1 = dorb;
+    args.d2 = dP;
+    args.M = (int64_t)S * dP;
+    args.N = N;
+    args.ldc = ldc;
+    args.strideC = strideC;
+    args.strideC2 = strideC2;
+    args.kblocks = (int)ceil_div(K, Cfg::BK);
+    args.tiles_m = S * (int)ceil_div(dP, Cfg::BM);
+    args.tiles_n = (int)ceil_div(N, Cfg::BN);
+    args.batch = batch;
+    args.a_batched = (batch > 1 && strideA8 != 0);
+    args.b_batched = b_batched;
+    args.zero = 0;
+    args.A8 = A8;
+    args.strideA8 = args.a_batched ? strideA8 : 0;
+    args.K = (int)K;
+    static unsigned long long attr_set = 0;
+    if (once_per_device(attr_set))
+        OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::LIN_SMEM_BYTES));
+    const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    dgemm_tn_kernel<Cfg, 2, 1><<<grid, Cfg::THREADS, Cfg::LIN_SMEM_BYTES, stream>>>(mapB, mapB, args);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -477,6 +602,27 @@ int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C
     dual.strideC2 = strideC2;
     return dgemm_tn_impl(At, B, C, (int64_t)d0 * dP, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC,
                          stream, dual);
+}
+
+// Quarter 1 from the 8-fold packed AO integrals A8[RS][PQ] (rows of dP doubles, RS over pairs of S = dorb orbitals):
+// see launch_tn_q1_packed8.  N = number of class columns (ldb, ldc even).
+int dgemm_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2, int dorb, int dP, int64_t N,
+                        int64_t K, int64_t ldb, int64_t ldc, int batch, int64_t strideA8, int64_t strideB,
+                        int64_t strideC, int64_t strideC2, cudaStream_t stream) {
+    OO_REQUIRE(A8 && B && C && C2 && dorb > 0 && K > 0 && K <= dorb && N > 0 && batch > 0);
+    OO_REQUIRE((int64_t)dP >= (int64_t)dorb * (dorb + 1) / 2 && (dP % 2) == 0);
+    OO_REQUIRE((ldb % 2) == 0 && (ldc % 2) == 0 && ldc >= N && (strideA8 % 2) == 0 && (strideB % 2) == 0);
+    OO_REQUIRE(((uintptr_t)A8 % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0);
+    if ((int64_t)dorb * dP >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
+#define OO_Q1(CFG)                                                                                                 \
+    return launch_tn_q1_packed8<CFG>(A8, B, C, C2, dorb, dorb, dP, N, K, ldb, ldc, batch, strideA8, strideB, strideC, \
+                                     strideC2, stream)
+    if (N > 64) OO_Q1(TnWide);
+    if (N > 48) OO_Q1(TnMid);
+    if (N > 32) OO_Q1(TnMid48);
+    if (N > 16) OO_Q1(TnNarrow);
+    OO_Q1(TnSlim);
+#undef OO_Q1
 }
 
 // Rows (r2, m), m < nclass, columns n < N (= nclass): only the class pairs n <= m are stored, packed, at

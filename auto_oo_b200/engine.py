@@ -149,10 +149,12 @@ class HotPathEngine:
     SYMMETRY_TOL = 1e-13
 
     def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None,
-                 n_geometries=0, eri_symmetry="auto"):
+                 n_geometries=0, eri_symmetry="auto", eri_packing="8fold"):
         """``eri_symmetry``: "auto" measures the 8-fold symmetry of ``int2e_ao`` on the device at first use and
         takes the symmetric class transform (half the quarter-1 work, packed AO integrals) when it holds to
         round-off, the general one otherwise; "off" always takes the general one.
+        ``eri_packing``: how the symmetric route keeps the AO integrals in HBM -- "8fold": both pairs packed,
+        g8[(r>=s), (p>=q)] (an eighth of N^4; quarter 1 unpacks in its producer), "pair": g[r, s, (p>=q)] (half).
         ``n_geometries`` > 0: ``int1e_ao (G,N,N)``, ``int2e_ao (G,N,N,N,N)``, ``oao_coeff (G,N,N)``,
         ``nuc (G,)`` hold one molecule geometry each (same orbital classes); evaluation ``b`` of a
         batch then uses geometry ``b`` (class path only)."""
@@ -182,7 +184,9 @@ class HotPathEngine:
             self.nuc_dev = None if G is None else self.dev(np.asarray(nuc, dtype=np.float64).reshape(G))
         self.nIp = pad_even(self.nI)                   # class index padded to even (TMA strides)
         self.g_pairT = None                            # g_ao[p,q,r,s] stored as [r,s,p,q]; built on first use
-        self.g_packed = None                           # g_ao[r,s,(p>=q)] when the integrals are 8-fold symmetric
+        self.g_packed = None                           # packed AO integrals when they are 8-fold symmetric
+        assert eri_packing in ("8fold", "pair")
+        self.eri_packing = eri_packing
         self.eri_symmetry = eri_symmetry
         self._eri_symmetric = None if eri_symmetry == "auto" else False
         self.eri_defect = None
@@ -482,14 +486,19 @@ class HotPathEngine:
         return self._eri_symmetric
 
     def packed_eri(self):
-        """g_packed[r,s,pq] = g_ao[r,s,p,q], p >= q (pairs of the ld padded orbitals, row padded to even)."""
+        """The symmetric route's copy of the AO integrals over the ld padded orbitals (row = packed pair p >= q,
+        padded to even): ``eri_packing="8fold"`` g8[(r>=s), (pq)], ``"pair"`` g[r, s, (pq)]."""
         if self.g_packed is None:
             ldp = int(self.lib.oo_pair_ld(self.ld))
             g = self.g_ao.reshape(-1, self.ld ** 4)
-            out = torch.empty(g.shape[0], self.ld, self.ld, ldp, dtype=F64, device=self.device)
+            if self.eri_packing == "8fold":
+                out = torch.empty(g.shape[0], self.ld * (self.ld + 1) // 2, ldp, dtype=F64, device=self.device)
+                pack, what = self.lib.oo_pack_eri_8fold_f64, "pack_eri_8fold"
+            else:
+                out = torch.empty(g.shape[0], self.ld, self.ld, ldp, dtype=F64, device=self.device)
+                pack, what = self.lib.oo_pack_eri_pairs_f64, "pack_eri_pairs"
             for i in range(g.shape[0]):
-                self._check(self.lib.oo_pack_eri_pairs_f64(_p(g[i]), _p(out[i]), self.ld, self.stream),
-                            "pack_eri_pairs")
+                self._check(pack(_p(g[i]), _p(out[i]), self.ld, self.stream), what)
             self.g_packed = out if self.n_geom else out[0]
         return self.g_packed
 
@@ -526,9 +535,10 @@ class HotPathEngine:
             nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM_SYM, self.N, ld, self.nI, B)
             ws = self.workspace("cls", nbytes)
             gp, sg = self._geo(self.packed_eri(), geo_lo, geo_lo + B)
+            flags = self.flags | (_lib.OO_FLAG_CLASS_ERI_8FOLD if self.eri_packing == "8fold" else 0)
             self._check(self.lib.oo_class_transform_sym_f64(_p(gp), sg, _p(C), ld * ld if B > 1 else 0,
                                                             self.N, ld, nIp, B, _p(cls), _p(ws), nbytes,
-                                                            self.flags, self.stream), "class_transform_sym")
+                                                            flags, self.stream), "class_transform_sym")
         else:
             nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM, self.N, ld, self.nI, B)
             ws = self.workspace("cls", nbytes)

@@ -249,12 +249,13 @@ class OO_energy:
     GRAPH_MAX_NAO = 128
 
     def __init__(self, mol, ncas, nelecas, oao_mo_coeff=None, freeze_active=False, interface='torch',
-                 device=None, integral_path="class", eri_symmetry="auto", cuda_graphs="auto"):
+                 device=None, integral_path="class", eri_symmetry="auto", cuda_graphs="auto", eri_packing="8fold"):
         """``integral_path``: ``"class"`` (default) transforms only the J/K integral classes that
         energy, gradient and Hessian read; ``"full"`` runs the complete four-index transform for
         every set of MO coefficients, as the reference does.  ``eri_symmetry``: ``"auto"`` lets the
         class path use the 8-fold symmetry of ``int2e_ao`` when the device check finds it (real-orbital
-        integrals always have it), ``"off"`` never assumes it.  ``cuda_graphs``: ``"auto"`` replays the batched
+        integrals always have it), ``"off"`` never assumes it.  ``eri_packing``: ``"8fold"`` keeps the symmetric
+        integrals with both pairs packed (an eighth of N^4, unpacked by the quarter-1 producer), ``"pair"`` with one.  ``cuda_graphs``: ``"auto"`` replays the batched
         evaluations (``energy_gradient_hessian``, ``energies_from_kappas``) from a CUDA graph when the basis has
         at most ``GRAPH_MAX_NAO`` orbitals, ``True`` / ``False`` force it."""
         assert integral_path in ("class", "full")
@@ -289,7 +290,8 @@ class OO_energy:
         self.int2e_ao = _as_tensor(mol.int2e_ao)
         self.oao_coeff = _as_tensor(mol.oao_coeff)
         self.engine = HotPathEngine(self.int1e_ao, self.int2e_ao, self.oao_coeff, self.nuc, self.nao,
-                                    no, na, self.params_idx, device=device, eri_symmetry=eri_symmetry)
+                                    no, na, self.params_idx, device=device, eri_symmetry=eri_symmetry,
+                                    eri_packing=eri_packing)
 
     # ------------------------------------------------------------------ orbitals
     @property

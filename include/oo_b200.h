@@ -75,8 +75,14 @@ enum {
                                                   the fused epilogues of its quarter-2 / last-quarter GEMMs           */
     OO_FLAG_HESSIAN_GROUP_UNSTREAMED = 16,     /* G blocks of the Hessian T-matrix with per-thread loads instead of the
                                                   cp.async.bulk + mbarrier streamed DMMA kernel                       */
-    OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 32   /* Hessian assembly without the bulk-async streamed kernel for the rows
+    OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 32,  /* Hessian assembly without the bulk-async streamed kernel for the rows
                                                   outside occ+act                                                     */
+    OO_FLAG_CLASS_Q2_RECTANGULAR = 64,         /* oo_class_transform_sym_f64: quarter 2 as the rectangular TN-GEMM that
+                                                  computes every class pair (m, n) and keeps n <= m in its epilogue,
+                                                  instead of the triangular kernel that only computes n <= m          */
+    OO_FLAG_CLASS_ERI_8FOLD = 128              /* oo_class_transform_sym_f64: `g_packed` is the 8-FOLD packed tensor of
+                                                  oo_pack_eri_8fold_f64 (an eighth of N^4) instead of the pair-packed
+                                                  one (half of N^4); quarter 1 unpacks it in its producer               */
 };
 /* oo_class_transform_sym_f64 only: run just the selected GEMM stages (k = 0: quarter 1 over packed pairs; 1, 2, 3:
  * quarters 2-4 of the Coulomb class; 4, 5, 6: of the exchange class) on the intermediates a complete call left in
@@ -243,6 +249,12 @@ int oo_class_transform_f64(const double *g_pairT, int64_t strideG, const double 
 int     oo_eri_symmetry_defect_f64(const double *g_ao, int ld, double *defect3, void *stream);
 int64_t oo_pair_ld(int ld);
 int     oo_pack_eri_pairs_f64(const double *g_ao, double *g_packed, int ld, void *stream);
+/* g_packed8[RS][PQ] = g[r,s,p,q], r >= s, p >= q, RS = r(r+1)/2 + s, PQ = p(p+1)/2 + q over the ld padded orbitals:
+ * ld(ld+1)/2 rows of oo_pair_ld(ld) doubles, an eighth of the full tensor (8.7 GB instead of 34.4 GB at N = 256).
+ * With OO_FLAG_CLASS_ERI_8FOLD the quarter-1 GEMM of oo_class_transform_sym_f64 reads this layout directly: the
+ * k-row r of the tile (s, PQ-range) is row RS(max(r,s), min(r,s)), fetched by one bulk copy; tiles that share a
+ * PQ panel run together so the second use of every row (as (r,s) and as (s,r)) comes from L2.    */
+int     oo_pack_eri_8fold_f64(const double *g_ao, double *g_packed8, int ld, void *stream);
 int     oo_class_transform_sym_f64(const double *g_packed, int64_t strideG, const double *C, int64_t strideC,
                                    int N, int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
                                    unsigned flags, void *stream);

@@ -179,6 +179,23 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     finally:
         eng.flags = 0
     assert torch.equal(Eu, Ec) and torch.equal(Gu, Gc) and torch.equal(Hf, Hc)
+    # quarter 2: triangular kernel (only class pairs n <= m are computed; default) against the rectangular GEMM
+    try:
+        eng.flags = _lib.OO_FLAG_CLASS_Q2_RECTANGULAR
+        Er, Gr, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.flags = 0
+    assert torch.equal(Er, Ec) and torch.equal(Gr, Gc) and torch.equal(Hf, Hc)     # same k order per element
+    # AO integrals with one pair packed (N^4 / 2, TMA-tiled quarter 1) against the default 8-fold packed tensor
+    # (N^4 / 8, quarter-1 rows gathered by bulk copies); both read the same g up to its own symmetry defect
+    eng.g_packed, eng.eri_packing = None, "pair"
+    try:
+        Ep, Gp, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.g_packed, eng.eri_packing = None, "8fold"
+        torch.cuda.empty_cache()
+    assert (Ep - Ec).abs().max().item() < TOL_E and (Gp - Gc).abs().max().item() < TOL_GH
+    assert (Hf - Hc).abs().max().item() < TOL_GH
     # general (no symmetry assumed) class route; the complete transform's N^4 workspace makes room first
     eng._eri_symmetric = False
     eng._ws.pop("i2e", None)

@@ -354,13 +354,15 @@ def test_gradient_vjp_matches_autograd(name):
     assert (g2.cpu() - r2).abs().max().item() < 1e-10
 
 
-@pytest.mark.parametrize("sym", ["auto", "off"])
+@pytest.mark.parametrize("sym", ["auto", "auto-pair", "off"])
 @pytest.mark.parametrize("name", ["n7_cas44", "n8_nocore", "n13_cas22", "n28_cas66", "mol_ch2nh_sto3g_cas44"])
 def test_class_transform_equals_slices_of_full_transform(name, sym):
     """J[m,n,a,b] = g'[a,b,m,n], K[n,m,a,b] = g'[a,m,n,b] and the h' row of the class buffer, through the
-    symmetric (packed-pair) and the general class transform."""
+    symmetric class transform (AO integrals 8-fold packed, or with one pair packed) and the general one."""
     c = load_case(name)
-    eng, p = engine_for(c, eri_symmetry=sym)
+    packing = "pair" if sym == "auto-pair" else "8fold"
+    sym = sym.split("-")[0]
+    eng, p = engine_for(c, eri_symmetry=sym, eri_packing=packing)
     assert eng.eri_is_symmetric() == (sym == "auto")
     Cp = eng.to_padded(c.ref["mo_coeff_rot"], 2)
     cls = eng.class_integrals(Cp)[0].cpu()
@@ -389,11 +391,17 @@ def test_eri_symmetry_defect_and_pair_packing(lib):
     ld = eng.ld
     assert eng.eri_is_symmetric() and max(eng.eri_defect[:2]) <= 1e-13 * eng.eri_defect[2]
     assert abs(eng.eri_defect[2] - np.abs(c.int2e_ao).max()) < 1e-15
-    gp = eng.packed_eri().cpu()
     ldp = int(lib.oo_pair_ld(ld))
-    assert gp.shape == (ld, ld, ldp) and ldp % 2 == 0 and ldp >= ld * (ld + 1) // 2
     g = eng.g_ao.cpu()
     rows, cols = np.tril_indices(ld)                              # p >= q, pq = p(p+1)/2 + q
+    assert eng.eri_packing == "8fold"                             # default: both pairs packed, g8[(r>=s), (p>=q)]
+    g8 = eng.packed_eri().cpu()
+    assert g8.shape == (len(rows), ldp) and ldp % 2 == 0 and ldp >= ld * (ld + 1) // 2
+    assert torch.equal(g8[:, :len(rows)], g[rows, cols][:, rows, cols])
+    assert g8[:, len(rows):].abs().max().item() == 0.0 if ldp > len(rows) else True
+    eng.g_packed, eng.eri_packing = None, "pair"                  # one pair packed, g[r, s, (p>=q)]
+    gp = eng.packed_eri().cpu()
+    assert gp.shape == (ld, ld, ldp)
     assert torch.equal(gp[:, :, :len(rows)], g[:, :, rows, cols])
     assert gp[:, :, len(rows):].abs().max().item() == 0.0 if ldp > len(rows) else True
     # break each symmetry in turn: the defect reports it and the engine falls back to the general route
