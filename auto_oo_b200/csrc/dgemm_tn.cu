@@ -20,14 +20,17 @@
 
 namespace oo {
 
-template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_>
+// NTC_ > 0: only the first NTC_ 8-column MMA tiles of the (single) warp column are computed and stored -- the
+// 24- and 40-column variants of the 32- and 48-wide tiles (the TMA boxes still fetch 16-column chunks of B).
+template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_, int NTC_ = 0>
 struct TnCfg {
     static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_;
     static constexpr int NCW = WGM * WGN;            // consumer warps (two warpgroups)
     static constexpr int THREADS = (NCW + 4) * 32;   // + one producer warpgroup (its first warp issues TMA)
     static_assert(NCW == 8, "register re-allocation below assumes 2 consumer warpgroups + 1 producer warpgroup");
     static constexpr int WTM = BM / WGM, WTN = BN / WGN;
-    static constexpr int MT = WTM / 8, NT = WTN / 8;
+    static constexpr int MT = WTM / 8, NT = NTC_ ? NTC_ : WTN / 8;
+    static_assert(NTC_ == 0 || (WGN_ == 1 && NTC_ * 8 <= WTN), "a trimmed warp tile needs a single warp column");
     static constexpr int CHUNK_BYTES = BK * 128;     // one TMA box: [BK][16 doubles]
     static constexpr int A_BYTES = (BM / 16) * CHUNK_BYTES;
     static constexpr int B_BYTES = (BN / 16) * CHUNK_BYTES;
@@ -71,6 +74,7 @@ struct TnArgs {
     const double *A8;
     int64_t strideA8;
     int K;
+    int last_subs;   // k4-substeps of the LAST k-block that hold rows below K (whole 8-row atoms beyond K are skipped)
     // Always 0, but opaque to the compiler: ANDed with bits of every fragment a consumer loaded from
     // a stage and added to the address of that stage's "empty" arrive.  The arrive thus has a true
     // register dependency on the LDS results, so it cannot be issued while a shared-memory load of
@@ -79,6 +83,9 @@ struct TnArgs {
     // and a stage was seen overwritten under a pending read).
     uint32_t zero;
 };
+
+struct FalseTag { static constexpr bool value = false; };
+struct TrueTag { static constexpr bool value = true; };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
@@ -264,29 +271,37 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_wait(&full_bar[stage], (it / Cfg::STAGES) & 1u);
                 load_frags(0, stage, 0, loaded);
             }
-            for (int kb = 0; kb < args.kblocks; ++kb, ++it) {
+            // One k-block.  LAST = the tile's final block: no next stage to prefetch from, and the 8-row atoms
+            // that lie entirely past K (zero rows: nothing to add) are skipped -- 114 orbitals are 7 1/8 blocks.
+            auto kblock = [&](auto last_tag) {
+                constexpr bool LAST = decltype(last_tag)::value;
                 const uint32_t stage = it & (Cfg::STAGES - 1);
 #pragma unroll
                 for (int sub = 0; sub < SUB; ++sub) {
                     const int cur = sub & 1, nxt = cur ^ 1;
                     if (sub + 1 < SUB) {
                         load_frags(nxt, stage, sub + 1, loaded);
-                    } else if (kb + 1 < args.kblocks) {
+                    } else if (!LAST) {
                         const uint32_t nstage = (it + 1) & (Cfg::STAGES - 1);
                         mbar_wait(&full_bar[nstage], ((it + 1) / Cfg::STAGES) & 1u);
                         load_frags(nxt, nstage, 0, loaded_next);
                     }
+                    if (!LAST || sub < args.last_subs) {
 #pragma unroll
-                    for (int mi = 0; mi < Cfg::MT; ++mi)
+                        for (int mi = 0; mi < Cfg::MT; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < Cfg::NT; ++ni)
-                            dmma884(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], bf[cur][ni]);
+                            for (int ni = 0; ni < Cfg::NT; ++ni)
+                                dmma884(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], bf[cur][ni]);
+                    }
                 }
                 // release the stage only once every load from it has landed in registers (see TnArgs::zero)
                 if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[stage]) + (loaded & args.zero));
                 loaded = loaded_next;
                 loaded_next = 0;
-            }
+                ++it;
+            };
+            for (int kb = 0; kb + 1 < args.kblocks; ++kb) kblock(FalseTag{});
+            kblock(TrueTag{});
 
             // epilogue: registers -> global (16-byte stores, rows of 64 B per MMA tile)
             const int b = (int)(tile / (uint32_t)tiles_per_batch);
@@ -450,6 +465,7 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     args.A8 = nullptr;
     args.strideA8 = 0;
     args.K = (int)K;
+    args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
 
     static unsigned long long attr_set = 0;
     if (once_per_device(attr_set)) {
@@ -523,6 +539,7 @@ static int launch_tn_q1_packed8(const double *A8, const double *B, double *C, do
     args.A8 = A8;
     args.strideA8 = args.a_batched ? strideA8 : 0;
     args.K = (int)K;
+    args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
     static unsigned long long attr_set = 0;
     if (once_per_device(attr_set))
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -538,7 +555,9 @@ static int launch_tn_q1_packed8(const double *A8, const double *B, double *C, do
 using TnWide = TnCfg<128, 128, 16, 2, 4, 4>;   // N > 64 : warp tile 64x32
 using TnMid = TnCfg<256, 64, 16, 4, 2, 4>;     // N in (48, 64]
 using TnMid48 = TnCfg<256, 48, 16, 8, 1, 4>;   // N in (32, 48] : warp tile 32x48 (class index nIp = 44 at N=256)
-using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (16, 32] : warp tile 32x32
+using TnMid40 = TnCfg<256, 48, 16, 8, 1, 4, 5>;   // N in (32, 40] : warp tile 32x40
+using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (24, 32] : warp tile 32x32
+using TnNarrow24 = TnCfg<256, 32, 16, 8, 1, 4, 3>;  // N in (16, 24] : warp tile 32x24 (class index 24 at 114 orbitals)
 using TnSlim = TnCfg<256, 16, 16, 8, 1, 4>;    // N <= 16 : warp tile 32x16
 
 static int dgemm_tn_impl(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
@@ -555,10 +574,14 @@ static int dgemm_tn_impl(const double *At, const double *B, double *C, int64_t M
         return launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 48)
         return launch_tn<TnMid>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
-    if (N > 32)
+    if (N > 40)
         return launch_tn<TnMid48>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
-    if (N > 16)
+    if (N > 32)
+        return launch_tn<TnMid40>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
+    if (N > 24)
         return launch_tn<TnNarrow>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
+    if (N > 16)
+        return launch_tn<TnNarrow24>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     return launch_tn<TnSlim>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
 }
 
@@ -619,8 +642,10 @@ int dgemm_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2
                                      strideC2, stream)
     if (N > 64) OO_Q1(TnWide);
     if (N > 48) OO_Q1(TnMid);
-    if (N > 32) OO_Q1(TnMid48);
-    if (N > 16) OO_Q1(TnNarrow);
+    if (N > 40) OO_Q1(TnMid48);
+    if (N > 32) OO_Q1(TnMid40);
+    if (N > 24) OO_Q1(TnNarrow);
+    if (N > 16) OO_Q1(TnNarrow24);
     OO_Q1(TnSlim);
 #undef OO_Q1
 }

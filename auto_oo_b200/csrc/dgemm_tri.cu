@@ -26,12 +26,14 @@ int encode_tmap_4d_f64(CUtensorMap *map, const void *base, const uint64_t dims[4
 
 namespace {
 
-template <int GP_, int STAGES_>
+// MTC_: 8-row MMA tiles per group that hold class indices (ceil(nclass / 8) <= GP / 8); tiles past it are padding
+template <int GP_, int MTC_, int STAGES_>
 struct TriCfg {
     static constexpr int GP = GP_, STAGES = STAGES_, BK = 16;
     static constexpr int NCW = 8;                         // consumer warps = groups per tile
     static constexpr int THREADS = (NCW + 4) * 32;
-    static constexpr int MT = GP / 8;                     // MMA tiles per side of the warp tile
+    static constexpr int MT = MTC_;                       // MMA tiles per side of the warp tile
+    static_assert(MTC_ * 8 <= GP_, "class tiles exceed the group");
     static constexpr int CPG = GP / 16;                   // 16-wide TMA chunks per group
     static constexpr int CHUNK_BYTES = BK * 128;
     static constexpr int A_BYTES = NCW * CPG * CHUNK_BYTES;
@@ -51,8 +53,12 @@ struct TriArgs {
     int64_t ngroups;
     int kblocks, tiles_per_batch, batch;
     int a_batched, b_batched;
+    int last_subs;          // substeps of the last k-block with rows below K
     uint32_t zero;
 };
+
+struct FalseTag { static constexpr bool value = false; };
+struct TrueTag { static constexpr bool value = true; };
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
                                             int c2, int c3) {
@@ -164,28 +170,35 @@ dgemm_tn_tri_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             mbar_wait(&full_bar[stage], (it / Cfg::STAGES) & 1u);
             load_frags(0, stage, 0, loaded);
         }
-        for (int kb = 0; kb < args.kblocks; ++kb, ++it) {
+        // one k-block; LAST: no next stage to prefetch, 8-row atoms entirely past K skipped (as in dgemm_tn.cu)
+        auto kblock = [&](auto last_tag) {
+            constexpr bool LAST = decltype(last_tag)::value;
             const uint32_t stage = it & (Cfg::STAGES - 1);
 #pragma unroll
             for (int sub = 0; sub < SUB; ++sub) {
                 const int cur = sub & 1, nxt = cur ^ 1;
                 if (sub + 1 < SUB) {
                     load_frags(nxt, stage, sub + 1, loaded);
-                } else if (kb + 1 < args.kblocks) {
+                } else if (!LAST) {
                     const uint32_t nstage = (it + 1) & (Cfg::STAGES - 1);
                     mbar_wait(&full_bar[nstage], ((it + 1) / Cfg::STAGES) & 1u);
                     load_frags(nxt, nstage, 0, loaded_next);
                 }
+                if (!LAST || sub < args.last_subs) {
 #pragma unroll
-                for (int mi = 0; mi < MT; ++mi)
+                    for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni <= mi; ++ni)         // the diagonal and below: columns n <= 8 mi + 7
-                        dmma884(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], bf[cur][ni]);
+                        for (int ni = 0; ni <= mi; ++ni)     // the diagonal and below: columns n <= 8 mi + 7
+                            dmma884(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], bf[cur][ni]);
+                }
             }
             if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[stage]) + (loaded & args.zero));
             loaded = loaded_next;
             loaded_next = 0;
-        }
+            ++it;
+        };
+        for (int kb = 0; kb + 1 < args.kblocks; ++kb) kblock(FalseTag{});
+        kblock(TrueTag{});
 
         // ---- epilogue: P[g'][m(m+1)/2 + n] for n <= m < nclass
         const int b = (int)(tile / (uint32_t)args.tiles_per_batch);
@@ -250,6 +263,7 @@ int launch_tri(const double *At, const double *B, double *P, int tri_rows, int n
     args.batch = batch;
     args.a_batched = a_batched;
     args.b_batched = b_batched;
+    args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
     args.zero = 0;
     static unsigned long long attr_set = 0;
     if (once_per_device(attr_set))
@@ -278,11 +292,14 @@ int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tr
     OO_REQUIRE((lda % 2) == 0 && (ldb % 2) == 0 && (strideA % 2) == 0 && (strideB % 2) == 0);
     OO_REQUIRE(((uintptr_t)At % 16) == 0 && ((uintptr_t)B % 16) == 0);
     if (ngroups >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
-    if (nclass <= 32)
-        return launch_tri<TriCfg<32, 4>>(At, B, P, tri_rows, nclass, dorb, ngroups, npair_ld, K, lda, ldb, batch, strideA,
-                                         strideB, strideP, stream);
-    return launch_tri<TriCfg<48, 4>>(At, B, P, tri_rows, nclass, dorb, ngroups, npair_ld, K, lda, ldb, batch, strideA,
-                                     strideB, strideP, stream);
+#define OO_TRI(GP, MTC)                                                                                              \
+    return launch_tri<TriCfg<GP, MTC, 4>>(At, B, P, tri_rows, nclass, dorb, ngroups, npair_ld, K, lda, ldb, batch, strideA, \
+                                          strideB, strideP, stream)
+    if (nclass <= 24) OO_TRI(32, 3);
+    if (nclass <= 32) OO_TRI(32, 4);
+    if (nclass <= 40) OO_TRI(48, 5);
+    OO_TRI(48, 6);
+#undef OO_TRI
 }
 
 }  // namespace oo
