@@ -2,19 +2,17 @@
 // plus the N x N products around it: C' = X C_oao U (:173-176, :201, :235) and
 // h' = C^T h C (:44-46).
 //
-// expm: scaling and squaring with the diagonal Pade-[7/7] approximant
-// (Higham 2005, theta_7 = 0.95).  With A = -K / 2^s:
-//   A2 = A A, A4 = A2 A2, A6 = A4 A2
-//   W = A (b7 A6 + b5 A4 + b3 A2 + b1 I),  V = b6 A6 + b4 A4 + b2 A2 + b0 I
-//   r(A) = (V - W)^{-1} (V + W),   U = r(A)^(2^s)
-// For skew A, V is symmetric and W skew, so V - W = (V + W)^T is normal with
-// eigenvalues ~ b0 exp(-i lambda / 2): perfectly conditioned and within
-// 2 sin(0.95/4) = 0.47 of b0 I.  The inverse is therefore formed by the
-// quadratically convergent Newton-Schulz iteration X <- X (2I - Q X) from
-// X = I (residuals 0.47 -> 0.22 -> .049 -> 2.4e-3 -> 5.7e-6 -> 3.3e-11 -> 1e-21),
-// which keeps the whole expm on batched DMMA GEMMs (dgemm_small.cu) with no
-// pivoting and no host synchronisation.  Bases of up to 64 orbitals run the whole
-// chain in ONE launch out of shared memory (expm_fused_kernel below).
+// expm: scaling and squaring around a degree-18 Taylor polynomial.  With A = -K / 2^s, ||A||_1 <= 0.95, the
+// truncation error 0.95^19 / 19! = 3e-18 is below the unit round-off, and for skew A every term is bounded by
+// ||A||^k / k! (exp(A) is orthogonal: no cancellation to lose digits to).  The polynomial is evaluated by
+// Paterson-Stockmeyer in blocks of four,
+//   A2 = A A, A3 = A2 A, A4 = A2 A2                                            (3 products)
+//   B_j = c_4j I + c_4j+1 A + c_4j+2 A2 + c_4j+3 A3   (j = 0..3),  B_4 = c_16 I + c_17 A + c_18 A2,   c_k = 1/k!
+//   R = B_4;  R <- R A4 + B_j  for j = 3, 2, 1, 0                              (4 products, B_j added in the epilogue)
+//   U = R^(2^s)                                                                (s products)
+// i.e. 7 + s DMMA GEMMs with no inverse, no pivoting and no host synchronisation (the first version used the
+// Pade-[7/7] approximant with a Newton-Schulz inverse: 17 + s products for the same accuracy).  Bases of up to 64
+// orbitals run the whole chain in ONE launch out of shared memory (expm_fused_kernel below).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -70,47 +68,69 @@ int lincomb(double *out, double c1, const double *X1, double c2, const double *X
 }
 
 constexpr int kExpmSlots = 10;
-constexpr int kNewtonSchulzIters = 5;
+constexpr int kTaylorDegree = 18;
+
+// c_k = 1 / k!
+__host__ __device__ inline double inv_factorial(int k) {
+    double f = 1.0;
+    for (int i = 2; i <= k; ++i) f *= (double)i;
+    return 1.0 / f;
+}
+
+// B_j = c_4j I + c_4j+1 A + c_4j+2 A2 + c_4j+3 A3 for j = 0..4 (terms past the degree dropped), all in one pass
+__global__ void taylor_blocks_kernel(const double *__restrict__ A, const double *__restrict__ A2,
+                                     const double *__restrict__ A3, double *__restrict__ B, int64_t slot, int N, int ld,
+                                     int64_t total) {
+    double c[kTaylorDegree + 1];
+#pragma unroll
+    for (int k = 0; k <= kTaylorDegree; ++k) c[k] = inv_factorial(k);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t e = i % ((int64_t)ld * ld);
+        const int row = (int)(e / ld), col = (int)(e % ld);
+        const double a1 = A[i], a2 = A2[i], a3 = A3[i];
+        const double eye = (row == col && row < N) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            double v = c[4 * j] * eye + c[4 * j + 1] * a1 + c[4 * j + 2] * a2;
+            if (4 * j + 3 <= kTaylorDegree) v += c[4 * j + 3] * a3;
+            B[j * slot + i] = v;
+        }
+    }
+}
 
 // expm of A (already scaled by 2^-s), in place workspace; result in U
 int expm_scaled(const double *A, int N, int ld, int batch, int squarings, double *U, double *ws,
                 cudaStream_t stream) {
     const int64_t mat = (int64_t)ld * ld;
     const int64_t sl = mat * batch;
-    double *A2 = ws + 0 * sl, *A4 = ws + 1 * sl, *A6 = ws + 2 * sl, *W = ws + 3 * sl;
-    double *V = ws + 4 * sl, *P = ws + 5 * sl, *Q = ws + 6 * sl, *X = ws + 7 * sl;
-    double *T = ws + 8 * sl, *Y = ws + 9 * sl;
-    // Pade-[7/7] coefficients normalised by b0 = 17297280
-    const double b0 = 17297280.0;
-    const double c1 = 8648640.0 / b0, c2 = 1995840.0 / b0, c3 = 277200.0 / b0, c4 = 25200.0 / b0,
-                 c5 = 1512.0 / b0, c6 = 56.0 / b0, c7 = 1.0 / b0;
+    double *A2 = ws + 0 * sl, *A3 = ws + 1 * sl, *A4 = ws + 2 * sl, *B = ws + 3 * sl;      // B_0 .. B_4: slots 3-7
+    double *T0 = ws + 8 * sl, *T1 = ws + 9 * sl;
     int rc;
-#define GEMM(a, b, alpha, e, beta, gam, d)                                                        \
-    if ((rc = dgemm_small(0, 0, ld, ld, ld, (alpha), (a), ld, mat, (b), ld, mat, (beta), (e), ld,  \
-                          mat, (gam), (d), ld, mat, batch, stream, N)))                           \
+#define GEMM(a, b, e, beta, d)                                                                          \
+    if ((rc = dgemm_small(0, 0, ld, ld, ld, 1.0, (a), ld, mat, (b), ld, mat, (beta), (e), ld, mat, 0.0, \
+                          (d), ld, mat, batch, stream, N)))                                             \
     return rc
-    GEMM(A, A, 1.0, nullptr, 0.0, 0.0, A2);
-    GEMM(A2, A2, 1.0, nullptr, 0.0, 0.0, A4);
-    GEMM(A4, A2, 1.0, nullptr, 0.0, 0.0, A6);
-    if ((rc = lincomb(W, c7, A6, c5, A4, c3, A2, c1, N, ld, batch, stream))) return rc;
-    if ((rc = lincomb(V, c6, A6, c4, A4, c2, A2, 1.0, N, ld, batch, stream))) return rc;
-    GEMM(A, W, 1.0, V, 1.0, 0.0, P);                                    // P = V + A W
-    if ((rc = lincomb(Q, 2.0, V, -1.0, P, 0.0, nullptr, 0.0, N, ld, batch, stream))) return rc;  // Q = V - A W
-    // Newton-Schulz: X1 = 2I - Q, then X <- X (2I - Q X)
-    if ((rc = lincomb(X, -1.0, Q, 0.0, nullptr, 0.0, nullptr, 2.0, N, ld, batch, stream))) return rc;
-    double *Xc = X, *Xn = Y;
-    for (int it = 0; it < kNewtonSchulzIters; ++it) {
-        GEMM(Q, Xc, -1.0, nullptr, 0.0, 2.0, T);                       // T = 2I - Q X
-        GEMM(Xc, T, 1.0, nullptr, 0.0, 0.0, Xn);
-        double *tmp = Xc; Xc = Xn; Xn = tmp;
+    GEMM(A, A, nullptr, 0.0, A2);
+    GEMM(A2, A, nullptr, 0.0, A3);
+    GEMM(A2, A2, nullptr, 0.0, A4);
+    {
+        int blocks = (int)ceil_div(sl, 256);
+        if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+        taylor_blocks_kernel<<<blocks, 256, 0, stream>>>(A, A2, A3, B, sl, N, ld, sl);
+        OO_LAUNCH_CHECK();
     }
-    // r = X P, then square; ping-pong so the last product lands in U
-    double *Rc = (squarings % 2 == 0) ? U : T;
-    double *Rn = (squarings % 2 == 0) ? T : U;
-    GEMM(Xc, P, 1.0, nullptr, 0.0, 0.0, Rc);
-    for (int s = 0; s < squarings; ++s) {
-        GEMM(Rc, Rc, 1.0, nullptr, 0.0, 0.0, Rn);
-        double *tmp = Rc; Rc = Rn; Rn = tmp;
+    // Horner in A4; the chain and the squarings ping-pong so that the last product lands in U
+    const int products = 4 + squarings;
+    double *Rc = B + 4 * sl;
+    for (int i = 0; i < products; ++i) {
+        double *Rn = (i == products - 1) ? U : ((i % 2 == 0) ? T0 : T1);
+        if (i < 4) {
+            GEMM(Rc, A4, B + (3 - i) * sl, 1.0, Rn);                    // R <- R A4 + B_(3-i)
+        } else {
+            GEMM(Rc, Rc, nullptr, 0.0, Rn);
+        }
+        Rc = Rn;
     }
 #undef GEMM
     return OO_OK;
@@ -119,8 +139,8 @@ int expm_scaled(const double *A, int N, int ld, int batch, int squarings, double
 
 // ---- fused expm for ld <= 64: one CTA per matrix, everything resident in shared memory -------------
 // The unfused route above costs 21 + s launches whose kernels are a few microseconds each; for the
-// small bases of the reference's molecules (7 ... 43 orbitals) the whole Pade / Newton-Schulz / squaring
-// chain fits five n8 x n8 shared-memory slots (n8 = N rounded up to 8), so one launch does all of it:
+// small bases of the reference's molecules (7 ... 43 orbitals) the whole Taylor / squaring
+// chain fits six n8 x n8 shared-memory slots (n8 = N rounded up to 8; 209 KB at n8 = 64), so one launch does all of it:
 // 16 warps, DMMA.8x8x4 straight from shared memory (row stride = 4 mod 16 doubles: conflict-free A and B
 // fragment loads), same arithmetic in the same order as expm_scaled().
 constexpr int kFusedMaxN8 = 64;
@@ -128,13 +148,16 @@ constexpr int kFusedThreads = 512;
 
 __host__ __device__ inline int fused_row_stride(int n8) { return ((n8 + 11) / 16) * 16 + 4; }   // >= n8, = 4 mod 16
 
-size_t fused_smem_bytes(int n8) { return (size_t)5 * n8 * fused_row_stride(n8) * sizeof(double); }
+size_t fused_smem_bytes(int n8) { return (size_t)6 * n8 * fused_row_stride(n8) * sizeof(double); }
 
 // D = alpha X Y + beta E + gamma I(rows < eyeN); D must not alias X, Y or E
+// P1, P2, P3 (optional): the epilogue also adds p1 P1 + p2 P2 + p3 P3 -- a Taylor block B_j formed on the fly
 template <int GR, int GC>
 __device__ __forceinline__ void smem_gemm(double *__restrict__ D, const double *X, const double *Y, int n8,
                                           int LS, double alpha, const double *E, double beta, double gamma,
-                                          int eyeN) {
+                                          int eyeN, const double *P1 = nullptr, double p1 = 0.0,
+                                          const double *P2 = nullptr, double p2 = 0.0, const double *P3 = nullptr,
+                                          double p3 = 0.0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int nt = n8 >> 3;
@@ -169,6 +192,9 @@ __device__ __forceinline__ void smem_gemm(double *__restrict__ D, const double *
                     const int col = 8 * (c0 + j) + 2 * t + c;
                     double v = alpha * acc[i][j][c];
                     if (E) v += beta * E[row * LS + col];
+                    if (P1) v += p1 * P1[row * LS + col];
+                    if (P2) v += p2 * P2[row * LS + col];
+                    if (P3) v += p3 * P3[row * LS + col];
                     if (row == col && row < eyeN) v += gamma;
                     D[row * LS + col] = v;
                 }
@@ -209,6 +235,7 @@ __global__ void __launch_bounds__(kFusedThreads) expm_fused_kernel(const FusedEx
     const int n8 = p.n8, LS = fused_row_stride(n8), N = p.N;
     const int slot = n8 * LS;
     double *S0 = sm, *S1 = sm + slot, *S2 = sm + 2 * slot, *S3 = sm + 3 * slot, *S4 = sm + 4 * slot;
+    double *S5 = sm + 5 * slot;
     const int b = blockIdx.x;
     // ---- A = scale * input into S0 (zero padded to n8)
     for (int e = threadIdx.x; e < slot; e += blockDim.x) S0[e] = 0.0;
@@ -251,29 +278,22 @@ __global__ void __launch_bounds__(kFusedThreads) expm_fused_kernel(const FusedEx
             __syncthreads();
         }
     }
-    const double b0 = 17297280.0;
-    const double c1 = 8648640.0 / b0, c2 = 1995840.0 / b0, c3 = 277200.0 / b0, c4 = 25200.0 / b0,
-                 c5 = 1512.0 / b0, c6 = 56.0 / b0, c7 = 1.0 / b0;
-    double *A = S0, *A2 = S1, *A4 = S2, *A6 = S3, *W = S4;
+    // degree-18 Taylor polynomial by Paterson-Stockmeyer (same arithmetic, same order as expm_scaled())
+    double c[kTaylorDegree + 1];
+#pragma unroll
+    for (int k = 0; k <= kTaylorDegree; ++k) c[k] = inv_factorial(k);
+    double *A = S0, *A2 = S1, *A3 = S2, *A4 = S3;
     smem_gemm<GR, GC>(A2, A, A, n8, LS, 1.0, nullptr, 0.0, 0.0, 0);
+    smem_gemm<GR, GC>(A3, A2, A, n8, LS, 1.0, nullptr, 0.0, 0.0, 0);
     smem_gemm<GR, GC>(A4, A2, A2, n8, LS, 1.0, nullptr, 0.0, 0.0, 0);
-    smem_gemm<GR, GC>(A6, A4, A2, n8, LS, 1.0, nullptr, 0.0, 0.0, 0);
-    smem_lincomb(W, c7, A6, c5, A4, c3, A2, c1, N, n8, LS);
-    double *V = S3;
-    smem_lincomb(V, c6, A6, c4, A4, c2, A2, 1.0, N, n8, LS);                 // in place over A6
-    double *P = S1;
-    smem_gemm<GR, GC>(P, A, W, n8, LS, 1.0, V, 1.0, 0.0, 0);                  // P = V + A W   (A2 dead)
-    double *Q = S2;
-    smem_lincomb(Q, 2.0, V, -1.0, P, 0.0, nullptr, 0.0, N, n8, LS);          // Q = V - A W   (A4 dead)
-    double *Xc = S4, *Xn = S3, *T = S0;
-    smem_lincomb(Xc, -1.0, Q, 0.0, nullptr, 0.0, nullptr, 2.0, N, n8, LS);   // X1 = 2I - Q    (W dead)
-    for (int it = 0; it < kNewtonSchulzIters; ++it) {
-        smem_gemm<GR, GC>(T, Q, Xc, n8, LS, -1.0, nullptr, 0.0, 2.0, N);     // T = 2I - Q X   (A, V dead)
-        smem_gemm<GR, GC>(Xn, Xc, T, n8, LS, 1.0, nullptr, 0.0, 0.0, 0);
-        double *tmp = Xc; Xc = Xn; Xn = tmp;
+    double *Rc = S4, *Rn = S5;
+    smem_lincomb(Rc, c[17], A, c[18], A2, 0.0, nullptr, c[16], N, n8, LS);               // B_4
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {                                                        // R <- R A4 + B_j
+        smem_gemm<GR, GC>(Rn, Rc, A4, n8, LS, 1.0, nullptr, 0.0, c[4 * j], N, A, c[4 * j + 1], A2, c[4 * j + 2], A3,
+                          c[4 * j + 3]);
+        double *tmp = Rc; Rc = Rn; Rn = tmp;
     }
-    double *Rc = S0, *Rn = S2;                                              // T and Q are dead now
-    smem_gemm<GR, GC>(Rc, Xc, P, n8, LS, 1.0, nullptr, 0.0, 0.0, 0);
     for (int s = 0; s < squarings; ++s) {
         smem_gemm<GR, GC>(Rn, Rc, Rc, n8, LS, 1.0, nullptr, 0.0, 0.0, 0);
         double *tmp = Rc; Rc = Rn; Rn = tmp;
