@@ -65,6 +65,8 @@ _SIGNATURES = {
     "oo_pack_eri_8fold_f64": (_i32, [_ptr, _ptr, _i32, _ptr]),
     "oo_class_transform_sym_f64": (_i32, [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _size, _u32,
                                           _ptr]),
+    "oo_class_transform_sym_slab_f64": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr,
+                                               _size, _u32, _ptr]),
     "oo_class_active_hamiltonian_f64": (_i32, [_ptr, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _ptr, _ptr, _ptr,
                                                _ptr, _ptr]),
     "oo_class_fock_gradient_f64": (_i32, [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32,

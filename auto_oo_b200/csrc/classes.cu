@@ -36,15 +36,16 @@ int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C
 
 int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
                         int64_t nrows2, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
-                        int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream);
+                        int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream, int64_t r2_offset = 0);
 
-int dgemm_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2, int dorb, int dP, int64_t N,
-                        int64_t K, int64_t ldb, int64_t ldc, int batch, int64_t strideA8, int64_t strideB,
-                        int64_t strideC, int64_t strideC2, cudaStream_t stream);
+int dgemm_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, const double *B, double *C,
+                        double *C2, int dorb, int dP, int64_t N, int64_t K, int64_t ldb, int64_t ldc, int batch,
+                        int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream);
 bool dgemm_tn_tri_supported(int nclass);
 int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
                             int64_t ngroups, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
-                            int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream);
+                            int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream,
+                            int64_t group_offset = 0);
 
 int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int transpose_mirror, int nclass, int dorb,
                           int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int64_t ld_out, int batch,
@@ -351,10 +352,18 @@ size_t class_transform_sym_ws_bytes(int ld, int nIp, int batch) {
     return (size_t)batch * (t1 + t1t + x + 4 * xp) * sizeof(double);
 }
 
+// slab_ld > 0: gpk is a SLAB of the 8-fold packed tensor, g8[RS][pq_lo + j], j < pq_cnt, row pitch slab_ld (sharded
+// evaluation).  Quarter 1 and the Coulomb quarter 2 then run over the slab's pairs only; every later step is linear
+// in the quarter-1 result, so the class buffer this call produces is this slab's ADDITIVE share of the complete
+// one (the caller sums the shares of all ranks).  The pair-unpacked quarter-1 copy and the quarter-2 output are
+// zeroed first: pairs outside the slab contribute nothing.
 int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int64_t strideC, int N, int ld,
                         int nIp, int batch, double *cls, void *ws, size_t ws_bytes, unsigned flags,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int64_t slab_ld = 0, int64_t pq_lo = 0, int64_t pq_cnt = 0) {
     const bool g_class_unfused_pack = (flags & OO_FLAG_CLASS_UNFUSED_PACK) != 0;   // separate pack / expand passes
+    const bool slab = slab_ld > 0;
+    if (slab && (!(flags & OO_FLAG_CLASS_ERI_8FOLD) || g_class_unfused_pack || ((flags >> 16) & 0x7fu)))
+        return OO_ERR_INVALID_ARG;
     OO_REQUIRE(gpk && C && cls && ws);
     OO_REQUIRE(N > 0 && ld >= N && (ld % 2) == 0 && nIp > 0 && (nIp % 2) == 0 && nIp <= ld && batch > 0);
     if (ws_bytes < class_transform_sym_ws_bytes(ld, nIp, batch)) return OO_ERR_WORKSPACE;
@@ -389,8 +398,13 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     if (!run(0)) {
     } else if (flags & OO_FLAG_CLASS_ERI_8FOLD) {
         // gpk is the 8-fold packed tensor g8[RS][PQ]: the quarter-1 producer gathers its k-rows from it
-        if ((rc = dgemm_tn_q1_packed8(gpk, C, T1, T1t, ld, (int)ldp, nIp, ld, ld, nIp, batch, strideG, strideC, sT1,
-                                      sT1t, stream)))
+        if (slab) {
+            OO_CUDA_CHECK(cudaMemsetAsync(T1t, 0, (size_t)batch * sT1t * sizeof(double), stream));
+            OO_CUDA_CHECK(cudaMemsetAsync(P0, 0, (size_t)batch * sXp * sizeof(double), stream));
+        }
+        if ((rc = dgemm_tn_q1_packed8(gpk, slab ? slab_ld : ldp, slab ? (int)pq_lo : 0, slab ? (int)pq_cnt : (int)ldp, C,
+                                      T1, T1t, ld, (int)ldp, nIp, ld, ld, nIp, batch, strideG, strideC, sT1, sT1t,
+                                      stream)))
             return rc;
     } else if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp,
                                           batch, strideG, strideC, sT1, sT1t, stream))) {
@@ -404,12 +418,16 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 1, sX, sXp);
         OO_LAUNCH_CHECK();
     } else if (tri_q2) {
-        if ((rc = dgemm_tn_tri_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * nIp, ld, batch, sT1, strideC, sXp,
-                                          stream)))
+        // (a slab: only its pairs -- groups pq_lo .. pq_lo + pq_cnt -- hold anything; the rest of P0 stays zero)
+        const int64_t g_lo = slab ? pq_lo : 0, g_cnt = slab ? pq_cnt : ldp;
+        if ((rc = dgemm_tn_tri_class_pack(T1 + g_lo * nIp, C, P0, 1, nIp, ld, g_cnt, npIp, ld, ldp * nIp, ld, batch, sT1,
+                                          strideC, sXp, stream, g_lo)))
             return rc;
-    } else if ((rc = dgemm_tn_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * nIp, ld, batch, sT1, strideC,
-                                         sXp, stream))) {
-        return rc;
+    } else {
+        const int64_t g_lo = slab ? pq_lo : 0, g_cnt = slab ? pq_cnt : ldp;
+        if ((rc = dgemm_tn_class_pack(T1 + g_lo * nIp, C, P0, 1, nIp, ld, g_cnt, npIp, ld, ldp * nIp, ld, batch, sT1,
+                                      strideC, sXp, stream, g_lo)))
+            return rc;
     }
     if (run(2)) Q(P0, sXp, P1, sXp, ld * npIp, ld);                      // X'[q,mn,a]
     if (!run(3)) {
@@ -479,6 +497,14 @@ int oo_class_transform_sym_f64(const double *g_packed, int64_t strideG, const do
                                unsigned flags, void *stream) {
     return oo::class_transform_sym(g_packed, strideG, C, strideC, N, ld, nIp, batch, cls, ws, ws_bytes, flags,
                                    (cudaStream_t)stream);
+}
+
+int oo_class_transform_sym_slab_f64(const double *g_packed8_slab, int64_t slab_ld, int64_t pq_lo, int64_t pq_cnt,
+                                    const double *C, int64_t strideC, int N, int ld, int nIp, int batch, double *cls,
+                                    void *ws, size_t ws_bytes, unsigned flags, void *stream) {
+    if (slab_ld <= 0 || pq_cnt <= 0) return OO_ERR_INVALID_ARG;
+    return oo::class_transform_sym(g_packed8_slab, 0, C, strideC, N, ld, nIp, batch, cls, ws, ws_bytes,
+                                   flags | OO_FLAG_CLASS_ERI_8FOLD, (cudaStream_t)stream, slab_ld, pq_lo, pq_cnt);
 }
 
 int oo_class_transform_f64(const double *g_pairT, int64_t strideG, const double *C, int64_t strideC, int N,

@@ -74,6 +74,12 @@ struct TnArgs {
     const double *A8;
     int64_t strideA8;
     int K;
+    // a SLAB of the pair columns (sharded evaluation: every rank holds A8[:, pq_lo : pq_lo + pq_cnt], row pitch a8_ld):
+    // the tiles cover PQ in [pq_lo, pq_lo + pq_cnt) only; the whole tensor is pq_lo = 0, pq_cnt = a8_ld = d2
+    int pq_lo, pq_cnt;
+    int64_t a8_ld;
+    // mode 3 (tri_rows): the row groups are the packed pairs r2_offset + r2 (a slab of the quarter-1 result)
+    int64_t r2_offset;
     int last_subs;   // k4-substeps of the LAST k-block that hold rows below K (whole 8-row atoms beyond K are skipped)
     // Always 0, but opaque to the compiler: ANDed with bits of every fragment a consumer loaded from
     // a stage and added to the address of that stage's "empty" arrive.  The arrive thus has a true
@@ -128,7 +134,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // AMODE 1 walks the m-tiles as (PQ-tile outer, s inner): the CTAs that run together share one PQ panel of
     // A8, and every row RS(r, s) of that panel is needed twice -- by tile s at step r and by tile r at step s --
     // so the second use is served from L2 (the 8-fold packed tensor is read from HBM about once).
-    auto lin_tile = [&](int mt, int &s, int &pq0) {
+    auto lin_tile = [&](int mt, int &s, int &pq0) {      // pq0: offset inside the slab
         s = mt % args.d0;
         pq0 = (mt / args.d0) * Cfg::BM;
     };
@@ -151,7 +157,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 lin_tile(rem / args.tiles_n, s, pq0);
                 const int n0 = (rem % args.tiles_n) * Cfg::BN;
                 const int bb = args.b_batched ? b : 0;
-                const int rows = (args.d2 - pq0) < Cfg::BM ? (args.d2 - pq0) : Cfg::BM;   // even: d2 and BM are
+                const int rows = (args.pq_cnt - pq0) < Cfg::BM ? (args.pq_cnt - pq0) : Cfg::BM;   // even: pq_cnt, BM are
                 const uint32_t row_bytes = (uint32_t)rows * 8u;
                 const double *Ab = args.A8 + (int64_t)b * args.strideA8 + pq0;
                 for (int kb = 0; kb < args.kblocks; ++kb) {
@@ -166,7 +172,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         int r = k0 + lane;
                         r = r < args.K ? r : args.K - 1;         // rows past K meet zero rows of B (TMA fill)
                         const int hi = r > s ? r : s, lo = r > s ? s : r;
-                        const double *src = Ab + ((int64_t)hi * (hi + 1) / 2 + lo) * args.d2;
+                        const double *src = Ab + ((int64_t)hi * (hi + 1) / 2 + lo) * args.a8_ld;
                         bulk_load_1d(sA + lane * Cfg::LIN_PITCH, src, row_bytes, &full_bar[stage]);
                     }
                     if (lane == 0) {
@@ -310,8 +316,8 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (AMODE) {                                   // rows (s, PQ) of one s: global row s * d2 + PQ
                 int s, pq0;
                 lin_tile(rem / args.tiles_n, s, pq0);
-                m0 = (int64_t)s * args.d2 + pq0;
-                m_end = (int64_t)(s + 1) * args.d2;
+                m0 = (int64_t)s * args.d2 + args.pq_lo + pq0;
+                m_end = (int64_t)s * args.d2 + args.pq_lo + args.pq_cnt;
             }
             const int n0 = (rem % args.tiles_n) * Cfg::BN;
             double *Cb = args.C + (int64_t)b * args.strideC;
@@ -376,10 +382,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         if (DUAL == 4) {
                             crow2 = base2 + r2 * args.d2;
                         } else {
-                            int p = (int)((sqrt(8.0 * (double)r2 + 1.0) - 1.0) * 0.5);
-                            while ((int64_t)(p + 1) * (p + 2) / 2 <= r2) ++p;
-                            while ((int64_t)p * (p + 1) / 2 > r2) --p;
-                            const int q = (int)(r2 - (int64_t)p * (p + 1) / 2);
+                            const int64_t pq = r2 + args.r2_offset;
+                            int p = (int)((sqrt(8.0 * (double)pq + 1.0) - 1.0) * 0.5);
+                            while ((int64_t)(p + 1) * (p + 2) / 2 <= pq) ++p;
+                            while ((int64_t)p * (p + 1) / 2 > pq) --p;
+                            const int q = (int)(pq - (int64_t)p * (p + 1) / 2);
                             if (p < args.d1) {
                                 crow2 = base2 + ((int64_t)p * args.d1 + q) * args.d2;
                                 crow3 = base2 + ((int64_t)q * args.d1 + p) * args.d2;
@@ -427,6 +434,7 @@ struct TnDual {
     int mode = 0;               // 1 = swap02, 2 = packed-pair unpack, 3 / 4 = class-pair packing (tri / plain rows), 5 = class-pair expansion
     int d0 = 0, d1 = 0, d2 = 0;
     int64_t strideC2 = 0;
+    int64_t r2_offset = 0;
 };
 
 template <class Cfg>
@@ -465,6 +473,9 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     args.A8 = nullptr;
     args.strideA8 = 0;
     args.K = (int)K;
+    args.pq_lo = args.pq_cnt = 0;
+    args.a8_ld = 0;
+    args.r2_offset = dual.r2_offset;
     args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
 
     static unsigned long long attr_set = 0;
@@ -510,9 +521,10 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
 //   T1[(s, PQ), m] = sum_r A8[RS(r, s)][PQ] C[r, m],   RS(r, s) = tri(max, min),
 // stored as C[(s PQ), m] and, pair unpacked, at C2 rows (q p s) and (p q s) (the mode-2 epilogue).
 template <class Cfg>
-static int launch_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2, int S, int dorb, int dP,
-                                int64_t N, int64_t K, int64_t ldb, int64_t ldc, int batch, int64_t strideA8,
-                                int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream) {
+static int launch_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, const double *B, double *C,
+                                double *C2, int S, int dorb, int dP, int64_t N, int64_t K, int64_t ldb, int64_t ldc,
+                                int batch, int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2,
+                                cudaStream_t stream) {
     CUtensorMap mapB;
     const int b_batched = (batch > 1 && strideB != 0);
     int rc = encode_tmap_3d_f64(&mapB, B, (uint64_t)N, (uint64_t)K, b_batched ? batch : 1, (uint64_t)ldb,
@@ -530,7 +542,7 @@ static int launch_tn_q1_packed8(const double *A8, const double *B, double *C, do
     args.strideC = strideC;
     args.strideC2 = strideC2;
     args.kblocks = (int)ceil_div(K, Cfg::BK);
-    args.tiles_m = S * (int)ceil_div(dP, Cfg::BM);
+    args.tiles_m = S * (int)ceil_div(pq_cnt, Cfg::BM);
     args.tiles_n = (int)ceil_div(N, Cfg::BN);
     args.batch = batch;
     args.a_batched = (batch > 1 && strideA8 != 0);
@@ -539,6 +551,10 @@ static int launch_tn_q1_packed8(const double *A8, const double *B, double *C, do
     args.A8 = A8;
     args.strideA8 = args.a_batched ? strideA8 : 0;
     args.K = (int)K;
+    args.pq_lo = pq_lo;
+    args.pq_cnt = pq_cnt;
+    args.a8_ld = a8_ld;
+    args.r2_offset = 0;
     args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
     static unsigned long long attr_set = 0;
     if (once_per_device(attr_set))
@@ -629,17 +645,20 @@ int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C
 
 // Quarter 1 from the 8-fold packed AO integrals A8[RS][PQ] (rows of dP doubles, RS over pairs of S = dorb orbitals):
 // see launch_tn_q1_packed8.  N = number of class columns (ldb, ldc even).
-int dgemm_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2, int dorb, int dP, int64_t N,
-                        int64_t K, int64_t ldb, int64_t ldc, int batch, int64_t strideA8, int64_t strideB,
-                        int64_t strideC, int64_t strideC2, cudaStream_t stream) {
+// A8 may be a slab of the pair columns: row pitch a8_ld, columns PQ in [pq_lo, pq_lo + pq_cnt) (both even).
+int dgemm_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, const double *B, double *C,
+                        double *C2, int dorb, int dP, int64_t N, int64_t K, int64_t ldb, int64_t ldc, int batch,
+                        int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream) {
     OO_REQUIRE(A8 && B && C && C2 && dorb > 0 && K > 0 && K <= dorb && N > 0 && batch > 0);
+    OO_REQUIRE(pq_lo >= 0 && pq_cnt > 0 && pq_lo + pq_cnt <= dP && (pq_lo % 2) == 0 && (pq_cnt % 2) == 0);
+    OO_REQUIRE(a8_ld >= pq_cnt && (a8_ld % 2) == 0);
     OO_REQUIRE((int64_t)dP >= (int64_t)dorb * (dorb + 1) / 2 && (dP % 2) == 0);
     OO_REQUIRE((ldb % 2) == 0 && (ldc % 2) == 0 && ldc >= N && (strideA8 % 2) == 0 && (strideB % 2) == 0);
     OO_REQUIRE(((uintptr_t)A8 % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0);
     if ((int64_t)dorb * dP >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
 #define OO_Q1(CFG)                                                                                                 \
-    return launch_tn_q1_packed8<CFG>(A8, B, C, C2, dorb, dorb, dP, N, K, ldb, ldc, batch, strideA8, strideB, strideC, \
-                                     strideC2, stream)
+    return launch_tn_q1_packed8<CFG>(A8, a8_ld, pq_lo, pq_cnt, B, C, C2, dorb, dorb, dP, N, K, ldb, ldc, batch,      \
+                                     strideA8, strideB, strideC, strideC2, stream)
     if (N > 64) OO_Q1(TnWide);
     if (N > 48) OO_Q1(TnMid);
     if (N > 40) OO_Q1(TnMid48);
@@ -657,7 +676,7 @@ int dgemm_tn_q1_packed8(const double *A8, const double *B, double *C, double *C2
 // pack_class_pairs fused into its epilogue.
 int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
                         int64_t nrows2, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
-                        int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream) {
+                        int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream, int64_t r2_offset) {
     OO_REQUIRE(P && nclass > 0 && dorb > 0 && nrows2 > 0 && npair_ld >= (int64_t)nclass * (nclass + 1) / 2);
     TnDual dual;
     dual.C2 = P;
@@ -666,6 +685,7 @@ int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_ro
     dual.d1 = dorb;
     dual.d2 = (int)npair_ld;
     dual.strideC2 = strideP;
+    dual.r2_offset = r2_offset;
     const int64_t ldc = nclass + (nclass & 1);
     return dgemm_tn_impl(At, B, P, nrows2 * nclass, nclass, K, lda, ldb, ldc, batch, strideA, strideB, 0, stream, dual);
 }

@@ -51,6 +51,7 @@ struct TriArgs {
     int tri_rows;           // 1: group = packed pair p(p+1)/2 + q of dorb orbitals, written at (p q) and (q p)
     int dorb;
     int64_t ngroups;
+    int64_t group_offset;   // tri_rows: the packed pair of group g is group_offset + g (a slab of the pairs)
     int kblocks, tiles_per_batch, batch;
     int a_batched, b_batched;
     int last_subs;          // substeps of the last k-block with rows below K
@@ -207,10 +208,11 @@ dgemm_tn_tri_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         double *row0 = nullptr, *row1 = nullptr;
         double *base = args.P + (int64_t)b * args.strideP;
         if (args.tri_rows) {
-            int p = (int)((sqrt(8.0 * (double)grp + 1.0) - 1.0) * 0.5);
-            while ((int64_t)(p + 1) * (p + 2) / 2 <= grp) ++p;
-            while ((int64_t)p * (p + 1) / 2 > grp) --p;
-            const int q = (int)(grp - (int64_t)p * (p + 1) / 2);
+            const int64_t pq = grp + args.group_offset;
+            int p = (int)((sqrt(8.0 * (double)pq + 1.0) - 1.0) * 0.5);
+            while ((int64_t)(p + 1) * (p + 2) / 2 <= pq) ++p;
+            while ((int64_t)p * (p + 1) / 2 > pq) --p;
+            const int q = (int)(pq - (int64_t)p * (p + 1) / 2);
             if (p >= args.dorb) continue;                    // padding of the pair index
             row0 = base + ((int64_t)p * args.dorb + q) * args.npair_ld;
             row1 = base + ((int64_t)q * args.dorb + p) * args.npair_ld;
@@ -239,7 +241,7 @@ dgemm_tn_tri_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 template <class Cfg>
 int launch_tri(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb, int64_t ngroups,
                int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch, int64_t strideA, int64_t strideB,
-               int64_t strideP, cudaStream_t stream) {
+               int64_t strideP, cudaStream_t stream, int64_t group_offset) {
     CUtensorMap mapA, mapB;
     const int a_batched = (batch > 1 && strideA != 0), b_batched = (batch > 1 && strideB != 0);
     const uint64_t dimsA[4] = {(uint64_t)nclass, (uint64_t)ngroups, (uint64_t)K, (uint64_t)(a_batched ? batch : 1)};
@@ -258,6 +260,7 @@ int launch_tri(const double *At, const double *B, double *P, int tri_rows, int n
     args.tri_rows = tri_rows;
     args.dorb = dorb;
     args.ngroups = ngroups;
+    args.group_offset = group_offset;
     args.kblocks = (int)ceil_div(K, Cfg::BK);
     args.tiles_per_batch = (int)ceil_div(ngroups, Cfg::NCW);
     args.batch = batch;
@@ -286,7 +289,8 @@ bool dgemm_tn_tri_supported(int nclass) { return nclass > 16 && nclass <= 48 && 
 // tri_rows: g = p(p+1)/2 + q is a packed pair of `dorb` orbitals and both P[(p q)] and P[(q p)] are written.
 int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
                             int64_t ngroups, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
-                            int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream) {
+                            int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream,
+                            int64_t group_offset) {
     OO_REQUIRE(At && B && P && nclass > 0 && ngroups > 0 && K > 0 && batch > 0 && dorb > 0);
     OO_REQUIRE(dgemm_tn_tri_supported(nclass) && npair_ld >= (int64_t)nclass * (nclass + 1) / 2);
     OO_REQUIRE((lda % 2) == 0 && (ldb % 2) == 0 && (strideA % 2) == 0 && (strideB % 2) == 0);
@@ -294,7 +298,7 @@ int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tr
     if (ngroups >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
 #define OO_TRI(GP, MTC)                                                                                              \
     return launch_tri<TriCfg<GP, MTC, 4>>(At, B, P, tri_rows, nclass, dorb, ngroups, npair_ld, K, lda, ldb, batch, strideA, \
-                                          strideB, strideP, stream)
+                                          strideB, strideP, stream, group_offset)
     if (nclass <= 24) OO_TRI(32, 3);
     if (nclass <= 32) OO_TRI(32, 4);
     if (nclass <= 40) OO_TRI(48, 5);

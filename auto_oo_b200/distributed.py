@@ -109,6 +109,60 @@ def sharded_evaluations(evaluate, kappas, group=None, gather=True):
 
 
 # --------------------------------------------------------------------------------------
+# one evaluation sharded over the packed AO pair index
+# --------------------------------------------------------------------------------------
+def pair_slab_range(n_pairs_ld, world_size, rank):
+    """Columns ``[lo, hi)`` of the 8-fold packed tensor ``g8[RS][PQ]`` (``n_pairs_ld`` = padded pair count, even)
+    that ``rank`` holds: contiguous, balanced, both ends even (16-byte alignment of every row slice)."""
+    half = int(n_pairs_ld) // 2
+    lo, hi = shard_range(half, world_size, rank)
+    return 2 * lo, 2 * hi
+
+
+class PairShard:
+    """ONE evaluation (E + gradient + Hessian) spread over the ranks of ``group`` by the packed pair index PQ of the
+    8-fold packed AO integrals ``g8[RS][PQ]`` (second decomposition; for bases whose integrals exceed one
+    GPU).  Rank ``r`` holds the columns :func:`pair_slab_range`; quarter 1 of the class transform -- the N^4 nI part
+    of the work and all of the N^4 memory -- runs on the slab alone, every later step is linear in its result, so
+    each rank ends with an additive share of the K / J rows of the class buffer and ONE ``all_reduce`` (NCCL over
+    NVLink / NVSwitch, in-switch reduction where NVLS is available) completes it on every rank.  Energy, gradient
+    and Hessian are then formed on every rank from the complete class buffer (replicated, a tenth of the work).
+
+    ``slab_given=True``: the ``int2e_ao`` handed to the engine / ``OO_energy`` IS this rank's slab
+    ``(ld (ld+1)/2, hi - lo)`` (pairs over the orbitals padded to even), for integrals that no single device ever
+    holds; ``False``: it is the full ``(N,N,N,N)`` tensor (tests, small problems) and the slab is cut out of it."""
+
+    def __init__(self, group=None, slab_given=False, all_reduce=None):
+        self.group, self.slab_given = group, bool(slab_given)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._all_reduce = all_reduce
+        self.pq_lo = self.pq_cnt = self.slab_ld = None
+        self.timing = None          # a list here collects (start, end) CUDA-event pairs around every all-reduce
+
+    def bind(self, engine):
+        from . import _lib
+        ldp = int(_lib.load().oo_pair_ld(engine.ld))
+        lo, hi = pair_slab_range(ldp, self.world, self.rank)
+        self.pq_lo, self.pq_cnt, self.slab_ld = lo, hi - lo, hi - lo
+        assert self.pq_cnt > 0, "more ranks than pair columns"
+
+    def all_reduce(self, t):
+        if self._all_reduce is not None:
+            return self._all_reduce(t)
+        if self.world > 1:
+            if self.timing is not None and t.is_cuda:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                ev[1].record()
+                self.timing.append(ev)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+# --------------------------------------------------------------------------------------
 # slab-parallel four-index transform
 # --------------------------------------------------------------------------------------
 def _cuda_gemm_tn(At, B, out):

@@ -149,12 +149,16 @@ class HotPathEngine:
     SYMMETRY_TOL = 1e-13
 
     def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None,
-                 n_geometries=0, eri_symmetry="auto", eri_packing="8fold"):
+                 n_geometries=0, eri_symmetry="auto", eri_packing="8fold", pair_shard=None):
         """``eri_symmetry``: "auto" measures the 8-fold symmetry of ``int2e_ao`` on the device at first use and
         takes the symmetric class transform (half the quarter-1 work, packed AO integrals) when it holds to
         round-off, the general one otherwise; "off" always takes the general one.
         ``eri_packing``: how the symmetric route keeps the AO integrals in HBM -- "8fold": both pairs packed,
         g8[(r>=s), (p>=q)] (an eighth of N^4; quarter 1 unpacks in its producer), "pair": g[r, s, (p>=q)] (half).
+        ``pair_shard``: ``None`` or a :class:`auto_oo_b200.distributed.PairShard` -- ONE evaluation spread over the
+        ranks of a process group: this rank keeps only its slab of pair columns of the 8-fold packed integrals
+        (``int2e_ao`` may then be the slab itself, see ``PairShard``), computes its additive share of the class
+        buffer and all-reduces it over NVLink; energy, gradient and Hessian are then formed on every rank.
         ``n_geometries`` > 0: ``int1e_ao (G,N,N)``, ``int2e_ao (G,N,N,N,N)``, ``oao_coeff (G,N,N)``,
         ``nuc (G,)`` hold one molecule geometry each (same orbital classes); evaluation ``b`` of a
         batch then uses geometry ``b`` (class path only)."""
@@ -180,15 +184,25 @@ class HotPathEngine:
         with torch.cuda.device(self.device):
             self.h_ao = None if int1e_ao is None else self.to_padded(int1e_ao, 2, batch=G)
             self.X = None if oao_coeff is None else self.to_padded(oao_coeff, 2, batch=G)
-            self.g_ao = None if int2e_ao is None else self.to_padded(int2e_ao, 4, batch=G)
+            slab_in = pair_shard is not None and pair_shard.slab_given
+            self.g_ao = None if (int2e_ao is None or slab_in) else self.to_padded(int2e_ao, 4, batch=G)
             self.nuc_dev = None if G is None else self.dev(np.asarray(nuc, dtype=np.float64).reshape(G))
         self.nIp = pad_even(self.nI)                   # class index padded to even (TMA strides)
         self.g_pairT = None                            # g_ao[p,q,r,s] stored as [r,s,p,q]; built on first use
         self.g_packed = None                           # packed AO integrals when they are 8-fold symmetric
         assert eri_packing in ("8fold", "pair")
         self.eri_packing = eri_packing
+        self.pair_shard = pair_shard
+        if pair_shard is not None:
+            assert self.n_geom == 0 and eri_packing == "8fold", "a pair shard is one problem on 8-fold packed integrals"
+            pair_shard.bind(self)
+            if pair_shard.slab_given:                  # the caller handed over this rank's slab, not the N^4 tensor
+                self.g_packed = self.dev(int2e_ao)
+                self.g_ao = None
         self.eri_symmetry = eri_symmetry
         self._eri_symmetric = None if eri_symmetry == "auto" else False
+        if pair_shard is not None:
+            self._eri_symmetric = True                 # the slab layout IS the symmetric representation
         self.eri_defect = None
         self._ws = {}
         self._icache = {}                              # kind -> (_IntegralsKey | None, MOIntegrals)
@@ -488,6 +502,15 @@ class HotPathEngine:
     def packed_eri(self):
         """The symmetric route's copy of the AO integrals over the ld padded orbitals (row = packed pair p >= q,
         padded to even): ``eri_packing="8fold"`` g8[(r>=s), (pq)], ``"pair"`` g[r, s, (pq)]."""
+        if self.g_packed is None and self.pair_shard is not None:
+            # full tensor given (small problems, tests): pack all of it, keep this rank's columns
+            sh, self.pair_shard = self.pair_shard, None
+            try:
+                full = self.packed_eri()
+            finally:
+                self.pair_shard = sh
+            self.g_packed = full[:, sh.pq_lo:sh.pq_lo + sh.slab_ld].contiguous()
+            del full
         if self.g_packed is None:
             ldp = int(self.lib.oo_pair_ld(self.ld))
             g = self.g_ao.reshape(-1, self.ld ** 4)
@@ -531,7 +554,18 @@ class HotPathEngine:
         B, ld, nIp, rows = C.shape[0], self.ld, self.nIp, self.class_rows()
         cls = out if out is not None and out.shape[0] == B else torch.empty(B, rows, ld, ld, dtype=F64,
                                                                            device=self.device)
-        if self.eri_is_symmetric():
+        if self.pair_shard is not None:
+            sh = self.pair_shard
+            nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM_SYM, self.N, ld, self.nI, B)
+            ws = self.workspace("cls", nbytes)
+            self._check(self.lib.oo_class_transform_sym_slab_f64(_p(self.packed_eri()), sh.slab_ld, sh.pq_lo, sh.pq_cnt,
+                                                                 _p(C), ld * ld if B > 1 else 0, self.N, ld, nIp, B,
+                                                                 _p(cls), _p(ws), nbytes, self.flags, self.stream),
+                        "class_transform_sym_slab")
+            # sum of the ranks' shares of the K and J rows (the whole contiguous buffer goes through the collective;
+            # its last row, h', is written below)
+            sh.all_reduce(cls)
+        elif self.eri_is_symmetric():
             nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_TRANSFORM_SYM, self.N, ld, self.nI, B)
             ws = self.workspace("cls", nbytes)
             gp, sg = self._geo(self.packed_eri(), geo_lo, geo_lo + B)

@@ -249,7 +249,8 @@ class OO_energy:
     GRAPH_MAX_NAO = 128
 
     def __init__(self, mol, ncas, nelecas, oao_mo_coeff=None, freeze_active=False, interface='torch',
-                 device=None, integral_path="class", eri_symmetry="auto", cuda_graphs="auto", eri_packing="8fold"):
+                 device=None, integral_path="class", eri_symmetry="auto", cuda_graphs="auto", eri_packing="8fold",
+                 shard=None, group=None):
         """``integral_path``: ``"class"`` (default) transforms only the J/K integral classes that
         energy, gradient and Hessian read; ``"full"`` runs the complete four-index transform for
         every set of MO coefficients, as the reference does.  ``eri_symmetry``: ``"auto"`` lets the
@@ -260,6 +261,16 @@ class OO_energy:
         at most ``GRAPH_MAX_NAO`` orbitals, ``True`` / ``False`` force it."""
         assert integral_path in ("class", "full")
         assert cuda_graphs in ("auto", True, False)
+        assert shard in (None, "pairs")
+        pair_shard = None
+        if shard == "pairs":
+            # ONE evaluation over the ranks of `group` (torch.distributed must be initialised): every rank builds the
+            # same OO_energy; `mol.int2e_ao` is the full tensor, or -- when `mol.int2e_packed_slab(lo, hi)` exists --
+            # only this rank's slab of the 8-fold packed integrals is ever materialised (distributed.PairShard)
+            from .distributed import PairShard
+            pair_shard = PairShard(group, slab_given=hasattr(mol, "int2e_packed_slab"))
+            assert integral_path == "class", "the sharded evaluation is the class path"
+            cuda_graphs = False                               # a collective sits in the middle of every evaluation
         self.integral_path = integral_path
         self.cuda_graphs = (mol.nao <= self.GRAPH_MAX_NAO) if cuda_graphs == "auto" else bool(cuda_graphs)
         if interface != 'torch':
@@ -287,11 +298,17 @@ class OO_energy:
 
         # integrals go to HBM once (padded layout); host copies are kept as the public attributes
         self.int1e_ao = _as_tensor(mol.int1e_ao)
-        self.int2e_ao = _as_tensor(mol.int2e_ao)
         self.oao_coeff = _as_tensor(mol.oao_coeff)
+        if pair_shard is not None and pair_shard.slab_given:
+            from .distributed import pair_slab_range
+            from .engine import pad_even
+            ldp = pad_even(pad_even(self.nao) * (pad_even(self.nao) + 1) // 2)
+            self.int2e_ao = _as_tensor(mol.int2e_packed_slab(*pair_slab_range(ldp, pair_shard.world, pair_shard.rank)))
+        else:
+            self.int2e_ao = _as_tensor(mol.int2e_ao)
         self.engine = HotPathEngine(self.int1e_ao, self.int2e_ao, self.oao_coeff, self.nuc, self.nao,
                                     no, na, self.params_idx, device=device, eri_symmetry=eri_symmetry,
-                                    eri_packing=eri_packing)
+                                    eri_packing=eri_packing, pair_shard=pair_shard)
 
     # ------------------------------------------------------------------ orbitals
     @property

@@ -30,6 +30,9 @@ CONFIG_SHAPES = {
     "n2_ccpvdz_cas66": (28, 14, 6, 6),
     "c6h6_ccpvdz_cas66": (114, 42, 6, 6),
     "synthetic_n256_cas1212": (256, 76, 12, 12),
+    # beyond BASELINE: capacity shapes for the pair-sharded evaluation (bench.py --mode strong)
+    "synthetic_n384_cas1212": (384, 76, 12, 12),
+    "synthetic_n512_cas1212": (512, 76, 12, 12),
 }
 
 
@@ -92,6 +95,28 @@ class SyntheticMol:
             torch.matmul(B2[a:a + step], B2.T, out=g[a:a + step])
         g.mul_(0.3)
         return g.view(N, N, N, N)
+
+    def int2e_packed_slab(self, lo, hi):
+        """Columns ``[lo, hi)`` of the 8-fold packed integrals ``g8[RS][PQ] = g[r,s,p,q]`` (``r >= s``, ``p >= q``,
+        pairs over the orbitals padded to even, zero padding) straight from the density-fitting factor -- the N^4
+        tensor is never formed.  What ``OO_energy(..., shard="pairs")`` asks every rank for
+        (:class:`auto_oo_b200.distributed.PairShard`)."""
+        N = self.nao
+        ld = N + (N & 1)
+        B = self._B
+        if ld > N:
+            Bp = torch.zeros(ld, ld, B.shape[2], dtype=B.dtype, device=B.device)
+            Bp[:N, :N] = B
+            B = Bp
+        rows, cols = np.tril_indices(ld)
+        rows_t = torch.as_tensor(rows, device=B.device)
+        cols_t = torch.as_tensor(cols, device=B.device)
+        packed = B[rows_t, cols_t]                                  # (npair, R)
+        slab = torch.zeros(hi - lo, packed.shape[1], dtype=B.dtype, device=B.device)
+        top = min(hi, packed.shape[0])
+        if top > lo:
+            slab[: top - lo] = packed[lo:top]
+        return (packed @ slab.T).mul_(0.3)
 
     # -- duck-typed Moldata_pyscf attributes (numpy on CPU, like PySCF arrays) --
     def _np(self, t):

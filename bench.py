@@ -278,6 +278,54 @@ def same_config_measurement(dev):
     return out
 
 
+def strong_arm(args, mol, ncas, nelecas, dev, world, rank, n_evals, max_over_ranks, barrier):
+    """ONE evaluation at a time spread over all ranks (pair-sharded class transform + one NCCL all-reduce of the
+    class buffer; E, G, H replicated): evaluations/s of the whole job, stage split and the all-reduce share."""
+    from auto_oo_b200 import OO_energy
+    from auto_oo_b200.synthetic import random_rdms, random_kappa
+    oo = OO_energy(mol, ncas, nelecas, oao_mo_coeff=mol.random_oao_mo_coeff, device=dev, shard="pairs")
+    eng = oo.engine
+    one, two = random_rdms(ncas, nelecas, seed=5, device=dev)
+    Coao = eng.to_padded(oo.oao_mo_coeff, 2)
+    nk = oo.n_kappa
+    kap = random_kappa(nk, seed=77, device=dev, batch=3 + n_evals)           # the SAME rotations on every rank
+    squarings = eng.squarings_for(kap)
+    H = torch.empty(1, nk, nk, dtype=F64, device=dev)
+    for i in range(3):
+        eng.evaluate(Coao, one, two, kappa=kap[i:i + 1], squarings=squarings, H_out=H)
+    barrier()
+    events, eng.pair_shard.timing = {}, []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3, 3 + n_evals):
+        E, G, _ = eng.evaluate(Coao, one, two, kappa=kap[i:i + 1], squarings=squarings, H_out=H, stage_events=events)
+    e1.record()
+    barrier()
+    t = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    t_ar = sum(a.elapsed_time(b) for a, b in eng.pair_shard.timing) * 1e-3
+    chk = torch.stack([E[0], G.abs().sum(), H.diagonal(dim1=1, dim2=2).sum()])
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    sh = eng.pair_shard
+    out = {"value": n_evals / t, "unit": UNIT, "ms_per_evaluation": t / n_evals * 1e3, "evaluations": n_evals,
+           "n_gpus": world, "scaling": "strong",
+           "stage_ms_per_evaluation": {k: sum(a.elapsed_time(b) for a, b in v) / n_evals for k, v in events.items()},
+           "allreduce_ms_per_evaluation": t_ar / n_evals * 1e3,
+           "allreduce_bytes": int(eng.class_rows() * eng.ld * eng.ld * 8),
+           "slab": {"pair_columns": [int(sh.pq_lo), int(sh.pq_lo + sh.pq_cnt)],
+                    "eri_bytes_per_gpu": int(eng.packed_eri().numel() * 8)},
+           "replicas_agree": bool(((hi - lo).abs() <= 1e-9 * (1 + hi.abs())).all().item()),
+           "what": "OO_energy(shard='pairs'): quarter 1 + Coulomb quarter 2 on this rank's pair columns of the 8-fold "
+                   "packed integrals, one NCCL all-reduce of the class buffer, E/G/H on every rank"}
+    checks = (E[0].item(), G[0].clone(), H[0].diagonal().sum().item())
+    del oo, eng
+    torch.cuda.empty_cache()
+    return out, checks
+
+
 # --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -290,6 +338,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-transform-arm", action="store_true")
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU evaluates its own rotations (replicas; the headline metric).  strong: "
+                         "every evaluation is spread over all GPUs (OO_energy(shard='pairs')); with --mode weak and "
+                         "N > 1 a short strong-mode arm is reported as well under `strong_scaling`")
+    ap.add_argument("--strong-evals", type=int, default=6)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                   # timing rule: W >= 3
@@ -329,11 +382,49 @@ def main():
     nao, nelec, ncas, nelecas = CONFIG_SHAPES[args.workload]
     B = args.batch_per_gpu
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(seconds):
+        t = torch.tensor([seconds], dtype=F64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    if args.mode == "strong":
+        # ---- only the sharded evaluation: the N^4 tensor is never formed, every rank builds its slab from the
+        #      density-fitting factor (this is the mode for bases whose integrals exceed one GPU)
+        mol = SyntheticMol(nao, nelec, seed=5, device=dev, build_eri=False)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.oo_launch_count()
+        strong, _ = strong_arm(args, mol, ncas, nelecas, dev, world, rank, max(args.steps, 1) * B, max_over_ranks,
+                               barrier)
+        launches = lib.oo_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            line = {"metric": METRIC, "value": strong["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": 3, "ms_per_step": strong["ms_per_evaluation"] * B, "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": args.workload, "nao": nao, "cas": [nelecas, ncas],
+                               "evals_per_step": B, "mode": strong["what"]},
+                    "gpu_launches": int(launches), "clocks": clocks, "strong_scaling": strong, "e2e": None,
+                    "roofline": None, "cpu_baseline": None}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- synthetic inputs, generated on the device from a fixed seed (every rank: same integrals)
     mol = SyntheticMol(nao, nelec, seed=5, device=dev)
     oo = OO_energy(mol, ncas, nelecas, oao_mo_coeff=mol.random_oao_mo_coeff, device=dev)
     mol._int2e = None                                      # the engine holds the only N^4 copy now
-    mol._B = None
+    want_strong = world > 1 or args.mode == "strong"
+    if not want_strong:
+        mol._B = None                                      # (the strong arm builds its slab from the factor)
     torch.cuda.empty_cache()
     eng = oo.engine
     one, two = random_rdms(ncas, nelecas, seed=5, device=dev)
@@ -347,17 +438,6 @@ def main():
     H_out = torch.empty(B, nk, nk, dtype=F64, device=dev)
 
     peak_tf = measure_fp64_dgemm_peak() if rank == 0 else 0.0
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(seconds):
-        t = torch.tensor([seconds], dtype=F64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
 
     def stage_seconds(events, name):
         return sum(a.elapsed_time(b) for a, b in events.get(name, [])) * 1e-3
@@ -514,6 +594,16 @@ def main():
                       "mode": "energy_gradient_newton_direction: E, G, dkappa = -(H + shift)^-1 G and lambda_0 back; "
                               "the time is dominated by the FP64 eigh of the n_kappa^2 Hessian (cuSOLVER via torch)"}
 
+    # ---- strong-scaling arm: every evaluation spread over all ranks ---------------------------------------------
+    strong = None
+    if want_strong:
+        eng.release_workspaces()
+        torch.cuda.empty_cache()
+        strong, chk = strong_arm(args, mol, ncas, nelecas, dev, world, rank, args.strong_evals, max_over_ranks, barrier)
+        strong["one_gpu_ms_per_evaluation_same_run"] = t_dev / (B * args.steps) * 1e3
+        strong["speedup_vs_one_gpu"] = strong["one_gpu_ms_per_evaluation_same_run"] / strong["ms_per_evaluation"]
+        mol._B = None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -606,7 +696,7 @@ def main():
                    "eri_symmetry_defect": eng.eri_defect,
                    "l2": "inputs larger than L2 (N^4 tensors of %.1f GB)" % (nao ** 4 * 8 / 1e9)
                    if nao ** 4 * 8 > 126e6 else "inputs fit L2; distinct kappa every evaluation"},
-        "e2e": e2e, "e2e_dense": e2e_dense, "e2e_newton": e2e_newton,
+        "e2e": e2e, "e2e_dense": e2e_dense, "e2e_newton": e2e_newton, "strong_scaling": strong,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_kernels": kernel_rows,
         "roofline_hbm": roofline_hbm, "roofline_full_transform": roofline_full, "stage_ms_per_evaluation": stage_ms,
         "cpu_baseline": cpu, "cpu_baseline_measured": cpu_measured,

@@ -258,6 +258,15 @@ int     oo_pack_eri_8fold_f64(const double *g_ao, double *g_packed8, int ld, voi
 int     oo_class_transform_sym_f64(const double *g_packed, int64_t strideG, const double *C, int64_t strideC,
                                    int N, int ld, int nIp, int batch, double *cls, void *ws, size_t ws_bytes,
                                    unsigned flags, void *stream);
+/* Sharded evaluation (second decomposition): every rank holds a SLAB of the pair columns of the 8-fold
+ * packed tensor, g_packed8_slab[RS][j] = g8[RS][pq_lo + j], j < pq_cnt, row pitch slab_ld (pq_lo, pq_cnt, slab_ld
+ * even).  Quarter 1 and the Coulomb quarter 2 run over the slab only; all later steps are linear in the quarter-1
+ * result, so `cls` receives this slab's ADDITIVE share of the K and J rows of the class buffer: the caller sums the
+ * shares over the ranks (one NCCL all-reduce over NVLink) and then writes the h' row.  Same workspace as
+ * oo_class_transform_sym_f64.                                                                                */
+int oo_class_transform_sym_slab_f64(const double *g_packed8_slab, int64_t slab_ld, int64_t pq_lo, int64_t pq_cnt,
+                                    const double *C, int64_t strideC, int N, int ld, int nIp, int batch, double *cls,
+                                    void *ws, size_t ws_bytes, unsigned flags, void *stream);
 int oo_class_active_hamiltonian_f64(const double *cls, int no, int na, int N, int ld, int nIp,
                                     int batch, double e_nuc, const double *e_nuc_batch, double *c0,
                                     double *c1, double *c2, void *stream);

@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from auto_oo_b200.distributed import SlabTransform, shard_range, sharded_evaluations, torch_gemm_tn
+from auto_oo_b200.distributed import (PairShard, SlabTransform, pair_slab_range, shard_range, sharded_evaluations,
+                                      torch_gemm_tn)
 
 
 def test_shard_range_partitions_everything():
@@ -21,6 +22,15 @@ def test_shard_range_partitions_everything():
             assert all(a[1] == b[0] for a, b in zip(got[:-1], got[1:]))
             sizes = [b - a for a, b in got]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_pair_slab_ranges_are_even_and_cover_the_pairs():
+    for ldp in (2, 78, 406, 32896):
+        for w in (1, 2, 3, 8):
+            got = [pair_slab_range(ldp, w, r) for r in range(w)]
+            assert got[0][0] == 0 and got[-1][1] == ldp
+            assert all(a[1] == b[0] for a, b in zip(got[:-1], got[1:]))
+            assert all(lo % 2 == 0 and hi % 2 == 0 for lo, hi in got)
 
 
 def _free_port():
@@ -46,6 +56,15 @@ def _worker(rank, world, port, n, tmp):
             err = (out - ref[lo:hi]).abs().max().item()
             assert err < 1e-10, (mode, err)
             assert tuple(st.slab_shape()) == tuple(st.take_slab(g).shape)
+
+        # pair shard: slab bookkeeping of this rank and the all-reduce that completes the class buffer
+        class _Eng:
+            ld = 28
+        sh = PairShard()
+        sh.bind(_Eng())
+        assert (sh.world, sh.rank) == (world, rank) and (sh.pq_lo, sh.pq_lo + sh.pq_cnt) == pair_slab_range(406, world, rank)
+        share = torch.full((3, 4), float(rank + 1), dtype=torch.float64)
+        assert torch.equal(sh.all_reduce(share), torch.full((3, 4), float(sum(range(1, world + 1))), dtype=torch.float64))
 
         # sharded batch: every rank ends up with the full, ordered result
         kap = torch.arange(10, dtype=torch.float64).reshape(5, 2)
