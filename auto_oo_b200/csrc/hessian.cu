@@ -878,8 +878,10 @@ int launch_assemble(const TView &tv, const double *F, const int32_t *pl, const i
         return OO_OK;
     }
     int *runs = reinterpret_cast<int *>(scratch);
-    hess_pair_runs_kernel<<<1, 1024, 0, stream>>>(pl, pr, nk, N, tv.nI, runs);
-    OO_LAUNCH_CHECK();
+    if (!(flags & OO_FLAG_HESSIAN_REUSE_OPERANDS)) {         // (same pair list as the previous call: runs are there)
+        hess_pair_runs_kernel<<<1, 1024, 0, stream>>>(pl, pr, nk, N, tv.nI, runs);
+        OO_LAUNCH_CHECK();
+    }
     const int rows_in = (tv.nI + 1) & ~1;
     const int rows_out = N > rows_in ? N - rows_in : 0;
     const int smax = tv.nI < 64 ? tv.nI : 64;
@@ -1090,16 +1092,23 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     double *Tg = reinterpret_cast<double *>(w + L.off_tg);
     double *T = reinterpret_cast<double *>(w + L.off_t);
 
+    // What depends on the RDMs alone -- the ELL lists and the C-block coefficients -- is still in the workspace when
+    // the caller says nothing changed since the previous call (a kappa sweep at fixed RDMs)
+    const bool reuse = (flags & OO_FLAG_HESSIAN_REUSE_OPERANDS) != 0;
     // ELL lists of what lies outside the dense blocks (one table per set of RDMs)
-    hess_sparse_build_kernel<<<dim3((unsigned)ceil_div(nI2, 8), (unsigned)nsets), 256, 0, stream>>>(
-        rdm, sd1, sd2, nIp, 1, L.width, cnt, idx, val, flag);
-    OO_LAUNCH_CHECK();
+    if (!reuse) {
+        hess_sparse_build_kernel<<<dim3((unsigned)ceil_div(nI2, 8), (unsigned)nsets), 256, 0, stream>>>(
+            rdm, sd1, sd2, nIp, 1, L.width, cnt, idx, val, flag);
+        OO_LAUNCH_CHECK();
+    }
     // C block: Tc[b] = Atc^T Bc[b]
     {
         int64_t blocks = ceil_div(L.krows_c * L.lda_c, 256);
-        hess_dense_at_kernel<<<dim3((unsigned)blocks, (unsigned)nsets), 256, 0, stream>>>(rdm, sd1, sd2, nIp, 1,
-                                                                                         L.lda_c, Atc);
-        OO_LAUNCH_CHECK();
+        if (!reuse) {
+            hess_dense_at_kernel<<<dim3((unsigned)blocks, (unsigned)nsets), 256, 0, stream>>>(rdm, sd1, sd2, nIp, 1,
+                                                                                             L.lda_c, Atc);
+            OO_LAUNCH_CHECK();
+        }
         int64_t bx = ceil_div(mat / 2, 256);
         if (bx > 64) bx = 64;
         hess_dense_b_kernel<<<dim3((unsigned)bx, (unsigned)L.krows_c, (unsigned)batch), 256, 0, stream>>>(

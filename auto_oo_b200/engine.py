@@ -637,9 +637,18 @@ class HotPathEngine:
         s1, s2 = self._rdm_strides(d1, d2, B)
         nbytes = self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.na, self.ld, self.nI, B)
         ws = self.workspace("chess", nbytes)
+        # operands that depend on the RDMs / the pair list alone stay in the workspace: reuse them when the very same
+        # tensors (kept alive here, so neither address can be recycled; unchanged version counters) come again
+        key = (ws.data_ptr(), B, self.flags, d1.data_ptr(), d1._version, d2.data_ptr(), d2._version, pl.data_ptr(),
+               pr.data_ptr(), nk)
+        prev = self._ws.get("chess_key")
+        # (never inside a CUDA-graph capture: a replay sees new RDM values in the same static buffers)
+        reuse = prev is not None and prev[0] == key and not self._ws.get("capturing", False)
+        flags = self.flags | (_lib.OO_FLAG_HESSIAN_REUSE_OPERANDS if reuse else 0)
+        self._ws["chess_key"] = (key, d1, d2, pl, pr)
         self._check(self.lib.oo_class_hessian_f64(_p(cls), _p(F), _p(d1), s1, _p(d2), s2, self.no, self.na, self.N,
                                                   self.ld, self.nIp, B, _p(pl), _p(pr), nk, _p(H), _p(ws), nbytes,
-                                                  self.flags, self.stream), "class_hessian")
+                                                  flags, self.stream), "class_hessian")
         return H
 
     def class_chunk(self, B):
@@ -889,14 +898,19 @@ class HotPathEngine:
         eager = {k: self._icache.pop(k) for k in list(self._icache)}
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(2):                                # sizes every workspace outside the capture
-                run()
-        cur.wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            out = run()
+        self._ws["capturing"] = True
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):                            # sizes every workspace outside the capture
+                    run()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run()
+        finally:
+            self._ws["capturing"] = False
+            self._ws.pop("chess_key", None)
         # the graph has the addresses of every workspace it touched baked in: keep those tensors alive even if
         # a later, larger call replaces them in the workspace table
         keep = ([v for v in self._ws.values() if torch.is_tensor(v)] + [self.g_packed, self.g_pairT]

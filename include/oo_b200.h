@@ -80,6 +80,10 @@ enum {
     OO_FLAG_CLASS_Q2_RECTANGULAR = 64,         /* oo_class_transform_sym_f64: quarter 2 as the rectangular TN-GEMM that
                                                   computes every class pair (m, n) and keeps n <= m in its epilogue,
                                                   instead of the triangular kernel that only computes n <= m          */
+    OO_FLAG_HESSIAN_REUSE_OPERANDS = 256,      /* oo_class_hessian_f64: same RDMs, pair list, batch and workspace as the
+                                                  previous call -- the sparse table, the C-block coefficients and the
+                                                  pair runs it left in the workspace are used again (a kappa sweep at
+                                                  fixed RDMs rebuilds nothing that does not depend on the integrals)  */
     OO_FLAG_CLASS_ERI_8FOLD = 128              /* oo_class_transform_sym_f64: `g_packed` is the 8-FOLD packed tensor of
                                                   oo_pack_eri_8fold_f64 (an eighth of N^4) instead of the pair-packed
                                                   one (half of N^4); quarter 1 unpacks it in its producer               */

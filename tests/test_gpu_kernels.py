@@ -629,3 +629,32 @@ def test_class_transform_with_wide_class_index(nao, nelec, ncas, nelecas):
                              nelec, ncas, nelecas, False)
     assert abs(Ec.item() - prob.energy(one, two, kap[0]).item()) < TOL_E
     assert (Gc[0].cpu() - prob.gradient(one, two, kap[0])).abs().max().item() < TOL_GH
+
+
+def test_hessian_operand_reuse_follows_the_rdms():
+    """A kappa sweep at fixed RDMs reuses the RDM-only operands of the class Hessian (sparse table, C-block
+    coefficients, pair runs) left in the workspace; new RDM tensors, or an in-place write into the same ones, rebuild
+    them -- and a CUDA-graph replay never skips them."""
+    c = load_case("n28_cas66")
+    eng, p = engine_for(c)
+    Coao = eng.to_padded(c.oao_mo_coeff, 2)
+    d1, d2 = eng.dev(c.one_rdm), eng.dev(c.two_rdm)
+    kap = torch.stack([c.kappa, 0.5 * c.kappa, -c.kappa]).cuda()
+    n0 = eng.lib.oo_launch_count()
+    _, _, H0 = eng.evaluate(Coao, d1, d2, kappa=kap[:1])
+    n1 = eng.lib.oo_launch_count()
+    _, _, H1 = eng.evaluate(Coao, d1, d2, kappa=kap[1:2])                    # same RDM tensors: fewer launches
+    n2 = eng.lib.oo_launch_count()
+    assert n2 - n1 < n1 - n0
+    assert np.abs(H0[0].cpu().numpy() - c.ref["H"]).max() < TOL_GH
+    d1b, d2b = (1.1 * d1).contiguous(), (0.9 * d2).contiguous()             # different RDMs
+    ref = eng.evaluate(Coao, d1b, d2b, kappa=kap[1:2])[2].clone()
+    d1.copy_(d1b)                                                            # in-place write: version counter moves
+    d2.copy_(d2b)
+    assert torch.equal(eng.evaluate(Coao, d1, d2, kappa=kap[1:2])[2], ref)
+    assert not torch.equal(ref, H1)
+    for _ in range(3):                                                       # third call replays a captured graph
+        Eg, Gg, Hg = eng.evaluate_graphed(Coao, d1b, d2b, kappa=kap[1:2])
+    assert torch.equal(Hg, ref)
+    E2, G2, H2 = eng.evaluate_graphed(Coao, eng.dev(c.one_rdm), eng.dev(c.two_rdm), kappa=kap[:1])   # replay, new RDM values
+    assert np.abs(H2[0].cpu().numpy() - c.ref["H"]).max() < TOL_GH
