@@ -1,5 +1,8 @@
-"""One class-path evaluation (E+G+H) at a config shape, for an ncu launch list:
-    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python tools/ncu_stage_sym.py [workload] [auto|off]"""
+"""One class-path evaluation (E+G+H) at a config shape for ncu.  Only the SECOND evaluation (warm instruction caches)
+lies between cudaProfilerStart / cudaProfilerStop, so with `--profile-from-start off` exactly its launches are taken:
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv \
+        python tools/ncu_stage_sym.py [workload] [auto|off]
+    ncu --profile-from-start off --set full --clock-control none -o report python tools/ncu_stage_sym.py"""
 import os
 import sys
 
@@ -25,7 +28,10 @@ one, two = random_rdms(ncas, nelecas, seed=5, device=dev)
 kap = random_kappa(oo.n_kappa, seed=3, device=dev, batch=2)
 H = torch.empty(1, eng.nk, eng.nk, dtype=torch.float64, device=dev)
 Coao = eng.to_padded(oo.oao_mo_coeff, 2)
-for b in range(2):                       # second evaluation = warm instruction caches
-    E, G, _ = eng.evaluate(Coao, one, two, kappa=kap[b:b + 1], H_out=H)
+E, G, _ = eng.evaluate(Coao, one, two, kappa=kap[:1], H_out=H)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
+E, G, _ = eng.evaluate(Coao, one, two, kappa=kap[1:2], H_out=H)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("E", E.item())
