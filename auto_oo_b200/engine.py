@@ -149,12 +149,15 @@ class HotPathEngine:
     SYMMETRY_TOL = 1e-13
 
     def __init__(self, int1e_ao, int2e_ao, oao_coeff, nuc, nao, no, na, params_idx, device=None,
-                 n_geometries=0, eri_symmetry="auto", eri_packing="8fold", pair_shard=None):
+                 n_geometries=0, eri_symmetry="auto", eri_packing="8fold", pair_shard=None, eri_packed8=None):
         """``eri_symmetry``: "auto" measures the 8-fold symmetry of ``int2e_ao`` on the device at first use and
         takes the symmetric class transform (half the quarter-1 work, packed AO integrals) when it holds to
         round-off, the general one otherwise; "off" always takes the general one.
         ``eri_packing``: how the symmetric route keeps the AO integrals in HBM -- "8fold": both pairs packed,
         g8[(r>=s), (p>=q)] (an eighth of N^4; quarter 1 unpacks in its producer), "pair": g[r, s, (p>=q)] (half).
+        ``eri_packed8``: the AO integrals already in the 8-fold packed layout ``g8[RS][PQ]`` (``(ld(ld+1)/2, pair_ld)``,
+        e.g. from ``io.load_problem(..., eri="packed")``) with ``int2e_ao=None``: the N^4 tensor is never formed; the
+        complete four-index transform is then unavailable, energy / gradient / Hessian run the symmetric class path.
         ``pair_shard``: ``None`` or a :class:`auto_oo_b200.distributed.PairShard` -- ONE evaluation spread over the
         ranks of a process group: this rank keeps only its slab of pair columns of the 8-fold packed integrals
         (``int2e_ao`` may then be the slab itself, see ``PairShard``), computes its additive share of the class
@@ -203,6 +206,13 @@ class HotPathEngine:
         self._eri_symmetric = None if eri_symmetry == "auto" else False
         if pair_shard is not None:
             self._eri_symmetric = True                 # the slab layout IS the symmetric representation
+        if eri_packed8 is not None:
+            assert int2e_ao is None and pair_shard is None and self.n_geom == 0 and eri_packing == "8fold"
+            rows = self.ld * (self.ld + 1) // 2
+            self.g_packed = self.dev(eri_packed8)
+            if tuple(self.g_packed.shape) != (rows, rows + (rows & 1)):
+                raise ValueError(f"eri_packed8 must be ({rows}, {rows + (rows & 1)}) for {self.N} orbitals")
+            self._eri_symmetric = True
         self.eri_defect = None
         self._ws = {}
         self._icache = {}                              # kind -> (_IntegralsKey | None, MOIntegrals)
@@ -419,6 +429,9 @@ class HotPathEngine:
         B = C0.shape[0]
         ld = self.ld
         g = self.g_ao if g_ao is None else g_ao
+        if g is None:
+            raise _lib.OOError("the complete four-index transform needs the dense AO integrals (this engine only holds "
+                               "their packed / sharded form: use the class path)")
         strideG = ld ** 4 if (g.dim() == 5 and g.shape[0] > 1) else 0
         if out is None:
             out = torch.empty((B, ld, ld, ld, ld), dtype=F64, device=self.device)

@@ -8,7 +8,10 @@
 
 Real-orbital two-electron integrals are 8-fold symmetric; ``save_problem`` then stores only the
 ``P(P+1)/2`` unique elements (``P = N(N+1)/2``, PySCF's ``s8`` order: lower triangle of the pair-by-pair
-matrix of lower-triangular pairs), an eighth of the dense tensor, and ``load_problem`` expands them.
+matrix of lower-triangular pairs), an eighth of the dense tensor, and ``load_problem`` expands them -- or, with
+``eri="packed"``, hands them over in the 8-fold packed DEVICE layout ``g8[RS][PQ]`` of the symmetric class transform
+(``oo_pack_eri_8fold_f64``): the N^4 tensor is then formed neither on the host nor on the device, quarter 1 of the
+class transform unpacks the pairs in its producer (``OO_energy`` sees ``mol.int2e_packed8``).
 ``save_trajectory`` / ``load_trajectory`` checkpoint the orbitals (and circuit parameters, energies) of an
 optimisation or of the geometries of a Berry-phase loop.
 """
@@ -24,15 +27,17 @@ class ArrayMol:
     """Duck-typed ``Moldata_pyscf`` built from arrays (``moldata_pyscf.py:19-56``): attributes
     ``int1e_ao, int2e_ao, overlap, oao_coeff, nuc, nao, nelectron`` and ``get_active_space_idx``."""
 
-    def __init__(self, int1e_ao, int2e_ao, overlap, oao_coeff, nuc, nelectron):
+    def __init__(self, int1e_ao, int2e_ao, overlap, oao_coeff, nuc, nelectron, int2e_packed8=None):
         self.int1e_ao = np.asarray(int1e_ao, dtype=np.float64)
-        self.int2e_ao = np.asarray(int2e_ao, dtype=np.float64)
+        self.int2e_ao = None if int2e_ao is None else np.asarray(int2e_ao, dtype=np.float64)
+        self.int2e_packed8 = int2e_packed8               # (ld(ld+1)/2, pair_ld) 8-fold packed, or None
         self.overlap = np.asarray(overlap, dtype=np.float64)
         self.oao_coeff = np.asarray(oao_coeff, dtype=np.float64)
         self.nuc = float(nuc)
         self.nelectron = int(nelectron)
         self.nao = self.int1e_ao.shape[0]
-        if self.int2e_ao.shape != (self.nao,) * 4 or self.overlap.shape != (self.nao,) * 2:
+        if self.overlap.shape != (self.nao,) * 2 or (self.int2e_ao is None) == (int2e_packed8 is None) or \
+                (self.int2e_ao is not None and self.int2e_ao.shape != (self.nao,) * 4):
             raise ValueError("inconsistent array shapes for an AO basis of size %d" % self.nao)
 
     def get_active_space_idx(self, ncas, nelecas):
@@ -80,6 +85,22 @@ def unpack_eri_s8(packed, nao):
     return g
 
 
+def s8_to_packed8(packed, nao):
+    """The ``s8`` vector as the 8-fold packed device layout ``g8[RS][PQ]`` of the symmetric class transform: pairs
+    ``tri(p, q)`` over the orbitals padded to an even count (the padding pairs come last: zero rows / columns), row
+    length rounded up to even.  ``(ld (ld+1)/2, pair_ld)`` doubles -- a quarter of the dense tensor's size, never N^4."""
+    P = nao * (nao + 1) // 2
+    a, b = np.tril_indices(P)
+    if packed.shape != (len(a),):
+        raise ValueError("packed integrals do not match a basis of size %d" % nao)
+    ld = nao + (nao & 1)
+    rows = ld * (ld + 1) // 2
+    out = np.zeros((rows, rows + (rows & 1)))
+    out[a, b] = packed
+    out[b, a] = packed
+    return out
+
+
 def save_problem(path, mol, nelectron=None, eri_packing="auto", **extras):
     """Write ``mol``'s integrals (and any extra arrays: ``oao_mo_coeff``, ``theta``, RDMs, ...).
     ``eri_packing``: ``"s8"`` stores the unique elements of the 8-fold symmetric ERI tensor (error if it is not
@@ -106,19 +127,25 @@ def save_problem(path, mol, nelectron=None, eri_packing="auto", **extras):
     np.savez_compressed(path, **data)
 
 
-def load_problem(path):
-    """Returns ``(ArrayMol, extras dict)``."""
+def load_problem(path, eri="dense"):
+    """Returns ``(ArrayMol, extras dict)``.  ``eri="packed"`` (s8 files only): the integrals stay 8-fold packed
+    (``mol.int2e_packed8``, ``mol.int2e_ao`` is None); ``OO_energy`` then runs the symmetric class path from them."""
+    if eri not in ("dense", "packed"):
+        raise ValueError("eri must be 'dense' or 'packed'")
     with np.load(path) as d:
         missing = [k for k in _REQUIRED if k not in d.files]
         if missing:
             raise ValueError(f"{path}: missing fields {missing}")
         if int(d["format_version"]) != FORMAT_VERSION:
             raise ValueError(f"{path}: unsupported format version {int(d['format_version'])}")
-        eri = d["int2e_ao"]
-        if eri.ndim == 1:                                    # s8-packed
-            eri = unpack_eri_s8(eri, d["int1e_ao"].shape[0])
-        mol = ArrayMol(d["int1e_ao"], eri, d["overlap"], d["oao_coeff"], float(d["nuc"]),
-                       int(d["nelectron"]))
+        stored, want_packed = d["int2e_ao"], eri == "packed"
+        nao = d["int1e_ao"].shape[0]
+        if want_packed and stored.ndim != 1:
+            raise ValueError(f"{path}: eri='packed' needs an s8-packed file (this one stores the dense tensor)")
+        dense = None if want_packed else (unpack_eri_s8(stored, nao) if stored.ndim == 1 else stored)
+        packed8 = s8_to_packed8(stored, nao) if want_packed else None
+        mol = ArrayMol(d["int1e_ao"], dense, d["overlap"], d["oao_coeff"], float(d["nuc"]), int(d["nelectron"]),
+                       int2e_packed8=packed8)
         extras = {k: d[k] for k in d.files if k not in _REQUIRED and k != "format_version"}
     return mol, extras
 

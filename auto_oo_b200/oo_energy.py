@@ -304,11 +304,17 @@ class OO_energy:
             from .engine import pad_even
             ldp = pad_even(pad_even(self.nao) * (pad_even(self.nao) + 1) // 2)
             self.int2e_ao = _as_tensor(mol.int2e_packed_slab(*pair_slab_range(ldp, pair_shard.world, pair_shard.rank)))
+            packed8 = None
         else:
-            self.int2e_ao = _as_tensor(mol.int2e_ao)
-        self.engine = HotPathEngine(self.int1e_ao, self.int2e_ao, self.oao_coeff, self.nuc, self.nao,
-                                    no, na, self.params_idx, device=device, eri_symmetry=eri_symmetry,
-                                    eri_packing=eri_packing, pair_shard=pair_shard)
+            # `mol.int2e_packed8`: 8-fold packed integrals (io.load_problem(..., eri="packed")) instead of the dense tensor
+            packed8 = getattr(mol, "int2e_packed8", None) if getattr(mol, "int2e_ao", None) is None else None
+            self.int2e_ao = None if packed8 is not None else _as_tensor(mol.int2e_ao)
+            if packed8 is not None and integral_path != "class":
+                raise ValueError("8-fold packed integrals serve the class path only (integral_path='class')")
+        self.engine = HotPathEngine(self.int1e_ao, self.int2e_ao if packed8 is None else None, self.oao_coeff, self.nuc,
+                                    self.nao, no, na, self.params_idx, device=device, eri_symmetry=eri_symmetry,
+                                    eri_packing=eri_packing, pair_shard=pair_shard,
+                                    eri_packed8=None if packed8 is None else _as_tensor(packed8))
 
     # ------------------------------------------------------------------ orbitals
     @property

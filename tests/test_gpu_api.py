@@ -362,3 +362,25 @@ def test_newton_direction_mode_equals_host_newton_step():
     for b in range(2):
         dp, l0 = NewtonStep(verbose=0).newton_step(Gh[b], Hh[b])
         assert abs(l0 - lam[b].item()) < 1e-8 and (dp - dk[b]).abs().max().item() < 1e-7 * max(1.0, dp.abs().max().item())
+
+
+@pytest.mark.parametrize("name", ["n13_bigkappa", "n28_cas66"])
+def test_evaluation_from_8fold_packed_file(tmp_path, name):
+    """Interchange file with s8-packed integrals -> load_problem(eri="packed") -> OO_energy: the N^4 tensor exists
+    neither on the host nor on the device, results equal the verbatim reference's."""
+    from auto_oo_b200 import OO_energy, _lib
+    from auto_oo_b200.io import load_problem, save_problem
+    c = load_case(name)
+    save_problem(tmp_path / "p.npz", c.mol(), nelectron=c.nelec, eri_packing="s8", oao_mo_coeff=c.oao_mo_coeff)
+    mol, extras = load_problem(tmp_path / "p.npz", eri="packed")
+    assert mol.int2e_ao is None
+    oo = OO_energy(mol, c.ncas, c.nelecas, oao_mo_coeff=extras["oao_mo_coeff"], freeze_active=c.freeze)
+    assert oo.engine.g_ao is None and oo.int2e_ao is None
+    E, G, H = oo.energy_gradient_hessian(c.kappa, c.one_rdm, c.two_rdm)
+    assert abs(E[0].item() - float(c.ref["E"])) < TOL_E
+    assert np.abs(G[0].numpy() - c.ref["G"]).max() < TOL_GH and np.abs(H[0].numpy() - c.ref["H"]).max() < TOL_GH
+    assert abs(oo.energy_from_mo_coeff(oo.mo_coeff, c.one_rdm, c.two_rdm).item() - float(c.ref["E0"])) < TOL_E
+    with pytest.raises(_lib.OOError):
+        oo.engine.int2e_transform(oo.engine.to_padded(torch.eye(c.nao, dtype=F64), 2)[None])
+    with pytest.raises(ValueError):
+        OO_energy(mol, c.ncas, c.nelecas, oao_mo_coeff=extras["oao_mo_coeff"], integral_path="full")

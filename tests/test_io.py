@@ -81,3 +81,27 @@ def load_problem_as_trajectory(tmp_path):
     mol = SyntheticMol(4, 4, seed=0)
     save_problem(tmp_path / "p.npz", mol)
     return load_trajectory(tmp_path / "p.npz")
+
+
+@pytest.mark.parametrize("nao", [8, 9])
+def test_packed_loading_is_the_device_layout(tmp_path, nao):
+    """eri="packed": the s8 file becomes g8[RS][PQ] over the orbitals padded to even -- the layout
+    oo_pack_eri_8fold_f64 produces on the device -- without the dense tensor ever being formed."""
+    mol = SyntheticMol(nao, 10, seed=4)
+    g = np.asarray(mol.int2e_ao)
+    save_problem(tmp_path / "s8.npz", mol)
+    save_problem(tmp_path / "dense.npz", mol, eri_packing="dense")
+    m2, _ = load_problem(tmp_path / "s8.npz", eri="packed")
+    assert m2.int2e_ao is None
+    ld = nao + (nao & 1)
+    gp = np.zeros((ld,) * 4)
+    gp[:nao, :nao, :nao, :nao] = g
+    r, s = np.tril_indices(ld)
+    expect = gp[r, s][:, r, s]
+    rows = ld * (ld + 1) // 2
+    assert m2.int2e_packed8.shape == (rows, rows + (rows & 1))
+    assert np.array_equal(m2.int2e_packed8[:, :rows], expect) and not m2.int2e_packed8[:, rows:].any()
+    with pytest.raises(ValueError):
+        load_problem(tmp_path / "dense.npz", eri="packed")
+    with pytest.raises(ValueError):
+        load_problem(tmp_path / "s8.npz", eri="sparse")
