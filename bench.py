@@ -500,13 +500,16 @@ def main():
         ldp, npIp = int(lib.oo_pair_ld(ld)), int(lib.oo_pair_ld(nIp))
         npair, npI = nao * (nao + 1) // 2, (no + na) * (no + na + 1) // 2
         nI = no + na
+        # needed flop per launch: the class index unpadded, quarter 2 over the class pairs n <= m it keeps
         stage_flop = [2.0 * nao * npair * nI * nao,               # quarter 1 over packed AO pairs
-                      2.0 * npair * nI * nI * nao,                # Coulomb quarter 2 (all n; n <= m kept)
+                      2.0 * npair * npI * nao,                    # Coulomb quarter 2 (class pairs n <= m)
                       2.0 * nao * npI * nao * nao, 2.0 * npI * nao * nao * nao,
-                      2.0 * nao * nao * nI * nI * nao,            # exchange quarter 2
+                      2.0 * nao * nao * npI * nao,                # exchange quarter 2 (class pairs n <= m)
                       2.0 * nao * npI * nao * nao, 2.0 * npI * nao * nao * nao]
-        names = ["Q1 (sum_r g[r,s,pq] C[r,m]; pair-unpack epilogue)", "J-Q2 (class-pack epilogue)", "J-Q3",
-                 "J-Q4 (class-expand epilogue)", "K-Q2 (class-pack epilogue)", "K-Q3", "K-Q4 (class-expand epilogue)"]
+        names = ["dgemm_tn_kernel Q1 (8-fold packed A rows gathered by bulk copies; pair-unpack epilogue)",
+                 "dgemm_tn_tri_kernel J-Q2 (class pairs n <= m)", "dgemm_tn_kernel J-Q3",
+                 "dgemm_tn_kernel J-Q4 (class-expand epilogue)", "dgemm_tn_tri_kernel K-Q2 (class pairs n <= m)",
+                 "dgemm_tn_kernel K-Q3", "dgemm_tn_kernel K-Q4 (class-expand epilogue)"]
         Cst = eng.mo_coeff(Coao, eng.rotation(kappas[0, :1], squarings))
         cbuf = eng.class_integrals(Cst)                    # complete call: every intermediate is in the workspace
         for k in range(7):
@@ -521,7 +524,7 @@ def main():
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / reps                  # includes the 18 us h' = C^T h C that rides along
-            kernel_rows.append({"kernel": "dgemm_tn_kernel " + names[k], "algorithmic_flop": stage_flop[k], "ms": ms,
+            kernel_rows.append({"kernel": names[k], "algorithmic_flop": stage_flop[k], "ms": ms,
                                 "achieved": stage_flop[k] / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                                 "frac": stage_flop[k] / (ms * 1e-3) / 1e12 / peak_tf})
         eng.flags = 0
@@ -614,10 +617,14 @@ def main():
     t_cls = stage_seconds(events, "transform")
     if symmetric:
         ldp, npIp = int(lib.oo_pair_ld(ld)), int(lib.oo_pair_ld(nIp))
-        cls_flop = (2.0 * ld * ldp * nIp * ld + 2.0 * ldp * nIp * nIp * ld + 2.0 * ld * ld * nIp * nIp * ld
-                    + 8.0 * ld ** 3 * npIp)
+        # needed flop of the seven launches: quarter 1 over packed AO pairs, quarter 2 over the class pairs n <= m
+        # (the triangular kernel computes nothing else), two quarters each on the packed class pairs
+        cls_flop = 2.0 * ld * ldp * nIp * ld + 2.0 * ldp * npIp * ld + 2.0 * ld * ld * npIp * ld + 8.0 * ld ** 3 * npIp
+        # round 1 counted quarter 2 over ALL class pairs (m, n) -- what its rectangular GEMM executed
+        cls_flop_r01 = (2.0 * ld * ldp * nIp * ld + 2.0 * ldp * nIp * nIp * ld + 2.0 * ld * ld * nIp * nIp * ld
+                        + 8.0 * ld ** 3 * npIp)
     else:
-        cls_flop = 2.0 * ld ** 4 * nIp + 12.0 * ld ** 3 * nIp * nIp
+        cls_flop = cls_flop_r01 = 2.0 * ld ** 4 * nIp + 12.0 * ld ** 3 * nIp * nIp
     traffic = None
     prof = os.path.join(ROOT, "profiles", "class_transform_traffic.json")
     if os.path.exists(prof):
@@ -636,8 +643,10 @@ def main():
                 "peak_source": "cuBLAS FP64 DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                "nominal B200 FP64 40 TFLOP/s => frac_of_nominal_40tf",
                 "frac_of_nominal_40tf": cls_flop * n_evals / t_cls / 1e12 / 40.0,
-                "note": "flop = the GEMM shapes of the seven launches (class index padded to even only, not to the "
-                        "8-wide MMA tile); launch_ms is per class transform"}
+                "frac_with_round1_flop_count": cls_flop_r01 * n_evals / t_cls / 1e12 / peak_tf,
+                "note": "flop = what the seven launches NEED (class index padded to even only, not to the 8-wide MMA "
+                        "tile; quarter 2 over class pairs n <= m); round 1 counted quarter 2 over all (m, n) "
+                        "(frac_with_round1_flop_count, for comparison with its 0.835); launch_ms is per class transform"}
     hbm_peak, hbm_src = hbm_peak_gbs()
     N = nao
     nI = no + na
