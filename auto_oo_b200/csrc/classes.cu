@@ -40,7 +40,8 @@ int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_ro
 
 int dgemm_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, const double *B, double *C,
                         double *C2, int dorb, int dP, int64_t N, int64_t K, int64_t ldb, int64_t ldc, int batch,
-                        int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream);
+                        int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream,
+                        bool direct_epilogue);
 bool dgemm_tn_tri_supported(int nclass);
 int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
                             int64_t ngroups, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
@@ -404,7 +405,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         }
         if ((rc = dgemm_tn_q1_packed8(gpk, slab ? slab_ld : ldp, slab ? (int)pq_lo : 0, slab ? (int)pq_cnt : (int)ldp, C,
                                       T1, T1t, ld, (int)ldp, nIp, ld, ld, nIp, batch, strideG, strideC, sT1, sT1t,
-                                      stream)))
+                                      stream, (flags & OO_FLAG_CLASS_Q1_DIRECT_STORES) != 0)))
             return rc;
     } else if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp,
                                           batch, strideG, strideC, sT1, sT1t, stream))) {

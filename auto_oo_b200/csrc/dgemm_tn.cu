@@ -43,6 +43,10 @@ struct TnCfg {
     static constexpr int LIN_A_BYTES = (BK * LIN_PITCH + 1023) / 1024 * 1024;      // B chunks stay 1024-aligned
     static constexpr int LIN_STAGE_BYTES = LIN_A_BYTES + B_BYTES;
     static constexpr int LIN_SMEM_BYTES = STAGES * LIN_STAGE_BYTES + 2 * STAGES * 8 + 1024;
+    // EPI 1 (below): a three-stage ring leaves room for one BM x BN result tile in shared memory
+    static constexpr int EPI_STAGES = 3;
+    static constexpr int EPI_TILE_BYTES = BM * BN * 8;
+    static constexpr int EPI_SMEM_BYTES = EPI_STAGES * LIN_STAGE_BYTES + EPI_TILE_BYTES + 2 * EPI_STAGES * 8 + 1024;
     static_assert(WTM % 16 == 0 && WTN % 16 == 0, "warp tile must cover whole 16-wide chunks");
     static_assert(BK % 8 == 0, "BK must be a multiple of 8");
     static_assert((BK / 4) % 2 == 0, "the substep double buffer assumes an even number of substeps per k-block");
@@ -93,6 +97,18 @@ struct TnArgs {
 struct FalseTag { static constexpr bool value = false; };
 struct TrueTag { static constexpr bool value = true; };
 
+// shared -> global bulk asynchronous copy (TMA store path; tracked by the issuing thread's bulk group)
+__device__ __forceinline__ void bulk_store_1d(void *gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
@@ -102,24 +118,33 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void *gsrc
 // DUAL: 0 = plain store, 1 = second store with rows (a b c) -> (c b a), 2 = packed-pair unpack,
 // 3 / 4 = class-pair packing, 5 = class-pair expansion instead of the plain store (see TnArgs)
 // AMODE: 0 = A through the tensor map (K-major matrix), 1 = A rows gathered from the 8-fold packed AO integrals
-template <class Cfg, int DUAL, int AMODE = 0>
+// EPI:   0 = the consumer warps store their accumulators to global memory themselves;
+//        1 = (DUAL 2, AMODE 1: quarter 1) they drop the tile into shared memory (24 STS.128 per thread) and go
+//            straight on to the next tile, while a warp of the producer warpgroup ships it with bulk asynchronous
+//            copies (cp.async.bulk shared -> global): ONE copy for the contiguous packed rows, one per row and order
+//            for the pair-unpacked rows.  The 288 KB of stores per tile then cost the tensor pipe nothing.
+template <class Cfg, int DUAL, int AMODE = 0, int EPI = 0>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const TnArgs args) {
+    static_assert(EPI == 0 || (DUAL == 2 && AMODE == 1), "the staged epilogue is written for quarter 1");
     constexpr int STAGE_BYTES = AMODE ? Cfg::LIN_STAGE_BYTES : Cfg::STAGE_BYTES;
     constexpr int A_BYTES = AMODE ? Cfg::LIN_A_BYTES : Cfg::A_BYTES;
+    constexpr int NST = EPI ? Cfg::EPI_STAGES : Cfg::STAGES;
+    constexpr int kBarFree = 1, kBarFull = 2, kBarThreads = (Cfg::NCW + 1) * 32;   // consumers + the shipping warp
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + Cfg::STAGES;
+    const uint32_t ctile = smem_base + NST * STAGE_BYTES;                           // EPI 1: the result tile
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NST * STAGE_BYTES + (EPI ? Cfg::EPI_TILE_BYTES : 0));
+    uint64_t *empty_bar = full_bar + NST;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < Cfg::STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], Cfg::NCW);
         }
@@ -181,12 +206,45 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         for (int c = 0; c < Cfg::BN / 16; ++c)
                             tma_load_3d(sB + c * Cfg::CHUNK_BYTES, &mapB, &full_bar[stage], n0 + 16 * c, k0, bb);
                     }
-                    if (++stage == Cfg::STAGES) {
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
             }
+        } else if (EPI && warp == Cfg::NCW + 1) {
+            // ===================== shipping warp (EPI 1) =====================
+            const uint32_t pitch = (uint32_t)args.N * 8u;            // tile rows hold the N valid columns, dense
+            named_bar_arrive(kBarFree, kBarThreads);                // the tile buffer starts out free
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = (int)(tile / tiles_per_batch);
+                const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
+                int s, pq0;
+                lin_tile(rem / args.tiles_n, s, pq0);
+                const int rows = (args.pq_cnt - pq0) < Cfg::BM ? (args.pq_cnt - pq0) : Cfg::BM;
+                const int pq_first = args.pq_lo + pq0;
+                named_bar_sync(kBarFull, kBarThreads);              // consumers have written (and fenced) the tile
+                if (lane == 0)                                       // packed rows (s, PQ): one contiguous run
+                    bulk_store_1d(args.C + (int64_t)b * args.strideC + ((int64_t)s * args.d2 + pq_first) * args.ldc, ctile,
+                                  (uint32_t)rows * pitch);
+                double *base2 = args.C2 + (int64_t)b * args.strideC2;
+                for (int r = lane; r < rows; r += 32) {
+                    const int pq = pq_first + r;
+                    int p = (int)((sqrtf(8.0f * (float)pq + 1.0f) - 1.0f) * 0.5f);
+                    while ((p + 1) * (p + 2) / 2 <= pq) ++p;
+                    while (p * (p + 1) / 2 > pq) --p;
+                    const int q = pq - p * (p + 1) / 2;
+                    if (p >= args.d1) continue;                      // padding of the pair index
+                    const uint32_t src = ctile + (uint32_t)r * pitch;
+                    bulk_store_1d(base2 + (((int64_t)q * args.d1 + p) * args.d0 + s) * args.ldc, src, pitch);
+                    if (p != q) bulk_store_1d(base2 + (((int64_t)p * args.d1 + q) * args.d0 + s) * args.ldc, src, pitch);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory has been read
+                __syncwarp();
+                named_bar_arrive(kBarFree, kBarThreads);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else if (warp == Cfg::NCW && lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -209,7 +267,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                     for (int c = 0; c < Cfg::BN / 16; ++c)
                         tma_load_3d(sB + c * Cfg::CHUNK_BYTES, &mapB, &full_bar[stage], n0 + 16 * c, k0, bb);
-                    if (++stage == Cfg::STAGES) {
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -238,7 +296,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // registers are the scarce resource here (3 warps share one SM sub-partition's file: 168 per
         // thread): one running k-block counter carries both the ring slot and its phase, and the
         // tile coordinates are re-derived in the epilogue instead of living across the k loop.
-        static_assert((Cfg::STAGES & (Cfg::STAGES - 1)) == 0, "STAGES must be a power of two");
+        // `it % NST` / `it / NST`: NST is a compile-time constant (a mask and a shift for the power-of-two rings)
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < (uint32_t)total_tiles; tile += gridDim.x) {
             double acc[Cfg::MT][Cfg::NT][2];
@@ -273,23 +331,23 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #endif
             };
             {
-                const uint32_t stage = it & (Cfg::STAGES - 1);
-                mbar_wait(&full_bar[stage], (it / Cfg::STAGES) & 1u);
+                const uint32_t stage = it % NST;
+                mbar_wait(&full_bar[stage], (it / NST) & 1u);
                 load_frags(0, stage, 0, loaded);
             }
             // One k-block.  LAST = the tile's final block: no next stage to prefetch from, and the 8-row atoms
             // that lie entirely past K (zero rows: nothing to add) are skipped -- 114 orbitals are 7 1/8 blocks.
             auto kblock = [&](auto last_tag) {
                 constexpr bool LAST = decltype(last_tag)::value;
-                const uint32_t stage = it & (Cfg::STAGES - 1);
+                const uint32_t stage = it % NST;
 #pragma unroll
                 for (int sub = 0; sub < SUB; ++sub) {
                     const int cur = sub & 1, nxt = cur ^ 1;
                     if (sub + 1 < SUB) {
                         load_frags(nxt, stage, sub + 1, loaded);
                     } else if (!LAST) {
-                        const uint32_t nstage = (it + 1) & (Cfg::STAGES - 1);
-                        mbar_wait(&full_bar[nstage], ((it + 1) / Cfg::STAGES) & 1u);
+                        const uint32_t nstage = (it + 1) % NST;
+                        mbar_wait(&full_bar[nstage], ((it + 1) / NST) & 1u);
                         load_frags(nxt, nstage, 0, loaded_next);
                     }
                     if (!LAST || sub < args.last_subs) {
@@ -309,6 +367,26 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int kb = 0; kb + 1 < args.kblocks; ++kb) kblock(FalseTag{});
             kblock(TrueTag{});
 
+            if (EPI) {
+                // staged epilogue: accumulators -> shared-memory tile (rows of N doubles), then on to the next tile
+                const uint32_t pitch = (uint32_t)args.N * 8u;
+                named_bar_sync(kBarFree, kBarThreads);              // the previous tile has been shipped
+#pragma unroll
+                for (int mi = 0; mi < Cfg::MT; ++mi) {
+                    const uint32_t rowaddr = ctile + (uint32_t)(wm * Cfg::WTM + mi * 8 + g) * pitch;
+#pragma unroll
+                    for (int ni = 0; ni < Cfg::NT; ++ni) {
+                        const int col = wn * Cfg::WTN + ni * 8 + 2 * t;
+                        if (col + 1 < args.N)
+                            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowaddr + (uint32_t)col * 8u),
+                                         "d"(acc[mi][ni][0]), "d"(acc[mi][ni][1])
+                                         : "memory");
+                    }
+                }
+                fence_proxy_async();                                // generic-proxy writes -> visible to the bulk copies
+                named_bar_arrive(kBarFull, kBarThreads);
+                continue;
+            }
             // epilogue: registers -> global (16-byte stores, rows of 64 B per MMA tile)
             const int b = (int)(tile / (uint32_t)tiles_per_batch);
             const int rem = (int)(tile - (uint32_t)b * (uint32_t)tiles_per_batch);
@@ -524,7 +602,7 @@ template <class Cfg>
 static int launch_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, const double *B, double *C,
                                 double *C2, int S, int dorb, int dP, int64_t N, int64_t K, int64_t ldb, int64_t ldc,
                                 int batch, int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, bool direct_epilogue) {
     CUtensorMap mapB;
     const int b_batched = (batch > 1 && strideB != 0);
     int rc = encode_tmap_3d_f64(&mapB, B, (uint64_t)N, (uint64_t)K, b_batched ? batch : 1, (uint64_t)ldb,
@@ -557,12 +635,22 @@ static int launch_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int 
     args.r2_offset = 0;
     args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
     static unsigned long long attr_set = 0;
-    if (once_per_device(attr_set))
+    if (once_per_device(attr_set)) {
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::LIN_SMEM_BYTES));
+        if (Cfg::EPI_SMEM_BYTES <= 227 * 1024)
+            OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2, 1, 1>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::EPI_SMEM_BYTES));
+    }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    dgemm_tn_kernel<Cfg, 2, 1><<<grid, Cfg::THREADS, Cfg::LIN_SMEM_BYTES, stream>>>(mapB, mapB, args);
+    // staged epilogue: one n-tile, dense rows (ldc == N), enough shared memory, and not asked for the direct stores
+    const bool staged = !direct_epilogue && Cfg::EPI_SMEM_BYTES <= 227 * 1024 && args.tiles_n == 1 && ldc == N &&
+                        (N % 2) == 0;
+    if (staged)
+        dgemm_tn_kernel<Cfg, 2, 1, 1><<<grid, Cfg::THREADS, Cfg::EPI_SMEM_BYTES, stream>>>(mapB, mapB, args);
+    else
+        dgemm_tn_kernel<Cfg, 2, 1><<<grid, Cfg::THREADS, Cfg::LIN_SMEM_BYTES, stream>>>(mapB, mapB, args);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
@@ -648,7 +736,8 @@ int dgemm_tn_pair_unpack(const double *At, const double *B, double *C, double *C
 // A8 may be a slab of the pair columns: row pitch a8_ld, columns PQ in [pq_lo, pq_lo + pq_cnt) (both even).
 int dgemm_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, const double *B, double *C,
                         double *C2, int dorb, int dP, int64_t N, int64_t K, int64_t ldb, int64_t ldc, int batch,
-                        int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream) {
+                        int64_t strideA8, int64_t strideB, int64_t strideC, int64_t strideC2, cudaStream_t stream,
+                        bool direct_epilogue) {
     OO_REQUIRE(A8 && B && C && C2 && dorb > 0 && K > 0 && K <= dorb && N > 0 && batch > 0);
     OO_REQUIRE(pq_lo >= 0 && pq_cnt > 0 && pq_lo + pq_cnt <= dP && (pq_lo % 2) == 0 && (pq_cnt % 2) == 0);
     OO_REQUIRE(a8_ld >= pq_cnt && (a8_ld % 2) == 0);
@@ -658,7 +747,7 @@ int dgemm_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, 
     if ((int64_t)dorb * dP >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
 #define OO_Q1(CFG)                                                                                                 \
     return launch_tn_q1_packed8<CFG>(A8, a8_ld, pq_lo, pq_cnt, B, C, C2, dorb, dorb, dP, N, K, ldb, ldc, batch,      \
-                                     strideA8, strideB, strideC, strideC2, stream)
+                                     strideA8, strideB, strideC, strideC2, stream, direct_epilogue)
     if (N > 64) OO_Q1(TnWide);
     if (N > 48) OO_Q1(TnMid);
     if (N > 40) OO_Q1(TnMid48);

@@ -186,6 +186,13 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     finally:
         eng.flags = 0
     assert torch.equal(Er, Ec) and torch.equal(Gr, Gc) and torch.equal(Hf, Hc)     # same k order per element
+    # quarter 1: accumulators staged in shared memory and shipped by bulk copies (default) against direct stores
+    try:
+        eng.flags = _lib.OO_FLAG_CLASS_Q1_DIRECT_STORES
+        Ed, Gd, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.flags = 0
+    assert torch.equal(Ed, Ec) and torch.equal(Gd, Gc) and torch.equal(Hf, Hc)
     # AO integrals with one pair packed (N^4 / 2, TMA-tiled quarter 1) against the default 8-fold packed tensor
     # (N^4 / 8, quarter-1 rows gathered by bulk copies); both read the same g up to its own symmetry defect
     eng.g_packed, eng.eri_packing = None, "pair"
