@@ -25,7 +25,7 @@ OO_WS_CLASS_TRANSFORM, OO_WS_CLASS_BUFFER, OO_WS_CLASS_HESSIAN, OO_WS_CLASS_TRAN
 OO_FLAG_HESSIAN_DENSE, OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT, OO_FLAG_HESSIAN_ASSEMBLE_TILED = 1, 2, 4
 OO_FLAG_CLASS_UNFUSED_PACK, OO_FLAG_HESSIAN_GROUP_UNSTREAMED, OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 8, 16, 32
 OO_FLAG_CLASS_Q2_RECTANGULAR, OO_FLAG_CLASS_ERI_8FOLD, OO_FLAG_HESSIAN_REUSE_OPERANDS = 64, 128, 256
-OO_FLAG_CLASS_Q1_DIRECT_STORES = 512
+OO_FLAG_CLASS_DIRECT_STORES, OO_FLAG_HESSIAN_SPMM_UNPAIRED = 512, 1024
 ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/oo_b200.h one to one

@@ -50,7 +50,11 @@ int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tr
 
 int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int transpose_mirror, int nclass, int dorb,
                           int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int64_t ld_out, int batch,
-                          int64_t strideA, int64_t strideB, int64_t strideOut, cudaStream_t stream);
+                          int64_t strideA, int64_t strideB, int64_t strideOut, cudaStream_t stream,
+                          bool direct_epilogue = false);
+int dgemm_tn_direct(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
+                    int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
+                    int64_t strideC, cudaStream_t stream);
 
 namespace {
 
@@ -363,6 +367,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
                         cudaStream_t stream, int64_t slab_ld = 0, int64_t pq_lo = 0, int64_t pq_cnt = 0) {
     const bool g_class_unfused_pack = (flags & OO_FLAG_CLASS_UNFUSED_PACK) != 0;   // separate pack / expand passes
     const bool slab = slab_ld > 0;
+    const bool direct = (flags & OO_FLAG_CLASS_DIRECT_STORES) != 0;       // no staged epilogues (A/B tests)
     if (slab && (!(flags & OO_FLAG_CLASS_ERI_8FOLD) || g_class_unfused_pack || ((flags >> 16) & 0x7fu)))
         return OO_ERR_INVALID_ARG;
     OO_REQUIRE(gpk && C && cls && ws);
@@ -383,9 +388,9 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     double *Kp = Jp + (int64_t)batch * sXp;
     double *Kout = cls, *Jout = cls + nI2 * ld2;
     int rc;
-#define Q(in, sIn, out, sOut, M, Ncols)                                                                  \
-    if ((rc = dgemm_tn((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), batch, (sIn), strideC, (sOut), \
-                       stream)))                                                                         \
+#define Q(in, sIn, out, sOut, M, Ncols)                                                                        \
+    if ((rc = (direct ? dgemm_tn_direct : dgemm_tn)((in), C, (out), (M), (Ncols), ld, (M), ld, (Ncols), batch, (sIn), \
+                                                    strideC, (sOut), stream)))                                     \
     return rc
     // OO_FLAG_CLASS_STAGE(k): run only the selected GEMM stages (k = 0: quarter 1; 1-3: Coulomb class; 4-6: exchange
     // class) on the intermediates a complete call left in the workspace -- per-kernel timing from the caller's side
@@ -405,7 +410,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         }
         if ((rc = dgemm_tn_q1_packed8(gpk, slab ? slab_ld : ldp, slab ? (int)pq_lo : 0, slab ? (int)pq_cnt : (int)ldp, C,
                                       T1, T1t, ld, (int)ldp, nIp, ld, ld, nIp, batch, strideG, strideC, sT1, sT1t,
-                                      stream, (flags & OO_FLAG_CLASS_Q1_DIRECT_STORES) != 0)))
+                                      stream, direct)))
             return rc;
     } else if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp,
                                           batch, strideG, strideC, sT1, sT1t, stream))) {
@@ -435,7 +440,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     } else if (g_class_unfused_pack) {
         Q(P1, sXp, Jp, sXp, npIp * ld, ld);                              // Jp[mn,a,b]
     } else if ((rc = dgemm_tn_class_expand(P1, C, Jout, 0, nIp, ld, npIp, ld, npIp * ld, ld, ld, batch, sXp,
-                                           strideC, sCls, stream))) {    // J[m,n,a,b] = J[n,m,a,b]
+                                           strideC, sCls, stream, direct))) {    // J[m,n,a,b] = J[n,m,a,b]
         return rc;
     }
     // ---- K: X2[p,s,m,n] = sum_q T1t[q,(p s m)] C[q,n], kept as X2p[p,s,mn]
@@ -459,7 +464,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         Q(P1, sXp, Kp, sXp, npIp * ld, ld);                              // Kp[mn,a,b]
     } else {
         if ((rc = dgemm_tn_class_expand(P1, C, Kout, 1, nIp, ld, npIp, ld, npIp * ld, ld, ld, batch, sXp, strideC,
-                                        sCls, stream)))                  // K[m,n,a,b], K[n,m,b,a]
+                                        sCls, stream, direct)))                  // K[m,n,a,b], K[n,m,b,a]
             return rc;
         return OO_OK;
     }

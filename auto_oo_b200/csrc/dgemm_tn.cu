@@ -47,6 +47,15 @@ struct TnCfg {
     static constexpr int EPI_STAGES = 3;
     static constexpr int EPI_TILE_BYTES = BM * BN * 8;
     static constexpr int EPI_SMEM_BYTES = EPI_STAGES * LIN_STAGE_BYTES + EPI_TILE_BYTES + 2 * EPI_STAGES * 8 + 1024;
+    // the same for the TMA-fed kernel (plain and class-expand stores): tile rows padded by 16 bytes so that the
+    // shipping warps can also read it column-wise (transposed mirror) with 4-way instead of 32-way bank conflicts;
+    // as many stages as fit next to it (two for the 128 x 128 tile: a k-block is 4096 clocks of DMMA, one stage
+    // in flight covers the memory latency)
+    static constexpr int EPI0_PITCH = BN * 8 + 16;
+    static constexpr int EPI0_TILE_BYTES = BM * EPI0_PITCH;
+    static constexpr int EPI0_STAGES = (227 * 1024 - 1024 - 64 - EPI0_TILE_BYTES) / STAGE_BYTES >= 4 ? 4
+                                       : (227 * 1024 - 1024 - 64 - EPI0_TILE_BYTES) / STAGE_BYTES;
+    static constexpr int EPI0_SMEM_BYTES = EPI0_STAGES * STAGE_BYTES + EPI0_TILE_BYTES + 2 * 4 * 8 + 1024;
     static_assert(WTM % 16 == 0 && WTN % 16 == 0, "warp tile must cover whole 16-wide chunks");
     static_assert(BK % 8 == 0, "BK must be a multiple of 8");
     static_assert((BK / 4) % 2 == 0, "the substep double buffer assumes an even number of substeps per k-block");
@@ -127,16 +136,19 @@ template <class Cfg, int DUAL, int AMODE = 0, int EPI = 0>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const TnArgs args) {
-    static_assert(EPI == 0 || (DUAL == 2 && AMODE == 1), "the staged epilogue is written for quarter 1");
+    static_assert(EPI == 0 || (DUAL == 2 && AMODE == 1) || (AMODE == 0 && (DUAL == 0 || DUAL == 5)),
+                  "the staged epilogue exists for quarter 1 and for the plain / class-expand stores");
     constexpr int STAGE_BYTES = AMODE ? Cfg::LIN_STAGE_BYTES : Cfg::STAGE_BYTES;
     constexpr int A_BYTES = AMODE ? Cfg::LIN_A_BYTES : Cfg::A_BYTES;
-    constexpr int NST = EPI ? Cfg::EPI_STAGES : Cfg::STAGES;
-    constexpr int kBarFree = 1, kBarFull = 2, kBarThreads = (Cfg::NCW + 1) * 32;   // consumers + the shipping warp
+    constexpr int NST = !EPI ? Cfg::STAGES : (AMODE ? Cfg::EPI_STAGES : (Cfg::EPI0_STAGES > 0 ? Cfg::EPI0_STAGES : 1));
+    constexpr int kShipWarps = AMODE ? 1 : 3;            // quarter 1: bulk copies only; else also a transposed mirror
+    constexpr int kBarFree = 1, kBarFull = 2, kBarThreads = (Cfg::NCW + kShipWarps) * 32;   // consumers + shippers
+    constexpr int TILE_BYTES = AMODE ? Cfg::EPI_TILE_BYTES : Cfg::EPI0_TILE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t ctile = smem_base + NST * STAGE_BYTES;                           // EPI 1: the result tile
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NST * STAGE_BYTES + (EPI ? Cfg::EPI_TILE_BYTES : 0));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NST * STAGE_BYTES + (EPI ? TILE_BYTES : 0));
     uint64_t *empty_bar = full_bar + NST;
 
     const int warp = threadIdx.x >> 5;
@@ -212,7 +224,64 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                 }
             }
-        } else if (EPI && warp == Cfg::NCW + 1) {
+        } else if (EPI && !AMODE && warp > Cfg::NCW) {
+            // ===================== shipping warps, plain / class-expand stores (EPI 1) =====================
+            // warp NCW+1 issues one bulk copy per tile row (and per mirror row of the Coulomb class); the transposed
+            // mirror of the exchange class, K[n,m][b][a] = K[m,n][a][b], is read column-wise from the tile by all
+            // three warps and written with coalesced stores.
+            const int sw = warp - Cfg::NCW - 1;                      // 0, 1, 2
+            named_bar_arrive(kBarFree, kBarThreads);                // the tile buffer starts out free
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = (int)(tile / tiles_per_batch);
+                const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
+                const int64_t m0 = (int64_t)(rem / args.tiles_n) * Cfg::BM;
+                const int n0 = (rem % args.tiles_n) * Cfg::BN;
+                const int rows = (args.M - m0) < Cfg::BM ? (int)(args.M - m0) : Cfg::BM;
+                const int ncols = (args.N - n0) < Cfg::BN ? (int)(args.N - n0) : Cfg::BN;   // even (N and BN are)
+                named_bar_sync(kBarFull, kBarThreads);
+                if (DUAL == 0) {
+                    if (sw == 0) {
+                        double *Cb = args.C + (int64_t)b * args.strideC + n0;
+                        for (int r = lane; r < rows; r += 32)
+                            bulk_store_1d(Cb + (m0 + r) * args.ldc, ctile + (uint32_t)r * Cfg::EPI0_PITCH, (uint32_t)ncols * 8u);
+                    }
+                } else {
+                    double *base2 = args.C2 + (int64_t)b * args.strideC2;
+                    const int64_t plane = (int64_t)args.d1 * args.ldc;
+                    const bool transposed = args.d2 != 0;
+                    for (int r = lane; r < rows; r += 32) {
+                        const int64_t row = m0 + r;
+                        const int a = (int)(row % args.d1);
+                        const int mn = (int)(row / args.d1);
+                        int m = (int)((sqrtf(8.0f * (float)mn + 1.0f) - 1.0f) * 0.5f);
+                        while ((m + 1) * (m + 2) / 2 <= mn) ++m;
+                        while (m * (m + 1) / 2 > mn) --m;
+                        const int n = mn - m * (m + 1) / 2;
+                        if (m >= args.d0) continue;                  // padding of the pair index
+                        const uint32_t src = ctile + (uint32_t)r * Cfg::EPI0_PITCH;
+                        if (sw == 0) {
+                            bulk_store_1d(base2 + ((int64_t)m * args.d0 + n) * plane + (int64_t)a * args.ldc + n0, src,
+                                          (uint32_t)ncols * 8u);
+                            if (m != n && !transposed)
+                                bulk_store_1d(base2 + ((int64_t)n * args.d0 + m) * plane + (int64_t)a * args.ldc + n0, src,
+                                              (uint32_t)ncols * 8u);
+                        }
+                        if (m != n && transposed) {                  // lanes = consecutive a: coalesced rows of the mirror
+                            double *mir = base2 + ((int64_t)n * args.d0 + m) * plane + a;
+                            for (int c = sw; c < ncols; c += kShipWarps)
+                                mir[(int64_t)(n0 + c) * args.ldc] = lds_f64(src + (uint32_t)c * 8u);
+                        }
+                    }
+                }
+                if (sw == 0) {
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();
+                named_bar_arrive(kBarFree, kBarThreads);
+            }
+            if (sw == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else if (EPI && AMODE && warp == Cfg::NCW + 1) {
             // ===================== shipping warp (EPI 1) =====================
             const uint32_t pitch = (uint32_t)args.N * 8u;            // tile rows hold the N valid columns, dense
             named_bar_arrive(kBarFree, kBarThreads);                // the tile buffer starts out free
@@ -368,8 +437,9 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             kblock(TrueTag{});
 
             if (EPI) {
-                // staged epilogue: accumulators -> shared-memory tile (rows of N doubles), then on to the next tile
-                const uint32_t pitch = (uint32_t)args.N * 8u;
+                // staged epilogue: accumulators -> shared-memory tile, then on to the next tile.  Quarter 1: rows of
+                // the N valid columns, dense (its packed rows leave as ONE bulk copy); otherwise rows of BN + 2
+                const uint32_t pitch = AMODE ? (uint32_t)args.N * 8u : (uint32_t)Cfg::EPI0_PITCH;
                 named_bar_sync(kBarFree, kBarThreads);              // the previous tile has been shipped
 #pragma unroll
                 for (int mi = 0; mi < Cfg::MT; ++mi) {
@@ -377,7 +447,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                     for (int ni = 0; ni < Cfg::NT; ++ni) {
                         const int col = wn * Cfg::WTN + ni * 8 + 2 * t;
-                        if (col + 1 < args.N)
+                        if (!AMODE || col + 1 < args.N)
                             asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowaddr + (uint32_t)col * 8u),
                                          "d"(acc[mi][ni][0]), "d"(acc[mi][ni][1])
                                          : "memory");
@@ -513,6 +583,7 @@ struct TnDual {
     int d0 = 0, d1 = 0, d2 = 0;
     int64_t strideC2 = 0;
     int64_t r2_offset = 0;
+    bool direct_epilogue = false;   // true: consumer warps store to global memory themselves (A/B tests)
 };
 
 template <class Cfg>
@@ -576,9 +647,36 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 5>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
+        if (Cfg::EPI0_STAGES >= 2) {
+#ifdef OO_TN_STAGE_PLAIN_STORES
+            OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 0, 0, 1>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::EPI0_SMEM_BYTES));
+#endif
+            OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 5, 0, 1>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::EPI0_SMEM_BYTES));
+        }
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());
+    // staged epilogue (tile -> shared memory -> bulk copies by the producer warpgroup's spare warps): big tiles only
+    // (the 128 x 128 configuration), even N (16-byte row pieces), at least two k-blocks to hide the shipping behind
+    const bool staged = !dual.direct_epilogue && Cfg::EPI0_STAGES >= 2 && Cfg::BN >= 128 && (N % 2) == 0 &&
+                        args.kblocks >= 2;
+    // (the plain store is NOT staged: its epilogue is 3 % of a 128 x 128 tile, less than what the two-stage ring that
+    //  makes room for the tile costs -- measured 0.99 -> 1.03 ms per quarter at N = 256; the kernel variant exists
+    //  behind OO_TN_STAGE_PLAIN_STORES for experiments)
+#ifdef OO_TN_STAGE_PLAIN_STORES
+    if (staged && !dual.C2) {
+        dgemm_tn_kernel<Cfg, 0, 0, 1><<<grid, Cfg::THREADS, Cfg::EPI0_SMEM_BYTES, stream>>>(mapA, mapB, args);
+        OO_LAUNCH_CHECK();
+        return OO_OK;
+    }
+#endif
+    if (staged && dual.C2 && dual.mode == 5) {
+        dgemm_tn_kernel<Cfg, 5, 0, 1><<<grid, Cfg::THREADS, Cfg::EPI0_SMEM_BYTES, stream>>>(mapA, mapB, args);
+        OO_LAUNCH_CHECK();
+        return OO_OK;
+    }
     if (dual.C2 && dual.mode == 5)
         dgemm_tn_kernel<Cfg, 5><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     else if (dual.C2 && dual.mode == 4)
@@ -695,6 +793,15 @@ int dgemm_tn(const double *At, const double *B, double *C, int64_t M, int64_t N,
     return dgemm_tn_impl(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, TnDual());
 }
 
+// the same product with the consumer warps storing their accumulators themselves (A/B tests of the staged epilogue)
+int dgemm_tn_direct(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
+                    int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
+                    int64_t strideC, cudaStream_t stream) {
+    TnDual dual;
+    dual.direct_epilogue = true;
+    return dgemm_tn_impl(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
+}
+
 // C[(a b c), n] and C2[(c b a), n] from one pass (M = d0*d1*d2, same ldc and batch stride for both)
 int dgemm_tn_swap02(const double *At, const double *B, double *C, double *C2, int d0, int d1, int d2,
                     int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA,
@@ -785,7 +892,8 @@ int dgemm_tn_class_pack(const double *At, const double *B, double *P, int tri_ro
 // dorb x ld_out doubles.  The last quarter of the symmetric class transform with expand_class fused into it.
 int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int transpose_mirror, int nclass, int dorb,
                           int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int64_t ld_out, int batch,
-                          int64_t strideA, int64_t strideB, int64_t strideOut, cudaStream_t stream) {
+                          int64_t strideA, int64_t strideB, int64_t strideOut, cudaStream_t stream,
+                          bool direct_epilogue) {
     OO_REQUIRE(Out && nclass > 0 && dorb > 0 && npair_ld >= (int64_t)nclass * (nclass + 1) / 2 && ld_out >= dorb);
     TnDual dual;
     dual.C2 = Out;
@@ -794,6 +902,7 @@ int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int tr
     dual.d1 = dorb;
     dual.d2 = transpose_mirror ? 1 : 0;
     dual.strideC2 = strideOut;
+    dual.direct_epilogue = direct_epilogue;
     return dgemm_tn_impl(At, B, Out, npair_ld * dorb, dorb, K, lda, ldb, ld_out, batch, strideA, strideB, 0, stream,
                          dual);
 }

@@ -440,10 +440,11 @@ __global__ void __launch_bounds__(256)
 hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__restrict__ cnt,
                  const int *__restrict__ idx, const double *__restrict__ val, int rdm_batched, int width, int no,
                  int na, int nIs, int64_t mat, double *__restrict__ T, double *__restrict__ Tc,
-                 double *__restrict__ Tg) {
+                 double *__restrict__ Tg, int skip_occ_pairs) {
     const int col = blockIdx.x;
     const int p = col / nIs, r = col % nIs, nI = no + na;
     if (p >= nI || r >= nI) return;
+    if (skip_occ_pairs && p < no && r < no && p != r) return;      // hess_spmm_pair_kernel does these
     const Blocks bl{no, na, nIs};
     const int home = bl.home(p, r);
     {
@@ -497,6 +498,86 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
         *o = t;
     } else {
         *reinterpret_cast<double2 *>(T + (int64_t)col * mat + c) = acc;
+    }
+}
+
+// The occ-occ off-diagonal columns in PAIRS: T[(i j), c] and T[(j i), c], i > j, from one pass over the rows either
+// of them needs.  Their two ELL lists name the same few rows of B -- the exchange rows (i j), (j i) and the Coulomb
+// rows (i j), (j i), which hold identical numbers (J[m,n] = J[n,m]) and are read through ONE index -- so a pair costs
+// 3 row reads + 2 row writes instead of 6 + 2, and every thread has 4 x 3 independent 16-byte loads in flight.
+// grid (pairs, column chunks of kPairChunk, batch); `skip` tells hess_spmm_kernel to leave these columns alone.
+constexpr int kPairUnroll = 4, kPairChunk = 256 * 2 * kPairUnroll, kPairMaxRows = 16;
+
+__global__ void __launch_bounds__(256)
+hess_spmm_pair_kernel(const double *__restrict__ B, int64_t b_stride, const int *__restrict__ cnt,
+                      const int *__restrict__ idx, const double *__restrict__ val, int rdm_batched, int width, int no,
+                      int nIs, int64_t mat, double *__restrict__ T) {
+    __shared__ int urow[kPairMaxRows];
+    __shared__ double uv0[kPairMaxRows], uv1[kPairMaxRows];
+    __shared__ int un;
+    int i = (int)((sqrtf(8.0f * (float)blockIdx.x + 1.0f) + 1.0f) * 0.5f);          // pair index -> i > j >= 0
+    while (i * (i - 1) / 2 > (int)blockIdx.x) --i;
+    while ((i + 1) * i / 2 <= (int)blockIdx.x) ++i;
+    const int j = (int)blockIdx.x - i * (i - 1) / 2;
+    const int64_t bz = blockIdx.z, nI2 = (int64_t)nIs * nIs;
+    B += bz * b_stride;
+    T += bz * nI2 * mat;
+    if (rdm_batched) {
+        cnt += bz * nI2;
+        idx += bz * nI2 * width;
+        val += bz * nI2 * width;
+    }
+    const int col0 = i * nIs + j, col1 = j * nIs + i;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int which = 0; which < 2; ++which) {
+            const int col = which ? col1 : col0;
+            for (int e = 0; e < cnt[col]; ++e) {
+                int k = idx[(int64_t)col * width + e];
+                if (k >= nI2 && k < 2 * nI2) {                        // Coulomb row (m n): read it as (max, min)
+                    const int kk = k - (int)nI2, m = kk / nIs, nn = kk % nIs;
+                    if (m < nn) k = (int)nI2 + nn * nIs + m;
+                }
+                int u = 0;
+                while (u < n && urow[u] != k) ++u;
+                if (u == n && n < kPairMaxRows) {
+                    urow[n] = k;
+                    uv0[n] = uv1[n] = 0.0;
+                    ++n;
+                }
+                if (u < kPairMaxRows) (which ? uv1 : uv0)[u] += val[(int64_t)col * width + e];
+            }
+        }
+        un = n;
+    }
+    __syncthreads();
+    const int n = un;
+    const int64_t c0 = (int64_t)blockIdx.y * kPairChunk + threadIdx.x * 2;
+    double2 a0[kPairUnroll], a1[kPairUnroll];
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) a0[u] = a1[u] = make_double2(0.0, 0.0);
+    for (int e = 0; e < n; ++e) {
+        const double *row = B + (int64_t)urow[e] * mat;
+        const double v0 = uv0[e], v1 = uv1[e];
+        double2 b[kPairUnroll];
+#pragma unroll
+        for (int u = 0; u < kPairUnroll; ++u) {
+            const int64_t c = c0 + (int64_t)u * 512;
+            b[u] = c < mat ? __ldg(reinterpret_cast<const double2 *>(row + c)) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < kPairUnroll; ++u) {
+            a0[u].x = fma(v0, b[u].x, a0[u].x); a0[u].y = fma(v0, b[u].y, a0[u].y);
+            a1[u].x = fma(v1, b[u].x, a1[u].x); a1[u].y = fma(v1, b[u].y, a1[u].y);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+        const int64_t c = c0 + (int64_t)u * 512;
+        if (c < mat) {
+            *reinterpret_cast<double2 *>(T + (int64_t)col0 * mat + c) = a0[u];
+            *reinterpret_cast<double2 *>(T + (int64_t)col1 * mat + c) = a1[u];
+        }
     }
 }
 
@@ -1159,11 +1240,19 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
     }
     // the rest (occ-occ pairs i != j), plus anything a block column has outside its block
     {
+        // occ-occ off-diagonal columns two at a time (they share their rows), everything else column by column
+        const bool pairs = no >= 2 && !(flags & OO_FLAG_HESSIAN_SPMM_UNPAIRED) && (mat % 2) == 0;
+        if (pairs) {
+            dim3 pgrid((unsigned)(no * (no - 1) / 2), (unsigned)ceil_div(mat, kPairChunk), (unsigned)batch);
+            hess_spmm_pair_kernel<<<pgrid, 256, 0, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no,
+                                                             nIp, mat, T);
+            OO_LAUNCH_CHECK();
+        }
         dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256), (unsigned)batch);
         const size_t smem = (size_t)L.width * (sizeof(double) + sizeof(int));
         if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
         hess_spmm_kernel<<<grid, 256, smem, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no, na,
-                                                   nIp, mat, T, Taa, Tg);
+                                                   nIp, mat, T, Taa, Tg, pairs ? 1 : 0);
         OO_LAUNCH_CHECK();
     }
     return launch_assemble(TView{T, Taa, Tg, no + na, nIp, no, na, nI2 * mat, L.ncol_c * mat,

@@ -84,9 +84,11 @@ enum {
                                                   previous call -- the sparse table, the C-block coefficients and the
                                                   pair runs it left in the workspace are used again (a kappa sweep at
                                                   fixed RDMs rebuilds nothing that does not depend on the integrals)  */
-    OO_FLAG_CLASS_Q1_DIRECT_STORES = 512,      /* oo_class_transform_sym_f64 (8-fold route): the quarter-1 consumer warps
-                                                  store their accumulators themselves instead of staging the tile in
-                                                  shared memory for a warp that ships it with bulk asynchronous copies */
+    OO_FLAG_CLASS_DIRECT_STORES = 512,         /* oo_class_transform_sym_f64: the consumer warps of its GEMMs store their
+                                                  accumulators themselves instead of staging the tile in shared memory
+                                                  for the warps that ship it with bulk asynchronous copies            */
+    OO_FLAG_HESSIAN_SPMM_UNPAIRED = 1024,      /* oo_class_hessian_f64: the occ-occ off-diagonal columns of the T-matrix one
+                                                  by one (generic ELL SpMM) instead of in pairs that share their rows   */
     OO_FLAG_CLASS_ERI_8FOLD = 128              /* oo_class_transform_sym_f64: `g_packed` is the 8-FOLD packed tensor of
                                                   oo_pack_eri_8fold_f64 (an eighth of N^4) instead of the pair-packed
                                                   one (half of N^4); quarter 1 unpacks it in its producer               */

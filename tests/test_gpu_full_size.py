@@ -186,9 +186,16 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
     finally:
         eng.flags = 0
     assert torch.equal(Er, Ec) and torch.equal(Gr, Gc) and torch.equal(Hf, Hc)     # same k order per element
-    # quarter 1: accumulators staged in shared memory and shipped by bulk copies (default) against direct stores
+    # occ-occ off-diagonal columns of the T-matrix in pairs sharing their rows (default) against column by column
     try:
-        eng.flags = _lib.OO_FLAG_CLASS_Q1_DIRECT_STORES
+        eng.flags = _lib.OO_FLAG_HESSIAN_SPMM_UNPAIRED
+        _, _, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
+    finally:
+        eng.flags = 0
+    assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())     # fma order within a column
+    # every GEMM of the transform: tiles staged in shared memory and shipped by bulk copies (default) against direct stores
+    try:
+        eng.flags = _lib.OO_FLAG_CLASS_DIRECT_STORES
         Ed, Gd, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
         eng.flags = 0

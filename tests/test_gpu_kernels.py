@@ -547,6 +547,12 @@ def test_class_hessian_sparse_and_dense_routes_agree(name, lib):
     finally:
         eng.flags = 0
     assert (Hs - Hd).abs().max().item() < 1e-11
+    try:                                                  # occ-occ columns one by one instead of in pairs
+        eng.flags = _lib.OO_FLAG_HESSIAN_SPMM_UNPAIRED
+        Hu = ints.hessian(F, d1, d2).clone()
+    finally:
+        eng.flags = 0
+    assert (Hs - Hu).abs().max().item() < 1e-11
     assert np.abs(Hs.cpu().numpy() - c.ref["H"]).max() < TOL_GH
     assert np.abs(Hd.cpu().numpy() - c.ref["H"]).max() < TOL_GH
     # assembly: row-tiled / shared-memory-transposed (default) against one thread per element; a pair list that
