@@ -93,6 +93,10 @@ struct TnArgs {
     int64_t a8_ld;
     // mode 3 (tri_rows): the row groups are the packed pairs r2_offset + r2 (a slab of the quarter-1 result)
     int64_t r2_offset;
+    // staged mode 5, Coulomb class: every d1 x d1 result block is symmetric, J[mn][a][b] = J[mn][b][a].  sym_T > 0
+    // (= d1 / BM tiles per side) walks only the tiles on and below the block diagonal -- sym_T (sym_T + 1) / 2 per
+    // block instead of sym_T^2 -- and the shipping warps also write the transpose of every off-diagonal tile.
+    int sym_T, sym_tiles_per_batch;
     int last_subs;   // k4-substeps of the LAST k-block that hold rows below K (whole 8-row atoms beyond K are skipped)
     // Always 0, but opaque to the compiler: ANDed with bits of every fragment a consumer loaded from
     // a stage and added to the address of that stage's "empty" arrive.  The arrive thus has a true
@@ -166,8 +170,26 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     __syncthreads();
 
-    const int tiles_per_batch = args.tiles_m * args.tiles_n;
+    const bool sym = DUAL == 5 && EPI && args.sym_T > 0;
+    const int tiles_per_batch = sym ? args.sym_tiles_per_batch : args.tiles_m * args.tiles_n;
     const int64_t total_tiles = (int64_t)tiles_per_batch * args.batch;
+    // tile number within a batch entry -> (m-tile, n-tile); `offdiag`: a tile below the diagonal of a symmetric block
+    auto tile_mn = [&](int rem, int &mt, int &nt, bool &offdiag) {
+        offdiag = false;
+        if (sym) {
+            const int TT = args.sym_T * (args.sym_T + 1) / 2;
+            const int blk = rem / TT, k = rem - blk * TT;
+            int ta = (int)((sqrtf(8.0f * (float)k + 1.0f) - 1.0f) * 0.5f);
+            while ((ta + 1) * (ta + 2) / 2 <= k) ++ta;
+            while (ta * (ta + 1) / 2 > k) --ta;
+            nt = k - ta * (ta + 1) / 2;
+            mt = blk * args.sym_T + ta;
+            offdiag = nt != ta;
+        } else {
+            mt = rem / args.tiles_n;
+            nt = rem - mt * args.tiles_n;
+        }
+    };
     // AMODE 1 walks the m-tiles as (PQ-tile outer, s inner): the CTAs that run together share one PQ panel of
     // A8, and every row RS(r, s) of that panel is needed twice -- by tile s at step r and by tile r at step s --
     // so the second use is served from L2 (the 8-fold packed tensor is read from HBM about once).
@@ -234,8 +256,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int b = (int)(tile / tiles_per_batch);
                 const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
-                const int64_t m0 = (int64_t)(rem / args.tiles_n) * Cfg::BM;
-                const int n0 = (rem % args.tiles_n) * Cfg::BN;
+                int mt, nt;
+                bool offdiag;
+                tile_mn(rem, mt, nt, offdiag);
+                const int64_t m0 = (int64_t)mt * Cfg::BM;
+                const int n0 = nt * Cfg::BN;
                 const int rows = (args.M - m0) < Cfg::BM ? (int)(args.M - m0) : Cfg::BM;
                 const int ncols = (args.N - n0) < Cfg::BN ? (int)(args.N - n0) : Cfg::BN;   // even (N and BN are)
                 named_bar_sync(kBarFull, kBarThreads);
@@ -270,6 +295,15 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             double *mir = base2 + ((int64_t)n * args.d0 + m) * plane + a;
                             for (int c = sw; c < ncols; c += kShipWarps)
                                 mir[(int64_t)(n0 + c) * args.ldc] = lds_f64(src + (uint32_t)c * 8u);
+                        }
+                        if (offdiag) {                               // symmetric block: the tile above the diagonal
+                            double *t1 = base2 + ((int64_t)m * args.d0 + n) * plane + a;
+                            double *t2 = base2 + ((int64_t)n * args.d0 + m) * plane + a;
+                            for (int c = sw; c < ncols; c += kShipWarps) {
+                                const double v = lds_f64(src + (uint32_t)c * 8u);
+                                t1[(int64_t)(n0 + c) * args.ldc] = v;
+                                if (m != n) t2[(int64_t)(n0 + c) * args.ldc] = v;
+                            }
                         }
                     }
                 }
@@ -320,8 +354,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int b = (int)(tile / tiles_per_batch);
                 const int rem = (int)(tile - (int64_t)b * tiles_per_batch);
-                const int m0 = (rem / args.tiles_n) * Cfg::BM;
-                const int n0 = (rem % args.tiles_n) * Cfg::BN;
+                int mt, nt;
+                bool offdiag;
+                tile_mn(rem, mt, nt, offdiag);
+                const int m0 = mt * Cfg::BM;
+                const int n0 = nt * Cfg::BN;
                 const int ba = args.a_batched ? b : 0;
                 const int bb = args.b_batched ? b : 0;
                 for (int kb = 0; kb < args.kblocks; ++kb) {
@@ -584,6 +621,7 @@ struct TnDual {
     int64_t strideC2 = 0;
     int64_t r2_offset = 0;
     bool direct_epilogue = false;   // true: consumer warps store to global memory themselves (A/B tests)
+    bool symmetric_blocks = false;  // mode 5: every d1 x d1 result block is symmetric (Coulomb class)
 };
 
 template <class Cfg>
@@ -625,6 +663,7 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     args.pq_lo = args.pq_cnt = 0;
     args.a8_ld = 0;
     args.r2_offset = dual.r2_offset;
+    args.sym_T = args.sym_tiles_per_batch = 0;
     args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
 
     static unsigned long long attr_set = 0;
@@ -673,7 +712,16 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     }
 #endif
     if (staged && dual.C2 && dual.mode == 5) {
-        dgemm_tn_kernel<Cfg, 5, 0, 1><<<grid, Cfg::THREADS, Cfg::EPI0_SMEM_BYTES, stream>>>(mapA, mapB, args);
+        int sgrid = grid;
+        if (dual.symmetric_blocks && Cfg::BM == Cfg::BN && dual.d1 % Cfg::BM == 0 && N == dual.d1 && M % dual.d1 == 0 &&
+            dual.d1 / Cfg::BM >= 2) {
+            // Coulomb class: only the tiles on and below the diagonal of every symmetric d1 x d1 block
+            args.sym_T = dual.d1 / Cfg::BM;
+            args.sym_tiles_per_batch = (int)(M / dual.d1) * args.sym_T * (args.sym_T + 1) / 2;
+            const int64_t stotal = (int64_t)args.sym_tiles_per_batch * batch;
+            sgrid = (int)(stotal < sm_count() ? stotal : sm_count());
+        }
+        dgemm_tn_kernel<Cfg, 5, 0, 1><<<sgrid, Cfg::THREADS, Cfg::EPI0_SMEM_BYTES, stream>>>(mapA, mapB, args);
         OO_LAUNCH_CHECK();
         return OO_OK;
     }
@@ -731,6 +779,7 @@ static int launch_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int 
     args.pq_cnt = pq_cnt;
     args.a8_ld = a8_ld;
     args.r2_offset = 0;
+    args.sym_T = args.sym_tiles_per_batch = 0;
     args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
     static unsigned long long attr_set = 0;
     if (once_per_device(attr_set)) {
@@ -903,6 +952,7 @@ int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int tr
     dual.d2 = transpose_mirror ? 1 : 0;
     dual.strideC2 = strideOut;
     dual.direct_epilogue = direct_epilogue;
+    dual.symmetric_blocks = !transpose_mirror;      // J[mn][a][b] = J[mn][b][a]; the exchange class has no such symmetry
     return dgemm_tn_impl(At, B, Out, npair_ld * dorb, dorb, K, lda, ldb, ld_out, batch, strideA, strideB, 0, stream,
                          dual);
 }

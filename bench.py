@@ -500,16 +500,18 @@ def main():
         ldp, npIp = int(lib.oo_pair_ld(ld)), int(lib.oo_pair_ld(nIp))
         npair, npI = nao * (nao + 1) // 2, (no + na) * (no + na + 1) // 2
         nI = no + na
-        # needed flop per launch: the class index unpadded, quarter 2 over the class pairs n <= m it keeps
+        # needed flop per launch: the class index unpadded, quarter 2 over the class pairs n <= m it keeps, the
+        # Coulomb quarter 4 over b <= a (J[mn][a][b] is symmetric; the kernel skips the tiles above the diagonal)
         stage_flop = [2.0 * nao * npair * nI * nao,               # quarter 1 over packed AO pairs
                       2.0 * npair * npI * nao,                    # Coulomb quarter 2 (class pairs n <= m)
-                      2.0 * nao * npI * nao * nao, 2.0 * npI * nao * nao * nao,
+                      2.0 * nao * npI * nao * nao, 2.0 * npI * nao * npair,
                       2.0 * nao * nao * npI * nao,                # exchange quarter 2 (class pairs n <= m)
                       2.0 * nao * npI * nao * nao, 2.0 * npI * nao * nao * nao]
         names = ["dgemm_tn_kernel Q1 (8-fold packed A rows gathered by bulk copies; pair-unpack epilogue)",
                  "dgemm_tn_tri_kernel J-Q2 (class pairs n <= m)", "dgemm_tn_kernel J-Q3",
-                 "dgemm_tn_kernel J-Q4 (class-expand epilogue)", "dgemm_tn_tri_kernel K-Q2 (class pairs n <= m)",
-                 "dgemm_tn_kernel K-Q3", "dgemm_tn_kernel K-Q4 (class-expand epilogue)"]
+                 "dgemm_tn_kernel J-Q4 (b <= a tiles, staged class-expand epilogue)",
+                 "dgemm_tn_tri_kernel K-Q2 (class pairs n <= m)",
+                 "dgemm_tn_kernel K-Q3", "dgemm_tn_kernel K-Q4 (staged class-expand epilogue)"]
         Cst = eng.mo_coeff(Coao, eng.rotation(kappas[0, :1], squarings))
         cbuf = eng.class_integrals(Cst)                    # complete call: every intermediate is in the workspace
         for k in range(7):
@@ -619,7 +621,8 @@ def main():
         ldp, npIp = int(lib.oo_pair_ld(ld)), int(lib.oo_pair_ld(nIp))
         # needed flop of the seven launches: quarter 1 over packed AO pairs, quarter 2 over the class pairs n <= m
         # (the triangular kernel computes nothing else), two quarters each on the packed class pairs
-        cls_flop = 2.0 * ld * ldp * nIp * ld + 2.0 * ldp * npIp * ld + 2.0 * ld * ld * npIp * ld + 8.0 * ld ** 3 * npIp
+        cls_flop = (2.0 * ld * ldp * nIp * ld + 2.0 * ldp * npIp * ld + 2.0 * ld * ld * npIp * ld + 6.0 * ld ** 3 * npIp
+                    + 2.0 * npIp * ld * ldp)                     # last term: Coulomb quarter 4 over b <= a
         # round 1 counted quarter 2 over ALL class pairs (m, n) -- what its rectangular GEMM executed
         cls_flop_r01 = (2.0 * ld * ldp * nIp * ld + 2.0 * ldp * nIp * nIp * ld + 2.0 * ld * ld * nIp * nIp * ld
                         + 8.0 * ld ** 3 * npIp)
@@ -631,8 +634,9 @@ def main():
         with open(prof) as f:
             traffic = json.load(f).get(args.workload)
     roofline = {"bound": "tensor",
-                "kernel": "dgemm_tn_kernel x7 (J/K-class transform of one evaluation: quarter 1 over packed AO pairs, "
-                          "three quarters each for the Coulomb and exchange classes; FP64 DMMA)",
+                "kernel": "dgemm_tn_kernel x5 + dgemm_tn_tri_kernel x2 (J/K-class transform of one evaluation: quarter 1 "
+                          "over 8-fold packed AO integrals, three quarters each for the Coulomb and exchange classes; "
+                          "FP64 DMMA)",
                 "achieved": cls_flop * n_evals / t_cls / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": cls_flop * n_evals / t_cls / 1e12 / peak_tf, "traffic": traffic,
                 "flop_per_unit": cls_flop, "unit_of_work": "one class transform (7 launches)",
@@ -645,8 +649,9 @@ def main():
                 "frac_of_nominal_40tf": cls_flop * n_evals / t_cls / 1e12 / 40.0,
                 "frac_with_round1_flop_count": cls_flop_r01 * n_evals / t_cls / 1e12 / peak_tf,
                 "note": "flop = what the seven launches NEED (class index padded to even only, not to the 8-wide MMA "
-                        "tile; quarter 2 over class pairs n <= m); round 1 counted quarter 2 over all (m, n) "
-                        "(frac_with_round1_flop_count, for comparison with its 0.835); launch_ms is per class transform"}
+                        "tile; quarter 2 over class pairs n <= m; Coulomb quarter 4 over b <= a); round 1 counted both "
+                        "over everything its rectangular GEMMs executed (frac_with_round1_flop_count, for comparison "
+                        "with its 0.835); launch_ms is per class transform"}
     hbm_peak, hbm_src = hbm_peak_gbs()
     N = nao
     nI = no + na

@@ -178,7 +178,8 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
         Eu, Gu, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
         eng.flags = 0
-    assert torch.equal(Eu, Ec) and torch.equal(Gu, Gc) and torch.equal(Hf, Hc)
+    assert (Eu - Ec).abs().max().item() < 1e-11 and (Gu - Gc).abs().max().item() < 1e-11
+    assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
     # quarter 2: triangular kernel (only class pairs n <= m are computed; default) against the rectangular GEMM
     try:
         eng.flags = _lib.OO_FLAG_CLASS_Q2_RECTANGULAR
@@ -199,7 +200,9 @@ def test_routes_agree_on_energy_gradient_hessian(prob):
         Ed, Gd, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=prob.kappa[:1], H_out=Hf, path="class")
     finally:
         eng.flags = 0
-    assert torch.equal(Ed, Ec) and torch.equal(Gd, Gc) and torch.equal(Hf, Hc)
+    # (the staged Coulomb quarter 4 computes J[mn][a][b] for a >= b only and mirrors it: round-off apart)
+    assert (Ed - Ec).abs().max().item() < 1e-11 and (Gd - Gc).abs().max().item() < 1e-11
+    assert (Hf - Hc).abs().max().item() < 1e-11 * max(1.0, Hc.abs().max().item())
     # AO integrals with one pair packed (N^4 / 2, TMA-tiled quarter 1) against the default 8-fold packed tensor
     # (N^4 / 8, quarter-1 rows gathered by bulk copies); both read the same g up to its own symmetry defect
     eng.g_packed, eng.eri_packing = None, "pair"
