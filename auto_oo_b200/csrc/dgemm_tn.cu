@@ -145,7 +145,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     constexpr int STAGE_BYTES = AMODE ? Cfg::LIN_STAGE_BYTES : Cfg::STAGE_BYTES;
     constexpr int A_BYTES = AMODE ? Cfg::LIN_A_BYTES : Cfg::A_BYTES;
     constexpr int NST = !EPI ? Cfg::STAGES : (AMODE ? Cfg::EPI_STAGES : (Cfg::EPI0_STAGES > 0 ? Cfg::EPI0_STAGES : 1));
-    constexpr int kShipWarps = AMODE ? 1 : 3;            // quarter 1: bulk copies only; else also a transposed mirror
+    constexpr int kShipWarps = 3;                        // the spare warps of the producer warpgroup ship the tile
     constexpr int kBarFree = 1, kBarFull = 2, kBarThreads = (Cfg::NCW + kShipWarps) * 32;   // consumers + shippers
     constexpr int TILE_BYTES = AMODE ? Cfg::EPI_TILE_BYTES : Cfg::EPI0_TILE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -315,8 +315,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 named_bar_arrive(kBarFree, kBarThreads);
             }
             if (sw == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        } else if (EPI && AMODE && warp == Cfg::NCW + 1) {
-            // ===================== shipping warp (EPI 1) =====================
+        } else if (EPI && AMODE && warp > Cfg::NCW) {
+            // ===================== shipping warps, quarter 1 (EPI 1) =====================
+            // (three of them: with a short K -- 114 orbitals are 8 k-blocks -- the 500 bulk copies of a tile would
+            //  take one warp longer than the tile's DMMAs)
+            const int sw = warp - Cfg::NCW - 1;
             const uint32_t pitch = (uint32_t)args.N * 8u;            // tile rows hold the N valid columns, dense
             named_bar_arrive(kBarFree, kBarThreads);                // the tile buffer starts out free
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -327,11 +330,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int rows = (args.pq_cnt - pq0) < Cfg::BM ? (args.pq_cnt - pq0) : Cfg::BM;
                 const int pq_first = args.pq_lo + pq0;
                 named_bar_sync(kBarFull, kBarThreads);              // consumers have written (and fenced) the tile
-                if (lane == 0)                                       // packed rows (s, PQ): one contiguous run
+                if (sw == 0 && lane == 0)                            // packed rows (s, PQ): one contiguous run
                     bulk_store_1d(args.C + (int64_t)b * args.strideC + ((int64_t)s * args.d2 + pq_first) * args.ldc, ctile,
                                   (uint32_t)rows * pitch);
                 double *base2 = args.C2 + (int64_t)b * args.strideC2;
-                for (int r = lane; r < rows; r += 32) {
+                for (int r = sw * 32 + lane; r < rows; r += 32 * kShipWarps) {
                     const int pq = pq_first + r;
                     int p = (int)((sqrtf(8.0f * (float)pq + 1.0f) - 1.0f) * 0.5f);
                     while ((p + 1) * (p + 2) / 2 <= pq) ++p;
