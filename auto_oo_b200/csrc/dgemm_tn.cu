@@ -203,7 +203,13 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // two consumer warpgroups grow to 232, which holds the 128 accumulator registers of the 64x32 /
     // 32x48 warp tiles plus fragments and addressing without spilling.
     if (warp >= Cfg::NCW) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        // (the shipping warps of the staged epilogue do address arithmetic a 40-register budget makes ptxas spill:
+        //  64 / 216 there.  The registers the consumers gain must not exceed what this warpgroup gives back --
+        //  128 x (168 - 64) >= 256 x (216 - 168) -- or setmaxnreg.inc waits for ever.)
+        static_assert(128 * (168 - 64) >= 256 * (216 - 168) && 128 * (168 - 40) >= 256 * (232 - 168),
+                      "setmaxnreg.inc would wait for registers the producer warpgroup never releases");
+        if (EPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ===================== TMA producer =====================
         if (AMODE && warp == Cfg::NCW) {
             // linear-A producer: the whole warp takes part, lane k issues the bulk copy of k-row k
@@ -384,7 +390,8 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        if (EPI) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ===================== DMMA consumers =====================
         const int g = lane >> 2, t = lane & 3;
         const int wm = warp / Cfg::WGN, wn = warp % Cfg::WGN;
@@ -689,7 +696,7 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 5>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
-        if (Cfg::EPI0_STAGES >= 2) {
+        if constexpr (Cfg::EPI0_STAGES >= 2 && Cfg::BN >= 128) {
 #ifdef OO_TN_STAGE_PLAIN_STORES
             OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 0, 0, 1>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::EPI0_SMEM_BYTES));
@@ -702,8 +709,9 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
     const int grid = (int)(total < sm_count() ? total : sm_count());
     // staged epilogue (tile -> shared memory -> bulk copies by the producer warpgroup's spare warps): big tiles only
     // (the 128 x 128 configuration), even N (16-byte row pieces), at least two k-blocks to hide the shipping behind
-    const bool staged = !dual.direct_epilogue && Cfg::EPI0_STAGES >= 2 && Cfg::BN >= 128 && (N % 2) == 0 &&
-                        args.kblocks >= 2;
+    constexpr bool kCanStage = Cfg::EPI0_STAGES >= 2 && Cfg::BN >= 128;
+    const bool staged = kCanStage && !dual.direct_epilogue && (N % 2) == 0 && args.kblocks >= 2;
+  if constexpr (kCanStage) {
     // (the plain store is NOT staged: its epilogue is 3 % of a 128 x 128 tile, less than what the two-stage ring that
     //  makes room for the tile costs -- measured 0.99 -> 1.03 ms per quarter at N = 256; the kernel variant exists
     //  behind OO_TN_STAGE_PLAIN_STORES for experiments)
@@ -728,6 +736,8 @@ static int launch_tn(const double *At, const double *B, double *C, int64_t M, in
         OO_LAUNCH_CHECK();
         return OO_OK;
     }
+  }
+    (void)staged;
     if (dual.C2 && dual.mode == 5)
         dgemm_tn_kernel<Cfg, 5><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, args);
     else if (dual.C2 && dual.mode == 4)
@@ -788,19 +798,21 @@ static int launch_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int 
     if (once_per_device(attr_set)) {
         OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::LIN_SMEM_BYTES));
-        if (Cfg::EPI_SMEM_BYTES <= 227 * 1024)
+        if constexpr (Cfg::EPI_SMEM_BYTES <= 227 * 1024)
             OO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_tn_kernel<Cfg, 2, 1, 1>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::EPI_SMEM_BYTES));
     }
     const int64_t total = (int64_t)args.tiles_m * args.tiles_n * batch;
     const int grid = (int)(total < sm_count() ? total : sm_count());
     // staged epilogue: one n-tile, dense rows (ldc == N), enough shared memory, and not asked for the direct stores
-    const bool staged = !direct_epilogue && Cfg::EPI_SMEM_BYTES <= 227 * 1024 && args.tiles_n == 1 && ldc == N &&
-                        (N % 2) == 0;
-    if (staged)
-        dgemm_tn_kernel<Cfg, 2, 1, 1><<<grid, Cfg::THREADS, Cfg::EPI_SMEM_BYTES, stream>>>(mapB, mapB, args);
-    else
-        dgemm_tn_kernel<Cfg, 2, 1><<<grid, Cfg::THREADS, Cfg::LIN_SMEM_BYTES, stream>>>(mapB, mapB, args);
+    constexpr bool kCanStage = Cfg::EPI_SMEM_BYTES <= 227 * 1024;
+    bool staged = false;
+    if constexpr (kCanStage) {
+        staged = !direct_epilogue && args.tiles_n == 1 && ldc == N && (N % 2) == 0;
+        if (staged)
+            dgemm_tn_kernel<Cfg, 2, 1, 1><<<grid, Cfg::THREADS, Cfg::EPI_SMEM_BYTES, stream>>>(mapB, mapB, args);
+    }
+    if (!staged) dgemm_tn_kernel<Cfg, 2, 1><<<grid, Cfg::THREADS, Cfg::LIN_SMEM_BYTES, stream>>>(mapB, mapB, args);
     OO_LAUNCH_CHECK();
     return OO_OK;
 }
