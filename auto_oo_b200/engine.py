@@ -322,6 +322,8 @@ class HotPathEngine:
     def resident_oao(self, oao_mo_coeff):
         """Padded device copy of ``OO_energy.oao_mo_coeff``, re-uploaded only when the tensor object or its version
         counter changes (callers re-assign it or write into it: oo_pqc.py:191, Berry cell 22)."""
+        if not torch.is_tensor(oao_mo_coeff):                  # (a numpy array assigned by the caller: no version counter)
+            return self.to_padded(oao_mo_coeff, 2)
         ent = self._ws.get("oao_dev")
         if ent is None or ent[0] is not oao_mo_coeff or ent[1] != oao_mo_coeff._version:
             ent = (oao_mo_coeff, oao_mo_coeff._version, self.to_padded(oao_mo_coeff, 2))

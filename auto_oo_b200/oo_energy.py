@@ -355,7 +355,7 @@ class OO_energy:
         counter, or equal values (compared on the host for host tensors), is a hit without a device round trip."""
         eng = self.engine
         if mo_coeff is None:
-            src = self.oao_mo_coeff
+            src = _as_tensor(self.oao_mo_coeff)               # (callers may have assigned a numpy array)
             if kappa is None:
                 make = lambda: eng.mo_coeff(eng.to_padded(src, 2))[0]
             else:

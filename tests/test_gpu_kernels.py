@@ -604,10 +604,12 @@ def test_unusual_orbital_spaces_against_the_oracle(nao, nelec, ncas, nelecas, fr
         assert (H[0].cpu() - Ho).abs().max().item() < TOL_GH, path
 
 
-@pytest.mark.parametrize("nao,nelec,ncas,nelecas", [(64, 64, 4, 4), (70, 100, 6, 6), (56, 36, 4, 4)])
+@pytest.mark.parametrize("nao,nelec,ncas,nelecas", [(64, 64, 4, 4), (70, 100, 6, 6), (56, 36, 4, 4), (60, 60, 4, 4),
+                                                    (57, 44, 6, 6), (129, 40, 4, 4)])
 def test_class_transform_with_wide_class_index(nao, nelec, ncas, nelecas):
-    """Class index nIp in (16, 64]: exercises the 32/48/64-wide GEMM tiles and the dual-store epilogue
-    (small fixtures only reach the 16-wide tile).  Class tensors must equal slices of the full transform,
+    """Class index nIp in (16, 64]: exercises the 24/32/40/48/64-wide GEMM tiles, every triangular quarter-2
+    configuration (nI = 20, 32, 34; 54 takes the rectangular GEMM), an odd basis size and, at 129 orbitals, the staged
+    128 x 128 class-expand epilogue with a ragged edge (small fixtures only reach the 16-wide tile).  Class tensors must equal slices of the full transform,
     and E / G / H of both paths must agree."""
     from auto_oo_b200.engine import HotPathEngine
     from auto_oo_b200.synthetic import SyntheticMol, random_rdms, random_kappa
