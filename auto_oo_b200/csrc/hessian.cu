@@ -471,8 +471,9 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
         vl[e] = val[(int64_t)col * width + e];
     }
     __syncthreads();
-    const int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2;
-    if (c >= mat) return;
+    // (grid.y may be smaller than the number of 512-column tiles: with the pair kernel taking the occ-occ columns, a
+    //  reference-shaped RDM leaves this kernel nothing to do, and 250 000 CTAs that only find that out cost 0.15 ms)
+    for (int64_t c = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 2; c < mat; c += (int64_t)gridDim.y * blockDim.x * 2) {
     double2 acc = make_double2(0.0, 0.0);
     int e = 0;
     for (; e + 4 <= n; e += 4) {
@@ -498,6 +499,7 @@ hess_spmm_kernel(const double *__restrict__ B, int64_t b_stride, const int *__re
         *o = t;
     } else {
         *reinterpret_cast<double2 *>(T + (int64_t)col * mat + c) = acc;
+    }
     }
 }
 
@@ -1248,7 +1250,9 @@ int class_hessian(const double *cls, const double *F, const double *d1, int64_t 
                                                              nIp, mat, T);
             OO_LAUNCH_CHECK();
         }
-        dim3 grid((unsigned)nI2, (unsigned)ceil_div(mat / 2, 256), (unsigned)batch);
+        int64_t ytiles = ceil_div(mat / 2, 256);
+        if (pairs && ytiles > 8) ytiles = 8;              // what is left is (almost always) nothing: few CTAs per column
+        dim3 grid((unsigned)nI2, (unsigned)ytiles, (unsigned)batch);
         const size_t smem = (size_t)L.width * (sizeof(double) + sizeof(int));
         if (smem > 48 * 1024) return OO_ERR_UNSUPPORTED;
         hess_spmm_kernel<<<grid, 256, smem, stream>>>(cls, cls_stride, cnt, idx, val, rdm_batched, L.width, no, na,
