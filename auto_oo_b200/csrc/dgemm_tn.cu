@@ -820,6 +820,8 @@ static int launch_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int 
 //                     BM   BN  BK WGM WGN STAGES
 using TnWide = TnCfg<128, 128, 16, 2, 4, 4>;   // N > 64 : warp tile 64x32
 using TnMid = TnCfg<256, 64, 16, 4, 2, 4>;     // N in (48, 64]
+using TnM192 = TnCfg<192, 64, 16, 4, 2, 4>;    // 128 < M <= 192 rows, many columns: the C block of the Hessian (M = na^2 + no
+                                               // = 176 at CAS(12,12), 32 core orbitals) would waste a third of 128-row tiles
 using TnMid48 = TnCfg<256, 48, 16, 8, 1, 4>;   // N in (32, 48] : warp tile 32x48 (class index nIp = 44 at N=256)
 using TnMid40 = TnCfg<256, 48, 16, 8, 1, 4, 5>;   // N in (32, 40] : warp tile 32x40
 using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (24, 32] : warp tile 32x32
@@ -836,6 +838,8 @@ static int dgemm_tn_impl(const double *At, const double *B, double *C, int64_t M
     OO_REQUIRE((strideA % 2) == 0 && (strideB % 2) == 0 && (strideC % 2) == 0);
     OO_REQUIRE(((uintptr_t)At % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0);
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
+    if (N > 64 && M > 128 && M <= 192 && N >= 64 * 148 && !dual.C2)
+        return launch_tn<TnM192>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 64)
         return launch_tn<TnWide>(At, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, stream, dual);
     if (N > 48)
