@@ -691,7 +691,8 @@ def main():
 
     cpu = cpu_measured = None
     if not args.no_cpu_baseline:
-        cpu = cpu_baseline_dict(cpu_reference_sample(args.workload, CPU_SAMPLE_NAO), nao)
+        cpu_reference_sample(args.workload, CPU_SAMPLE_NAO)                # warm-up (thread pool, allocator)
+        cpu = cpu_baseline_dict(cpu_reference_sample(args.workload, CPU_SAMPLE_NAO, reps=2), nao)   # best of two
         if args.workload == "synthetic_n256_cas1212":
             eng.release_workspaces()
             torch.cuda.empty_cache()
