@@ -666,3 +666,29 @@ def test_hessian_operand_reuse_follows_the_rdms():
     assert torch.equal(Hg, ref)
     E2, G2, H2 = eng.evaluate_graphed(Coao, eng.dev(c.one_rdm), eng.dev(c.two_rdm), kappa=kap[:1])   # replay, new RDM values
     assert np.abs(H2[0].cpu().numpy() - c.ref["H"]).max() < TOL_GH
+
+
+def test_class_transform_is_reproducible_bit_for_bit():
+    """The staged epilogues and bulk-copy pipelines of the class transform hand shared-memory buffers back and forth
+    between warps; a buffer overwritten under a pending read would show up as a sporadic difference between
+    repetitions of the same transform (tools/transform_stress.py runs the long version)."""
+    from auto_oo_b200.engine import HotPathEngine
+    from auto_oo_b200.synthetic import SyntheticMol
+    from oracle import oo_oracle as orc
+    nao, nelec, ncas, nelecas = 114, 42, 6, 6
+    mol = SyntheticMol(nao, nelec, seed=3)
+    occ, act, virt = mol.get_active_space_idx(ncas, nelecas)
+    eng = HotPathEngine(mol.int1e_ao, mol.int2e_ao, mol.oao_coeff, mol.nuc, nao, len(occ), ncas,
+                        orc.non_redundant_indices(occ, act, virt, False))
+    C = eng.mo_coeff(eng.to_padded(mol.random_oao_mo_coeff, 2))
+    ref = eng.class_integrals(C).clone()
+    out = torch.empty_like(ref)
+    for _ in range(60):
+        eng.class_integrals(C, out=out)
+        assert torch.equal(out, ref)
+    eng.flags = _lib.OO_FLAG_CLASS_DIRECT_STORES
+    try:
+        direct = eng.class_integrals(C)
+    finally:
+        eng.flags = 0
+    assert (direct - ref).abs().max().item() <= 1e-12 * ref.abs().max().item()
