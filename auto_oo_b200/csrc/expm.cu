@@ -15,7 +15,10 @@
 // orbitals run the whole chain in ONE launch out of shared memory (expm_fused_kernel below).
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+#include "panel.cuh"
 
 namespace oo {
 
@@ -332,6 +335,240 @@ int expm_fused(FusedExpmArgs p, int batch, cudaStream_t stream) {
     return launch_expm_fused<2, 2>(p, batch, stream);
 }
 
+
+// ---- single-launch chain for 64 < N <= 256: one cooperative kernel, a grid barrier between the products -----------
+// The multi-launch route costs 1 memset + 1 scatter + 1 block kernel + 7 + s GEMM launches of 4-8 us each (and, when
+// the caller has not fixed s, a host round trip to choose it).  Here the grid stays resident: every product of the
+// chain is a phase whose 32 x 32 output tiles (panel GEMM of panel.cuh: both K panels staged at once, DMMA from shared
+// memory) are dealt round-robin to the CTAs, the Taylor blocks B_j are formed in the epilogues from the A, A2, A3
+// tiles, and grid.sync() stands where a kernel boundary was: 8 + s barriers, same arithmetic in the same order as
+// expm_scaled().  s < 0: chosen on the device, max over the batch of ceil(log2(||A_b||_1 / 0.95)) -- the rule of
+// engine.squarings_for, without its device->host round trip.
+namespace cg = cooperative_groups;
+
+struct ChainArgs {
+    const double *kappa;          // (batch, nk) packed rotation parameters, or nullptr
+    const int32_t *pl, *pr;
+    int nk;
+    const double *Ain;            // (batch, ld, ld) dense input when kappa == nullptr
+    double sign;                  // A = sign * K(kappa) / 2^s   resp.   A = sign * Ain / 2^s
+    int N, ld, batch, squarings;
+    double *ws;                   // rotation_ws_bytes(ld, batch)
+    double *U;                    // (batch, ld, ld)
+};
+
+struct ChainProduct {             // D = X Y (+ B),  B = c0 I + c1 P1 + c2 P2 (+ c3 P3);  D2 = d0 I + d1 P1 + d2 D
+    const double *X, *Y;
+    double *D;
+    const double *P1, *P2, *P3;
+    double c0, c1, c2, c3;
+    double *D2;
+    double d0, d1, d2;
+};
+
+__device__ __forceinline__ void chain_tile(const ChainProduct &q, int b, int m0, int n0, int N, int ld, int K,
+                                           double *psm) {
+    using namespace panel;
+    const int K4 = (K + 3) & ~3;
+    const int64_t off = (int64_t)b * ld * ld;
+    double *sA = psm, *sB = psm + TS * panel_ls(K);
+    stage_panel(sA, q.X + off, ld, true, m0, ld, K, K4);
+    stage_panel(sB, q.Y + off, ld, false, n0, ld, K, K4);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    double acc[2][2][2];
+    if (tile_mma(sA, sB, true, false, K, K4, psm, acc)) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int g = lane >> 2, t = lane & 3;
+        const int wm = ((warp & 3) >> 1) * 16, wn = (warp & 1) * 16;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int row = m0 + wm + i * 8 + g;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = n0 + wn + j * 8 + 2 * t + c;
+                    if (row >= ld || col >= ld) continue;
+                    const int64_t o = off + (int64_t)row * ld + col;
+                    const double eye = (row == col && row < N) ? 1.0 : 0.0;
+                    double v = acc[i][j][c];
+                    if (q.P2) {
+                        double bj = q.c0 * eye + q.c1 * q.P1[o] + q.c2 * q.P2[o];
+                        if (q.P3) bj += q.c3 * q.P3[o];
+                        v += bj;
+                    }
+                    q.D[o] = v;
+                    if (q.D2) q.D2[o] = q.d0 * eye + q.d1 * q.P1[o] + q.d2 * v;
+                }
+        }
+    }
+    __syncthreads();                                              // the reduction buffer aliases the next tile's panels
+}
+
+__device__ __forceinline__ void chain_phase(const ChainProduct *q, int nprod, int batch, int N, int ld, int K,
+                                            double *psm) {
+    const int nt = (ld + panel::TS - 1) / panel::TS;
+    const int items = nprod * batch * nt * nt;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int tile = it % (nt * nt), rest = it / (nt * nt);
+        chain_tile(q[rest % nprod], rest / nprod, (tile / nt) * panel::TS, (tile % nt) * panel::TS, N, ld, K, psm);
+    }
+}
+
+__global__ void __launch_bounds__(panel::PTHREADS) expm_chain_kernel(const ChainArgs p) {
+    extern __shared__ __align__(16) double psm[];
+    cg::grid_group grid = cg::this_grid();
+    const int N = p.N, ld = p.ld, batch = p.batch;
+    const int64_t mat = (int64_t)ld * ld, sl = mat * batch;
+    double *A2 = p.ws + 0 * sl, *A3 = p.ws + 1 * sl, *A4 = p.ws + 2 * sl, *norms = p.ws + 3 * sl;
+    double *R0 = p.ws + 7 * sl, *T0 = p.ws + 8 * sl, *T1 = p.ws + 9 * sl, *A = p.ws + (int64_t)kExpmSlots * sl;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+
+    // ---- phase 0: A = 0 (packed input) and, when s is ours to choose, ||sign * input_b||_1 per matrix
+    if (p.kappa)
+        for (int64_t i = gtid; i < sl; i += gthreads) A[i] = 0.0;
+    int squarings = p.squarings;
+    if (squarings < 0) {
+        double *colsum = psm;
+        for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+            for (int c = threadIdx.x; c < ld; c += blockDim.x) colsum[c] = 0.0;
+            __syncthreads();
+            if (p.kappa) {
+                const double *kap = p.kappa + (int64_t)b * p.nk;
+                for (int j = threadIdx.x; j < p.nk; j += blockDim.x) {
+                    const double v = fabs(kap[j]);
+                    atomicAdd(&colsum[p.pl[j]], v);
+                    atomicAdd(&colsum[p.pr[j]], v);
+                }
+            } else {
+                const double *Ab = p.Ain + (int64_t)b * mat;
+                for (int c = threadIdx.x; c < N; c += blockDim.x) {
+                    double acc = 0.0;
+                    for (int r = 0; r < N; ++r) acc += fabs(Ab[(int64_t)r * ld + c]);
+                    colsum[c] = acc;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                double m = 0.0;
+                for (int c = threadIdx.x; c < ld; c += 32) m = fmax(m, colsum[c]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (threadIdx.x == 0) norms[b] = m;
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        double m = 0.0;
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) m = fmax(m, norms[b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        double *wmax = psm;                                       // one value per warp
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+        __syncthreads();
+        double norm1 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) norm1 = fmax(norm1, wmax[w]);
+        __syncthreads();
+        squarings = 0;
+        if (norm1 > 0.95 && norm1 < 1e300) squarings = min(64, (int)ceil(log2(norm1 / 0.95)));
+    } else {
+        grid.sync();
+    }
+    // ---- phase 1: A = sign * input / 2^s
+    const double scale = p.sign * ldexp(1.0, -squarings);
+    if (p.kappa) {
+        for (int64_t i = gtid; i < (int64_t)batch * p.nk; i += gthreads) {
+            const int b = (int)(i / p.nk), j = (int)(i - (int64_t)b * p.nk);
+            const double v = scale * p.kappa[i];
+            double *Ab = A + (int64_t)b * mat;
+            const int l = p.pl[j], r = p.pr[j];
+            Ab[(int64_t)l * ld + r] = v;
+            Ab[(int64_t)r * ld + l] = -v;
+        }
+    } else {
+        for (int64_t i = gtid; i < sl; i += gthreads) {
+            const int64_t e = i % mat;
+            const int row = (int)(e / ld), col = (int)(e % ld);
+            A[i] = (row < N && col < N) ? scale * p.Ain[i] : 0.0;
+        }
+    }
+    grid.sync();
+
+    double c[kTaylorDegree + 1];
+#pragma unroll
+    for (int k = 0; k <= kTaylorDegree; ++k) c[k] = inv_factorial(k);
+    const int K = ld;
+    ChainProduct q[2];
+    // A2 = A A, and R0 = B_4 = c16 I + c17 A + c18 A2 from the same tile
+    q[0] = ChainProduct{A, A, A2, A, nullptr, nullptr, 0.0, 0.0, 0.0, 0.0, R0, c[16], c[17], c[18]};
+    chain_phase(q, 1, batch, N, ld, K, psm);
+    grid.sync();
+    // A3 = A2 A and A4 = A2 A2 in one phase
+    q[0] = ChainProduct{A2, A, A3, nullptr, nullptr, nullptr, 0.0, 0.0, 0.0, 0.0, nullptr, 0.0, 0.0, 0.0};
+    q[1] = ChainProduct{A2, A2, A4, nullptr, nullptr, nullptr, 0.0, 0.0, 0.0, 0.0, nullptr, 0.0, 0.0, 0.0};
+    chain_phase(q, 2, batch, N, ld, K, psm);
+    grid.sync();
+    // Horner in A4, then the squarings; the products ping-pong so that the last one lands in U
+    const int products = 4 + squarings;
+    const double *Rc = R0;
+    for (int i = 0; i < products; ++i) {
+        double *Rn = (i == products - 1) ? p.U : ((i % 2 == 0) ? T0 : T1);
+        if (i < 4) {
+            const int j = 3 - i;                                  // R <- R A4 + B_j
+            q[0] = ChainProduct{Rc, A4, Rn, A, A2, A3, c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3],
+                                nullptr, 0.0, 0.0, 0.0};
+        } else {
+            q[0] = ChainProduct{Rc, Rc, Rn, nullptr, nullptr, nullptr, 0.0, 0.0, 0.0, 0.0, nullptr, 0.0, 0.0, 0.0};
+        }
+        chain_phase(q, 1, batch, N, ld, K, psm);
+        if (i + 1 < products) grid.sync();
+        Rc = Rn;
+    }
+}
+
+constexpr int kChainMaxN = panel::PK_MAX;
+
+bool expm_chain_enabled() {
+    static const bool on = getenv("OO_OPT_EXPM_UNFUSED") == nullptr && getenv("OO_OPT_EXPM_MULTI_LAUNCH") == nullptr;
+    return on;
+}
+
+// The chain applies when the panel GEMM does (even ld <= 256, 16-byte aligned slots) and the device can hold a
+// cooperative grid; *launched = false leaves the work to the multi-launch route.
+int expm_chain(const ChainArgs &p, cudaStream_t stream, bool *launched) {
+    *launched = false;
+    if (!expm_chain_enabled() || p.ld > kChainMaxN || p.ld < 8 || (p.ld & 1)) return OO_OK;
+    if ((reinterpret_cast<uintptr_t>(p.ws) | reinterpret_cast<uintptr_t>(p.U)) & 15) return OO_OK;
+    static unsigned long long configured = 0;
+    static int coop[64] = {};
+    int dev = 0;
+    OO_CUDA_CHECK(cudaGetDevice(&dev));
+    if (once_per_device(configured)) {
+        OO_CUDA_CHECK(cudaFuncSetAttribute(expm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)panel::smem_bytes(kChainMaxN, 0, 0)));
+        int v = 0;
+        OO_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev));
+        if (dev < 64) coop[dev] = v;
+    }
+    if (dev >= 64 || !coop[dev]) return OO_OK;
+    size_t smem = panel::smem_bytes(p.ld, 0, 0);
+    if (smem < (size_t)p.ld * sizeof(double)) smem = (size_t)p.ld * sizeof(double);       // column sums of phase 0
+    int per_sm = 0;
+    OO_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expm_chain_kernel, panel::PTHREADS, smem));
+    if (per_sm < 1) return OO_OK;
+    const int nt = (p.ld + panel::TS - 1) / panel::TS;
+    int64_t grid = (int64_t)2 * p.batch * nt * nt;                 // the widest phase: A3 and A4
+    if (grid > (int64_t)per_sm * sm_count()) grid = (int64_t)per_sm * sm_count();
+    void *args[] = {const_cast<ChainArgs *>(&p)};
+    OO_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)expm_chain_kernel, dim3((unsigned)grid),
+                                              dim3(panel::PTHREADS), args, smem, stream));
+    *launched = true;
+    return OO_OK;
+}
+
 }  // namespace
 
 size_t rotation_ws_bytes(int ld, int batch) {
@@ -350,8 +587,14 @@ int kappa_rotation(const double *kappa, const int32_t *pl, const int32_t *pr, in
                         squarings, U};
         return expm_fused(p, batch, stream);
     }
-    if (squarings < 0) return OO_ERR_UNSUPPORTED;      // the multi-launch route needs the host's choice
     double *w = reinterpret_cast<double *>(ws);
+    {
+        ChainArgs c{kappa, pl, pr, nk, nullptr, -1.0, N, ld, batch, squarings, w, U};
+        bool launched = false;
+        const int rc = expm_chain(c, stream, &launched);
+        if (rc || launched) return rc;
+    }
+    if (squarings < 0) return OO_ERR_UNSUPPORTED;      // the multi-launch route needs the host's choice
     const int64_t sl = (int64_t)batch * ld * ld;
     double *A = w + (int64_t)kExpmSlots * sl;
     OO_CUDA_CHECK(cudaMemsetAsync(A, 0, sl * sizeof(double), stream));
@@ -374,6 +617,12 @@ int expm_general(const double *Ain, double sign, int N, int ld, int batch, int s
         return expm_fused(p, batch, stream);
     }
     double *w = reinterpret_cast<double *>(ws);
+    {
+        ChainArgs c{nullptr, nullptr, nullptr, 0, Ain, sign, N, ld, batch, squarings, w, U};
+        bool launched = false;
+        const int rc = expm_chain(c, stream, &launched);
+        if (rc || launched) return rc;
+    }
     const int64_t sl = (int64_t)batch * ld * ld;
     double *A = w + (int64_t)kExpmSlots * sl;
     int rc = lincomb(A, sign * ldexp(1.0, -squarings), Ain, 0.0, nullptr, 0.0, nullptr, 0.0, N, ld,
@@ -422,7 +671,10 @@ int int1e_transform(const double *h, int64_t stride_h, const double *C, int64_t 
 
 extern "C" {
 
-int oo_expm_device_squarings_max_n(void) { return oo::expm_fused_enabled() ? oo::kFusedMaxN8 : 0; }
+int oo_expm_device_squarings_max_n(void) {
+    if (oo::expm_chain_enabled()) return oo::kChainMaxN;      // single-launch chain (cooperative grid)
+    return oo::expm_fused_enabled() ? oo::kFusedMaxN8 : 0;
+}
 
 int oo_kappa_rotation_f64(const double *kappa, const int32_t *pair_l, const int32_t *pair_r, int nk,
                           int N, int ld, int batch, int squarings, double *U, void *ws,

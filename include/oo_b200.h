@@ -132,16 +132,18 @@ int oo_dgemm_small_f64(int transA, int transB, int M, int N, int K,
  * (vector_to_skew_symmetric) and :226-230 (math.expm(-kappa_matrix)).
  * kappa[b][nk]; pair_l/pair_r[nk] = (row, col) of each non-redundant parameter
  * (row > col): K[l,r] = +kappa, K[r,l] = -kappa.  `squarings` >= ceil(log2(||K||_1/0.95))
- * (host-chosen; Pade-[7/7] of K/2^s, Newton-Schulz solve, s squarings).
- * N <= oo_expm_device_squarings_max_n(): the whole chain is ONE launch out of shared memory, and
- * `squarings` = -1 lets the kernel apply the same rule per matrix on the device (no host round trip).
+ * (host-chosen; degree-18 Taylor polynomial of -K/2^s by Paterson-Stockmeyer, s squarings).
+ * N <= oo_expm_device_squarings_max_n(): the whole chain is ONE launch (N <= 64: one CTA per matrix out of
+ * shared memory; N <= 256: one cooperative grid, a grid barrier between the products), and `squarings` = -1
+ * lets the kernel apply the same rule on the device (per matrix for N <= 64, the maximum over the batch
+ * above; no host round trip).
  * U[b] is ld x ld.  ws: oo_workspace_bytes(OO_WS_ROTATION, N, ld, 0, batch).      */
 int oo_kappa_rotation_f64(const double *kappa, const int32_t *pair_l, const int32_t *pair_r,
                           int nk, int N, int ld, int batch, int squarings,
                           double *U, void *ws, size_t ws_bytes, void *stream);
 
-/* largest N for which `squarings` = -1 is accepted (0 when the fused kernel is disabled by
- * the environment variable OO_OPT_EXPM_UNFUSED, kept for A/B tests)               */
+/* largest N for which `squarings` = -1 is accepted: 256 (64 with the environment variable
+ * OO_OPT_EXPM_MULTI_LAUNCH, 0 with OO_OPT_EXPM_UNFUSED; both kept for A/B tests)       */
 int oo_expm_device_squarings_max_n(void);
 
 /* expm(sign * A) of arbitrary (not nec. skew) ld x ld matrices with ||A||_1 <= 0.95 * 2^squarings */

@@ -143,10 +143,12 @@ def test_expm_general_matrix(lib):
     assert (U.cpu()[:, :N, :N] - ref).abs().max().item() < 1e-12
 
 
-@pytest.mark.parametrize("N", [5, 8, 31, 40, 47, 56, 64, 65, 70, 130])
+@pytest.mark.parametrize("N", [5, 8, 31, 40, 47, 56, 64, 65, 70, 114, 130, 199, 255, 256, 258, 300])
 def test_rotation_fused_and_multi_launch_routes(lib, N):
-    """expm(-K) for sizes on both sides of the shared-memory limit (64): explicit squaring count (both routes),
-    and the device-side per-matrix choice of the fused kernel, against torch.linalg.matrix_exp."""
+    """expm(-K) for sizes on both sides of the shared-memory limit (64: one CTA per matrix) and of the single-launch
+    chain (256: one cooperative grid; above it one launch per product): explicit squaring count, and the
+    device-side choice (per matrix in the fused kernel, max over the batch in the chain), against
+    torch.linalg.matrix_exp."""
     from auto_oo_b200.engine import tril_pair_table
     gen = torch.Generator().manual_seed(N)
     ld = N + (N & 1)
@@ -154,6 +156,8 @@ def test_rotation_fused_and_multi_launch_routes(lib, N):
     pl, pr = tril_pair_table(N, np.arange(nk))
     B = 4
     scale = torch.tensor([0.0, 0.02, 0.3, 2.5])[:, None] / np.sqrt(N)
+    if N == 199:                                     # a batch wider than the grid: every CTA walks several tiles
+        B, scale = 40, torch.linspace(0.0, 1.5, 40)[:, None] / np.sqrt(N)
     kap = torch.randn(B, nk, dtype=F64, generator=gen) * scale
     K = torch.zeros(B, N, N, dtype=F64)
     K[:, pl.astype(np.int64), pr.astype(np.int64)] = kap
@@ -176,6 +180,50 @@ def test_rotation_fused_and_multi_launch_routes(lib, N):
     if N > lib.oo_expm_device_squarings_max_n():      # the multi-launch route needs the host's choice
         assert lib.oo_kappa_rotation_f64(kd.data_ptr(), pld.data_ptr(), prd.data_ptr(), nk, N, ld, B, -1,
                                          U.data_ptr(), ws.data_ptr(), nbytes, _stream()) == -2
+
+
+def test_expm_general_matrix_single_launch_chain(lib):
+    """oo_expm_f64 on dense (not skew) matrices of 100 rows: the cooperative chain with an explicit squaring count."""
+    gen = torch.Generator().manual_seed(12)
+    N, ld, B = 99, 100, 3
+    A = torch.randn(B, N, N, dtype=F64, generator=gen) * (0.6 / np.sqrt(N))
+    Ap = torch.zeros(B, ld, ld, dtype=F64)
+    Ap[:, :N, :N] = A
+    Ap = Ap.cuda()
+    U = torch.full_like(Ap, float("nan"))
+    s = max(0, int(np.ceil(np.log2(A.abs().sum(1).max().item() / 0.95))))
+    nbytes = lib.oo_workspace_bytes(1, N, ld, 0, B)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    for sign in (-1.0, 1.0):
+        assert lib.oo_expm_f64(Ap.data_ptr(), sign, N, ld, B, s, U.data_ptr(), ws.data_ptr(), nbytes, _stream()) == 0
+        ref = torch.linalg.matrix_exp(sign * A)
+        assert (U.cpu()[:, :N, :N] - ref).abs().max().item() < 1e-12
+        assert U[:, N:, :].abs().max().item() == 0 and U[:, :, N:].abs().max().item() == 0
+
+
+def test_graph_replay_above_the_shared_memory_limit():
+    """70 orbitals: the rotation is the cooperative single-launch chain with the squaring count chosen on the device;
+    it is captured into the evaluation's CUDA graph like any other launch, and replays follow new kappa values
+    (small and large norm: different squaring counts through the same graph)."""
+    from auto_oo_b200 import OO_energy
+    from auto_oo_b200.synthetic import SyntheticMol, random_rdms
+    dev = torch.device("cuda", 0)
+    mol = SyntheticMol(70, 20, seed=8, device=dev)
+    oo = OO_energy(mol, 4, 4, oao_mo_coeff=mol.random_oao_mo_coeff, device=dev)
+    eng = oo.engine
+    assert eng.N <= eng.lib.oo_expm_device_squarings_max_n()
+    one, two = random_rdms(4, 4, seed=8, device=dev)
+    Coao = eng.to_padded(oo.oao_mo_coeff, 2)
+    gen = torch.Generator().manual_seed(9)
+    for trial, amp in enumerate([0.01, 0.02, 1.0, 0.003]):
+        kap = (torch.randn(2, eng.nk, dtype=F64, generator=gen) * amp).cuda()
+        Eg, Gg, Hg = eng.evaluate_graphed(Coao, one, two, kappa=kap)
+        E, G, H = eng.evaluate(Coao, one, two, kappa=kap)
+        assert torch.equal(Eg, E) and torch.equal(Gg, G) and torch.equal(Hg, H)
+        s = eng.squarings_for(kap)
+        Es, Gs, Hs = eng.evaluate(Coao, one, two, kappa=kap, squarings=s)          # host-chosen count: same arithmetic
+        assert torch.equal(Es, E) and torch.equal(Hs, H)
+    assert len(eng._ws["graphs"]) == 1
 
 
 def test_graph_replay_equals_direct_evaluation():
