@@ -565,6 +565,7 @@ int expm_chain(const ChainArgs &p, cudaStream_t stream, bool *launched) {
     void *args[] = {const_cast<ChainArgs *>(&p)};
     OO_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)expm_chain_kernel, dim3((unsigned)grid),
                                               dim3(panel::PTHREADS), args, smem, stream));
+    OO_LAUNCH_CHECK();
     *launched = true;
     return OO_OK;
 }

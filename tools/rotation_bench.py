@@ -45,7 +45,9 @@ def measure():
             call()
         e1.record()
         torch.cuda.synchronize()
-        out[f"n{N}_batch{B}"] = {"squarings": s, "us_per_call": 1e3 * e0.elapsed_time(e1) / reps}
+        import hashlib
+        out[f"n{N}_batch{B}"] = {"squarings": s, "us_per_call": 1e3 * e0.elapsed_time(e1) / reps,
+                                 "sha1_of_U": hashlib.sha1(U.cpu().numpy().tobytes()).hexdigest()}
     return out
 
 
