@@ -25,7 +25,13 @@ OO_WS_CLASS_TRANSFORM, OO_WS_CLASS_BUFFER, OO_WS_CLASS_HESSIAN, OO_WS_CLASS_TRAN
 OO_FLAG_HESSIAN_DENSE, OO_FLAG_HESSIAN_ASSEMBLE_PER_ELEMENT, OO_FLAG_HESSIAN_ASSEMBLE_TILED = 1, 2, 4
 OO_FLAG_CLASS_UNFUSED_PACK, OO_FLAG_HESSIAN_GROUP_UNSTREAMED, OO_FLAG_HESSIAN_ASSEMBLE_UNSTREAMED = 8, 16, 32
 OO_FLAG_CLASS_Q2_RECTANGULAR, OO_FLAG_CLASS_ERI_8FOLD, OO_FLAG_HESSIAN_REUSE_OPERANDS = 64, 128, 256
-OO_FLAG_CLASS_DIRECT_STORES, OO_FLAG_HESSIAN_SPMM_UNPAIRED = 512, 1024
+OO_FLAG_CLASS_DIRECT_STORES, OO_FLAG_HESSIAN_SPMM_UNPAIRED, OO_FLAG_CLASS_Q1_UNPAIRED = 512, 1024, 2048
+
+
+def OO_FLAG_CLASS_STAGE(k):
+    """Run only GEMM stage k (0: quarter 1; 1-3: Coulomb class; 4-6: exchange class) of the symmetric class transform."""
+    return 1 << (16 + k)
+
 ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/oo_b200.h one to one

@@ -46,7 +46,7 @@ bool dgemm_tn_tri_supported(int nclass);
 int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
                             int64_t ngroups, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
                             int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream,
-                            int64_t group_offset = 0);
+                            int64_t group_offset = 0, int64_t group_ld = 0, int halves = 1);
 
 int dgemm_tn_class_expand(const double *At, const double *B, double *Out, int transpose_mirror, int nclass, int dorb,
                           int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int64_t ld_out, int batch,
@@ -314,6 +314,16 @@ __global__ void __launch_bounds__(256) expand_class_kernel(const double *__restr
     }
 }
 
+// Ccat[j][k][h * nIp + n] = C[2 j + h][k][n], n < nIp: the class columns of two evaluations side by side
+__global__ void concat_class_columns_kernel(const double *__restrict__ C, int64_t strideC, int ld, int nIp,
+                                            double *__restrict__ Ccat) {
+    const int k = blockIdx.x, j = blockIdx.y;
+    for (int c = threadIdx.x; c < 2 * nIp; c += blockDim.x) {
+        const int h = c / nIp, n = c - h * nIp;
+        Ccat[((int64_t)j * ld + k) * (2 * nIp) + c] = C[(int64_t)(2 * j + h) * strideC + (int64_t)k * ld + n];
+    }
+}
+
 }  // namespace
 
 int64_t pair_ld(int ld) {                       // packed pair count rounded up to even (TMA strides)
@@ -399,6 +409,16 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     const bool tri_q2 = dgemm_tn_tri_supported(nIp) && !(flags & OO_FLAG_CLASS_Q2_RECTANGULAR);
     const unsigned stage_mask = (flags >> 16) & 0x7fu;
     auto run = [&](int k) { return stage_mask == 0 || ((stage_mask >> k) & 1u); };
+    // Narrow class ranges (2 nIp <= 48, e.g. 24 at 114 orbitals CAS(6,6)): evaluations that share the integrals go
+    // through quarter 1 in PAIRS -- one GEMM with the 2 nIp columns [C_2j | C_2j+1] reads the packed integrals once
+    // for both and runs on the 48-column tiles (twice the DMMAs per A fragment); its output rows are 2 nIp wide,
+    // and the triangular quarter-2 launches pick their evaluation's columns through the group stride.  Everything
+    // after quarter 2 is unchanged.  An odd last evaluation goes through on its own.
+    const bool pair_q1 = (flags & OO_FLAG_CLASS_ERI_8FOLD) && !(flags & OO_FLAG_CLASS_Q1_UNPAIRED) && !slab && tri_q2 &&
+                         !g_class_unfused_pack && batch >= 2 && strideG == 0 && strideC != 0 && 2 * nIp <= 48;
+    const int npairs = pair_q1 ? batch / 2 : 0;
+    const int64_t first_single = 2 * (int64_t)npairs;
+    const int nsingle = batch - 2 * npairs;
     if (stage_mask && g_class_unfused_pack) return OO_ERR_INVALID_ARG;
     // Q1: rows (s, pq); the epilogue also writes T1t[q,p,s,m] and T1t[p,q,s,m]
     if (!run(0)) {
@@ -408,9 +428,19 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
             OO_CUDA_CHECK(cudaMemsetAsync(T1t, 0, (size_t)batch * sT1t * sizeof(double), stream));
             OO_CUDA_CHECK(cudaMemsetAsync(P0, 0, (size_t)batch * sXp * sizeof(double), stream));
         }
-        if ((rc = dgemm_tn_q1_packed8(gpk, slab ? slab_ld : ldp, slab ? (int)pq_lo : 0, slab ? (int)pq_cnt : (int)ldp, C,
-                                      T1, T1t, ld, (int)ldp, nIp, ld, ld, nIp, batch, strideG, strideC, sT1, sT1t,
-                                      stream, direct)))
+        if (npairs) {
+            // two evaluations per GEMM: B operand [C_2j | C_2j+1] (2 nIp <= 48 columns), quarter-1 rows 2 nIp wide
+            concat_class_columns_kernel<<<dim3((unsigned)ld, (unsigned)npairs), 64, 0, stream>>>(C, strideC, ld, nIp, X);
+            OO_LAUNCH_CHECK();
+            if ((rc = dgemm_tn_q1_packed8(gpk, ldp, 0, (int)ldp, X, T1, T1t, ld, (int)ldp, 2 * nIp, ld, 2 * nIp, 2 * nIp,
+                                          npairs, 0, (int64_t)ld * 2 * nIp, 2 * sT1, 2 * sT1t, stream, direct)))
+                return rc;
+        }
+        if (nsingle &&
+            (rc = dgemm_tn_q1_packed8(gpk + first_single * strideG, slab ? slab_ld : ldp, slab ? (int)pq_lo : 0,
+                                      slab ? (int)pq_cnt : (int)ldp, C + first_single * strideC, T1 + first_single * sT1,
+                                      T1t + first_single * sT1t, ld, (int)ldp, nIp, ld, ld, nIp, nsingle, strideG, strideC,
+                                      sT1, sT1t, stream, direct)))
             return rc;
     } else if ((rc = dgemm_tn_pair_unpack(gpk, C, T1, T1t, ld, ld, (int)ldp, nIp, ld, (int64_t)ld * ldp, ld, nIp,
                                           batch, strideG, strideC, sT1, sT1t, stream))) {
@@ -426,8 +456,14 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     } else if (tri_q2) {
         // (a slab: only its pairs -- groups pq_lo .. pq_lo + pq_cnt -- hold anything; the rest of P0 stays zero)
         const int64_t g_lo = slab ? pq_lo : 0, g_cnt = slab ? pq_cnt : ldp;
-        if ((rc = dgemm_tn_tri_class_pack(T1 + g_lo * nIp, C, P0, 1, nIp, ld, g_cnt, npIp, ld, ldp * nIp, ld, batch, sT1,
-                                          strideC, sXp, stream, g_lo)))
+        if (npairs &&                                      // evaluation 2 j + h: columns h nIp .. of the paired rows
+            (rc = dgemm_tn_tri_class_pack(T1, C, P0, 1, nIp, ld, ldp, npIp, ld, ldp * 2 * nIp, ld, npairs, 2 * sT1,
+                                          strideC, sXp, stream, 0, 2 * nIp, 2)))
+            return rc;
+        if (nsingle &&
+            (rc = dgemm_tn_tri_class_pack(T1 + first_single * sT1 + g_lo * nIp, C + first_single * strideC,
+                                          P0 + first_single * sXp, 1, nIp, ld, g_cnt, npIp, ld, ldp * nIp, ld, nsingle,
+                                          sT1, strideC, sXp, stream, g_lo)))
             return rc;
     } else {
         const int64_t g_lo = slab ? pq_lo : 0, g_cnt = slab ? pq_cnt : ldp;
@@ -451,8 +487,13 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
         pack_class_pairs_kernel<<<pgrid, 128, 0, stream>>>(X, P0, ld, nIp, (int)npIp, 0, sX, sXp);
         OO_LAUNCH_CHECK();
     } else if (tri_q2) {
-        if ((rc = dgemm_tn_tri_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * nIp, ld, batch, sT1t, strideC,
-                                          sXp, stream)))
+        if (npairs &&
+            (rc = dgemm_tn_tri_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * 2 * nIp, ld, npairs, 2 * sT1t,
+                                          strideC, sXp, stream, 0, 2 * nIp, 2)))
+            return rc;
+        if (nsingle &&
+            (rc = dgemm_tn_tri_class_pack(T1t + first_single * sT1t, C + first_single * strideC, P0 + first_single * sXp,
+                                          0, nIp, ld, ld2, npIp, ld, ld2 * nIp, ld, nsingle, sT1t, strideC, sXp, stream)))
             return rc;
     } else if ((rc = dgemm_tn_class_pack(T1t, C, P0, 0, nIp, ld, ld2, npIp, ld, ld2 * nIp, ld, batch, sT1t, strideC,
                                          sXp, stream))) {

@@ -53,6 +53,10 @@ struct TriArgs {
     int64_t ngroups;
     int64_t group_offset;   // tri_rows: the packed pair of group g is group_offset + g (a slab of the pairs)
     int kblocks, tiles_per_batch, batch;
+    int halves;             // 2: every group row holds the class columns of TWO evaluations side by side (quarter 1 ran
+                            // on [C_2j | C_2j+1]); tile u of batch element j is half u % 2 of group tile u / 2, reads
+                            // columns h nclass .., multiplies by C_(2j+h) and writes P_(2j+h).  The two halves of a
+                            // group tile run back to back, so the second finds the rows in L2.
     int a_batched, b_batched;
     int last_subs;          // substeps of the last k-block with rows below K
     uint32_t zero;
@@ -101,8 +105,10 @@ dgemm_tn_tri_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             uint32_t phase = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int b = (int)(tile / args.tiles_per_batch);
-                const int g0 = (int)(tile - (int64_t)b * args.tiles_per_batch) * Cfg::NCW;
-                const int ba = args.a_batched ? b : 0, bb = args.b_batched ? b : 0;
+                const int u = (int)(tile - (int64_t)b * args.tiles_per_batch);
+                const int h = u % args.halves, g0 = (u / args.halves) * Cfg::NCW;
+                const int ba = args.a_batched ? b : 0, bb = args.b_batched ? b * args.halves + h : 0;
+                const int m0 = h * args.nclass;
                 for (int kb = 0; kb < args.kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -113,8 +119,8 @@ dgemm_tn_tri_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     for (int w = 0; w < Cfg::NCW; ++w)
 #pragma unroll
                         for (int c = 0; c < Cfg::CPG; ++c)
-                            tma_load_4d(sA + (w * Cfg::CPG + c) * Cfg::CHUNK_BYTES, &mapA, &full_bar[stage], 16 * c,
-                                        g0 + w, k0, ba);
+                            tma_load_4d(sA + (w * Cfg::CPG + c) * Cfg::CHUNK_BYTES, &mapA, &full_bar[stage],
+                                        m0 + 16 * c, g0 + w, k0, ba);
 #pragma unroll
                     for (int c = 0; c < Cfg::CPG; ++c)
                         tma_load_3d(sB + c * Cfg::CHUNK_BYTES, &mapB, &full_bar[stage], 16 * c, k0, bb);
@@ -203,10 +209,11 @@ dgemm_tn_tri_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
         // ---- epilogue: P[g'][m(m+1)/2 + n] for n <= m < nclass
         const int b = (int)(tile / (uint32_t)args.tiles_per_batch);
-        const int64_t grp = (int64_t)(tile - (uint32_t)b * (uint32_t)args.tiles_per_batch) * Cfg::NCW + warp;
+        const int u = (int)(tile - (uint32_t)b * (uint32_t)args.tiles_per_batch);
+        const int64_t grp = (int64_t)(u / args.halves) * Cfg::NCW + warp;
         if (grp >= args.ngroups) continue;
         double *row0 = nullptr, *row1 = nullptr;
-        double *base = args.P + (int64_t)b * args.strideP;
+        double *base = args.P + (int64_t)(b * args.halves + u % args.halves) * args.strideP;
         if (args.tri_rows) {
             const int64_t pq = grp + args.group_offset;
             int p = (int)((sqrt(8.0 * (double)pq + 1.0) - 1.0) * 0.5);
@@ -241,15 +248,18 @@ dgemm_tn_tri_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 template <class Cfg>
 int launch_tri(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb, int64_t ngroups,
                int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch, int64_t strideA, int64_t strideB,
-               int64_t strideP, cudaStream_t stream, int64_t group_offset) {
+               int64_t strideP, cudaStream_t stream, int64_t group_offset, int64_t group_ld, int halves) {
     CUtensorMap mapA, mapB;
-    const int a_batched = (batch > 1 && strideA != 0), b_batched = (batch > 1 && strideB != 0);
-    const uint64_t dimsA[4] = {(uint64_t)nclass, (uint64_t)ngroups, (uint64_t)K, (uint64_t)(a_batched ? batch : 1)};
-    const uint64_t strA[3] = {(uint64_t)nclass, (uint64_t)lda, (uint64_t)(a_batched ? strideA : lda * K)};
+    const int a_batched = (batch > 1 && strideA != 0);
+    const int b_batched = ((batch > 1 || halves > 1) && strideB != 0);
+    // (halves = 2: the innermost extent is the whole paired row, of which a tile reads the columns of its half)
+    const uint64_t dimsA[4] = {(uint64_t)(halves > 1 ? group_ld : nclass), (uint64_t)ngroups, (uint64_t)K,
+                               (uint64_t)(a_batched ? batch : 1)};
+    const uint64_t strA[3] = {(uint64_t)group_ld, (uint64_t)lda, (uint64_t)(a_batched ? strideA : lda * K)};
     const uint32_t boxA[4] = {16, 1, (uint32_t)Cfg::BK, 1};
     int rc = encode_tmap_4d_f64(&mapA, At, dimsA, strA, boxA);
     if (rc) return rc;
-    rc = encode_tmap_3d_f64(&mapB, B, (uint64_t)nclass, (uint64_t)K, b_batched ? batch : 1, (uint64_t)ldb,
+    rc = encode_tmap_3d_f64(&mapB, B, (uint64_t)nclass, (uint64_t)K, b_batched ? batch * halves : 1, (uint64_t)ldb,
                             b_batched ? (uint64_t)strideB : (uint64_t)ldb * K, 16, Cfg::BK);
     if (rc) return rc;
     TriArgs args;
@@ -262,8 +272,9 @@ int launch_tri(const double *At, const double *B, double *P, int tri_rows, int n
     args.ngroups = ngroups;
     args.group_offset = group_offset;
     args.kblocks = (int)ceil_div(K, Cfg::BK);
-    args.tiles_per_batch = (int)ceil_div(ngroups, Cfg::NCW);
+    args.tiles_per_batch = (int)ceil_div(ngroups, Cfg::NCW) * halves;
     args.batch = batch;
+    args.halves = halves;
     args.a_batched = a_batched;
     args.b_batched = b_batched;
     args.last_subs = 2 * (int)ceil_div(K - (int64_t)(args.kblocks - 1) * Cfg::BK, 8);
@@ -287,18 +298,24 @@ bool dgemm_tn_tri_supported(int nclass) { return nclass > 16 && nclass <= 48 && 
 // X[(g, m), n] = sum_k At[k, (g m)] B[k, n] for n <= m only, stored as P[g'][m(m+1)/2 + n] (rows of npair_ld doubles).
 // At: K x (ngroups * nclass), leading dimension lda (= ngroups * nclass rows back to back), B: K x nclass (ldb).
 // tri_rows: g = p(p+1)/2 + q is a packed pair of `dorb` orbitals and both P[(p q)] and P[(q p)] are written.
+// group_ld > nclass: the groups lie group_ld doubles apart (a column slice of a wider quarter-1 result).
+// halves = 2 (group_ld >= 2 nclass): every group row holds two evaluations side by side; batch counts such PAIRS
+// (strideA between pairs), B and P hold 2 batch matrices (strideB, strideP between consecutive evaluations).
 int dgemm_tn_tri_class_pack(const double *At, const double *B, double *P, int tri_rows, int nclass, int dorb,
                             int64_t ngroups, int64_t npair_ld, int64_t K, int64_t lda, int64_t ldb, int batch,
                             int64_t strideA, int64_t strideB, int64_t strideP, cudaStream_t stream,
-                            int64_t group_offset) {
+                            int64_t group_offset, int64_t group_ld, int halves) {
     OO_REQUIRE(At && B && P && nclass > 0 && ngroups > 0 && K > 0 && batch > 0 && dorb > 0);
+    if (group_ld == 0) group_ld = nclass;
+    OO_REQUIRE((halves == 1 || halves == 2) && group_ld >= (int64_t)halves * nclass && (group_ld % 2) == 0);
+    OO_REQUIRE(lda >= (ngroups - 1) * group_ld + (int64_t)halves * nclass);
     OO_REQUIRE(dgemm_tn_tri_supported(nclass) && npair_ld >= (int64_t)nclass * (nclass + 1) / 2);
     OO_REQUIRE((lda % 2) == 0 && (ldb % 2) == 0 && (strideA % 2) == 0 && (strideB % 2) == 0);
     OO_REQUIRE(((uintptr_t)At % 16) == 0 && ((uintptr_t)B % 16) == 0);
-    if (ngroups >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
+    if (ngroups * halves >= (1ll << 31) || K >= (1ll << 31)) return OO_ERR_UNSUPPORTED;
 #define OO_TRI(GP, MTC)                                                                                              \
     return launch_tri<TriCfg<GP, MTC, 4>>(At, B, P, tri_rows, nclass, dorb, ngroups, npair_ld, K, lda, ldb, batch, strideA, \
-                                          strideB, strideP, stream, group_offset)
+                                          strideB, strideP, stream, group_offset, group_ld, halves)
     if (nclass <= 24) OO_TRI(32, 3);
     if (nclass <= 32) OO_TRI(32, 4);
     if (nclass <= 40) OO_TRI(48, 5);

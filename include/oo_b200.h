@@ -89,6 +89,9 @@ enum {
                                                   for the warps that ship it with bulk asynchronous copies            */
     OO_FLAG_HESSIAN_SPMM_UNPAIRED = 1024,      /* oo_class_hessian_f64: the occ-occ off-diagonal columns of the T-matrix one
                                                   by one (generic ELL SpMM) instead of in pairs that share their rows   */
+    OO_FLAG_CLASS_Q1_UNPAIRED = 2048,          /* oo_class_transform_sym_f64: every evaluation of a batch through its
+                                                  own quarter-1 GEMM, also when two narrow class ranges (2 nIp <= 48
+                                                  columns) would share one                                              */
     OO_FLAG_CLASS_ERI_8FOLD = 128              /* oo_class_transform_sym_f64: `g_packed` is the 8-FOLD packed tensor of
                                                   oo_pack_eri_8fold_f64 (an eighth of N^4) instead of the pair-packed
                                                   one (half of N^4); quarter 1 unpacks it in its producer               */

@@ -253,6 +253,27 @@ def test_batch_equals_members_and_redundant_rotations_leave_energy_unchanged(pro
     assert abs(Ea.item() - Eb.item()) < TOL_E * max(1.0, abs(Ea.item()) * 1e-2)
 
 
+def test_paired_quarter_one_equals_one_gemm_per_evaluation(prob):
+    """Class ranges of at most 24 orbitals (114 orbitals CAS(6,6)): two evaluations of a batch share ONE quarter-1 GEMM
+    over the packed integrals (48 columns [C_2j | C_2j+1]) and the quarter-2 launches read their halves of its rows;
+    an odd last evaluation runs alone.  Same k order per element: bit-identical to one GEMM per evaluation."""
+    eng, nk = prob.eng, prob.oo.n_kappa
+    kap = torch.cat([prob.kappa, 0.5 * prob.kappa[:1]])                    # a pair and an odd one
+    H3 = torch.empty(3, nk, nk, dtype=F64, device=prob.dev) if prob.nao <= 128 else None
+    E3, G3, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=kap, want_hessian=H3 is not None, H_out=H3)
+    H1 = None if H3 is None else torch.empty_like(H3)
+    try:
+        eng.flags = _lib.OO_FLAG_CLASS_Q1_UNPAIRED
+        E1, G1, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=kap, want_hessian=H1 is not None, H_out=H1)
+    finally:
+        eng.flags = 0
+    assert torch.equal(E3, E1) and torch.equal(G3, G1)
+    assert H3 is None or torch.equal(H3, H1)
+    for b in range(3):                  # and each member on its own (its own squaring count in expm: round-off apart)
+        Eb, Gb, _ = eng.evaluate(prob.Coao, prob.one, prob.two, kappa=kap[b:b + 1], want_hessian=False)
+        assert (Eb[0] - E3[b]).abs().item() < TOL_E and (Gb[0] - G3[b]).abs().max().item() < TOL_GH
+
+
 def test_gradient_and_hessian_are_derivatives_of_the_energy(prob):
     eng, nk = prob.eng, prob.oo.n_kappa
     H = torch.empty(1, nk, nk, dtype=F64, device=prob.dev)
