@@ -409,13 +409,14 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
     const bool tri_q2 = dgemm_tn_tri_supported(nIp) && !(flags & OO_FLAG_CLASS_Q2_RECTANGULAR);
     const unsigned stage_mask = (flags >> 16) & 0x7fu;
     auto run = [&](int k) { return stage_mask == 0 || ((stage_mask >> k) & 1u); };
-    // Narrow class ranges (2 nIp <= 48, e.g. 24 at 114 orbitals CAS(6,6)): evaluations that share the integrals go
-    // through quarter 1 in PAIRS -- one GEMM with the 2 nIp columns [C_2j | C_2j+1] reads the packed integrals once
-    // for both and runs on the 48-column tiles (twice the DMMAs per A fragment); its output rows are 2 nIp wide,
-    // and the triangular quarter-2 launches pick their evaluation's columns through the group stride.  Everything
-    // after quarter 2 is unchanged.  An odd last evaluation goes through on its own.
+    // Evaluations that share the integrals go through quarter 1 in PAIRS where a tile configuration fits the 2 nIp
+    // columns [C_2j | C_2j+1] (up to 48: e.g. 2 x 24 at 114 orbitals CAS(6,6); 81 .. 96: 2 x 44 at N=256, which
+    // fill 88 of 88 computed columns where one evaluation fills 44 of 48): one GEMM reads the packed integrals once
+    // for both; its output rows are 2 nIp wide, and the triangular quarter-2 launch reads each evaluation's half of
+    // them.  Everything after quarter 2 is unchanged.  An odd last evaluation goes through on its own.
+    const bool pair_cols = 2 * nIp <= 48 || (2 * nIp > 80 && 2 * nIp <= 96);
     const bool pair_q1 = (flags & OO_FLAG_CLASS_ERI_8FOLD) && !(flags & OO_FLAG_CLASS_Q1_UNPAIRED) && !slab && tri_q2 &&
-                         !g_class_unfused_pack && batch >= 2 && strideG == 0 && strideC != 0 && 2 * nIp <= 48;
+                         !g_class_unfused_pack && batch >= 2 && strideG == 0 && strideC != 0 && pair_cols;
     const int npairs = pair_q1 ? batch / 2 : 0;
     const int64_t first_single = 2 * (int64_t)npairs;
     const int nsingle = batch - 2 * npairs;
@@ -429,7 +430,7 @@ int class_transform_sym(const double *gpk, int64_t strideG, const double *C, int
             OO_CUDA_CHECK(cudaMemsetAsync(P0, 0, (size_t)batch * sXp * sizeof(double), stream));
         }
         if (npairs) {
-            // two evaluations per GEMM: B operand [C_2j | C_2j+1] (2 nIp <= 48 columns), quarter-1 rows 2 nIp wide
+            // two evaluations per GEMM: B operand [C_2j | C_2j+1], quarter-1 rows 2 nIp wide
             concat_class_columns_kernel<<<dim3((unsigned)ld, (unsigned)npairs), 64, 0, stream>>>(C, strideC, ld, nIp, X);
             OO_LAUNCH_CHECK();
             if ((rc = dgemm_tn_q1_packed8(gpk, ldp, 0, (int)ldp, X, T1, T1t, ld, (int)ldp, 2 * nIp, ld, 2 * nIp, 2 * nIp,

@@ -827,6 +827,10 @@ using TnMid40 = TnCfg<256, 48, 16, 8, 1, 4, 5>;   // N in (32, 40] : warp tile 3
 using TnNarrow = TnCfg<256, 32, 16, 8, 1, 4>;  // N in (24, 32] : warp tile 32x32
 using TnNarrow24 = TnCfg<256, 32, 16, 8, 1, 4, 3>;  // N in (16, 24] : warp tile 32x24 (class index 24 at 114 orbitals)
 using TnSlim = TnCfg<256, 16, 16, 8, 1, 4>;    // N <= 16 : warp tile 32x16
+// quarter 1 of TWO evaluations side by side (classes.cu: columns [C_2j | C_2j+1], 2 x 44 at N=256): warp tile 16x88 / 16x96
+// -- 88 accumulator registers, and the 128 x 88 result tile (90 KB) still fits next to a three-stage ring
+using TnPair88 = TnCfg<128, 96, 16, 8, 1, 4, 11>;
+using TnPair96 = TnCfg<128, 96, 16, 8, 1, 4>;
 
 static int dgemm_tn_impl(const double *At, const double *B, double *C, int64_t M, int64_t N, int64_t K,
                          int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
@@ -923,6 +927,8 @@ int dgemm_tn_q1_packed8(const double *A8, int64_t a8_ld, int pq_lo, int pq_cnt, 
 #define OO_Q1(CFG)                                                                                                 \
     return launch_tn_q1_packed8<CFG>(A8, a8_ld, pq_lo, pq_cnt, B, C, C2, dorb, dorb, dP, N, K, ldb, ldc, batch,      \
                                      strideA8, strideB, strideC, strideC2, stream, direct_epilogue)
+    if (N > 88 && N <= 96) OO_Q1(TnPair96);
+    if (N > 80 && N <= 88) OO_Q1(TnPair88);
     if (N > 64) OO_Q1(TnWide);
     if (N > 48) OO_Q1(TnMid);
     if (N > 40) OO_Q1(TnMid48);

@@ -258,7 +258,7 @@ class HotPathEngine:
     def workspace(self, key, nbytes):
         buf = self._ws.get(key)
         if buf is None or buf.numel() < nbytes:
-            self._ws[key] = None
+            self._ws[key] = buf = None                       # the old block goes back to the allocator first
             buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             self._ws[key] = buf
         return buf
@@ -666,14 +666,34 @@ class HotPathEngine:
                                                   flags, self.stream), "class_hessian")
         return H
 
+    def pairs_quarter_one(self):
+        """True when `oo_class_transform_sym_f64` sends two evaluations of a batch through one quarter-1 GEMM (the
+        same conditions as in csrc/classes.cu: 8-fold packed integrals shared by the batch, triangular quarter 2, a
+        tile configuration for the 2 nIp columns)."""
+        w = 2 * self.nIp
+        off = _lib.OO_FLAG_CLASS_Q1_UNPAIRED | _lib.OO_FLAG_CLASS_UNFUSED_PACK | _lib.OO_FLAG_CLASS_Q2_RECTANGULAR
+        return (self.eri_packing == "8fold" and self.pair_shard is None and self.n_geom == 0 and not (self.flags & off)
+                and 16 < self.nIp <= 48 and (w <= 48 or 80 < w <= 96) and self.eri_is_symmetric())
+
     def class_chunk(self, B):
         """How many evaluations the class path processes per batched launch: as many as keep the
-        transform + Hessian workspaces under ~8 GB (always at least one)."""
+        transform + Hessian workspaces under ~8 GB (always at least one) -- and two where quarter 1 runs on pairs
+        of evaluations and the device has the room (N=256: 2 x 16 GB)."""
         which = _lib.OO_WS_CLASS_TRANSFORM_SYM if self.eri_is_symmetric() else _lib.OO_WS_CLASS_TRANSFORM
         per = (self.lib.oo_workspace_bytes(which, self.N, self.ld, self.nI, 1)
                + self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_HESSIAN, self.na, self.ld, self.nI, 1)
                + self.lib.oo_workspace_bytes(_lib.OO_WS_CLASS_BUFFER, self.N, self.ld, self.nI, 1))
-        return int(max(1, min(B, (8 << 30) // max(per, 1))))
+        n = int(max(1, min(B, (8 << 30) // max(per, 1))))
+        if n < 2 <= B and self.pairs_quarter_one():
+            room = self._ws.get("pair_room")                 # asked once (cudaMemGetInfo is not free); forgotten with
+            if room is None:                                 # the workspaces (release_workspaces)
+                free, _ = torch.cuda.mem_get_info(self.device)
+                free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+                held = sum(self._ws[k].numel() for k in ("cls", "chess") if torch.is_tensor(self._ws.get(k)))
+                room = self._ws["pair_room"] = bool(2 * per <= 0.6 * (free + held))
+            if room:
+                n = 2
+        return n
 
     # ------------------------------------------------------------------ K3
     def active_hamiltonian(self, h, g):

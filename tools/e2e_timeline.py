@@ -17,8 +17,11 @@ oo = OO_energy(mol, ncas, nelecas, oao_mo_coeff=mol.random_oao_mo_coeff, device=
 mol._int2e = mol._B = None
 oo.int2e_ao = None
 oo.engine.drop_full_eri()
+if len(sys.argv) > 1 and sys.argv[1] == "unpaired":          # one quarter-1 GEMM per evaluation (A/B)
+    from auto_oo_b200 import _lib
+    oo.engine.flags = _lib.OO_FLAG_CLASS_Q1_UNPAIRED
 one, two = random_rdms(ncas, nelecas, seed=5)
-B, steps = 4, 6
+B, steps = 4, 8
 kap = random_kappa(oo.n_kappa, seed=1, batch=B * steps).reshape(steps, B, -1)
 kw = dict(hessian_format="packed", pinned_results=True)
 for s in range(2):
