@@ -343,7 +343,9 @@ int expm_fused(FusedExpmArgs p, int batch, cudaStream_t stream) {
 // memory) are dealt round-robin to the CTAs, the Taylor blocks B_j are formed in the epilogues from the A, A2, A3
 // tiles, and grid.sync() stands where a kernel boundary was: 8 + s barriers, same arithmetic in the same order as
 // expm_scaled().  s < 0: chosen on the device, max over the batch of ceil(log2(||A_b||_1 / 0.95)) -- the rule of
-// engine.squarings_for, without its device->host round trip.
+// engine.squarings_for, without its device->host round trip.  (The column sums of |K| are accumulated with shared-memory
+// atomics, as the host rule's index_add_ is: their last bits depend on the order of the adds, which can only matter
+// for a norm within round-off of 0.95 * 2^s -- either count is then equally valid.)
 namespace cg = cooperative_groups;
 
 struct ChainArgs {
