@@ -66,3 +66,24 @@ def test_pending_evaluation_copies_or_aliases():
     assert fresh[2] is None and torch.equal(fresh[0], E) and fresh[0].data_ptr() != E.data_ptr()
     same = PendingEvaluation((E, G, H), None, copy=False)
     assert same.wait()[1].data_ptr() == G.data_ptr() and same.wait()[1].data_ptr() == G.data_ptr()
+
+
+def test_quarter_one_pairing_rule_matches_the_library():
+    """engine.pairs_quarter_one mirrors the condition in csrc/classes.cu: 8-fold packed integrals shared by the batch,
+    triangular quarter 2 (16 < nIp <= 48), 2 nIp columns that fit a tile configuration (<= 48 or 81 .. 96), no A/B flag."""
+    from types import SimpleNamespace
+    from auto_oo_b200 import _lib
+    from auto_oo_b200.engine import HotPathEngine
+
+    def eng(nIp, **kw):
+        d = dict(nIp=nIp, eri_packing="8fold", pair_shard=None, n_geom=0, flags=0, eri_is_symmetric=lambda: True)
+        d.update(kw)
+        return SimpleNamespace(**d)
+    rule = HotPathEngine.pairs_quarter_one
+    assert rule(eng(24)) and rule(eng(18)) and rule(eng(44)) and rule(eng(48)) and rule(eng(42))
+    assert not rule(eng(16)) and not rule(eng(26)) and not rule(eng(40)) and not rule(eng(50))
+    assert not rule(eng(24, eri_packing="pair")) and not rule(eng(24, n_geom=4)) and not rule(eng(24, pair_shard=object()))
+    assert not rule(eng(24, eri_is_symmetric=lambda: False))
+    for fl in (_lib.OO_FLAG_CLASS_Q1_UNPAIRED, _lib.OO_FLAG_CLASS_UNFUSED_PACK, _lib.OO_FLAG_CLASS_Q2_RECTANGULAR):
+        assert not rule(eng(44, flags=fl))
+    assert rule(eng(44, flags=_lib.OO_FLAG_CLASS_DIRECT_STORES))
